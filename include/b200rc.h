@@ -1,0 +1,286 @@
+/*
+ * b200rc.h -- C ABI of the B200-native direct-volume-ray-casting path.
+ *
+ * This is the drop-in boundary: everything a Voreen
+ * `Processor` needs to replace the GL draw call of SingleVolumeRaycaster /
+ * MultiVolumeRaycaster / MeshEntryExitPoints / OptimizedProxyGeometry with
+ * hand-written sm_100a CUDA.  Plain pointers and sizes only; no C++ types, no
+ * torch types.  All entry points return an int status (0 = B200RC_OK); none
+ * throws.  `b200rc_last_error()` returns a human readable message for the last
+ * failing call on a context.
+ *
+ * Conventions (all taken from the reference):
+ *   - matrices are float[16], row-major, column-vector convention (M * v),
+ *     i.e. the memory order of tgt::mat4::elem (V/ext/tgt/matrix.h).
+ *   - texture space = [0,1]^3 with voxel i centred at (i+0.5)/dim
+ *     (V/src/core/datastructures/volume/volumebase.cpp:221-231).
+ *   - images are row-major, row 0 = bottom row (GL window coordinates,
+ *     gl_FragCoord.y = row + 0.5), pixel (x,y) at index y*width + x.
+ *   - colours are RGBA, premultiplied exactly as the GLSL compositing leaves them
+ *     (V/modules/core/glsl/modules/mod_compositing.frag:47-59).
+ *
+ * V/ = /root/reference/voreen/
+ */
+#ifndef B200RC_H
+#define B200RC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200RC_ABI_VERSION 1
+#define B200RC_MAX_VOLUMES 4   /* MultiVolumeRaycaster: volume1..4 (multivolumeraycaster.cpp:41-65) */
+#define B200RC_MAX_CHANNELS 4  /* SingleVolumeRaycaster: NUM_CHANNELS 1..4 (singlevolumeraycaster.cpp:440-445) */
+#define B200RC_MAX_OUTPUTS 3   /* image.output, image.output1, image.output2 (volumeraycaster.cpp:44-49) */
+
+typedef struct b200rc_ctx b200rc_ctx;
+
+/* ---- status codes ------------------------------------------------------------------------- */
+enum {
+    B200RC_OK = 0,
+    B200RC_ERR_INVALID = 1,      /* bad argument / unsupported combination (reference logs LERROR) */
+    B200RC_ERR_CUDA = 2,         /* CUDA runtime error, see b200rc_last_error */
+    B200RC_ERR_NO_DEVICE = 3,    /* no sm_100 device: there is NO CPU fallback */
+    B200RC_ERR_NOT_READY = 4,    /* missing volume / TF (Processor::isReady() == false) */
+    B200RC_ERR_OOM = 5
+};
+
+/* ---- enums mirroring the reference's option strings ------------------------------------------ */
+/* volume element types the GL path accepts (V/src/core/datastructures/volume/volumegl.cpp:122-139) */
+enum { B200RC_U8 = 1, B200RC_U16 = 2, B200RC_F32 = 3 };
+
+/* "gradient" property (V/src/core/processors/volumeraycaster.cpp:126-131,197-207) */
+enum { B200RC_GRAD_NONE = 0, B200RC_GRAD_FORWARD = 1, B200RC_GRAD_CENTRAL = 2, B200RC_GRAD_SOBEL = 3, B200RC_GRAD_FILTERED = 4 };
+
+/* "classification" property (V/src/core/utils/classificationmodes.cpp:84-90).  The three pre-integrated modes differ
+ * only in how the table is built; the marcher sees B200RC_CLASS_PREINT. */
+enum { B200RC_CLASS_TF = 0, B200RC_CLASS_PREINT = 1, B200RC_CLASS_TF2D = 2 };
+
+/* pre-integration table builders (classificationmodes.cpp:56-73, preintegrationtable.cpp:67-204, preintegration.frag) */
+enum { B200RC_PI_CPU = 0, B200RC_PI_APPROX = 1, B200RC_PI_GPU = 2 };
+
+/* "shading" property (V/src/core/utils/glsl.cpp:397-437) */
+enum {
+    B200RC_SHADE_NONE = 0, B200RC_SHADE_PHONG_D = 1, B200RC_SHADE_PHONG_S = 2, B200RC_SHADE_PHONG_DA = 3,
+    B200RC_SHADE_PHONG_DS = 4, B200RC_SHADE_PHONG = 5, B200RC_SHADE_TOON = 6, B200RC_SHADE_COOK_TORRANCE = 7,
+    B200RC_SHADE_OREN_NAYAR = 8, B200RC_SHADE_WARD = 9
+};
+
+/* "compositing[,2,3]" properties (volumeraycaster.cpp:250-272,379-388) */
+enum { B200RC_COMP_DVR = 0, B200RC_COMP_MIP = 1, B200RC_COMP_MOP = 2, B200RC_COMP_MIDA = 3, B200RC_COMP_ISO = 4, B200RC_COMP_FHP = 5, B200RC_COMP_FHN = 6 };
+
+/* VolumePort texture access properties (V/src/core/ports/volumeport.cpp:262-287) */
+enum { B200RC_FILTER_NEAREST = 0, B200RC_FILTER_LINEAR = 1 };
+enum { B200RC_CLAMP_TO_EDGE = 0, B200RC_CLAMP_TO_BORDER = 1 };
+
+/* how the CUDA marcher fetches voxels (north star: "hardware-trilinear 3D texture fetches or ... staging") */
+enum {
+    B200RC_SAMPLER_EXACT = 0,   /* fp32 trilinear from the bricked pool, GL-spec float weights (bit-faithful to the oracle) */
+    B200RC_SAMPLER_TEX = 1      /* cudaArray + texture units (1.8 fixed-point weights) */
+};
+
+/* output pixel formats */
+enum {
+    B200RC_OUT_RGBA32F = 0,     /* unclamped float4, for analysis */
+    B200RC_OUT_RGBA16 = 1       /* GL_RGBA16 unorm: clamp to [0,1], round(v*65535) (RenderPort default, renderport.h:116) */
+};
+
+/* MeshEntryExitPoints "cameraInsideVolumeTechnique" (meshentryexitpoints.cpp:71) */
+enum { B200RC_INSIDE_NONE = 0, B200RC_INSIDE_GPU = 1 };
+
+/* OptimizedProxyGeometry "modeString" (optimizedproxygeometry.cpp:107-114).  The library itself builds the
+ * bounding-box cube (processCube :420-448); for the TF-dependent modes the host mirror classifies the min/max
+ * regions (b200rc_region_minmax) with the TF keys and hands the resulting cubes over as explicit boxes. */
+enum { B200RC_PROXY_BBOX = 0, B200RC_PROXY_MINBBOX = 1, B200RC_PROXY_VISIBLE_BRICKS = 2 };
+
+/* ---- PODs ------------------------------------------------------------------------------------ */
+
+/* What VolumeBase exposes to GLSL::setUniform (V/src/core/utils/glsl.cpp:38-83). */
+typedef struct b200rc_volume_desc {
+    int32_t dims[3];            /* voxels */
+    int32_t channels;           /* 1..4 */
+    int32_t dtype;              /* B200RC_U8 / U16 / F32 */
+    float   spacing[3];         /* VolumeBase::getSpacing */
+    float   offset[3];          /* VolumeBase::getOffset (position of voxel 0 centre in physical space) */
+    float   phys_to_world[16];  /* VolumeBase::getPhysicalToWorldMatrix */
+    float   rwm_scale;          /* RealWorldMapping slope  (u16 default 65535, realworldmappingmetadata.h:72-88) */
+    float   rwm_offset;         /* RealWorldMapping intercept */
+    /* Sort-last sharding: this context holds voxels [shard_lo, shard_hi) of a global volume of `dims` voxels
+     * (plus an apron of `shard_apron` voxels on every interior face, already included in the uploaded data).
+     * All zero = the whole volume is resident. */
+    int32_t shard_lo[3];
+    int32_t shard_hi[3];
+    int32_t shard_apron;
+    int32_t data_on_device;     /* 1: `data` passed to b200rc_upload_volume is a device pointer */
+} b200rc_volume_desc;
+
+/* VolumeRenderer light + material properties (V/src/core/processors/volumerenderer.cpp:41-71). */
+typedef struct b200rc_light {
+    float position[4];          /* world space, lightPosition */
+    float ambient[3];
+    float diffuse[3];
+    float specular[3];
+    float attenuation[3];       /* constant, linear, quadratic */
+    float shininess;            /* materialShininess */
+    int32_t apply_attenuation;  /* PHONG_APPLY_ATTENUATION */
+} b200rc_light;
+
+/* tgt::Camera as the raycaster and MeshEntryExitPoints consume it. */
+typedef struct b200rc_camera {
+    float view[16];             /* Camera::getViewMatrix */
+    float proj[16];             /* Camera::getProjectionMatrix(viewport) */
+    float position[3];          /* Camera::getPositionWithOffsets (world) */
+    float near_dist, far_dist;  /* for const_to_z_* (volumeraycaster.cpp:280-287) */
+} b200rc_camera;
+
+/* Per-volume settings (SingleVolumeRaycaster uses entry 0 only). */
+typedef struct b200rc_volume_params {
+    int32_t classification;     /* B200RC_CLASS_* (MultiVolumeRaycaster: classification, classification2..4) */
+    int32_t shading;            /* B200RC_SHADE_* (MultiVolumeRaycaster: shading1..4) */
+    int32_t filter;             /* B200RC_FILTER_* */
+    int32_t clamp;              /* B200RC_CLAMP_* */
+    float   border_intensity;   /* textureBorderIntensity */
+} b200rc_volume_params;
+
+/* Everything VolumeRaycaster::generateHeader + process() turn into #defines and uniforms. */
+typedef struct b200rc_params {
+    int32_t num_volumes;        /* 1 = SingleVolumeRaycaster semantics (texture-space rays);
+                                   >=1 with multi_volume=1 = MultiVolumeRaycaster semantics (world-space rays) */
+    int32_t multi_volume;
+    b200rc_volume_params vol[B200RC_MAX_VOLUMES];
+    float   sampling_step;      /* samplingStepSize_ : texture space (single) / world space (multi) */
+    float   mv_opacity_correction_factor;   /* mvOpacityCorrectionFactor_ (multivolumeraycaster.cpp:352-357) */
+    int32_t gradient;           /* B200RC_GRAD_* */
+    int32_t compositing[B200RC_MAX_OUTPUTS];
+    int32_t output_connected[B200RC_MAX_OUTPUTS];
+    float   iso_value;
+    float   mida_gamma[B200RC_MAX_OUTPUTS]; /* gammaValue1_..3_ as the shader receives them */
+    int32_t enable_channel_shift;
+    float   channel_shift[B200RC_MAX_CHANNELS][3];  /* already divided by dims (singlevolumeraycaster.cpp:270-279) */
+    b200rc_light light;
+    /* implementation knobs (no reference counterpart; never change pixels beyond the stated tolerance) */
+    int32_t sampler;            /* B200RC_SAMPLER_* */
+    int32_t empty_space_skipping;   /* 0/1: macro-cell skipping inside [entry,exit]; result-identical */
+    int32_t out_format;         /* B200RC_OUT_* */
+    int32_t quantize_depth24;   /* 1: depth rounded to GL_DEPTH_COMPONENT24 */
+    int32_t collect_stats;      /* 1: count classified samples / cast rays (slower) */
+} b200rc_params;
+
+/* MeshEntryExitPoints + proxy geometry settings for b200rc_render_camera / b200rc_entry_exit. */
+typedef struct b200rc_eep_params {
+    int32_t proxy_mode;         /* B200RC_PROXY_* */
+    int32_t proxy_cell_size;    /* macro-cell edge in voxels (OptimizedProxyGeometry stepSize) */
+    float   proxy_threshold;    /* "threshold" property (alpha <= 1e-4*threshold is empty) */
+    int32_t inside_technique;   /* B200RC_INSIDE_* */
+    int32_t jitter;             /* jitterEntryPoints */
+    float   jitter_step_length; /* jitterStepLength */
+    int32_t world_coords;       /* outputCoordinateSystem == "world" (RGBA16F storage) */
+    int32_t enable_clipping;    /* OptimizedProxyGeometry clip region, voxel coords */
+    float   clip_llf[3], clip_urb[3];
+    /* explicit proxy cubes in texture space (llf.xyz, urb.xyz each); n_boxes == 0: the (clipped) bounding box of the
+     * volume in slot 0 is used.  Host pointer. */
+    const float* boxes;
+    int32_t n_boxes;
+} b200rc_eep_params;
+
+typedef struct b200rc_stats {
+    double   last_render_ms;        /* device time of the last render call's kernels (CUDA events) */
+    double   last_march_ms;         /* ... of the ray-marching kernel alone */
+    double   last_eep_ms;
+    uint64_t rays_cast;             /* pixels with entry != exit */
+    uint64_t samples_classified;    /* samples that reached classification */
+    uint64_t samples_shaded;        /* samples with alpha > 0 */
+    uint64_t samples_nominal;       /* sum over rays of floor(tEnd/step)+1 */
+    uint64_t cells_touched;         /* 16^3 macro-cells marched (for V_touched) */
+    uint64_t kernel_launches;       /* launches since context creation */
+} b200rc_stats;
+
+/* ---- lifetime -------------------------------------------------------------------------------- */
+/* Replaces Processor::initialize()/deinitialize() GPU resource handling
+ * (pattern: V/modules/opencl/processors/openclprocessor.cpp:44-58). */
+int b200rc_abi_version(void);
+int b200rc_device_count(void);
+int b200rc_create(int device, b200rc_ctx** out_ctx);
+int b200rc_destroy(b200rc_ctx* ctx);
+const char* b200rc_last_error(const b200rc_ctx* ctx);
+/* Run all work of this context on `cuda_stream` (a cudaStream_t); NULL = the context's own stream. */
+int b200rc_set_stream(b200rc_ctx* ctx, void* cuda_stream);
+int b200rc_synchronize(b200rc_ctx* ctx);
+int b200rc_get_stats(b200rc_ctx* ctx, b200rc_stats* out);
+
+/* ---- volume: replaces VolumeGL::generateTexture + GLSL::bindVolumeTexture
+ *      (V/src/core/datastructures/volume/volumegl.cpp:106-139,336-381; V/src/core/utils/glsl.cpp:85-112).
+ *      Builds the bricked pool (and the cudaArray for B200RC_SAMPLER_TEX) plus the min/max macro-cell grid. */
+int b200rc_upload_volume(b200rc_ctx* ctx, int slot, const void* data, const b200rc_volume_desc* desc);
+int b200rc_release_volume(b200rc_ctx* ctx, int slot);
+/* Deterministic synthetic "CT-like" volume generated directly in HBM; u16, 1 channel. */
+int b200rc_synth_volume(b200rc_ctx* ctx, int slot, const b200rc_volume_desc* desc, uint64_t seed);
+/* Copies the resident (linear, x-fastest) volume back, for tests. */
+int b200rc_download_volume(b200rc_ctx* ctx, int slot, void* host_dst, size_t bytes);
+/* Min/max macro-cell grid: replaces StructureProxyGeometryBackgroundThread::computeRegionStructure
+ * (V/modules/base/processors/proxygeometry/optimizedproxygeometry.cpp:894-987).  out_minmax holds, per cell
+ * (x fastest) and channel, {min,max} in real-world units.  cells[] receives the grid size. */
+int b200rc_region_minmax(b200rc_ctx* ctx, int slot, int cell_size, int32_t cells[3], float* out_minmax, size_t out_floats);
+
+/* ---- transfer functions: replaces TransFuncBase::getTexture()->bind + TransFunc1D::setUniform
+ *      (V/src/core/datastructures/transfunc/1d/transfunc1d.cpp:184-194) and ClassificationModes::bindTexture
+ *      (V/src/core/utils/classificationmodes.cpp:56-73).  `chan` = channel (single volume) or volume slot (multi). */
+int b200rc_set_tf1d(b200rc_ctx* ctx, int chan, const uint8_t* rgba8, int width, float domain_lo, float domain_hi);
+/* Upload a host-built pre-integration table (PreIntegrationTable::getTable, rgba32f, res*res, row = sb). */
+int b200rc_set_preint(b200rc_ctx* ctx, int chan, const float* rgba32f, int res);
+/* Build the table on the device from the TF set with b200rc_set_tf1d: mode B200RC_PI_GPU follows
+ * preintegration.frag:35-87 incl. RGBA16 quantisation; B200RC_PI_CPU / _APPROX follow
+ * PreIntegrationTable::computeTable (the TF texture must then have exactly `res` texels). */
+int b200rc_build_preint(b200rc_ctx* ctx, int chan, int res, float sampling_step, int mode);
+int b200rc_download_preint(b200rc_ctx* ctx, int chan, float* rgba32f, int res);
+/* 2D TF (intensity x gradient magnitude), rgba8, LINEAR filtered (transfunc2dprimitives). */
+int b200rc_set_tf2d(b200rc_ctx* ctx, int chan, const uint8_t* rgba8, int width, int height,
+                    float domain_lo_x, float domain_hi_x, float domain_lo_y, float domain_hi_y);
+
+/* ---- entry/exit points: replaces MeshEntryExitPoints::process
+ *      (V/modules/base/processors/entryexitpoints/meshentryexitpoints.cpp:188-273) with the proxy geometry of
+ *      OptimizedProxyGeometry.  Buffers are float4 per pixel (rgb = position, a = coverage) + float depth; any
+ *      output pointer may be NULL.  Host pointers. */
+int b200rc_entry_exit(b200rc_ctx* ctx, const b200rc_eep_params* eep, const b200rc_camera* cam, int width, int height,
+                      float* entry_rgba, float* entry_depth, float* exit_rgba, float* exit_depth);
+
+/* ---- render: replaces SingleVolumeRaycaster::process / MultiVolumeRaycaster::process
+ *      (V/modules/base/processors/render/singlevolumeraycaster.cpp:246-425, multivolumeraycaster.cpp:225-417).
+ *
+ * b200rc_render consumes entry/exit buffers produced elsewhere (download of the reference's RenderPorts,
+ * pattern V/modules/base/processors/render/cpuraycaster.cpp:166-169): float4 RGBA + float depth, host memory.
+ * For multi-volume rendering entry/exit arrays hold [global, vol1..volN] consecutively.
+ * out_color[i] (i < 3) receives output i when non-NULL and output_connected[i]; out_depth the depth of output 0.
+ * Output memory: host pointers (pinned for best throughput); pixel type per params->out_format. */
+int b200rc_render(b200rc_ctx* ctx, const b200rc_params* params, const b200rc_camera* cam, int width, int height,
+                  const float* entry_rgba, const float* entry_depth, const float* exit_rgba, const float* exit_depth,
+                  void* out_color[B200RC_MAX_OUTPUTS], float* out_depth);
+
+/* Entry/exit generated on the device, then marched; nothing but parameters crosses PCIe on the way in. */
+int b200rc_render_camera(b200rc_ctx* ctx, const b200rc_params* params, const b200rc_eep_params* eep,
+                         const b200rc_camera* cam, int width, int height,
+                         void* out_color[B200RC_MAX_OUTPUTS], float* out_depth);
+
+/* Same as b200rc_render_camera but the outputs stay in HBM: out_color_dev / out_depth_dev are DEVICE pointers
+ * (used by the sort-last compositor and by device-resident benchmarks). */
+int b200rc_render_camera_device(b200rc_ctx* ctx, const b200rc_params* params, const b200rc_eep_params* eep,
+                                const b200rc_camera* cam, int width, int height,
+                                void* out_color_dev[B200RC_MAX_OUTPUTS], float* out_depth_dev);
+
+/* ---- sort-last compositing (new work; semantics = premultiplied front-to-back over, depth = min;
+ *      SURVEY section 5 / 8e).  All pointers are DEVICE pointers; float4 colour + float depth, n pixels.
+ *      dst = front OVER back.  `front` may alias dst.  With mode = compositing mode of the output:
+ *      DVR -> over; MIP/MOP -> max-alpha/intensity select (w channel carries the key); FHP/FHN/ISO -> nearer depth. */
+int b200rc_composite(b200rc_ctx* ctx, int mode, const float* front_rgba, const float* front_depth,
+                     const float* back_rgba, const float* back_depth, float* dst_rgba, float* dst_depth, size_t n);
+/* ERT finalisation after merging (alpha >= 0.95 -> 1.0, mod_raysetup.frag:65-74) and conversion to out_format. */
+int b200rc_finalize(b200rc_ctx* ctx, const float* rgba_dev, const float* depth_dev, size_t n, int out_format,
+                    void* out_color_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RC_H */

@@ -1,0 +1,488 @@
+// api.cu -- the C ABI declared in include/b200rc.h: context lifetime, parameter translation, frame orchestration.
+// No entry point throws; every failure is an error code + b200rc_last_error().  There is no CPU fallback: without an
+// sm_100 device b200rc_create fails with B200RC_ERR_NO_DEVICE.
+#include "ctx.hpp"
+#include <cmath>
+#include <cstring>
+#include <cfloat>
+#include <new>
+
+// ---- host matrix helpers, tgt semantics (V/ext/tgt/matrix.h:1327-1376 and operator*) -------------------------------
+void rc_mat4_mul(const float a[16], const float b[16], float out[16]) {
+    float r[16];
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            float s = 0.f;
+            for (int k = 0; k < 4; ++k) s += a[i * 4 + k] * b[k * 4 + j];
+            r[i * 4 + j] = s;
+        }
+    memcpy(out, r, sizeof r);
+}
+bool rc_mat4_invert(const float m[16], float out[16]) {
+    float tmp[16], res[16];
+    memcpy(tmp, m, sizeof tmp);
+    for (int i = 0; i < 16; ++i) res[i] = (i % 5 == 0) ? 1.f : 0.f;
+    for (int i = 0; i < 4; ++i) {
+        int swap = i;
+        for (int j = i + 1; j < 4; ++j)
+            if (fabsf(tmp[j * 4 + i]) > fabsf(tmp[i * 4 + i])) swap = j;
+        if (swap != i)
+            for (int k = 0; k < 4; ++k) {
+                float t = tmp[i * 4 + k]; tmp[i * 4 + k] = tmp[swap * 4 + k]; tmp[swap * 4 + k] = t;
+                t = res[i * 4 + k]; res[i * 4 + k] = res[swap * 4 + k]; res[swap * 4 + k] = t;
+            }
+        if (tmp[i * 4 + i] == 0.f) return false;
+        float t = tmp[i * 4 + i];
+        for (int k = 0; k < 4; ++k) { tmp[i * 4 + k] /= t; res[i * 4 + k] /= t; }
+        for (int j = 0; j < 4; ++j)
+            if (j != i) {
+                t = tmp[j * 4 + i];
+                for (int k = 0; k < 4; ++k) { tmp[j * 4 + k] -= tmp[i * 4 + k] * t; res[j * 4 + k] -= res[i * 4 + k] * t; }
+            }
+    }
+    memcpy(out, res, sizeof res);
+    return true;
+}
+// VolumeBase::getTextureToWorldMatrix (V/src/core/datastructures/volume/volumebase.cpp:190-231)
+void rc_texture_to_world(const b200rc_volume_desc* d, float out[16]) {
+    const float T1[16] = {1, 0, 0, -0.5f, 0, 1, 0, -0.5f, 0, 0, 1, -0.5f, 0, 0, 0, 1};
+    const float S1[16] = {(float)d->dims[0], 0, 0, 0, 0, (float)d->dims[1], 0, 0, 0, 0, (float)d->dims[2], 0, 0, 0, 0, 1};
+    const float T2[16] = {1, 0, 0, d->offset[0], 0, 1, 0, d->offset[1], 0, 0, 1, d->offset[2], 0, 0, 0, 1};
+    const float S2[16] = {d->spacing[0], 0, 0, 0, 0, d->spacing[1], 0, 0, 0, 0, d->spacing[2], 0, 0, 0, 0, 1};
+    float a[16], b[16], v2w[16];
+    rc_mat4_mul(T1, S1, a);
+    rc_mat4_mul(T2, S2, b);
+    rc_mat4_mul(d->phys_to_world, b, v2w);
+    rc_mat4_mul(v2w, a, out);
+}
+static void mat4_mul_v4(const float m[16], const float v[4], float r[4]) {
+    for (int i = 0; i < 4; ++i) r[i] = ((m[i * 4] * v[0] + m[i * 4 + 1] * v[1]) + m[i * 4 + 2] * v[2]) + m[i * 4 + 3] * v[3];
+}
+
+// ---- lifetime -------------------------------------------------------------------------------------------------------
+extern "C" int b200rc_abi_version(void) { return B200RC_ABI_VERSION; }
+
+extern "C" int b200rc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int b200rc_create(int device, b200rc_ctx** out_ctx) {
+    if (!out_ctx) return B200RC_ERR_INVALID;
+    *out_ctx = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) { cudaGetLastError(); return B200RC_ERR_NO_DEVICE; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { cudaGetLastError(); return B200RC_ERR_NO_DEVICE; }
+    if (prop.major != 10) return B200RC_ERR_NO_DEVICE;      // kernels are built for sm_100a only
+    b200rc_ctx* ctx = new (std::nothrow) b200rc_ctx();
+    if (!ctx) return B200RC_ERR_OOM;
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError(); delete ctx; return B200RC_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    for (int i = 0; i < 6; ++i) cudaEventCreate(&ctx->ev[i]);
+    cudaMalloc(&ctx->d_stats, 8 * sizeof(unsigned long long));
+    cudaMalloc(&ctx->d_tile_counter, sizeof(unsigned int));
+    *out_ctx = ctx;
+    return B200RC_OK;
+}
+
+extern "C" int b200rc_destroy(b200rc_ctx* ctx) {
+    if (!ctx) return B200RC_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int s = 0; s < B200RC_MAX_VOLUMES; ++s) rc_volume_release(ctx, s);
+    for (int c = 0; c < B200RC_MAX_CHANNELS; ++c) {
+        ClassifierSlot& k = ctx->cls[c];
+        if (k.preint_tex) cudaDestroyTextureObject(k.preint_tex);
+        if (k.preint_array) cudaFreeArray(k.preint_array);
+        cudaFree(k.tf); cudaFree(k.corr_lut); cudaFree(k.preint); cudaFree(k.tf2d); cudaFree(k.nz_tf); cudaFree(k.nz_pi); cudaFree(k.nz_2d);
+    }
+    cudaFree(ctx->d_entry); cudaFree(ctx->d_exit); cudaFree(ctx->d_entry_depth); cudaFree(ctx->d_exit_depth);
+    for (int o = 0; o < 3; ++o) cudaFree(ctx->d_out[o]);
+    cudaFree(ctx->d_out_depth); cudaFree(ctx->d_stats); cudaFree(ctx->d_tile_counter); cudaFree(ctx->d_boxes);
+    for (int i = 0; i < 6; ++i) cudaEventDestroy(ctx->ev[i]);
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return B200RC_OK;
+}
+
+extern "C" const char* b200rc_last_error(const b200rc_ctx* ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+
+extern "C" int b200rc_set_stream(b200rc_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return B200RC_ERR_INVALID;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return B200RC_OK;
+}
+
+extern "C" int b200rc_synchronize(b200rc_ctx* ctx) {
+    if (!ctx) return B200RC_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    RC_CHECK(cudaStreamSynchronize(ctx->stream));
+    return B200RC_OK;
+}
+
+extern "C" int b200rc_get_stats(b200rc_ctx* ctx, b200rc_stats* out) {
+    if (!ctx || !out) return B200RC_ERR_INVALID;
+    ctx->stats.kernel_launches = ctx->launches;
+    *out = ctx->stats;
+    return B200RC_OK;
+}
+
+#define CTX_GUARD()                                            \
+    if (!ctx) return B200RC_ERR_INVALID;                       \
+    if (cudaSetDevice(ctx->device) != cudaSuccess) { cudaGetLastError(); ctx->set_error("cudaSetDevice failed"); return B200RC_ERR_CUDA; }
+
+// ---- volume / TF pass-throughs ---------------------------------------------------------------------------------------
+extern "C" int b200rc_upload_volume(b200rc_ctx* ctx, int slot, const void* data, const b200rc_volume_desc* desc) { CTX_GUARD(); return rc_volume_upload(ctx, slot, data, desc); }
+extern "C" int b200rc_release_volume(b200rc_ctx* ctx, int slot) { CTX_GUARD(); if (slot < 0 || slot >= B200RC_MAX_VOLUMES) return B200RC_ERR_INVALID; return rc_volume_release(ctx, slot); }
+extern "C" int b200rc_synth_volume(b200rc_ctx* ctx, int slot, const b200rc_volume_desc* desc, uint64_t seed) { CTX_GUARD(); return rc_volume_synth(ctx, slot, desc, seed); }
+extern "C" int b200rc_download_volume(b200rc_ctx* ctx, int slot, void* host_dst, size_t bytes) {
+    CTX_GUARD(); if (slot < 0 || slot >= B200RC_MAX_VOLUMES || !host_dst) return B200RC_ERR_INVALID; return rc_volume_download(ctx, slot, host_dst, bytes);
+}
+extern "C" int b200rc_region_minmax(b200rc_ctx* ctx, int slot, int cell_size, int32_t cells[3], float* out_minmax, size_t out_floats) {
+    CTX_GUARD(); if (slot < 0 || slot >= B200RC_MAX_VOLUMES || !cells) return B200RC_ERR_INVALID; return rc_volume_region_minmax(ctx, slot, cell_size, cells, out_minmax, out_floats);
+}
+extern "C" int b200rc_set_tf1d(b200rc_ctx* ctx, int chan, const uint8_t* rgba8, int width, float lo, float hi) { CTX_GUARD(); return rc_tf_set_1d(ctx, chan, rgba8, width, lo, hi); }
+extern "C" int b200rc_set_preint(b200rc_ctx* ctx, int chan, const float* rgba32f, int res) { CTX_GUARD(); return rc_tf_set_preint(ctx, chan, rgba32f, res); }
+extern "C" int b200rc_build_preint(b200rc_ctx* ctx, int chan, int res, float step, int mode) { CTX_GUARD(); return rc_tf_build_preint(ctx, chan, res, step, mode); }
+extern "C" int b200rc_download_preint(b200rc_ctx* ctx, int chan, float* rgba32f, int res) {
+    CTX_GUARD();
+    if (chan < 0 || chan >= B200RC_MAX_CHANNELS || !rgba32f || ctx->cls[chan].pres != res || !ctx->cls[chan].preint) { ctx->set_error("no such pre-integration table"); return B200RC_ERR_INVALID; }
+    RC_CHECK(cudaMemcpyAsync(rgba32f, ctx->cls[chan].preint, (size_t)res * res * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    RC_CHECK(cudaStreamSynchronize(ctx->stream));
+    return B200RC_OK;
+}
+extern "C" int b200rc_set_tf2d(b200rc_ctx* ctx, int chan, const uint8_t* rgba8, int w, int h, float lox, float hix, float loy, float hiy) {
+    CTX_GUARD(); return rc_tf_set_2d(ctx, chan, rgba8, w, h, lox, hix, loy, hiy);
+}
+
+// ---- frame buffers ------------------------------------------------------------------------------------------------------
+static int ensure_frame_buffers(b200rc_ctx* ctx, size_t pixels, int images) {
+    const size_t need = pixels * (size_t)images;
+    if (need > ctx->eep_capacity) {
+        cudaFree(ctx->d_entry); cudaFree(ctx->d_exit); cudaFree(ctx->d_entry_depth); cudaFree(ctx->d_exit_depth);
+        ctx->d_entry = ctx->d_exit = nullptr; ctx->d_entry_depth = ctx->d_exit_depth = nullptr; ctx->eep_capacity = 0;
+        RC_CHECK(cudaMalloc(&ctx->d_entry, need * sizeof(float4)));
+        RC_CHECK(cudaMalloc(&ctx->d_exit, need * sizeof(float4)));
+        RC_CHECK(cudaMalloc(&ctx->d_entry_depth, need * sizeof(float)));
+        RC_CHECK(cudaMalloc(&ctx->d_exit_depth, need * sizeof(float)));
+        ctx->eep_capacity = need;
+    }
+    if (pixels > ctx->out_capacity) {
+        for (int o = 0; o < 3; ++o) { cudaFree(ctx->d_out[o]); ctx->d_out[o] = nullptr; }
+        cudaFree(ctx->d_out_depth); ctx->d_out_depth = nullptr; ctx->out_capacity = 0;
+        for (int o = 0; o < 3; ++o) RC_CHECK(cudaMalloc(&ctx->d_out[o], pixels * sizeof(float4)));
+        RC_CHECK(cudaMalloc(&ctx->d_out_depth, pixels * sizeof(float)));
+        ctx->out_capacity = pixels;
+    }
+    return B200RC_OK;
+}
+
+// ---- parameter translation: VolumeRaycaster::generateHeader + process() -> DevParams ------------------------------------
+static bool lattice_is_exact(float step, int max_samples) {
+    // t_k = fl(t_{k-1} + step) equals k*step for every k iff k*m fits the 24-bit significand, m = odd part of step
+    if (!(step > 0.f) || !std::isfinite(step)) return false;
+    int e; float fr = frexpf(step, &e);
+    uint32_t m = (uint32_t)ldexpf(fr, 24);
+    while (m && !(m & 1u)) m >>= 1;
+    return (unsigned long long)m * (unsigned long long)max_samples < (1ull << 24);
+}
+
+static int build_params(b200rc_ctx* ctx, const b200rc_params* P, const b200rc_camera* cam, int W, int H, DevParams& p, int* out_nch, int* out_dtype) {
+    memset(&p, 0, sizeof p);
+    if (!P || !cam || W < 1 || H < 1) { ctx->set_error("render: bad arguments"); return B200RC_ERR_INVALID; }
+    const int nv = P->multi_volume ? P->num_volumes : 1;
+    if (nv < 1 || nv > B200RC_MAX_VOLUMES) { ctx->set_error("render: bad volume count"); return B200RC_ERR_INVALID; }
+    if (!(P->sampling_step > 0.f)) { ctx->set_error("render: sampling step must be positive"); return B200RC_ERR_INVALID; }
+    p.W = W; p.H = H;
+    p.nvol = nv; p.multi = P->multi_volume ? 1 : 0;
+    p.step = P->sampling_step; p.mv_factor = P->mv_opacity_correction_factor;
+    p.gradient = P->gradient;
+    p.iso = P->iso_value;
+    p.light = P->light;
+    p.near_d = cam->near_dist; p.far_d = cam->far_dist;
+    p.out_format = P->out_format; p.quantize_depth24 = P->quantize_depth24;
+    p.collect_stats = P->collect_stats;
+    p.ert_snap = 1;
+    bool ert = true;
+    for (int o = 0; o < 3; ++o) {
+        p.comp[o] = P->compositing[o]; p.connected[o] = P->output_connected[o] ? 1 : 0; p.gamma[o] = P->mida_gamma[o];
+        if (p.comp[o] < B200RC_COMP_DVR || p.comp[o] > B200RC_COMP_FHN) { ctx->set_error("render: unknown compositing mode"); return B200RC_ERR_INVALID; }
+        // USE_EARLY_TERMINATION (volumeraycaster.cpp:225-233, usePortgroup_)
+        const bool can = ((p.comp[o] != B200RC_COMP_MIP) && (p.comp[o] != B200RC_COMP_MOP) && (p.comp[o] != B200RC_COMP_MIDA)) || !p.connected[o];
+        ert = ert && can;
+    }
+    p.ert = ert ? 1 : 0;
+    if (!p.connected[0] && !p.connected[1] && !p.connected[2]) { ctx->set_error("render: no output connected (isReady() == false)"); return B200RC_ERR_NOT_READY; }
+    p.preint_comp = (P->vol[0].classification == B200RC_CLASS_PREINT) ? 1 : 0;     // volumeraycaster.cpp:216-221
+    p.channel_shift = (!P->multi_volume && P->enable_channel_shift) ? 1 : 0;
+    memcpy(p.shift, P->channel_shift, sizeof p.shift);
+    float w2p[16];
+    for (int v = 0; v < nv; ++v) {
+        VolumeSlot& vs = ctx->vol[v];
+        if (!vs.valid) { ctx->set_error("render: volume slot is empty"); return B200RC_ERR_NOT_READY; }
+        const b200rc_volume_params& vp = P->vol[v];
+        VolDev& d = p.vol[v];
+        d.bricks = vs.bricks;
+        for (int a = 0; a < 3; ++a) {
+            d.dims[a] = vs.desc.dims[a]; d.res_lo[a] = vs.res_lo[a]; d.res_dims[a] = vs.res_dims[a];
+            d.own_lo[a] = vs.own_lo[a]; d.own_hi[a] = vs.own_hi[a];
+            d.clamp_lo[a] = vs.res_lo[a] > 0 ? vs.res_lo[a] : 0;
+            const int hi = vs.res_lo[a] + vs.res_dims[a] - 1;
+            d.clamp_hi[a] = hi < vs.desc.dims[a] - 1 ? hi : vs.desc.dims[a] - 1;
+            d.dimf[a] = (float)vs.desc.dims[a]; d.dims_rcp[a] = 1.f / (float)vs.desc.dims[a];       // glsl.cpp:43-44
+            d.spacing[a] = vs.desc.spacing[a]; d.spacing_rcp[a] = 1.f / vs.desc.spacing[a];
+            d.offset[a] = vs.desc.offset[a];
+            d.occ0_dims[a] = vs.cells[a]; d.occ1_dims[a] = vs.occ1_dims[a];
+        }
+        d.sharded = vs.sharded ? 1 : 0;
+        d.nbx = vs.nbx; d.nby = vs.nby;
+        d.nch = vs.desc.channels; d.dtype = vs.desc.dtype; d.stored_nch = vs.stored_nch;
+        d.rwm_scale = vs.desc.rwm_scale; d.rwm_offset = vs.desc.rwm_offset;
+        d.filter = vp.filter; d.clamp = vp.clamp; d.border = vp.border_intensity;
+        d.occ0 = vs.occ0; d.occ1 = vs.occ1; d.occ0_wpr = vs.occ0_wpr; d.occ1_wpr = vs.occ1_wpr;
+        p.classification[v] = vp.classification; p.shading[v] = vp.shading;
+        if (vp.classification < B200RC_CLASS_TF || vp.classification > B200RC_CLASS_TF2D || vp.shading < 0 || vp.shading > B200RC_SHADE_WARD) { ctx->set_error("render: unknown classification/shading mode"); return B200RC_ERR_INVALID; }
+        if (P->sampler == B200RC_SAMPLER_TEX) {
+            int rc = rc_volume_ensure_texture(ctx, v, vp.filter, vp.clamp, vp.border_intensity);
+            if (rc) return rc;
+            d.tex = vs.tex;
+        }
+        // camera / light position in volume physical coordinates (glsl.cpp:62-72)
+        if (!rc_mat4_invert(vs.desc.phys_to_world, w2p)) for (int i = 0; i < 16; ++i) w2p[i] = (i % 5 == 0) ? 1.f : 0.f;
+        const float cp[4] = {cam->position[0], cam->position[1], cam->position[2], 1.f};
+        float r[4];
+        mat4_mul_v4(w2p, cp, r); d.cam_phys[0] = r[0]; d.cam_phys[1] = r[1]; d.cam_phys[2] = r[2];
+        mat4_mul_v4(w2p, P->light.position, r); d.light_phys[0] = r[0]; d.light_phys[1] = r[1]; d.light_phys[2] = r[2];
+        float t2w[16];
+        rc_texture_to_world(&vs.desc, t2w);
+        if (!rc_mat4_invert(t2w, d.w2t)) { ctx->set_error("render: singular textureToWorld matrix"); return B200RC_ERR_INVALID; }
+    }
+    // classifiers: per channel (single volume) or per volume (multi)
+    const int ncls = P->multi_volume ? nv : ctx->vol[0].desc.channels;
+    for (int c = 0; c < ncls; ++c) {
+        ClassifierSlot& k = ctx->cls[c];
+        const int mode = P->multi_volume ? P->vol[c].classification : P->vol[0].classification;
+        ClsDev& d = p.cls[c];
+        d.dom_lo = k.dom[0]; d.dom_hi = k.dom[1]; d.domy_lo = k.domy[0]; d.domy_hi = k.domy[1];
+        if (mode == B200RC_CLASS_TF) {
+            if (!k.tf) { ctx->set_error("render: no 1D transfer function for channel/volume"); return B200RC_ERR_NOT_READY; }
+            int rc = rc_tf_update_lut(ctx, c, P->sampling_step);
+            if (rc) return rc;
+            d.tf = k.tf; d.tf_width = k.tf_width; d.corr_lut = k.corr_lut;
+        } else if (mode == B200RC_CLASS_PREINT) {
+            if (!k.preint) { ctx->set_error("render: no pre-integration table for channel/volume"); return B200RC_ERR_NOT_READY; }
+            d.preint = k.preint; d.pres = k.pres; d.preint_tex = k.preint_tex;
+        } else {
+            if (!k.tf2d) { ctx->set_error("render: no 2D transfer function for channel/volume"); return B200RC_ERR_NOT_READY; }
+            d.tf2d = k.tf2d; d.tf2d_w = k.tf2d_w; d.tf2d_h = k.tf2d_h;
+        }
+    }
+    // empty-space skipping (single volume, unsharded, no channel shift): occupancy for the current TFs
+    if (P->empty_space_skipping && !P->multi_volume && !p.channel_shift && !ctx->vol[0].sharded) {
+        int modes[4];
+        for (int c = 0; c < ncls; ++c) modes[c] = P->vol[0].classification;
+        int rc = rc_volume_build_occupancy(ctx, 0, modes, ncls, false);
+        if (rc) return rc;
+        p.vol[0].ess = 1;
+    }
+    p.lattice_exact = (!P->multi_volume && lattice_is_exact(P->sampling_step, 65536)) ? 1 : 0;
+    p.stats = ctx->d_stats;
+    p.tile_counter = ctx->d_tile_counter;
+    p.tiles_x = (((W + 7) / 8) + 7) / 8 * 8;
+    p.tiles_y = (((H + 3) / 4) + 7) / 8 * 8;
+    if (P->collect_stats && !P->multi_volume) {
+        VolumeSlot& vs = ctx->vol[0];
+        const size_t n = (size_t)vs.touched_dims[0] * vs.touched_dims[1] * vs.touched_dims[2];
+        if (!vs.touched) RC_CHECK(cudaMalloc(&vs.touched, n));
+        RC_CHECK(cudaMemsetAsync(vs.touched, 0, n, ctx->stream));
+        p.touched = vs.touched;
+        for (int a = 0; a < 3; ++a) p.touched_dims[a] = vs.touched_dims[a];
+    }
+    *out_nch = P->multi_volume ? 1 : ctx->vol[0].desc.channels;
+    *out_dtype = ctx->vol[0].desc.dtype;
+    return B200RC_OK;
+}
+
+__global__ void count_touched_kernel(const unsigned char* __restrict__ f, size_t n, unsigned long long* out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned v = (i < n && f[i]) ? 1u : 0u;
+    v = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, (unsigned long long)v);
+}
+
+int rc_march_launch(b200rc_ctx* ctx, const DevParams& p, int sampler, int nch, int dtype) {
+    int rc = B200RC_OK;
+    if (rc_march_fast(ctx, p, sampler, nch, dtype, &rc)) return rc;
+    return rc_march_generic(ctx, p, sampler, nch);
+}
+
+static int run_march(b200rc_ctx* ctx, const b200rc_params* P, DevParams& p, int nch, int dtype) {
+    if (P->collect_stats) RC_CHECK(cudaMemsetAsync(ctx->d_stats, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    RC_CHECK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    int rc = rc_march_launch(ctx, p, P->sampler, nch, dtype);
+    if (rc) return rc;
+    RC_CHECK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    if (P->collect_stats && p.touched) {
+        const size_t n = (size_t)p.touched_dims[0] * p.touched_dims[1] * p.touched_dims[2];
+        count_touched_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(p.touched, n, ctx->d_stats + 5);
+        ctx->launches++;
+    }
+    return B200RC_OK;
+}
+
+static int finish_frame(b200rc_ctx* ctx, const b200rc_params* P, bool had_eep) {
+    RC_CHECK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    if (had_eep) { cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->stats.last_eep_ms = ms; } else ctx->stats.last_eep_ms = 0.0;
+    cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->stats.last_march_ms = ms;
+    cudaEventElapsedTime(&ms, had_eep ? ctx->ev[0] : ctx->ev[2], ctx->ev[3]); ctx->stats.last_render_ms = ms;
+    if (P->collect_stats) {
+        unsigned long long h[8];
+        RC_CHECK(cudaMemcpy(h, ctx->d_stats, sizeof h, cudaMemcpyDeviceToHost));
+        ctx->stats.rays_cast = h[0]; ctx->stats.samples_classified = h[1]; ctx->stats.samples_shaded = h[2];
+        ctx->stats.samples_nominal = h[3]; ctx->stats.cells_touched = h[5];
+    }
+    return B200RC_OK;
+}
+
+static size_t out_pixel_bytes(int fmt) { return fmt == B200RC_OUT_RGBA16 ? 8 : 16; }
+
+// ---- entry/exit -----------------------------------------------------------------------------------------------------------
+static int default_boxes(b200rc_ctx* ctx, const b200rc_eep_params* eep, const VolumeSlot& vs, float box[6]) {
+    (void)ctx;
+    // OptimizedProxyGeometry::processCube (optimizedproxygeometry.cpp:420-448)
+    for (int a = 0; a < 3; ++a) {
+        float lo = 0.f - 0.5f, hi = (float)(vs.desc.dims[a] - 1) + 0.5f;
+        if (eep->enable_clipping) { lo = fmaxf(lo, eep->clip_llf[a] - 0.5f); hi = fminf(hi, eep->clip_urb[a] + 0.5f); }
+        box[a] = (1.0f / (float)vs.desc.dims[a]) * (lo + 0.5f);        // getVoxelToTextureMatrix = scale(1/dim) * translate(0.5)
+        box[3 + a] = (1.0f / (float)vs.desc.dims[a]) * (hi + 0.5f);
+    }
+    return B200RC_OK;
+}
+
+static int run_eep(b200rc_ctx* ctx, const b200rc_eep_params* eep, const b200rc_camera* cam, int W, int H) {
+    const VolumeSlot& vs = ctx->vol[0];
+    if (!vs.valid) { ctx->set_error("entry/exit: volume slot 0 is empty"); return B200RC_ERR_NOT_READY; }
+    float model[16];
+    rc_texture_to_world(&vs.desc, model);
+    float box[6];
+    const float* boxes = eep->boxes; int nb = eep->n_boxes;
+    if (!boxes || nb <= 0) { default_boxes(ctx, eep, vs, box); boxes = box; nb = 1; }
+    RC_CHECK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    int rc = rc_eep_launch(ctx, eep, cam, boxes, nb, model, W, H, ctx->d_entry, ctx->d_entry_depth, ctx->d_exit, ctx->d_exit_depth);
+    if (rc) return rc;
+    RC_CHECK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    return B200RC_OK;
+}
+
+extern "C" int b200rc_entry_exit(b200rc_ctx* ctx, const b200rc_eep_params* eep, const b200rc_camera* cam, int W, int H,
+                                 float* entry_rgba, float* entry_depth, float* exit_rgba, float* exit_depth) {
+    CTX_GUARD();
+    if (!eep || !cam || W < 1 || H < 1) { ctx->set_error("entry_exit: bad arguments"); return B200RC_ERR_INVALID; }
+    const size_t px = (size_t)W * H;
+    int rc = ensure_frame_buffers(ctx, px, 1);
+    if (rc) return rc;
+    rc = run_eep(ctx, eep, cam, W, H);
+    if (rc) return rc;
+    if (entry_rgba) RC_CHECK(cudaMemcpyAsync(entry_rgba, ctx->d_entry, px * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    if (exit_rgba) RC_CHECK(cudaMemcpyAsync(exit_rgba, ctx->d_exit, px * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    if (entry_depth) RC_CHECK(cudaMemcpyAsync(entry_depth, ctx->d_entry_depth, px * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (exit_depth) RC_CHECK(cudaMemcpyAsync(exit_depth, ctx->d_exit_depth, px * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    RC_CHECK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->stats.last_eep_ms = ms;
+    return B200RC_OK;
+}
+
+// ---- render ---------------------------------------------------------------------------------------------------------------
+static int copy_outputs(b200rc_ctx* ctx, const b200rc_params* P, size_t px, void* out_color[3], float* out_depth, cudaMemcpyKind kind, const DevParams& p) {
+    for (int o = 0; o < 3; ++o)
+        if (out_color && out_color[o] && p.out[o] && p.out[o] != out_color[o])
+            RC_CHECK(cudaMemcpyAsync(out_color[o], p.out[o], px * out_pixel_bytes(P->out_format), kind, ctx->stream));
+    if (out_depth && p.out_depth && p.out_depth != out_depth) RC_CHECK(cudaMemcpyAsync(out_depth, p.out_depth, px * sizeof(float), kind, ctx->stream));
+    return B200RC_OK;
+}
+
+extern "C" int b200rc_render(b200rc_ctx* ctx, const b200rc_params* P, const b200rc_camera* cam, int W, int H,
+                             const float* entry_rgba, const float* entry_depth, const float* exit_rgba, const float* exit_depth,
+                             void* out_color[B200RC_MAX_OUTPUTS], float* out_depth) {
+    CTX_GUARD();
+    if (!entry_rgba || !exit_rgba || !entry_depth || !exit_depth) { ctx->set_error("render: entry/exit buffers missing (isReady() == false)"); return B200RC_ERR_NOT_READY; }
+    DevParams p; int nch = 1, dtype = 0;
+    int rc = build_params(ctx, P, cam, W, H, p, &nch, &dtype);
+    if (rc) return rc;
+    const size_t px = (size_t)W * H;
+    const int images = P->multi_volume ? 1 + P->num_volumes : 1;
+    rc = ensure_frame_buffers(ctx, px, images);
+    if (rc) return rc;
+    RC_CHECK(cudaMemcpyAsync(ctx->d_entry, entry_rgba, px * images * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    RC_CHECK(cudaMemcpyAsync(ctx->d_exit, exit_rgba, px * images * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    RC_CHECK(cudaMemcpyAsync(ctx->d_entry_depth, entry_depth, px * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    RC_CHECK(cudaMemcpyAsync(ctx->d_exit_depth, exit_depth, px * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    p.entry = ctx->d_entry; p.exitp = ctx->d_exit; p.entry_depth = ctx->d_entry_depth; p.exit_depth = ctx->d_exit_depth;
+    for (int o = 0; o < 3; ++o) p.out[o] = (p.connected[o] && out_color && out_color[o]) ? ctx->d_out[o] : nullptr;
+    p.out_depth = out_depth ? ctx->d_out_depth : nullptr;
+    rc = run_march(ctx, P, p, nch, dtype);
+    if (rc) return rc;
+    rc = copy_outputs(ctx, P, px, out_color, out_depth, cudaMemcpyDeviceToHost, p);
+    if (rc) return rc;
+    return finish_frame(ctx, P, false);
+}
+
+static int render_camera_impl(b200rc_ctx* ctx, const b200rc_params* P, const b200rc_eep_params* eep, const b200rc_camera* cam, int W, int H,
+                              void* out_color[3], float* out_depth, bool device_out) {
+    if (!eep) { ctx->set_error("render_camera: eep params missing"); return B200RC_ERR_INVALID; }
+    if (P && P->multi_volume) { ctx->set_error("render_camera: multi-volume rendering takes explicit entry/exit buffers (b200rc_render)"); return B200RC_ERR_INVALID; }
+    DevParams p; int nch = 1, dtype = 0;
+    int rc = build_params(ctx, P, cam, W, H, p, &nch, &dtype);
+    if (rc) return rc;
+    const size_t px = (size_t)W * H;
+    rc = ensure_frame_buffers(ctx, px, 1);
+    if (rc) return rc;
+    rc = run_eep(ctx, eep, cam, W, H);
+    if (rc) return rc;
+    p.entry = ctx->d_entry; p.exitp = ctx->d_exit; p.entry_depth = ctx->d_entry_depth; p.exit_depth = ctx->d_exit_depth;
+    for (int o = 0; o < 3; ++o) {
+        if (!(p.connected[o] && out_color && out_color[o])) p.out[o] = nullptr;
+        else p.out[o] = device_out ? out_color[o] : ctx->d_out[o];
+    }
+    p.out_depth = out_depth ? (device_out ? out_depth : ctx->d_out_depth) : nullptr;
+    rc = run_march(ctx, P, p, nch, dtype);
+    if (rc) return rc;
+    if (!device_out) {
+        rc = copy_outputs(ctx, P, px, out_color, out_depth, cudaMemcpyDeviceToHost, p);
+        if (rc) return rc;
+    }
+    return finish_frame(ctx, P, true);
+}
+
+extern "C" int b200rc_render_camera(b200rc_ctx* ctx, const b200rc_params* P, const b200rc_eep_params* eep, const b200rc_camera* cam, int W, int H,
+                                    void* out_color[B200RC_MAX_OUTPUTS], float* out_depth) {
+    CTX_GUARD();
+    return render_camera_impl(ctx, P, eep, cam, W, H, out_color, out_depth, false);
+}
+
+extern "C" int b200rc_render_camera_device(b200rc_ctx* ctx, const b200rc_params* P, const b200rc_eep_params* eep, const b200rc_camera* cam, int W, int H,
+                                           void* out_color_dev[B200RC_MAX_OUTPUTS], float* out_depth_dev) {
+    CTX_GUARD();
+    return render_camera_impl(ctx, P, eep, cam, W, H, out_color_dev, out_depth_dev, true);
+}
+
+// ---- sort-last ---------------------------------------------------------------------------------------------------------------
+extern "C" int b200rc_composite(b200rc_ctx* ctx, int mode, const float* front_rgba, const float* front_depth, const float* back_rgba, const float* back_depth,
+                                float* dst_rgba, float* dst_depth, size_t n) {
+    CTX_GUARD();
+    if (!front_rgba || !back_rgba || !dst_rgba) { ctx->set_error("composite: null image"); return B200RC_ERR_INVALID; }
+    return rc_composite_launch(ctx, mode, front_rgba, front_depth, back_rgba, back_depth, dst_rgba, dst_depth, n);
+}
+
+extern "C" int b200rc_finalize(b200rc_ctx* ctx, const float* rgba_dev, const float* depth_dev, size_t n, int out_format, void* out_color_dev) {
+    CTX_GUARD();
+    if (!rgba_dev || !out_color_dev) { ctx->set_error("finalize: null image"); return B200RC_ERR_INVALID; }
+    return rc_finalize_launch(ctx, rgba_dev, depth_dev, n, out_format, out_color_dev);
+}

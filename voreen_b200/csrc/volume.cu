@@ -1,0 +1,535 @@
+// volume.cu -- brick-pool volume upload to HBM, cudaArray view for the texture units, the min/max macro-cell grid
+// and the TF-dependent occupancy bits used for empty-space skipping, plus the synthetic benchmark volume.
+//
+// Replaces VolumeGL::generateTexture (V/src/core/datastructures/volume/volumegl.cpp:106-139,336-381) and
+// StructureProxyGeometryBackgroundThread::computeRegionStructure
+// (V/modules/base/processors/proxygeometry/optimizedproxygeometry.cpp:894-987).
+//
+// HBM layout: 8x8x8-voxel bricks (1 KiB for u16), bricks x-fastest over the resident range, channels interleaved per
+// voxel (3 channels padded to 4).  A brick is 8 consecutive 128-byte lines, one 8x8 xy-slab each, so the 8 taps of a
+// trilinear fetch touch two lines and a warp marching an 8x4 pixel tile touches a handful of lines per tap.
+#include "ctx.hpp"
+#include <cstring>
+#include <cstdio>
+
+// ------------------------------------------------------------------------------------------------------------------
+// linear -> bricks
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void brick_rows_kernel(const T* __restrict__ lin, T* __restrict__ bricks, int dx, int dy, int dz, int nbx, int nby, int nbz,
+                                  int nch_in, int nch_st, T pad_value) {
+    // one thread per 8-voxel brick row; consecutive threads write consecutive rows of the pool (coalesced stores)
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nrows = (long long)nbx * nby * nbz * 64;
+    if (row >= nrows) return;
+    const long long brick = row >> 6;
+    const int within = (int)(row & 63);
+    const int bx = (int)(brick % nbx), by = (int)((brick / nbx) % nby), bz = (int)(brick / ((long long)nbx * nby));
+    const int y = min(by * 8 + (within & 7), dy - 1), z = min(bz * 8 + (within >> 3), dz - 1);
+    const T* src = lin + ((long long)z * dy + y) * dx * nch_in;
+    T* dst = bricks + row * 8 * nch_st;
+    for (int i = 0; i < 8; ++i) {
+        const int x = min(bx * 8 + i, dx - 1);
+        for (int c = 0; c < nch_st; ++c) dst[i * nch_st + c] = (c < nch_in) ? src[(long long)x * nch_in + c] : pad_value;
+    }
+}
+
+// vector path: 1 channel u16, dx % 8 == 0 -> one 16-byte load and one 16-byte store per thread
+__global__ void brick_rows_u16x8_kernel(const uint4* __restrict__ lin, uint4* __restrict__ bricks, int dx8, int dy, int dz, int nbx, int nby, int nbz) {
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nrows = (long long)nbx * nby * nbz * 64;
+    if (row >= nrows) return;
+    const long long brick = row >> 6;
+    const int within = (int)(row & 63);
+    const int bx = (int)(brick % nbx), by = (int)((brick / nbx) % nby), bz = (int)(brick / ((long long)nbx * nby));
+    const int y = min(by * 8 + (within & 7), dy - 1), z = min(bz * 8 + (within >> 3), dz - 1);
+    bricks[row] = __ldg(lin + ((long long)z * dy + y) * dx8 + bx);
+}
+
+template <typename T>
+__global__ void debrick_kernel(const T* __restrict__ bricks, T* __restrict__ lin, int dx, int dy, int dz, int nbx, int nby, int nch_out, int nch_st) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = (long long)dx * dy * dz;
+    if (i >= n) return;
+    const int x = (int)(i % dx), y = (int)((i / dx) % dy), z = (int)(i / ((long long)dx * dy));
+    const long long e = brick_off_x(x) + brick_off_y(y, nbx) + brick_off_z(z, nbx, nby);
+    for (int c = 0; c < nch_out; ++c) lin[i * nch_out + c] = bricks[e * nch_st + c];
+}
+
+// bricks -> cudaArray through a surface (no linear staging copy of a 16 GiB volume)
+template <typename T>
+__global__ void bricks_to_surface_kernel(const T* __restrict__ bricks, cudaSurfaceObject_t surf, int dx, int dy, int dz, int nbx, int nby, int nch_st) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = (long long)dx * dy * dz;
+    if (i >= n) return;
+    const int x = (int)(i % dx), y = (int)((i / dx) % dy), z = (int)(i / ((long long)dx * dy));
+    const long long e = (brick_off_x(x) + brick_off_y(y, nbx) + brick_off_z(z, nbx, nby)) * nch_st;
+    const int bytes = (int)sizeof(T) * nch_st;
+    if (nch_st == 1) surf3Dwrite(bricks[e], surf, x * bytes, y, z);
+    else if (nch_st == 2) {
+        if (sizeof(T) == 1) surf3Dwrite(make_uchar2((unsigned char)bricks[e], (unsigned char)bricks[e + 1]), surf, x * bytes, y, z);
+        else if (sizeof(T) == 2) surf3Dwrite(make_ushort2((unsigned short)bricks[e], (unsigned short)bricks[e + 1]), surf, x * bytes, y, z);
+        else surf3Dwrite(make_float2((float)bricks[e], (float)bricks[e + 1]), surf, x * bytes, y, z);
+    } else {
+        if (sizeof(T) == 1) surf3Dwrite(make_uchar4((unsigned char)bricks[e], (unsigned char)bricks[e + 1], (unsigned char)bricks[e + 2], (unsigned char)bricks[e + 3]), surf, x * bytes, y, z);
+        else if (sizeof(T) == 2) surf3Dwrite(make_ushort4((unsigned short)bricks[e], (unsigned short)bricks[e + 1], (unsigned short)bricks[e + 2], (unsigned short)bricks[e + 3]), surf, x * bytes, y, z);
+        else surf3Dwrite(make_float4((float)bricks[e], (float)bricks[e + 1], (float)bricks[e + 2], (float)bricks[e + 3]), surf, x * bytes, y, z);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// synthetic "CT-like" volume, written straight into the brick pool.  Integer noise + non-contracted fp32
+// so that voreen_b200/synth.py reproduces it bit for bit on the CPU.
+// ------------------------------------------------------------------------------------------------------------------
+struct SynthSpheres { float cx[64], cy[64], cz[64], r2[64]; };
+
+__host__ __device__ inline uint32_t hash32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+
+__global__ void synth_kernel(unsigned short* __restrict__ bricks, int gx, int gy, int gz, int lox, int loy, int loz, int rx, int ry, int rz,
+                             int nbx, int nby, int nbz, float rcpx, float rcpy, float rcpz, float fall_scale, uint32_t seed,
+                             const __grid_constant__ SynthSpheres sph) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = (long long)nbx * nby * nbz * 512;
+    if (e >= n) return;
+    const long long brick = e >> 9;
+    const int within = (int)(e & 511);
+    const int bx = (int)(brick % nbx), by = (int)((brick / nbx) % nby), bz = (int)(brick / ((long long)nbx * nby));
+    const int x = min(bx * 8 + (within & 7), rx - 1) + lox, y = min(by * 8 + ((within >> 3) & 7), ry - 1) + loy, z = min(bz * 8 + (within >> 6), rz - 1) + loz;
+    const float px = xsub(xmul(xadd((float)x, 0.5f), rcpx), 0.5f), py = xsub(xmul(xadd((float)y, 0.5f), rcpy), 0.5f), pz = xsub(xmul(xadd((float)z, 0.5f), rcpz), 0.5f);
+    const float xx = xmul(px, px), yy = xmul(py, py), zz = xmul(pz, pz);
+    const float r2 = xadd(xadd(xx, yy), zz);
+    // soft ellipsoid "tissue": semi-axes (0.42, 0.36, 0.40), 0.35 inside, smooth ~4-voxel falloff
+    const float q2 = xadd(xadd(xmul(xx, 5.6689343f), xmul(yy, 7.7160494f)), xmul(zz, 6.25f));
+    const float q = __fsqrt_rn(q2);
+    float fall = xmul(xmul(xsub(1.0f, q), fall_scale), 0.25f);
+    fall = fminf(fmaxf(fall, 0.0f), 1.0f);
+    const float s = xmul(xmul(fall, fall), xsub(3.0f, xmul(2.0f, fall)));
+    float f = xmul(0.35f, s);
+    // 64 small bright spheres
+    bool hit = false;
+    for (int i = 0; i < 64; ++i) {
+        const float ax = xsub(px, sph.cx[i]), ay = xsub(py, sph.cy[i]), az = xsub(pz, sph.cz[i]);
+        const float d2 = xadd(xadd(xmul(ax, ax), xmul(ay, ay)), xmul(az, az));
+        hit = hit || (d2 <= sph.r2[i]);
+    }
+    if (hit) f = fmaxf(f, 0.6f);
+    // solid sphere shell r in [0.30, 0.32]
+    if (r2 >= 0.09f && r2 <= 0.1024f) f = fmaxf(f, 0.85f);
+    int val = (int)floorf(xadd(xmul(f, 65535.0f), 0.5f));
+    // additive noise ~ N(0, 0.01): Irwin-Hall sum of four 16-bit uniforms, integer arithmetic only
+    const uint32_t h = hash32((uint32_t)x * 73856093u ^ (uint32_t)y * 19349663u ^ (uint32_t)z * 83492791u ^ seed * 0x9e3779b9u);
+    const uint32_t h2 = hash32(h ^ 0x68bc21ebu);
+    const int sum = (int)(h & 0xffffu) + (int)(h >> 16) + (int)(h2 & 0xffffu) + (int)(h2 >> 16);
+    val += ((sum - 131070) * 1135) >> 16;
+    val = min(max(val, 0), 65535);
+    bricks[e] = (unsigned short)val;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// min/max macro-cell grid (level 0: 8^3 voxels + apron)
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void minmax_kernel(const T* __restrict__ bricks, float2* __restrict__ out, int rx, int ry, int rz, int nbx, int nby,
+                              int ncx, int ncy, int ncz, int nch, int nch_st, float norm) {
+    // one warp per cell; region = [c*8-1, c*8+9] per axis (taps of every sample whose base index lies in the cell,
+    // plus one voxel of slack on both sides for float fuzz at the cell faces), clamped to the resident range
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long ncell = (long long)ncx * ncy * ncz;
+    if (warp >= ncell) return;
+    const int cx = (int)(warp % ncx), cy = (int)((warp / ncx) % ncy), cz = (int)(warp / ((long long)ncx * ncy));
+    const int x0 = max(cx * 8 - 1, 0), x1 = min(cx * 8 + 9, rx - 1);
+    const int y0 = max(cy * 8 - 1, 0), y1 = min(cy * 8 + 9, ry - 1);
+    const int z0 = max(cz * 8 - 1, 0), z1 = min(cz * 8 + 9, rz - 1);
+    const int ex = x1 - x0 + 1, ey = y1 - y0 + 1, ez = z1 - z0 + 1;
+    const int total = ex * ey * ez;
+    float mn[4] = {3.0e38f, 3.0e38f, 3.0e38f, 3.0e38f}, mx[4] = {-3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};
+    for (int i = lane; i < total; i += 32) {
+        const int x = x0 + i % ex, y = y0 + (i / ex) % ey, z = z0 + i / (ex * ey);
+        const long long e = (brick_off_x(x) + brick_off_y(y, nbx) + brick_off_z(z, nbx, nby)) * nch_st;
+        for (int c = 0; c < nch; ++c) {
+            const float v = (float)bricks[e + c];
+            mn[c] = fminf(mn[c], v); mx[c] = fmaxf(mx[c], v);
+        }
+    }
+    for (int c = 0; c < nch; ++c) {
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
+            mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+        }
+        // same normalisation as the sampler: raw * (1/65535) -- monotone, so min/max commute with it
+        if (lane == 0) out[warp * nch + c] = make_float2(__fmul_rn(mn[c], norm), __fmul_rn(mx[c], norm));
+    }
+}
+
+// reference-style region structure with arbitrary cell size (for b200rc_region_minmax / proxy geometry):
+// min/max over [llf-1, urb+1] clamped, real-world units (optimizedproxygeometry.cpp:944-968)
+template <typename T>
+__global__ void region_minmax_kernel(const T* __restrict__ bricks, float* __restrict__ out, int dx, int dy, int dz, int nbx, int nby,
+                                     int step, int ncx, int ncy, int ncz, int nch, int nch_st, float norm_div, float sc, float of) {
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long ncell = (long long)ncx * ncy * ncz;
+    if (warp >= ncell) return;
+    const int cx = (int)(warp % ncx), cy = (int)((warp / ncx) % ncy), cz = (int)(warp / ((long long)ncx * ncy));
+    int lo[3] = {cx * step, cy * step, cz * step}, hi[3] = {(cx + 1) * step - 1, (cy + 1) * step - 1, (cz + 1) * step - 1};
+    const int dim[3] = {dx, dy, dz};
+    for (int a = 0; a < 3; ++a) {
+        hi[a] = min(hi[a], dim[a] - 1);
+        lo[a] = min(max(lo[a] - 1, 0), dim[a] - 1);
+        hi[a] = min(max(hi[a] + 1, 0), dim[a] - 1);
+    }
+    const int ex = hi[0] - lo[0] + 1, ey = hi[1] - lo[1] + 1, ez = hi[2] - lo[2] + 1;
+    const long long total = (long long)ex * ey * ez;
+    float mn[4] = {3.402823466e38f, 3.402823466e38f, 3.402823466e38f, 3.402823466e38f};
+    float mx[4] = {1.175494351e-38f, 1.175494351e-38f, 1.175494351e-38f, 1.175494351e-38f};   // numeric_limits<float>::min() (quirk kept)
+    for (long long i = lane; i < total; i += 32) {
+        const int x = lo[0] + (int)(i % ex), y = lo[1] + (int)((i / ex) % ey), z = lo[2] + (int)(i / ((long long)ex * ey));
+        const long long e = (brick_off_x(x) + brick_off_y(y, nbx) + brick_off_z(z, nbx, nby)) * nch_st;
+        for (int c = 0; c < nch; ++c) {
+            float v = (float)bricks[e + c];
+            if (norm_div > 0.f) v = __fdiv_rn(v, norm_div);             // VolumeRAM::getVoxelNormalized
+            v = __fadd_rn(__fmul_rn(v, sc), of);                        // RealWorldMapping::normalizedToRealWorld
+            mn[c] = fminf(mn[c], v); mx[c] = fmaxf(mx[c], v);
+        }
+    }
+    for (int c = 0; c < nch; ++c) {
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
+            mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+        }
+        if (lane == 0) { out[(warp * nch + c) * 2] = mn[c]; out[(warp * nch + c) * 2 + 1] = mx[c]; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// occupancy bits for the current transfer function(s)
+// ------------------------------------------------------------------------------------------------------------------
+struct OccCls { const int* nz; int res; int linear; float lo, hi; };
+struct OccArgs { OccCls c[4]; int nch; float rwm_scale, rwm_offset; };
+
+__device__ __forceinline__ float occ_rw_to_tex(float lo, float hi, float v) {
+    if (v <= lo) return 0.0f;
+    if (v >= hi) return 1.0f;
+    if (hi == lo) return 0.0f;
+    return __fdiv_rn(__fsub_rn(v, lo), __fsub_rn(hi, lo));
+}
+
+__global__ void occupancy0_kernel(const float2* __restrict__ minmax, uint32_t* __restrict__ occ, int ncx, int ncy, int ncz, int wpr,
+                                  const __grid_constant__ OccArgs a) {
+    // thread per cell, x padded to 32 so that one ballot = one occupancy word
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int xpad = wpr * 32;
+    const long long total = (long long)xpad * ncy * ncz;
+    if (t >= total) return;
+    const int cx = (int)(t % xpad), cy = (int)((t / xpad) % ncy), cz = (int)(t / ((long long)xpad * ncy));
+    bool nonempty = false;
+    if (cx < ncx) {
+        const long long cell = ((long long)cz * ncy + cy) * ncx + cx;
+        for (int c = 0; c < a.nch && !nonempty; ++c) {
+            const OccCls& k = a.c[c];
+            if (!k.nz) { nonempty = true; break; }
+            const float2 mm = minmax[cell * a.nch + c];
+            const float vmin = __fadd_rn(__fmul_rn(mm.x, a.rwm_scale), a.rwm_offset), vmax = __fadd_rn(__fmul_rn(mm.y, a.rwm_scale), a.rwm_offset);
+            const float s0 = occ_rw_to_tex(k.lo, k.hi, fminf(vmin, vmax)), s1 = occ_rw_to_tex(k.lo, k.hi, fmaxf(vmin, vmax));
+            int i0, i1;
+            if (k.linear) { i0 = __float2int_rd(s0 * (float)k.res - 0.5f) - 1; i1 = __float2int_rd(s1 * (float)k.res - 0.5f) + 2; }
+            else { i0 = __float2int_rd(s0 * (float)k.res) - 1; i1 = __float2int_rd(s1 * (float)k.res) + 1; }
+            i0 = min(max(i0, 0), k.res - 1); i1 = min(max(i1, 0), k.res - 1);
+            nonempty = (k.nz[i1 + 1] - k.nz[i0]) != 0;
+        }
+    }
+    const uint32_t word = __ballot_sync(0xffffffffu, nonempty);
+    if ((threadIdx.x & 31) == 0) occ[((long long)cz * ncy + cy) * wpr + (cx >> 5)] = word;
+}
+
+__global__ void occupancy1_kernel(const uint32_t* __restrict__ occ0, uint32_t* __restrict__ occ1, int n0x, int n0y, int n0z, int wpr0,
+                                  int n1x, int n1y, int n1z, int wpr1) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int xpad = wpr1 * 32;
+    const long long total = (long long)xpad * n1y * n1z;
+    if (t >= total) return;
+    const int cx = (int)(t % xpad), cy = (int)((t / xpad) % n1y), cz = (int)(t / ((long long)xpad * n1y));
+    bool nonempty = false;
+    if (cx < n1x) {
+        for (int z = cz * 8; z < min(cz * 8 + 8, n0z) && !nonempty; ++z)
+            for (int y = cy * 8; y < min(cy * 8 + 8, n0y) && !nonempty; ++y) {
+                const uint32_t w = occ0[((long long)z * n0y + y) * wpr0 + ((cx * 8) >> 5)];
+                nonempty = ((w >> ((cx * 8) & 31)) & 0xffu) != 0;
+            }
+    }
+    const uint32_t word = __ballot_sync(0xffffffffu, nonempty);
+    if ((threadIdx.x & 31) == 0) occ1[((long long)cz * n1y + cy) * wpr1 + (cx >> 5)] = word;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------------
+static size_t dtype_bytes(int dt) { return dt == B200RC_U8 ? 1 : (dt == B200RC_U16 ? 2 : 4); }
+
+int rc_volume_release(b200rc_ctx* ctx, int slot) {
+    VolumeSlot& v = ctx->vol[slot];
+    if (v.tex) cudaDestroyTextureObject(v.tex);
+    if (v.array) cudaFreeArray(v.array);
+    cudaFree(v.bricks); cudaFree(v.minmax); cudaFree(v.occ0); cudaFree(v.occ1); cudaFree(v.touched);
+    v = VolumeSlot();
+    return B200RC_OK;
+}
+
+static int volume_prepare(b200rc_ctx* ctx, int slot, const b200rc_volume_desc* desc) {
+    if (slot < 0 || slot >= B200RC_MAX_VOLUMES || !desc) { ctx->set_error("bad volume slot/desc"); return B200RC_ERR_INVALID; }
+    if (desc->channels < 1 || desc->channels > 4 || desc->dtype < B200RC_U8 || desc->dtype > B200RC_F32 ||
+        desc->dims[0] < 1 || desc->dims[1] < 1 || desc->dims[2] < 1) { ctx->set_error("unsupported volume format"); return B200RC_ERR_INVALID; }
+    rc_volume_release(ctx, slot);
+    VolumeSlot& v = ctx->vol[slot];
+    v.desc = *desc;
+    v.sharded = false;
+    for (int a = 0; a < 3; ++a) {
+        v.res_lo[a] = 0; v.res_dims[a] = desc->dims[a]; v.own_lo[a] = 0; v.own_hi[a] = desc->dims[a];
+    }
+    const bool shard = desc->shard_hi[0] > desc->shard_lo[0] && desc->shard_hi[1] > desc->shard_lo[1] && desc->shard_hi[2] > desc->shard_lo[2];
+    if (shard) {
+        v.sharded = true;
+        for (int a = 0; a < 3; ++a) {
+            int lo = desc->shard_lo[a] - desc->shard_apron, hi = desc->shard_hi[a] + desc->shard_apron;
+            lo = lo < 0 ? 0 : lo; hi = hi > desc->dims[a] ? desc->dims[a] : hi;
+            v.res_lo[a] = lo; v.res_dims[a] = hi - lo;
+            v.own_lo[a] = desc->shard_lo[a]; v.own_hi[a] = desc->shard_hi[a];
+        }
+    }
+    v.stored_nch = desc->channels == 3 ? 4 : desc->channels;
+    v.elem_bytes = dtype_bytes(desc->dtype);
+    v.nbx = (v.res_dims[0] + 7) / 8; v.nby = (v.res_dims[1] + 7) / 8; v.nbz = (v.res_dims[2] + 7) / 8;
+    v.brick_bytes = (size_t)v.nbx * v.nby * v.nbz * 512 * v.stored_nch * v.elem_bytes;
+    if (cudaMalloc(&v.bricks, v.brick_bytes) != cudaSuccess) { cudaGetLastError(); ctx->set_error("out of device memory for the brick pool"); return B200RC_ERR_OOM; }
+    return B200RC_OK;
+}
+
+static int volume_build_minmax(b200rc_ctx* ctx, int slot) {
+    VolumeSlot& v = ctx->vol[slot];
+    for (int a = 0; a < 3; ++a) v.cells[a] = (v.res_dims[a] + 7) / 8;
+    const long long ncell = (long long)v.cells[0] * v.cells[1] * v.cells[2];
+    RC_CHECK(cudaMalloc(&v.minmax, sizeof(float2) * ncell * v.desc.channels));
+    const int threads = 256;
+    const long long blocks = (ncell * 32 + threads - 1) / threads;
+    const int nch = v.desc.channels;
+    if (v.desc.dtype == B200RC_U16)
+        minmax_kernel<unsigned short><<<(unsigned)blocks, threads, 0, ctx->stream>>>((const unsigned short*)v.bricks, v.minmax, v.res_dims[0], v.res_dims[1], v.res_dims[2],
+                                                                                    v.nbx, v.nby, v.cells[0], v.cells[1], v.cells[2], nch, v.stored_nch, 1.0f / 65535.0f);
+    else if (v.desc.dtype == B200RC_U8)
+        minmax_kernel<unsigned char><<<(unsigned)blocks, threads, 0, ctx->stream>>>((const unsigned char*)v.bricks, v.minmax, v.res_dims[0], v.res_dims[1], v.res_dims[2],
+                                                                                   v.nbx, v.nby, v.cells[0], v.cells[1], v.cells[2], nch, v.stored_nch, 1.0f / 255.0f);
+    else
+        minmax_kernel<float><<<(unsigned)blocks, threads, 0, ctx->stream>>>((const float*)v.bricks, v.minmax, v.res_dims[0], v.res_dims[1], v.res_dims[2],
+                                                                           v.nbx, v.nby, v.cells[0], v.cells[1], v.cells[2], nch, v.stored_nch, 1.0f);
+    ctx->launches++;
+    RC_CHECK(cudaGetLastError());
+    v.occ0_wpr = (v.cells[0] + 31) / 32;
+    for (int a = 0; a < 3; ++a) v.occ1_dims[a] = (v.cells[a] + 7) / 8;
+    v.occ1_wpr = (v.occ1_dims[0] + 31) / 32;
+    RC_CHECK(cudaMalloc(&v.occ0, sizeof(uint32_t) * (size_t)v.occ0_wpr * v.cells[1] * v.cells[2]));
+    RC_CHECK(cudaMalloc(&v.occ1, sizeof(uint32_t) * (size_t)v.occ1_wpr * v.occ1_dims[1] * v.occ1_dims[2]));
+    v.occ_key = 0;
+    for (int a = 0; a < 3; ++a) v.touched_dims[a] = (v.desc.dims[a] + B200RC_STAT_CELL - 1) / B200RC_STAT_CELL;
+    v.valid = true;
+    return B200RC_OK;
+}
+
+int rc_volume_upload(b200rc_ctx* ctx, int slot, const void* data, const b200rc_volume_desc* desc) {
+    if (!data) { ctx->set_error("null volume data"); return B200RC_ERR_INVALID; }
+    int rc = volume_prepare(ctx, slot, desc);
+    if (rc) return rc;
+    VolumeSlot& v = ctx->vol[slot];
+    // `data` holds the RESIDENT range (res_dims), x fastest, channels interleaved
+    const size_t lin_bytes = (size_t)v.res_dims[0] * v.res_dims[1] * v.res_dims[2] * desc->channels * v.elem_bytes;
+    const void* d_lin = data;
+    void* staging = nullptr;
+    if (!desc->data_on_device) {
+        if (cudaMalloc(&staging, lin_bytes) != cudaSuccess) { cudaGetLastError(); ctx->set_error("out of device memory for upload staging"); return B200RC_ERR_OOM; }
+        RC_CHECK(cudaMemcpyAsync(staging, data, lin_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        d_lin = staging;
+    }
+    const long long nrows = (long long)v.nbx * v.nby * v.nbz * 64;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((nrows + threads - 1) / threads);
+    const int dx = v.res_dims[0], dy = v.res_dims[1], dz = v.res_dims[2];
+    if (desc->dtype == B200RC_U16 && desc->channels == 1 && dx % 8 == 0 && ((uintptr_t)d_lin % 16) == 0)
+        brick_rows_u16x8_kernel<<<blocks, threads, 0, ctx->stream>>>((const uint4*)d_lin, (uint4*)v.bricks, dx / 8, dy, dz, v.nbx, v.nby, v.nbz);
+    else if (desc->dtype == B200RC_U16)
+        brick_rows_kernel<unsigned short><<<blocks, threads, 0, ctx->stream>>>((const unsigned short*)d_lin, (unsigned short*)v.bricks, dx, dy, dz, v.nbx, v.nby, v.nbz, desc->channels, v.stored_nch, (unsigned short)65535);
+    else if (desc->dtype == B200RC_U8)
+        brick_rows_kernel<unsigned char><<<blocks, threads, 0, ctx->stream>>>((const unsigned char*)d_lin, (unsigned char*)v.bricks, dx, dy, dz, v.nbx, v.nby, v.nbz, desc->channels, v.stored_nch, (unsigned char)255);
+    else
+        brick_rows_kernel<float><<<blocks, threads, 0, ctx->stream>>>((const float*)d_lin, (float*)v.bricks, dx, dy, dz, v.nbx, v.nby, v.nbz, desc->channels, v.stored_nch, 1.0f);
+    ctx->launches++;
+    RC_CHECK(cudaGetLastError());
+    if (staging) { RC_CHECK(cudaStreamSynchronize(ctx->stream)); cudaFree(staging); }
+    return volume_build_minmax(ctx, slot);
+}
+
+// the 64 spheres of the synthetic volume; voreen_b200/synth.py mirrors this arithmetic exactly
+static void synth_spheres(uint64_t seed, SynthSpheres& s) {
+    const uint32_t sd = (uint32_t)seed;
+    for (int i = 0; i < 64; ++i) {
+        const uint32_t h0 = hash32(sd * 0x9e3779b9u + (uint32_t)(i * 4 + 0)), h1 = hash32(sd * 0x9e3779b9u + (uint32_t)(i * 4 + 1));
+        const uint32_t h2 = hash32(sd * 0x9e3779b9u + (uint32_t)(i * 4 + 2)), h3 = hash32(sd * 0x9e3779b9u + (uint32_t)(i * 4 + 3));
+        s.cx[i] = ((float)(h0 & 0xffffu) * (1.0f / 65536.0f) - 0.5f) * 0.76f;
+        s.cy[i] = ((float)(h1 & 0xffffu) * (1.0f / 65536.0f) - 0.5f) * 0.76f;
+        s.cz[i] = ((float)(h2 & 0xffffu) * (1.0f / 65536.0f) - 0.5f) * 0.76f;
+        const float r = 0.012f + (float)(h3 & 0xffffu) * (1.0f / 65536.0f) * 0.02f;
+        s.r2[i] = r * r;
+    }
+}
+
+int rc_volume_synth(b200rc_ctx* ctx, int slot, const b200rc_volume_desc* desc, uint64_t seed) {
+    if (!desc || desc->dtype != B200RC_U16 || desc->channels != 1) { ctx->set_error("synthetic volume is u16, 1 channel"); return B200RC_ERR_INVALID; }
+    int rc = volume_prepare(ctx, slot, desc);
+    if (rc) return rc;
+    VolumeSlot& v = ctx->vol[slot];
+    SynthSpheres sph;
+    synth_spheres(seed, sph);
+    const long long n = (long long)v.nbx * v.nby * v.nbz * 512;
+    const int threads = 256;
+    const int mind = desc->dims[0] < desc->dims[1] ? (desc->dims[0] < desc->dims[2] ? desc->dims[0] : desc->dims[2]) : (desc->dims[1] < desc->dims[2] ? desc->dims[1] : desc->dims[2]);
+    const float fall_scale = 0.36f * (float)mind;
+    synth_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, ctx->stream>>>(
+        (unsigned short*)v.bricks, desc->dims[0], desc->dims[1], desc->dims[2], v.res_lo[0], v.res_lo[1], v.res_lo[2], v.res_dims[0], v.res_dims[1], v.res_dims[2],
+        v.nbx, v.nby, v.nbz, 1.0f / (float)desc->dims[0], 1.0f / (float)desc->dims[1], 1.0f / (float)desc->dims[2], fall_scale, (uint32_t)seed, sph);
+    ctx->launches++;
+    RC_CHECK(cudaGetLastError());
+    return volume_build_minmax(ctx, slot);
+}
+
+int rc_volume_download(b200rc_ctx* ctx, int slot, void* host_dst, size_t bytes) {
+    VolumeSlot& v = ctx->vol[slot];
+    if (!v.valid) { ctx->set_error("no volume in slot"); return B200RC_ERR_NOT_READY; }
+    const long long n = (long long)v.res_dims[0] * v.res_dims[1] * v.res_dims[2];
+    const size_t need = (size_t)n * v.desc.channels * v.elem_bytes;
+    if (bytes < need) { ctx->set_error("download buffer too small"); return B200RC_ERR_INVALID; }
+    void* lin = nullptr;
+    RC_CHECK(cudaMalloc(&lin, need));
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+    if (v.desc.dtype == B200RC_U16) debrick_kernel<unsigned short><<<blocks, threads, 0, ctx->stream>>>((const unsigned short*)v.bricks, (unsigned short*)lin, v.res_dims[0], v.res_dims[1], v.res_dims[2], v.nbx, v.nby, v.desc.channels, v.stored_nch);
+    else if (v.desc.dtype == B200RC_U8) debrick_kernel<unsigned char><<<blocks, threads, 0, ctx->stream>>>((const unsigned char*)v.bricks, (unsigned char*)lin, v.res_dims[0], v.res_dims[1], v.res_dims[2], v.nbx, v.nby, v.desc.channels, v.stored_nch);
+    else debrick_kernel<float><<<blocks, threads, 0, ctx->stream>>>((const float*)v.bricks, (float*)lin, v.res_dims[0], v.res_dims[1], v.res_dims[2], v.nbx, v.nby, v.desc.channels, v.stored_nch);
+    ctx->launches++;
+    RC_CHECK(cudaGetLastError());
+    RC_CHECK(cudaMemcpyAsync(host_dst, lin, need, cudaMemcpyDeviceToHost, ctx->stream));
+    RC_CHECK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(lin);
+    return B200RC_OK;
+}
+
+int rc_volume_ensure_texture(b200rc_ctx* ctx, int slot, int filter, int clamp, float border) {
+    VolumeSlot& v = ctx->vol[slot];
+    if (!v.valid) { ctx->set_error("no volume in slot"); return B200RC_ERR_NOT_READY; }
+    if (!v.array) {
+        cudaChannelFormatDesc fd;
+        const int bits = (int)v.elem_bytes * 8;
+        const cudaChannelFormatKind kind = v.desc.dtype == B200RC_F32 ? cudaChannelFormatKindFloat : cudaChannelFormatKindUnsigned;
+        fd = cudaCreateChannelDesc(bits, v.stored_nch >= 2 ? bits : 0, v.stored_nch >= 4 ? bits : 0, v.stored_nch >= 4 ? bits : 0, kind);
+        cudaExtent ext = make_cudaExtent((size_t)v.res_dims[0], (size_t)v.res_dims[1], (size_t)v.res_dims[2]);
+        if (cudaMalloc3DArray(&v.array, &fd, ext, cudaArraySurfaceLoadStore) != cudaSuccess) {
+            ctx->set_error(std::string("cudaMalloc3DArray: ") + cudaGetErrorString(cudaGetLastError()));
+            v.array = nullptr;
+            return B200RC_ERR_OOM;
+        }
+        cudaResourceDesc rd; memset(&rd, 0, sizeof rd);
+        rd.resType = cudaResourceTypeArray; rd.res.array.array = v.array;
+        cudaSurfaceObject_t surf = 0;
+        RC_CHECK(cudaCreateSurfaceObject(&surf, &rd));
+        const long long n = (long long)v.res_dims[0] * v.res_dims[1] * v.res_dims[2];
+        const int threads = 256;
+        const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+        if (v.desc.dtype == B200RC_U16) bricks_to_surface_kernel<unsigned short><<<blocks, threads, 0, ctx->stream>>>((const unsigned short*)v.bricks, surf, v.res_dims[0], v.res_dims[1], v.res_dims[2], v.nbx, v.nby, v.stored_nch);
+        else if (v.desc.dtype == B200RC_U8) bricks_to_surface_kernel<unsigned char><<<blocks, threads, 0, ctx->stream>>>((const unsigned char*)v.bricks, surf, v.res_dims[0], v.res_dims[1], v.res_dims[2], v.nbx, v.nby, v.stored_nch);
+        else bricks_to_surface_kernel<float><<<blocks, threads, 0, ctx->stream>>>((const float*)v.bricks, surf, v.res_dims[0], v.res_dims[1], v.res_dims[2], v.nbx, v.nby, v.stored_nch);
+        ctx->launches++;
+        RC_CHECK(cudaGetLastError());
+        RC_CHECK(cudaStreamSynchronize(ctx->stream));
+        cudaDestroySurfaceObject(surf);
+    }
+    if (v.tex && (v.tex_filter != filter || v.tex_clamp != clamp || v.tex_border != border)) { cudaDestroyTextureObject(v.tex); v.tex = 0; }
+    if (!v.tex) {
+        cudaResourceDesc rd; memset(&rd, 0, sizeof rd);
+        rd.resType = cudaResourceTypeArray; rd.res.array.array = v.array;
+        cudaTextureDesc td; memset(&td, 0, sizeof td);
+        const cudaTextureAddressMode am = clamp == B200RC_CLAMP_TO_BORDER ? cudaAddressModeBorder : cudaAddressModeClamp;
+        td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = am;
+        td.filterMode = filter == B200RC_FILTER_NEAREST ? cudaFilterModePoint : cudaFilterModeLinear;
+        td.readMode = v.desc.dtype == B200RC_F32 ? cudaReadModeElementType : cudaReadModeNormalizedFloat;
+        td.normalizedCoords = 0;
+        td.borderColor[0] = td.borderColor[1] = td.borderColor[2] = td.borderColor[3] = border;
+        RC_CHECK(cudaCreateTextureObject(&v.tex, &rd, &td, nullptr));
+        v.tex_filter = filter; v.tex_clamp = clamp; v.tex_border = border;
+    }
+    return B200RC_OK;
+}
+
+int rc_volume_region_minmax(b200rc_ctx* ctx, int slot, int cell_size, int32_t cells[3], float* out, size_t out_floats) {
+    VolumeSlot& v = ctx->vol[slot];
+    if (!v.valid || v.sharded) { ctx->set_error("region_minmax needs a resident, unsharded volume"); return B200RC_ERR_NOT_READY; }
+    if (cell_size < 1) cell_size = 1;
+    for (int a = 0; a < 3; ++a) cells[a] = (v.desc.dims[a] + cell_size - 1) / cell_size;
+    const long long ncell = (long long)cells[0] * cells[1] * cells[2];
+    const size_t need = (size_t)ncell * v.desc.channels * 2;
+    if (!out) return B200RC_OK;
+    if (out_floats < need) { ctx->set_error("region_minmax output too small"); return B200RC_ERR_INVALID; }
+    float* d_out = nullptr;
+    RC_CHECK(cudaMalloc(&d_out, need * sizeof(float)));
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((ncell * 32 + threads - 1) / threads);
+    const int nch = v.desc.channels;
+    if (v.desc.dtype == B200RC_U16)
+        region_minmax_kernel<unsigned short><<<blocks, threads, 0, ctx->stream>>>((const unsigned short*)v.bricks, d_out, v.desc.dims[0], v.desc.dims[1], v.desc.dims[2], v.nbx, v.nby, cell_size, cells[0], cells[1], cells[2], nch, v.stored_nch, 65535.0f, v.desc.rwm_scale, v.desc.rwm_offset);
+    else if (v.desc.dtype == B200RC_U8)
+        region_minmax_kernel<unsigned char><<<blocks, threads, 0, ctx->stream>>>((const unsigned char*)v.bricks, d_out, v.desc.dims[0], v.desc.dims[1], v.desc.dims[2], v.nbx, v.nby, cell_size, cells[0], cells[1], cells[2], nch, v.stored_nch, 255.0f, v.desc.rwm_scale, v.desc.rwm_offset);
+    else
+        region_minmax_kernel<float><<<blocks, threads, 0, ctx->stream>>>((const float*)v.bricks, d_out, v.desc.dims[0], v.desc.dims[1], v.desc.dims[2], v.nbx, v.nby, cell_size, cells[0], cells[1], cells[2], nch, v.stored_nch, 0.0f, v.desc.rwm_scale, v.desc.rwm_offset);
+    ctx->launches++;
+    RC_CHECK(cudaGetLastError());
+    RC_CHECK(cudaMemcpyAsync(out, d_out, need * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    RC_CHECK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_out);
+    return B200RC_OK;
+}
+
+int rc_volume_build_occupancy(b200rc_ctx* ctx, int slot, const int* cls_modes, int n_channels, bool multi_slot) {
+    VolumeSlot& v = ctx->vol[slot];
+    // key = TF generations + modes
+    unsigned long long key = 1469598103934665603ull;
+    OccArgs a; memset(&a, 0, sizeof a);
+    a.nch = n_channels; a.rwm_scale = v.desc.rwm_scale; a.rwm_offset = v.desc.rwm_offset;
+    for (int c = 0; c < n_channels; ++c) {
+        const ClassifierSlot& k = ctx->cls[multi_slot ? slot : c];
+        const int mode = cls_modes[c];
+        OccCls& o = a.c[c];
+        o.lo = k.dom[0]; o.hi = k.dom[1];
+        if (mode == B200RC_CLASS_TF) { o.nz = k.nz_tf; o.res = k.tf_width; o.linear = 0; }
+        else if (mode == B200RC_CLASS_PREINT) { o.nz = k.nz_pi; o.res = k.pres; o.linear = 1; }
+        else { o.nz = k.nz_2d; o.res = k.tf2d_w; o.linear = 1; }
+        key = (key ^ k.generation) * 1099511628211ull;
+        key = (key ^ (unsigned long long)(mode + 1)) * 1099511628211ull;
+    }
+    if (key == v.occ_key) return B200RC_OK;
+    const int threads = 256;
+    {
+        const long long total = (long long)v.occ0_wpr * 32 * v.cells[1] * v.cells[2];
+        occupancy0_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, ctx->stream>>>(v.minmax, v.occ0, v.cells[0], v.cells[1], v.cells[2], v.occ0_wpr, a);
+        ctx->launches++;
+        RC_CHECK(cudaGetLastError());
+    }
+    {
+        const long long total = (long long)v.occ1_wpr * 32 * v.occ1_dims[1] * v.occ1_dims[2];
+        occupancy1_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, ctx->stream>>>(v.occ0, v.occ1, v.cells[0], v.cells[1], v.cells[2], v.occ0_wpr,
+                                                                                                 v.occ1_dims[0], v.occ1_dims[1], v.occ1_dims[2], v.occ1_wpr);
+        ctx->launches++;
+        RC_CHECK(cudaGetLastError());
+    }
+    v.occ_key = key;
+    return B200RC_OK;
+}
