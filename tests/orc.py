@@ -1,0 +1,216 @@
+"""ctypes binding of the CPU oracle (oracle/liborc.so).  TEST INFRASTRUCTURE: only tests/, smoke() and bench.py's
+cpu_baseline / --impl reference legs import this module."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from voreen_b200 import abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORC_DIR = os.path.join(ROOT, "oracle")
+LIB = os.path.join(ORC_DIR, "liborc.so")
+PROBE = os.path.join(ORC_DIR, "_ref", "tgt_probe")
+
+
+class TFKey(C.Structure):
+    _fields_ = [("intensity", C.c_float), ("color_l", C.c_uint8 * 4), ("color_r", C.c_uint8 * 4), ("split", C.c_int32)]
+
+
+class TF1D(C.Structure):
+    _fields_ = [("keys", C.POINTER(TFKey)), ("n_keys", C.c_int32), ("threshold", C.c_float * 2), ("gamma", C.c_float),
+                ("alpha_mode", C.c_int32), ("domain", C.c_float * 2)]
+
+
+class Volume(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("desc", abi.VolumeDesc)]
+
+
+class Classifier(C.Structure):
+    _fields_ = [("tf_rgba8", C.c_void_p), ("tf_width", C.c_int32), ("domain", C.c_float * 2),
+                ("preint", C.POINTER(C.c_float)), ("preint_res", C.c_int32),
+                ("tf2d_rgba8", C.c_void_p), ("tf2d_w", C.c_int32), ("tf2d_h", C.c_int32), ("domain_y", C.c_float * 2)]
+
+
+_lib = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", ORC_DIR, "liborc.so"])
+    if os.path.isdir("/root/reference/voreen/ext/tgt"):
+        subprocess.check_call(["make", "-s", "-C", ORC_DIR, "ref"])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            build()
+        _lib = C.CDLL(LIB)
+        pf = C.POINTER(C.c_float)
+        _lib.orc_mat4_mul.argtypes = [pf, pf, pf]
+        _lib.orc_mat4_invert.argtypes = [pf, pf]
+        _lib.orc_mat4_invert.restype = C.c_int
+        _lib.orc_look_at.argtypes = [pf, pf, pf, pf]
+        _lib.orc_perspective.argtypes = [C.c_float, C.c_float, C.c_float, C.c_float, pf]
+        _lib.orc_camera_projection.argtypes = [C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, pf]
+        _lib.orc_texture_to_world.argtypes = [C.POINTER(abi.VolumeDesc), pf]
+        _lib.orc_tf1d_texture.argtypes = [C.POINTER(TF1D), C.c_int, C.c_void_p]
+        _lib.orc_preint_cpu.argtypes = [C.POINTER(TF1D), C.c_int, C.c_float, C.c_int, pf]
+        _lib.orc_preint_gpu.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, pf]
+        _lib.orc_preint_classify.argtypes = [pf, C.c_int, C.c_float, C.c_float, pf]
+        _lib.orc_region_minmax.argtypes = [C.POINTER(Volume), C.c_int, C.POINTER(C.c_int32 * 3), pf]
+        _lib.orc_proxy_boxes.argtypes = [C.POINTER(Volume), C.POINTER(TF1D), C.c_int, C.POINTER(abi.EepParams), pf, C.c_int]
+        _lib.orc_proxy_boxes.restype = C.c_int
+        _lib.orc_entry_exit.argtypes = [pf, C.c_int, pf, C.POINTER(abi.EepParams), C.POINTER(abi.Camera), C.c_int, C.c_int, pf, pf, pf, pf]
+        _lib.orc_raycast.argtypes = [C.POINTER(Volume), C.POINTER(Classifier), C.POINTER(abi.Params), C.POINTER(abi.Camera), C.c_int, C.c_int,
+                                     pf, pf, pf, pf, C.POINTER(pf * 3), pf, C.POINTER(abi.Stats)]
+        _lib.orc_sample3d.argtypes = [C.POINTER(Volume), C.c_int, C.c_int, C.c_float, pf, pf]
+        _lib.orc_unorm16.argtypes = [C.c_float]; _lib.orc_unorm16.restype = C.c_float
+        _lib.orc_depth24.argtypes = [C.c_float]; _lib.orc_depth24.restype = C.c_float
+        _lib.orc_composite.argtypes = [C.c_int, pf, pf, pf, pf, pf, pf, C.c_size_t]
+        _lib.orc_image_diff_count.argtypes = [pf, pf, C.c_int, C.c_int, C.c_float, C.c_int]
+        _lib.orc_image_diff_count.restype = C.c_int64
+        _lib.orc_set_threads.argtypes = [C.c_int]
+    return _lib
+
+
+def fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+# ---- convenience wrappers ------------------------------------------------------------------------------------------
+def make_tf(keys, domain=(0.0, 1.0), threshold=(0.0, 1.0), gamma=1.0, alpha_mode=1):
+    """keys: [(intensity, (r,g,b,a))] or [(intensity, colorL, colorR)] sorted by intensity."""
+    arr = (TFKey * len(keys))()
+    for i, k in enumerate(keys):
+        arr[i].intensity = k[0]
+        arr[i].color_l[:] = list(k[1])
+        if len(k) > 2:
+            arr[i].color_r[:] = list(k[2]); arr[i].split = 1
+        else:
+            arr[i].color_r[:] = list(k[1]); arr[i].split = 0
+    tf = TF1D()
+    tf.keys = arr
+    tf._keep = arr
+    tf.n_keys = len(keys)
+    tf.threshold[:] = list(threshold)
+    tf.gamma = gamma
+    tf.alpha_mode = alpha_mode
+    tf.domain[:] = list(domain)
+    return tf
+
+
+def tf1d_texture(tf, width):
+    out = np.zeros((width, 4), np.uint8)
+    lib().orc_tf1d_texture(C.byref(tf), width, out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def preint_cpu(tf, res, step, use_integral=False):
+    out = np.zeros((res, res, 4), np.float32)
+    lib().orc_preint_cpu(C.byref(tf), res, step, 1 if use_integral else 0, fp(out))
+    return out
+
+
+def preint_gpu(tf_tex, res, step):
+    tf_tex = np.ascontiguousarray(tf_tex, np.uint8)
+    out = np.zeros((res, res, 4), np.float32)
+    lib().orc_preint_gpu(tf_tex.ctypes.data_as(C.c_void_p), tf_tex.shape[0], res, step, fp(out))
+    return out
+
+
+def look_at(eye, focus, up):
+    out = np.zeros(16, np.float32)
+    e, f, u = (np.asarray(v, np.float32) for v in (eye, focus, up))
+    lib().orc_look_at(fp(e), fp(f), fp(u), fp(out))
+    return out
+
+
+def camera_projection(fovy_deg, frustum_ratio, near, far, window_ratio):
+    out = np.zeros(16, np.float32)
+    lib().orc_camera_projection(fovy_deg, frustum_ratio, near, far, window_ratio, fp(out))
+    return out
+
+
+def make_camera(eye, focus=(0, 0, 0), up=(0, 1, 0), fovy=45.0, near=0.1, far=50.0, W=256, H=256, frustum_ratio=1.0):
+    cam = abi.Camera()
+    cam.view[:] = look_at(eye, focus, up).tolist()
+    cam.proj[:] = camera_projection(fovy, frustum_ratio, near, far, float(np.float32(W) / np.float32(H))).tolist()
+    cam.position[:] = [float(np.float32(v)) for v in eye]
+    cam.near_dist = near
+    cam.far_dist = far
+    return cam
+
+
+def texture_to_world(desc):
+    out = np.zeros(16, np.float32)
+    lib().orc_texture_to_world(C.byref(desc), fp(out))
+    return out
+
+
+def make_volume(data, desc):
+    v = Volume()
+    data = np.ascontiguousarray(data)
+    v._keep = data
+    v.data = data.ctypes.data
+    v.desc = desc
+    return v
+
+
+def bbox_boxes(vol, eep, tfs=None):
+    out = np.zeros((1 << 16, 6), np.float32)
+    if tfs:
+        arr = (TF1D * len(tfs))(*tfs)
+        n = lib().orc_proxy_boxes(C.byref(vol), arr, len(tfs), C.byref(eep), fp(out), out.shape[0])
+    else:
+        n = lib().orc_proxy_boxes(C.byref(vol), None, 0, C.byref(eep), fp(out), out.shape[0])
+    return out[:n].copy()
+
+
+def entry_exit(boxes, model, eep, cam, W, H):
+    boxes = np.ascontiguousarray(boxes, np.float32).reshape(-1, 6)
+    model = np.ascontiguousarray(model, np.float32)
+    e = np.zeros((H, W, 4), np.float32); x = np.zeros((H, W, 4), np.float32)
+    ed = np.zeros((H, W), np.float32); xd = np.zeros((H, W), np.float32)
+    lib().orc_entry_exit(fp(boxes), boxes.shape[0], fp(model), C.byref(eep), C.byref(cam), W, H, fp(e), fp(ed), fp(x), fp(xd))
+    return e, ed, x, xd
+
+
+def make_classifier(tf_tex=None, domain=(0.0, 1.0), preint=None, tf2d=None, domain_y=(0.0, 1.0)):
+    c = Classifier()
+    c._keep = []
+    if tf_tex is not None:
+        t = np.ascontiguousarray(tf_tex, np.uint8); c._keep.append(t)
+        c.tf_rgba8 = t.ctypes.data; c.tf_width = t.shape[0]
+    if preint is not None:
+        t = np.ascontiguousarray(preint, np.float32); c._keep.append(t)
+        c.preint = fp(t); c.preint_res = t.shape[0]
+    if tf2d is not None:
+        t = np.ascontiguousarray(tf2d, np.uint8); c._keep.append(t)
+        c.tf2d_rgba8 = t.ctypes.data; c.tf2d_h, c.tf2d_w = t.shape[0], t.shape[1]
+    c.domain[:] = list(domain)
+    c.domain_y[:] = list(domain_y)
+    return c
+
+
+def raycast(vols, classifiers, params, cam, W, H, entry, entry_depth, exitp, exit_depth):
+    va = (Volume * len(vols))(*vols)
+    ca = (Classifier * len(classifiers))(*classifiers)
+    outs = [np.zeros((H, W, 4), np.float32) if params.output_connected[o] else None for o in range(3)]
+    depth = np.zeros((H, W), np.float32)
+    pf = C.POINTER(C.c_float)
+    ptrs = (pf * 3)(*[fp(o) if o is not None else None for o in outs])
+    st = abi.Stats()
+    entry = np.ascontiguousarray(entry, np.float32); exitp = np.ascontiguousarray(exitp, np.float32)
+    lib().orc_raycast(va, ca, C.byref(params), C.byref(cam), W, H, fp(entry), fp(np.ascontiguousarray(entry_depth, np.float32)),
+                      fp(exitp), fp(np.ascontiguousarray(exit_depth, np.float32)), C.byref(ptrs), fp(depth), C.byref(st))
+    return outs, depth, st
+
+
+def image_diff_count(a, b, tol=0.02, radius=1):
+    a = np.ascontiguousarray(a, np.float32); b = np.ascontiguousarray(b, np.float32)
+    return int(lib().orc_image_diff_count(fp(a), fp(b), a.shape[1], a.shape[0], tol, radius))

@@ -287,7 +287,7 @@ static int build_params(b200rc_ctx* ctx, const b200rc_params* P, const b200rc_ca
     if (P->empty_space_skipping && !P->multi_volume && !p.channel_shift && !ctx->vol[0].sharded) {
         int modes[4];
         for (int c = 0; c < ncls; ++c) modes[c] = P->vol[0].classification;
-        int rc = rc_volume_build_occupancy(ctx, 0, modes, ncls, false);
+        int rc = rc_volume_build_occupancy(ctx, 0, modes, ncls, false, P->vol[0].clamp, P->vol[0].border_intensity);
         if (rc) return rc;
         p.vol[0].ess = 1;
     }

@@ -74,7 +74,7 @@ int rc_volume_release(b200rc_ctx* ctx, int slot);
 int rc_volume_download(b200rc_ctx* ctx, int slot, void* host_dst, size_t bytes);
 int rc_volume_ensure_texture(b200rc_ctx* ctx, int slot, int filter, int clamp, float border);
 int rc_volume_region_minmax(b200rc_ctx* ctx, int slot, int cell_size, int32_t cells[3], float* out, size_t out_floats);
-int rc_volume_build_occupancy(b200rc_ctx* ctx, int slot, const int* cls_modes, int n_channels, bool multi_slot);
+int rc_volume_build_occupancy(b200rc_ctx* ctx, int slot, const int* cls_modes, int n_channels, bool multi_slot, int clamp, float border);
 // preint.cu
 int rc_tf_set_1d(b200rc_ctx* ctx, int chan, const uint8_t* rgba8, int width, float lo, float hi);
 int rc_tf_set_preint(b200rc_ctx* ctx, int chan, const float* rgba32f, int res);

@@ -92,12 +92,16 @@ __global__ void preint_approx_kernel(const uchar4* __restrict__ tf, const float4
     table[(size_t)sb * res + sf] = make_float4(fminf(fmaxf(col.x, 0.f), 1.f), fminf(fmaxf(col.y, 0.f), 1.f), fminf(fmaxf(col.z, 0.f), 1.f), fminf(fmaxf(col.w, 0.f), 1.f));
 }
 
-// nz[i] = 1 iff row i or column i of the table holds any alpha > 0; thread per i
+// nz[i] = 1 iff the table holds alpha > 0 on the diagonal at i or next to it.  A pre-integration table entry (sf, sb)
+// composites the TF entries between sf and sb, so "every diagonal entry in [lo, hi] is zero" <=> "every entry of
+// [lo, hi]^2 is zero" (preintegrationtable.cpp:105-133); the off-diagonal neighbours make that robust against the
+// opacity-correction pow() underflowing on the diagonal only.
 __global__ void preint_nz_kernel(const float4* __restrict__ table, int res, int* __restrict__ nz) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= res) return;
-    int f = 0;
-    for (int j = 0; j < res && !f; ++j) f = (table[(size_t)i * res + j].w > 0.f) || (table[(size_t)j * res + i].w > 0.f);
+    int f = table[(size_t)i * res + i].w > 0.f;
+    if (i + 1 < res) f |= (table[(size_t)i * res + i + 1].w > 0.f) || (table[(size_t)(i + 1) * res + i].w > 0.f);
+    if (i > 0) f |= (table[(size_t)i * res + i - 1].w > 0.f) || (table[(size_t)(i - 1) * res + i].w > 0.f);
     nz[i] = f;
 }
 __global__ void exclusive_scan_small_kernel(const int* __restrict__ in, int n, int* __restrict__ out) {

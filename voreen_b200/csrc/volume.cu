@@ -209,7 +209,7 @@ __global__ void region_minmax_kernel(const T* __restrict__ bricks, float* __rest
 // occupancy bits for the current transfer function(s)
 // ------------------------------------------------------------------------------------------------------------------
 struct OccCls { const int* nz; int res; int linear; float lo, hi; };
-struct OccArgs { OccCls c[4]; int nch; float rwm_scale, rwm_offset; };
+struct OccArgs { OccCls c[4]; int nch; float rwm_scale, rwm_offset; int border_on; float border; };
 
 __device__ __forceinline__ float occ_rw_to_tex(float lo, float hi, float v) {
     if (v <= lo) return 0.0f;
@@ -232,7 +232,11 @@ __global__ void occupancy0_kernel(const float2* __restrict__ minmax, uint32_t* _
         for (int c = 0; c < a.nch && !nonempty; ++c) {
             const OccCls& k = a.c[c];
             if (!k.nz) { nonempty = true; break; }
-            const float2 mm = minmax[cell * a.nch + c];
+            float2 mm = minmax[cell * a.nch + c];
+            // CLAMP_TO_BORDER: samples next to the volume faces blend in the border colour
+            if (a.border_on && (cx == 0 || cy == 0 || cz == 0 || cx == ncx - 1 || cy == ncy - 1 || cz == ncz - 1)) {
+                mm.x = fminf(mm.x, a.border); mm.y = fmaxf(mm.y, a.border);
+            }
             const float vmin = __fadd_rn(__fmul_rn(mm.x, a.rwm_scale), a.rwm_offset), vmax = __fadd_rn(__fmul_rn(mm.y, a.rwm_scale), a.rwm_offset);
             const float s0 = occ_rw_to_tex(k.lo, k.hi, fminf(vmin, vmax)), s1 = occ_rw_to_tex(k.lo, k.hi, fmaxf(vmin, vmax));
             int i0, i1;
@@ -498,12 +502,14 @@ int rc_volume_region_minmax(b200rc_ctx* ctx, int slot, int cell_size, int32_t ce
     return B200RC_OK;
 }
 
-int rc_volume_build_occupancy(b200rc_ctx* ctx, int slot, const int* cls_modes, int n_channels, bool multi_slot) {
+int rc_volume_build_occupancy(b200rc_ctx* ctx, int slot, const int* cls_modes, int n_channels, bool multi_slot, int clamp, float border) {
     VolumeSlot& v = ctx->vol[slot];
     // key = TF generations + modes
     unsigned long long key = 1469598103934665603ull;
     OccArgs a; memset(&a, 0, sizeof a);
     a.nch = n_channels; a.rwm_scale = v.desc.rwm_scale; a.rwm_offset = v.desc.rwm_offset;
+    a.border_on = clamp == B200RC_CLAMP_TO_BORDER; a.border = border;
+    if (a.border_on) { unsigned int bits; memcpy(&bits, &border, 4); key = (key ^ (0x100000000ull | bits)) * 1099511628211ull; }
     for (int c = 0; c < n_channels; ++c) {
         const ClassifierSlot& k = ctx->cls[multi_slot ? slot : c];
         const int mode = cls_modes[c];
