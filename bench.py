@@ -1,0 +1,443 @@
+#!/usr/bin/env python
+"""bench.py -- the measurement contract for the direct-volume-ray-casting hot path.
+
+One "step" = one frame of the BASELINE.json workload ("2048^3 u16 DVR @2048^2": synthetic CT-like volume, pre-integrated
+classification, empty-space skipping, central-difference gradients + Phong, sampling rate 2, early ray termination) at
+one view of the 36-view orbit of SURVEY.md 8d (step k renders view k mod 36).
+
+value    = reference-equivalent Gsamples/s: the samples the reference's fragment shader executes for these frames
+           (classified + skipped-by-ESS, i.e. with ERT but without empty-space skipping, which never changes a pixel)
+           divided by the device time of the timed region; inputs (volume, TF, camera) resident in HBM.
+e2e      = the same metric through the drop-in call a SingleVolumeRaycaster processor makes: b200rc_render with HOST
+           (pinned) entry/exit buffers in and HOST RGBA16 + depth out, copies inside the timed region.
+roofline = HBM: algorithmic bytes (voxels of the touched 16^3 macro-cells x 2 B + image I/O) / march-kernel
+           time, against MEASURED_PEAKS.json.
+N > 1    = strong scaling, sort-last: the same volume split into N bricks (one per rank/GPU), partial images merged by
+           binary-swap over compositing (voreen_b200/sortlast.py).
+
+`--impl reference` times the CPU restatement of the reference's GLSL path (oracle/, OpenMP on all host cores) on a
+bounded sample (a centred crop of each frame) of the same workload.  The reference itself is GLSL behind an OpenGL
+driver + Qt and cannot be built here, so `kind` is "port".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+N_VIEWS = 36
+METRIC = "dvr_reference_equivalent_gsamples_per_s"
+UNIT = "Gsamples/s"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# workload definition
+# ---------------------------------------------------------------------------------------------------------------------
+CT_KEYS = [(0.00, (0, 0, 0, 0)), (0.25, (0, 0, 0, 0)), (0.30, (255, 140, 60, 8)), (0.55, (255, 230, 200, 40)),
+           (0.80, (255, 255, 255, 200)), (1.00, (255, 255, 255, 255))]
+
+
+def orbit_eye(k, n=N_VIEWS, radius=3.5):
+    th = 2.0 * math.pi * (k % n) / n
+    return (radius * math.sin(th), radius * 0.3, radius * math.cos(th))
+
+
+def workload_name(args):
+    return (f"synthetic CT-like {args.size}^3 u16, {args.classification} classification, ESS, central-diff + Phong, "
+            f"DVR, rate {args.rate:g}, {args.image}^2, {N_VIEWS}-view orbit")
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.lines = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.kill()
+        self.proc.wait()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU leg: the oracle on a bounded sample (centred crop) of the same frames
+# ---------------------------------------------------------------------------------------------------------------------
+class CpuSample:
+    """Holds what the oracle needs to march a centred crop of the workload's frames: a window of the synthetic volume
+    (generated on the CPU, identical bytes to the device generator), the TF / pre-integration table, the cameras."""
+
+    def __init__(self, args, dims):
+        import orc
+        from voreen_b200 import abi
+        from voreen_b200 import raycaster as rc
+        self.orc, self.abi, self.rc = orc, abi, rc
+        self.args, self.dims = args, tuple(dims)
+        self.W = self.H = args.image
+        self.step = float(np.float32(1.0) / (np.float32(max(dims)) * np.float32(args.rate)))
+        self.cores = os.cpu_count() or 1
+        orc.lib().orc_set_threads(self.cores)
+        tf = orc.make_tf(CT_KEYS, domain=(0.0, 65535.0))
+        self.tf_tex = orc.tf1d_texture(tf, 4096)
+        self.preint = None
+        if args.classification == "preint":
+            tf1k = orc.make_tf(CT_KEYS, domain=(0.0, 65535.0))
+            self.preint = orc.preint_cpu(tf1k, 1024, self.step)
+        self.params = rc.default_params(self.step, classification=abi.CLASS_PREINT if self.preint is not None else abi.CLASS_TF,
+                                        empty_space_skipping=0, out_format=abi.OUT_RGBA32F)
+        self.params.collect_stats = 1
+        self.full_desc = rc.make_volume_desc(self.dims)
+        self.eep = rc.default_eep()
+        self.window = {}
+
+    def crop_eep(self, view, cw, ch):
+        orc = self.orc
+        cam = orc.make_camera(orbit_eye(view), W=self.W, H=self.H)
+        vol = orc.Volume(); vol.desc = self.full_desc
+        boxes = orc.bbox_boxes(vol, self.eep)
+        key = ("eep", view)
+        if key not in self.window:
+            self.window[key] = orc.entry_exit(boxes, orc.texture_to_world(self.full_desc), self.eep, cam, self.W, self.H)
+        e, ed, x, xd = self.window[key]
+        y0, x0 = (self.H - ch) // 2, (self.W - cw) // 2
+        sl = (slice(y0, y0 + ch), slice(x0, x0 + cw))
+        return cam, tuple(np.ascontiguousarray(a[sl]) for a in (e, ed, x, xd))
+
+    def volume_window(self, crops):
+        """Synthesize only the voxels the crop's rays can touch (+ apron for gradients)."""
+        lo = np.array([1e9] * 3); hi = np.array([-1e9] * 3)
+        for (e, ed, x, xd) in crops:
+            m = np.any(e[..., :3] != x[..., :3], axis=2)
+            if not m.any():
+                continue
+            pts = np.concatenate([e[m][:, :3], x[m][:, :3]])
+            lo = np.minimum(lo, pts.min(axis=0)); hi = np.maximum(hi, pts.max(axis=0))
+        d = np.array(self.dims, np.float64)
+        vlo = np.clip(np.floor(lo * d - 0.5).astype(int) - 4, 0, self.dims)
+        vhi = np.clip(np.ceil(hi * d - 0.5).astype(int) + 5, 0, self.dims)
+        key = ("vol", tuple(vlo), tuple(vhi))
+        if key not in self.window:
+            rd = tuple(int(v) for v in (vhi - vlo))
+            data = self.orc.synth_volume(self.dims, self.args.seed, tuple(int(v) for v in vlo), rd)
+            desc = self.rc.make_volume_desc(self.dims, shard_lo=tuple(int(v) for v in vlo), shard_hi=tuple(int(v) for v in vhi), shard_apron=0)
+            self.window = {k: v for k, v in self.window.items() if k[0] != "vol"}
+            self.window[key] = (data, desc)
+        return self.window[key]
+
+    def march(self, cam, crop, vol):
+        orc = self.orc
+        data, desc = vol
+        ov = orc.make_volume(data, desc)
+        cls = [orc.make_classifier(self.tf_tex, (0.0, 65535.0), preint=self.preint)]
+        e, ed, x, xd = crop
+        t0 = time.perf_counter()
+        outs, depth, st = orc.raycast([ov], cls, self.params, cam, e.shape[1], e.shape[0], e, ed, x, xd)
+        dt = time.perf_counter() - t0
+        return dt, int(st.samples_classified)
+
+    def calibrate(self, target_s):
+        """Pick the crop edge so that one step costs about target_s seconds of CPU work."""
+        edge = 32
+        cam, crop = self.crop_eep(0, edge, edge)
+        vol = self.volume_window([crop])
+        dt, ns = self.march(cam, crop, vol)
+        per_px = max(dt, 1e-4) / (edge * edge)
+        edge2 = int(max(16, min(self.W, math.sqrt(target_s / per_px))) // 8 * 8)
+        return max(16, edge2)
+
+
+def run_reference(args, rank, world):
+    """`--impl reference`: the oracle (CPU port of the reference's GLSL path) on the host cores, rank 0 only."""
+    if rank != 0:
+        return
+    dims = (args.size,) * 3
+    cs = CpuSample(args, dims)
+    total_steps = args.steps + args.warmup
+    edge = cs.calibrate(target_s=min(8.0, max(0.5, 150.0 / max(1, total_steps))))
+    crops = []
+    views = [k % N_VIEWS for k in range(total_steps)]
+    for v in sorted(set(views)):
+        crops.append((v,) + cs.crop_eep(v, edge, edge))
+    vol = cs.volume_window([c[2] for c in crops])
+    by_view = {c[0]: (c[1], c[2]) for c in crops}
+    for k in range(args.warmup):
+        cs.march(*by_view[views[k]], vol)
+    t, samples = 0.0, 0
+    for k in range(args.warmup, total_steps):
+        dt, ns = cs.march(*by_view[views[k]], vol)
+        t += dt; samples += ns
+    value = samples / t / 1e9
+    sample = f"centred {edge}x{edge}-pixel crop of each {args.image}^2 frame (all samples of those rays, ERT on, no ESS), volume window synthesized on the CPU"
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": workload_name(args), "l2": "CPU run"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cs.cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU leg
+# ---------------------------------------------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import voreen_b200 as vb
+    from voreen_b200 import abi, host
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = vb.Context(local_rank)
+    stream = torch.cuda.Stream(device=dev)
+    ctx.set_stream(stream.cuda_stream)
+
+    dims = (args.size,) * 3
+    W = H = args.image
+    step = float(np.float32(1.0) / (np.float32(max(dims)) * np.float32(args.rate)))
+    use_pi = args.classification == "preint"
+    sampler = abi.SAMPLER_TEX if args.sampler == "tex" else abi.SAMPLER_EXACT
+
+    sl = None
+    if world > 1:
+        from voreen_b200 import sortlast
+        sl = sortlast.SortLast(ctx, dims, rank, world, W, H, device=dev, stream=stream)
+        desc = sl.shard_desc()
+    else:
+        desc = vb.make_volume_desc(dims)
+    t0 = time.perf_counter()
+    ctx.synth_volume(0, desc, args.seed)
+    ctx.synchronize()
+    t_synth = time.perf_counter() - t0
+
+    if use_pi:
+        ctx.set_tf1d(0, host.tf1d_texture(CT_KEYS, 1024), (0.0, 65535.0))
+        ctx.build_preint(0, 1024, step, abi.PI_CPU)      # PreIntegrationTable::computeTable on the device
+    ctx.set_tf1d(0, host.tf1d_texture(CT_KEYS, 4096), (0.0, 65535.0))
+    params = vb.default_params(step, classification=abi.CLASS_PREINT if use_pi else abi.CLASS_TF, sampler=sampler,
+                               empty_space_skipping=1, out_format=abi.OUT_RGBA16)
+    eep = vb.default_eep()
+    cams = [host.make_camera(orbit_eye(k), W=W, H=H) for k in range(N_VIEWS)]
+
+    px = W * H
+    out_rgba = torch.empty((H, W, 4), dtype=torch.int16, device=dev)
+    out_depth = torch.empty((H, W), dtype=torch.float32, device=dev)
+
+    def frame(k):
+        if sl is not None:
+            return sl.render(params, eep, cams[k % N_VIEWS], out_rgba, out_depth)
+        ctx.render_camera_ptrs(params, eep, cams[k % N_VIEWS], W, H, [out_rgba.data_ptr(), 0, 0], out_depth.data_ptr(), device=True)
+        return ctx.stats().last_march_ms
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- statistics pass (outside the timed region): reference-equivalent samples and touched macro-cells per view ----
+    params.collect_stats = 1
+    ref_samples, classified, cells16, nominal = [], [], [], []
+    for k in range(N_VIEWS):
+        frame(k)
+        st = ctx.stats()
+        ref_samples.append(st.samples_classified + st.samples_skipped); classified.append(st.samples_classified)
+        cells16.append(st.cells_touched); nominal.append(st.samples_nominal)
+    params.collect_stats = 0
+    if world > 1:
+        t = torch.tensor([ref_samples, classified, nominal], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        ref_samples, classified, nominal = (t[i].tolist() for i in range(3))
+
+    # ---- timed region -------------------------------------------------------------------------------------------------
+    for k in range(args.warmup):
+        frame(k)
+    barrier()
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = ctx.stats().kernel_launches
+    march_ms = []
+    ev0.record(stream)
+    for k in range(args.steps):
+        march_ms.append(frame(args.warmup + k))
+    ev1.record(stream)
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = ctx.stats().kernel_launches - launches0
+    clk = clocks.stop() if clocks else None
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    steps_views = [(args.warmup + k) % N_VIEWS for k in range(args.steps)]
+    S = sum(ref_samples[v] for v in steps_views)
+    value = S / (ms_total * 1e-3) / 1e9
+
+    # ---- roofline of the dominant kernel (march) on this rank -----------------------------------------------------------
+    peak, peak_src = peaks()
+    img_bytes = px * (8 + 4) + px * 2 * 8          # RGBA16 + depth written, entry/exit read
+    alg_bytes = [cells16[v] * 4096 * 2 + img_bytes for v in steps_views]
+    ach = [b / (m * 1e-3) / 1e9 for b, m in zip(alg_bytes, march_ms)]
+    achieved = sum(alg_bytes) / (sum(march_ms) * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "kernel": "march_kernel", "kernel_ms_avg": sum(march_ms) / len(march_ms),
+                "kernel_share_of_step": sum(march_ms) / ms_total,
+                "alg_bytes_per_launch_avg": sum(alg_bytes) / len(alg_bytes), "frac_min": min(ach) / peak, "frac_max": max(ach) / peak,
+                "whole_volume_bytes": int(np.prod(dims)) * 2 + img_bytes,
+                "whole_volume_frac": (int(np.prod(dims)) * 2 / world + img_bytes) / (sum(march_ms) / len(march_ms) * 1e-3) / 1e9 / peak}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            roofline["traffic"] = json.load(open(traffic_file)).get("march_kernel_dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- e2e: the drop-in call with host buffers ------------------------------------------------------------------------
+    e2e = None
+    if world == 1 and not args.no_e2e:
+        n_e2e_views = 6
+        ev = [k * (N_VIEWS // n_e2e_views) for k in range(n_e2e_views)]
+        host = []
+        for v in ev:
+            e, ed, x, xd = ctx.entry_exit(eep, cams[v], W, H)          # what MeshEntryExitPoints hands to the raycaster
+            host.append(tuple(torch.from_numpy(a).pin_memory() for a in (e, ed, x, xd)))
+        h_rgba = torch.empty((H, W, 4), dtype=torch.int16).pin_memory()
+        h_depth = torch.empty((H, W), dtype=torch.float32).pin_memory()
+        import ctypes as C
+        pf = C.POINTER(C.c_float)
+
+        def e2e_frame(i):
+            e, ed, x, xd = host[i % n_e2e_views]
+            ptrs = (C.c_void_p * 3)(h_rgba.data_ptr(), None, None)
+            rc = ctx.lib.b200rc_render(ctx.h, C.byref(params), C.byref(cams[ev[i % n_e2e_views]]), W, H,
+                                       C.cast(e.data_ptr(), pf), C.cast(ed.data_ptr(), pf), C.cast(x.data_ptr(), pf), C.cast(xd.data_ptr(), pf),
+                                       C.byref(ptrs), C.cast(h_depth.data_ptr(), pf))
+            ctx._check(rc, "render")
+        for i in range(max(3, args.warmup)):
+            e2e_frame(i)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            e2e_frame(i)
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        S2 = sum(ref_samples[ev[i % n_e2e_views]] for i in range(args.steps))
+        e2e = {"value": S2 / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": px * (16 + 16 + 4 + 4), "d2h_bytes_per_step": px * (8 + 4),
+               "ms_per_step": 1e3 * dt / args.steps, "call": "b200rc_render (host entry/exit in, host RGBA16 + depth out, pinned)"}
+
+    # ---- CPU baseline: the oracle on a bounded sample of the same frames --------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cs = CpuSample(args, dims)
+        edge = cs.calibrate(target_s=4.0)
+        t, ns = 0.0, 0
+        views = [0, 9, 18, 27]
+        crops = [(v,) + cs.crop_eep(v, edge, edge) for v in views]
+        vol = cs.volume_window([c[2] for c in crops])
+        for c in crops:
+            dt, n_ = cs.march(c[1], c[2], vol)
+            t += dt; ns += n_
+        cpu = {"value": ns / t / 1e9, "unit": UNIT, "cores": cs.cores, "kind": "port",
+               "sample": f"centred {edge}x{edge}-pixel crops of views {views} of the same frames ({t:.1f} s of oracle work, ERT on, no ESS)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args), "sampler": args.sampler, "parallelism": f"sort-last x{world}" if world > 1 else "single GPU",
+                       "l2": f"volume {int(np.prod(dims)) * 2 / 2**30:.1f} GiB >> 126 MB L2, a different view every step"},
+            "ms_per_frame": ms_total / args.steps,
+            "gsamples_classified_per_s": sum(classified[v] for v in steps_views) / (ms_total * 1e-3) / 1e9,
+            "gsamples_nominal_per_s": sum(nominal[v] for v in steps_views) / (ms_total * 1e-3) / 1e9,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+            "synth_s": t_synth,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=36)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=2048)
+    ap.add_argument("--image", type=int, default=2048)
+    ap.add_argument("--rate", type=float, default=2.0)
+    ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--classification", default="preint", choices=["preint", "tf"])
+    ap.add_argument("--sampler", default="exact", choices=["exact", "tex"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus and args.gpus > 1:
+        raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})")
+    run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -196,6 +196,8 @@ typedef struct b200rc_stats {
     uint64_t samples_nominal;       /* sum over rays of floor(tEnd/step)+1 */
     uint64_t cells_touched;         /* 16^3 macro-cells marched (for V_touched) */
     uint64_t kernel_launches;       /* launches since context creation */
+    uint64_t samples_skipped;       /* lattice samples jumped over by empty-space skipping (classified + skipped =
+                                       the samples the reference shader executes for the same frame) */
 } b200rc_stats;
 
 /* ---- lifetime -------------------------------------------------------------------------------- */

@@ -1,0 +1,93 @@
+/*
+ * b200rc_host.h -- flat C view of the C++ host-side mirror (voreen_b200/host/) of the reference's processor
+ * interface for the ray-casting path: tgt::Camera, TransFunc1DKeys, VolumeRaycaster / SingleVolumeRaycaster
+ * properties (identical IDs and option strings), MeshEntryExitPoints over an OptimizedProxyGeometry cube.
+ *
+ * Inside Voreen none of this is needed -- the drop-in processor (custommodules/b200raycast/) takes camera, transfer
+ * function and properties from Voreen itself and calls include/b200rc.h directly.  Outside Voreen (tests, bench.py,
+ * standalone tools) this library plays Voreen's role, so that parity tests read like the reference's own regression
+ * workspaces: set properties by ID, attach a volume, process(), compare images.
+ *
+ * All functions return 0 on success (B200RC_OK) unless stated.  V/ = /root/reference/voreen/
+ */
+#ifndef B200RC_HOST_H
+#define B200RC_HOST_H
+
+#include "b200rc.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* TransFuncMappingKey (V/src/core/datastructures/transfunc/1d/1dkeys/utils/transfuncmappingkey.cpp:30-35) */
+typedef struct b200host_tf_key {
+    float   intensity;          /* [0,1] position in the TF domain */
+    uint8_t color_l[4];         /* RGBA left of the key */
+    uint8_t color_r[4];         /* RGBA right of the key (== color_l unless split) */
+    int32_t split;
+} b200host_tf_key;
+
+/* ---- tgt::Camera (V/ext/tgt/camera.cpp:133-217, V/ext/tgt/matrix.h:1196-1248) ------------------------------ */
+/* view = createLookAt(position, focus, up); proj = Camera::getProjectionMatrix(width/height) (PERSPECTIVE, fovy clamped
+ * to [6,175] degrees).  Fills every field of `out`. */
+int b200host_camera(const float position[3], const float focus[3], const float up[3], float fovy_deg, float frustum_ratio,
+                    float near_dist, float far_dist, int width, int height, b200rc_camera* out);
+
+/* ---- TransFunc1DKeys::getTexture (V/src/core/datastructures/transfunc/1d/transfunc1d.cpp:85-116,
+ *      1dkeys/transfunc1dkeys.cpp:119-154, transfuncbase.cpp:177-210): keys -> RGBA8 texels.  alpha_mode: 0 zero, 1 use, 2 one. */
+int b200host_tf1d_keys_texture(const b200host_tf_key* keys, int n_keys, const float threshold[2], float gamma, int alpha_mode,
+                               int width, uint8_t* out_rgba8);
+/* TransFuncPropertyBase texture width for a volume (transfuncpropertybase.cpp:155-165, transfunc1dkeysproperty.cpp:94-97) */
+int b200host_tf1d_width_for(int dtype, int* out_width);
+
+/* ---- VolumeBase meta data with the reference's defaults (denormalising RealWorldMapping for integer formats,
+ *      V/include/voreen/core/datastructures/meta/realworldmappingmetadata.h:72-88); spacing/offset/phys_to_world may be NULL
+ *      (unit cube [-1,1]^3 * dims/max(dims) like the bundled data, identity). */
+int b200host_volume_desc(const int32_t dims[3], int channels, const char* format /* "uint8" "uint16" "float" */,
+                         const float* spacing, const float* offset, const float* phys_to_world, b200rc_volume_desc* out);
+
+/* ---- SingleVolumeRaycaster mirror (V/modules/base/processors/render/singlevolumeraycaster.cpp:46-170,246-425) ---- */
+typedef struct b200host_svrc b200host_svrc;
+
+int  b200host_svrc_create(int device, b200host_svrc** out);
+void b200host_svrc_destroy(b200host_svrc* p);
+const char* b200host_svrc_last_error(const b200host_svrc* p);
+b200rc_ctx* b200host_svrc_context(b200host_svrc* p);
+
+/* "-c Processor.Property=value" (V/apps/voreentool/voreentool.cpp:338-350): property IDs and option strings of
+ * VolumeRaycaster / VolumeRenderer / SingleVolumeRaycaster / MeshEntryExitPoints / VolumePort, e.g.
+ *   samplingRate=2  compositing=dvr compositing2=mip gradient=central-differences classification=pre-integrated-cpu
+ *   shading=phong isoValue=0.5 gammaValue=0.1 lightPosition="2.3 1.5 1.5 1" materialShininess=60
+ *   textureFilterMode=linear textureClampMode=clamp-to-edge textureBorderIntensity=0 enableChannelShift=true
+ *   channelShift1="1 0 0" applyLightAttenuation=false lightAttenuation="1 0 0" interactionQuality=1
+ *   cameraInsideVolumeTechnique=gpu jitterEntryPoints=false jitterStepLength=0.005 useFloatRenderTargets=false
+ * and the implementation knobs emptySpaceSkipping=true sampler=exact|texture outputFormat=rgba16|rgba32f.
+ * Unknown IDs / options return B200RC_ERR_INVALID (the reference logs "property not found"). */
+int b200host_svrc_set_property(b200host_svrc* p, const char* id, const char* value);
+int b200host_svrc_get_sampling_step(b200host_svrc* p, float* out);     /* VolumeRaycaster::getSamplingStepSize */
+
+/* volumehandle.volumehandle: the VolumeRAM pointer + meta data; uploads to the brick pool. */
+int b200host_svrc_set_volume(b200host_svrc* p, const void* data, const b200rc_volume_desc* desc);
+/* synthetic benchmark volume generated in HBM (no host copy) */
+int b200host_svrc_set_synthetic_volume(b200host_svrc* p, const b200rc_volume_desc* desc, uint64_t seed);
+/* transferFunction, transferFunction1..3 (channel 0..3): keys + domain (real-world units) + threshold + gamma */
+int b200host_svrc_set_transfer_function(b200host_svrc* p, int channel, const b200host_tf_key* keys, int n_keys,
+                                        float domain_lo, float domain_hi, const float threshold[2], float gamma);
+/* camera property */
+int b200host_svrc_set_camera(b200host_svrc* p, const float position[3], const float focus[3], const float up[3],
+                             float fovy_deg, float near_dist, float far_dist);
+/* image.output / image.output1 / image.output2 connected? (default: only image.output) */
+int b200host_svrc_connect_output(b200host_svrc* p, int port, int connected);
+/* image.entrypoints / image.exitpoints handed over as host float buffers (what the reference's RenderPorts hold);
+ * pass NULLs to detach: process() then runs the MeshEntryExitPoints mirror on the device. */
+int b200host_svrc_set_entry_exit(b200host_svrc* p, int width, int height, const float* entry_rgba, const float* entry_depth,
+                                 const float* exit_rgba, const float* exit_depth);
+/* Processor::isReady (singlevolumeraycaster.cpp:192-205): 1 ready, 0 not */
+int b200host_svrc_is_ready(b200host_svrc* p);
+/* beforeProcess + process: out_color[i] / out_depth are host buffers (pixel type per outputFormat) or NULL. */
+int b200host_svrc_process(b200host_svrc* p, int width, int height, void* out_color[B200RC_MAX_OUTPUTS], float* out_depth);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -389,7 +389,21 @@ static inline v4 texel_fetch(const orc_volume* v, int x, int y, int z, int clamp
         if (x < 0) x = 0; if (x > d[0] - 1) x = d[0] - 1;
         if (y < 0) y = 0; if (y > d[1] - 1) y = d[1] - 1;
         if (z < 0) z = 0; if (z > d[2] - 1) z = d[2] - 1;
-        int64_t base = (((int64_t)z * d[1] + y) * d[0] + x) * nc;
+        /* windowed storage (bench.py's bounded CPU sample): `data` holds only voxels [shard_lo - apron, shard_hi + apron)
+         * of the global volume; indices outside the window are clamped into it (memory safety only -- the caller sizes
+         * the window so that no sample of the rays it casts reaches outside) */
+        int rl[3] = {0, 0, 0}, rd[3] = {d[0], d[1], d[2]};
+        if (v->desc.shard_hi[0] > v->desc.shard_lo[0])
+            for (int a = 0; a < 3; ++a) {
+                int lo = v->desc.shard_lo[a] - v->desc.shard_apron, hi = v->desc.shard_hi[a] + v->desc.shard_apron;
+                if (lo < 0) lo = 0; if (hi > d[a]) hi = d[a];
+                rl[a] = lo; rd[a] = hi - lo;
+            }
+        x -= rl[0]; y -= rl[1]; z -= rl[2];
+        if (x < 0) x = 0; if (x > rd[0] - 1) x = rd[0] - 1;
+        if (y < 0) y = 0; if (y > rd[1] - 1) y = rd[1] - 1;
+        if (z < 0) z = 0; if (z > rd[2] - 1) z = rd[2] - 1;
+        int64_t base = (((int64_t)z * rd[1] + y) * rd[0] + x) * nc;
         for (int i = 0; i < nc; ++i) c[i] = raw_texel(v, base + i);
     }
     switch (nc) {
@@ -1412,4 +1426,77 @@ int64_t orc_image_diff_count(const float* a, const float* b, int W, int H, float
             }
         }
     return bad;
+}
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* synthetic "CT-like" benchmark volume -- no reference counterpart; this is the CPU twin  */
+/* of b200rc_synth_volume (voreen_b200/csrc/volume.cu synth_kernel), same integer noise and the same un-contracted */
+/* fp32 sequence, so that both produce identical bytes (tests/test_gpu_parity.py::test_synth_volume_matches).     */
+/* ------------------------------------------------------------------------------------------------------------ */
+static inline uint32_t synth_hash32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+
+void orc_synth_volume(const int32_t dims[3], const int32_t lo[3], const int32_t rdims[3], uint64_t seed, uint16_t* out) {
+    float cx[64], cy[64], cz[64], r2[64];
+    const uint32_t sd = (uint32_t)seed;
+    for (int i = 0; i < 64; ++i) {
+        const uint32_t h0 = synth_hash32(sd * 0x9e3779b9u + (uint32_t)(i * 4 + 0)), h1 = synth_hash32(sd * 0x9e3779b9u + (uint32_t)(i * 4 + 1));
+        const uint32_t h2 = synth_hash32(sd * 0x9e3779b9u + (uint32_t)(i * 4 + 2)), h3 = synth_hash32(sd * 0x9e3779b9u + (uint32_t)(i * 4 + 3));
+        cx[i] = ((float)(h0 & 0xffffu) * (1.0f / 65536.0f) - 0.5f) * 0.76f;
+        cy[i] = ((float)(h1 & 0xffffu) * (1.0f / 65536.0f) - 0.5f) * 0.76f;
+        cz[i] = ((float)(h2 & 0xffffu) * (1.0f / 65536.0f) - 0.5f) * 0.76f;
+        const float r = 0.012f + (float)(h3 & 0xffffu) * (1.0f / 65536.0f) * 0.02f;
+        r2[i] = r * r;
+    }
+    const int mind = dims[0] < dims[1] ? (dims[0] < dims[2] ? dims[0] : dims[2]) : (dims[1] < dims[2] ? dims[1] : dims[2]);
+    const float fall_scale = 0.36f * (float)mind;
+    const float rcpx = 1.0f / (float)dims[0], rcpy = 1.0f / (float)dims[1], rcpz = 1.0f / (float)dims[2];
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int zz_ = 0; zz_ < rdims[2]; ++zz_) {
+        const int z = zz_ + lo[2];
+        const float pz = ((float)z + 0.5f) * rcpz - 0.5f;
+        const float zz = pz * pz;
+        /* spheres that can touch this slice / row: az*az <= r2 is implied by d2 <= r2 (rounded sums of non-negative
+         * terms are monotone), so the candidate lists are exactly conservative */
+        int cz_list[64], ncz = 0;
+        for (int i = 0; i < 64; ++i) { const float az = pz - cz[i]; if (az * az <= r2[i]) cz_list[ncz++] = i; }
+        for (int yy_ = 0; yy_ < rdims[1]; ++yy_) {
+            const int y = yy_ + lo[1];
+            const float py = ((float)y + 0.5f) * rcpy - 0.5f;
+            const float yy = py * py;
+            int cy_list[64], ncy = 0;
+            for (int k = 0; k < ncz; ++k) { const int i = cz_list[k]; const float ay = py - cy[i]; if (ay * ay <= r2[i]) cy_list[ncy++] = i; }
+            uint16_t* row = out + ((size_t)zz_ * rdims[1] + yy_) * rdims[0];
+            for (int xx_ = 0; xx_ < rdims[0]; ++xx_) {
+                const int x = xx_ + lo[0];
+                const float px = ((float)x + 0.5f) * rcpx - 0.5f;
+                const float xx = px * px;
+                const float rr = (xx + yy) + zz;
+                const float q2 = ((xx * 5.6689343f) + (yy * 7.7160494f)) + (zz * 6.25f);
+                const float q = sqrtf(q2);
+                float fall = ((1.0f - q) * fall_scale) * 0.25f;
+                fall = fminf(fmaxf(fall, 0.0f), 1.0f);
+                const float s = (fall * fall) * (3.0f - (2.0f * fall));
+                float f = 0.35f * s;
+                int hit = 0;
+                for (int k = 0; k < ncy && !hit; ++k) {
+                    const int i = cy_list[k];
+                    const float ax = px - cx[i], ay = py - cy[i], az = pz - cz[i];
+                    const float d2 = ((ax * ax) + (ay * ay)) + (az * az);
+                    hit = d2 <= r2[i];
+                }
+                if (hit) f = fmaxf(f, 0.6f);
+                if (rr >= 0.09f && rr <= 0.1024f) f = fmaxf(f, 0.85f);
+                int val = (int)floorf((f * 65535.0f) + 0.5f);
+                const uint32_t h = synth_hash32((uint32_t)x * 73856093u ^ (uint32_t)y * 19349663u ^ (uint32_t)z * 83492791u ^ sd * 0x9e3779b9u);
+                const uint32_t hb = synth_hash32(h ^ 0x68bc21ebu);
+                const int sum = (int)(h & 0xffffu) + (int)(h >> 16) + (int)(hb & 0xffffu) + (int)(hb >> 16);
+                val += ((sum - 131070) * 1135) >> 16;
+                val = val < 0 ? 0 : (val > 65535 ? 65535 : val);
+                row[xx_] = (uint16_t)val;
+            }
+        }
+    }
 }

@@ -129,6 +129,10 @@ void orc_composite(int mode, const float* front_rgba, const float* front_depth, 
  * returns the number of pixels whose RGBA distance/2 exceeds `tolerance` after a radius-`radius` neighbour search. */
 int64_t orc_image_diff_count(const float* a, const float* b, int width, int height, float tolerance, int radius);
 
+/* --- synthetic "CT-like" benchmark volume: CPU twin of b200rc_synth_volume, identical bytes.
+ * Writes voxels [lo, lo+rdims) of a global volume of `dims` voxels, x fastest. --- */
+void orc_synth_volume(const int32_t dims[3], const int32_t lo[3], const int32_t rdims[3], uint64_t seed, uint16_t* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,6 +75,7 @@ def lib():
         _lib.orc_image_diff_count.argtypes = [pf, pf, C.c_int, C.c_int, C.c_float, C.c_int]
         _lib.orc_image_diff_count.restype = C.c_int64
         _lib.orc_set_threads.argtypes = [C.c_int]
+        _lib.orc_synth_volume.argtypes = [C.POINTER(C.c_int32 * 3), C.POINTER(C.c_int32 * 3), C.POINTER(C.c_int32 * 3), C.c_uint64, C.c_void_p]
     return _lib
 
 
@@ -214,3 +215,12 @@ def raycast(vols, classifiers, params, cam, W, H, entry, entry_depth, exitp, exi
 def image_diff_count(a, b, tol=0.02, radius=1):
     a = np.ascontiguousarray(a, np.float32); b = np.ascontiguousarray(b, np.float32)
     return int(lib().orc_image_diff_count(fp(a), fp(b), a.shape[1], a.shape[0], tol, radius))
+
+
+def synth_volume(dims, seed=1234, lo=(0, 0, 0), rdims=None):
+    """CPU twin of Context.synth_volume (identical bytes): voxels [lo, lo+rdims) of the global `dims` volume."""
+    rdims = tuple(rdims) if rdims is not None else tuple(dims)
+    out = np.empty((rdims[2], rdims[1], rdims[0]), np.uint16)
+    a = (C.c_int32 * 3)(*dims); b = (C.c_int32 * 3)(*lo); c = (C.c_int32 * 3)(*rdims)
+    lib().orc_synth_volume(C.byref(a), C.byref(b), C.byref(c), seed, out.ctypes.data_as(C.c_void_p))
+    return out

@@ -13,7 +13,7 @@ from voreen_b200 import abi  # noqa: E402
 
 
 def main():
-    sizes = [int(a) for a in sys.argv[1:]] or [512]
+    sizes = [int(a) for a in sys.argv[1:] if not a.startswith('--')] or [512]
     ctx = vb.Context(0)
     for n in sizes:
         img = 1024 if n <= 512 else 2048
@@ -28,8 +28,8 @@ def main():
         step = 1.0 / (n * 2.0)
         pi = None
         for cls in ("tf", "pi"):
-            for sampler in (abi.SAMPLER_EXACT, abi.SAMPLER_TEX):
-                for ess in (1, 0):
+            for sampler in ((abi.SAMPLER_EXACT, abi.SAMPLER_TEX) if '--tex' in sys.argv else (abi.SAMPLER_EXACT,)):
+                for ess in ((1, 0) if '--noess' in sys.argv else (1,)):
                     if n >= 2048 and ess == 0 and sampler == abi.SAMPLER_EXACT:
                         continue
                     p = vb.default_params(step, sampler=sampler, empty_space_skipping=ess, out_format=abi.OUT_RGBA16)

@@ -143,3 +143,53 @@ def test_rgba16_output(ctx):
     q = c_outs[0].astype(np.float32) / np.float32(65535.0)
     frac, mx = scenes.parity_report(o_outs[0], q)
     assert frac >= 0.999 and c_outs[0].dtype == np.uint16
+
+
+def test_synth_volume_matches_cpu_twin(ctx):
+    """b200rc_synth_volume (device) and orc_synth_volume (CPU) must produce identical bytes, whole and windowed."""
+    from voreen_b200 import raycaster as rc
+    dims = (72, 64, 40)
+    ctx.synth_volume(0, rc.make_volume_desc(dims), 1234)
+    g = ctx.download_volume(0)
+    c = orc.synth_volume(dims, 1234)
+    assert np.array_equal(g, c)
+    assert 0.5 < float((c < 0.25 * 65535).mean()) < 0.95      # mostly "air" below the first opaque TF key
+    d = rc.make_volume_desc(dims, shard_lo=(8, 16, 8), shard_hi=(40, 48, 32), shard_apron=2)
+    ctx.synth_volume(0, d, 1234)
+    g = ctx.download_volume(0)
+    assert np.array_equal(g, c[6:34, 14:50, 6:42])
+
+
+def test_host_mirror_processor(ctx):
+    """The C++ SingleVolumeRaycaster mirror (property IDs / option strings of the reference) renders the same image
+    as the oracle driven with the equivalent parameter block."""
+    from voreen_b200 import host
+    vol = scenes.ct_like_volume(40)
+    for props in ({"compositing": "dvr", "classification": "transfer-function", "shading": "phong", "gradient": "central-differences"},
+                  {"compositing": "iso", "isoValue": "0.15", "shading": "phong-diffuse", "gradient": "sobel", "samplingRate": "4"},
+                  {"compositing": "dvr", "classification": "pre-integrated-cpu", "shading": "none"}):
+        s = scenes.Scene(vol, W=80, H=72, sampling_rate=float(props.get("samplingRate", 2.0)),
+                         compositing=[abi.COMP[props["compositing"]]] * 3, shading=abi.SHADE[props.get("shading", "phong")],
+                         gradient=abi.GRAD[props.get("gradient", "central-differences")], iso_value=float(props.get("isoValue", 0.5)))
+        if props.get("classification", "").startswith("pre-integrated"):
+            s.use_preint("cpu")
+        o_outs, o_depth, _ = s.oracle_render()
+        p = host.SingleVolumeRaycaster(0)
+        try:
+            for k, v in props.items():
+                p.set_property(k, v)
+            p.set_volume(vol, s.desc)
+            p.set_transfer_function(0, scenes.CT_KEYS, (0.0, s.desc.rwm_scale))
+            p.set_camera((1.2, 1.05, 3.1))
+            assert p.is_ready()
+            outs, depth = p.process(80, 72)
+        finally:
+            p.close()
+        frac, mx = scenes.parity_report(o_outs[0], outs[0])
+        assert frac >= 0.999, (props, frac, mx)
+        assert float((np.abs(o_depth - depth) <= 1e-4).mean()) >= 0.999
+    p = host.SingleVolumeRaycaster(0)
+    with pytest.raises(abi.B200RCError):
+        p.set_property("compositing", "no-such-mode")
+    assert not p.is_ready()
+    p.close()

@@ -5,4 +5,5 @@ of the reference's processor / transfer-function / camera interface) and thin ct
 bench.py.  PyTorch is used for device memory, streams and torch.distributed only.
 """
 from . import abi  # noqa: F401
+from . import host  # noqa: F401
 from .raycaster import Context, default_params, default_eep, make_volume_desc  # noqa: F401

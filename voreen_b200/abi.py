@@ -73,7 +73,8 @@ class EepParams(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("last_render_ms", C.c_double), ("last_march_ms", C.c_double), ("last_eep_ms", C.c_double),
                 ("rays_cast", C.c_uint64), ("samples_classified", C.c_uint64), ("samples_shaded", C.c_uint64),
-                ("samples_nominal", C.c_uint64), ("cells_touched", C.c_uint64), ("kernel_launches", C.c_uint64)]
+                ("samples_nominal", C.c_uint64), ("cells_touched", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("samples_skipped", C.c_uint64)]
 
 
 class B200RCError(RuntimeError):

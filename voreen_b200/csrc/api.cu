@@ -4,6 +4,7 @@
 #include "ctx.hpp"
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <cfloat>
 #include <new>
 
@@ -80,6 +81,7 @@ extern "C" int b200rc_create(int device, b200rc_ctx** out_ctx) {
     if (!ctx) return B200RC_ERR_OOM;
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
+    { const char* m = getenv("B200RC_MARCHER"); ctx->use_slab = !(m && strcmp(m, "ray") == 0); }
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
         cudaGetLastError(); delete ctx; return B200RC_ERR_CUDA;
     }
@@ -318,6 +320,7 @@ __global__ void count_touched_kernel(const unsigned char* __restrict__ f, size_t
 
 int rc_march_launch(b200rc_ctx* ctx, const DevParams& p, int sampler, int nch, int dtype) {
     int rc = B200RC_OK;
+    if (ctx->use_slab && rc_march_slab(ctx, p, sampler, nch, dtype, &rc)) return rc;
     if (rc_march_fast(ctx, p, sampler, nch, dtype, &rc)) return rc;
     return rc_march_generic(ctx, p, sampler, nch);
 }
@@ -346,7 +349,7 @@ static int finish_frame(b200rc_ctx* ctx, const b200rc_params* P, bool had_eep) {
         unsigned long long h[8];
         RC_CHECK(cudaMemcpy(h, ctx->d_stats, sizeof h, cudaMemcpyDeviceToHost));
         ctx->stats.rays_cast = h[0]; ctx->stats.samples_classified = h[1]; ctx->stats.samples_shaded = h[2];
-        ctx->stats.samples_nominal = h[3]; ctx->stats.cells_touched = h[5];
+        ctx->stats.samples_nominal = h[3]; ctx->stats.samples_skipped = h[4]; ctx->stats.cells_touched = h[5];
     }
     return B200RC_OK;
 }

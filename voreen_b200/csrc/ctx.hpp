@@ -63,6 +63,7 @@ struct b200rc_ctx {
     float* d_boxes = nullptr; int boxes_capacity = 0;
     b200rc_stats stats{};
     unsigned long long launches = 0;
+    bool use_slab = true;               // B200RC_MARCHER=ray (environment) selects the per-ray kernels for A/B measurements
     void set_error(const std::string& s) { error = s; }
 };
 
@@ -88,6 +89,7 @@ int rc_proxy_boxes(b200rc_ctx* ctx, int slot, const b200rc_eep_params* eep, floa
 // march_generic.cu / march_fast.cu
 int rc_march_generic(b200rc_ctx* ctx, const DevParams& p, int sampler, int nch);
 bool rc_march_fast(b200rc_ctx* ctx, const DevParams& p, int sampler, int nch, int dtype, int* rc_out);
+bool rc_march_slab(b200rc_ctx* ctx, const DevParams& p, int sampler, int nch, int dtype, int* rc_out);
 int rc_march_launch(b200rc_ctx* ctx, const DevParams& p, int sampler, int nch, int dtype);
 // composite.cu
 int rc_composite_launch(b200rc_ctx* ctx, int mode, const float* fc, const float* fd, const float* bc, const float* bd, float* dc, float* dd, size_t n);

@@ -1,0 +1,68 @@
+// march_slab.cu -- instantiations + launcher of the shared-memory brick-staging marcher (march_slab.cuh).
+#include "ctx.hpp"
+#include "march_slab.cuh"
+#include <cstdlib>
+
+template <int DT, int CLS, int COMP, int SHADE> using SlabCfg = MarchCfg<B200RC_SAMPLER_EXACT, 1, DT, CLS, B200RC_GRAD_CENTRAL, SHADE, COMP, true, false>;
+
+template <class C>
+static int launch_slab(b200rc_ctx* ctx, const DevParams& p0) {
+    DevParams p = p0;
+    p.tiles_x = (((p.W + SLAB_TILE - 1) / SLAB_TILE) + 7) / 8 * 8;
+    p.tiles_y = (((p.H + SLAB_TILE - 1) / SLAB_TILE) + 7) / 8 * 8;
+    // shared memory: two CTAs per SM (227 KB usable); the 1D TF (+ LUT) sits behind the staged region
+    size_t tf_bytes = 0;
+    if (C::CLS == B200RC_CLASS_TF && p.cls[0].tf) tf_bytes = (size_t)p.cls[0].tf_width * 4 + 1024;
+    if (tf_bytes > 40 * 1024) return -1;            // TF too wide for the staged layout: caller falls back
+    static int env_depth = -1, env_cap = -1;
+    if (env_depth < 0) {
+        const char* d = getenv("B200RC_SLAB_DEPTH"); env_depth = d ? atoi(d) : 8;
+        const char* c = getenv("B200RC_SLAB_KB"); env_cap = c ? atoi(c) : 88;
+        if (env_depth < 2 || env_depth > 32) env_depth = 8;
+        if (env_cap < 32 || env_cap > 200) env_cap = 88;
+    }
+    SlabArgs sa; sa.depth = env_depth; sa.cap_floats = env_cap * 256;
+    // pre-integration + empty-space skipping restores lastIntensity from the staged footprint: needs <= 1 voxel per step
+    if (C::CLS == B200RC_CLASS_PREINT && p.vol[0].ess) {
+        const float m = fmaxf(p.vol[0].dimf[0], fmaxf(p.vol[0].dimf[1], p.vol[0].dimf[2]));
+        if (p.step * m > 1.0f) return -1;
+    }
+    const size_t smem = (size_t)sa.cap_floats * sizeof(float) + tf_bytes;
+    auto kern = march_slab_kernel<C>;
+    RC_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    RC_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SLAB_THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    const long long tiles = (long long)p.tiles_x * p.tiles_y;
+    long long grid = (long long)ctx->num_sms * per_sm;      // persistent: one wave, a multiple of the SM count
+    if (grid > tiles) grid = tiles;
+    if (grid < 1) grid = 1;
+    RC_CHECK(cudaMemsetAsync(p.tile_counter, 0, sizeof(unsigned int), ctx->stream));
+    kern<<<(unsigned)grid, SLAB_THREADS, smem, ctx->stream>>>(p, sa);
+    ctx->launches++;
+    RC_CHECK(cudaGetLastError());
+    return B200RC_OK;
+}
+
+#define SLAB_CASE(DT, CLS, COMP, SHADE)                                                                       \
+    if ((DT == 0 || dtype == DT) && cls == CLS && comp == COMP && (SHADE < 0 || p.shading[0] == SHADE)) {    \
+        const int rc = launch_slab<SlabCfg<DT, CLS, COMP, SHADE>>(ctx, p);                                   \
+        if (rc >= 0) { *rc_out = rc; return true; }                                                          \
+    }
+
+// Returns true when the configuration is covered (and launched); the caller falls back to the per-ray kernels otherwise.
+bool rc_march_slab(b200rc_ctx* ctx, const DevParams& p, int sampler, int nch, int dtype, int* rc_out) {
+    if (sampler != B200RC_SAMPLER_EXACT || p.multi || nch != 1 || p.channel_shift) return false;
+    if (!p.connected[0] || p.connected[1] || p.connected[2]) return false;
+    if (p.gradient != B200RC_GRAD_CENTRAL) return false;
+    if (p.vol[0].filter != B200RC_FILTER_LINEAR || p.vol[0].clamp != B200RC_CLAMP_TO_EDGE) return false;
+    const int cls = p.classification[0], comp = p.comp[0];
+    SLAB_CASE(B200RC_U16, B200RC_CLASS_PREINT, B200RC_COMP_DVR, B200RC_SHADE_PHONG)
+    SLAB_CASE(B200RC_U16, B200RC_CLASS_TF, B200RC_COMP_DVR, B200RC_SHADE_PHONG)
+    SLAB_CASE(B200RC_U16, B200RC_CLASS_TF, B200RC_COMP_MIP, B200RC_SHADE_PHONG)
+    SLAB_CASE(B200RC_U16, B200RC_CLASS_TF, B200RC_COMP_ISO, B200RC_SHADE_PHONG)
+    SLAB_CASE(B200RC_U16, B200RC_CLASS_PREINT, B200RC_COMP_ISO, B200RC_SHADE_PHONG)
+    SLAB_CASE(0, B200RC_CLASS_TF, B200RC_COMP_DVR, -1)
+    SLAB_CASE(0, B200RC_CLASS_PREINT, B200RC_COMP_DVR, -1)
+    return false;
+}

@@ -1,0 +1,441 @@
+// march_slab.cuh -- the shared-memory brick-staging marcher for the hot configuration (one u8/u16/f32 channel, linear
+// filtering, clamp-to-edge, one connected output, central-difference gradients).
+//
+// Why it exists (profiles/r1_pass1_*): the per-ray marcher of march.cuh is instruction-issue bound -- 76 % issue-slot
+// utilisation, ~1300 warp instructions per shaded sample, half of them 64-bit brick addressing, index clamps and
+// u16->f32 conversions for the 8 + 32 taps, and its gathers cost ~20 sectors per request in L1.  HBM traffic is
+// irrelevant at that point (2.8 % of peak).  Here one CTA owns a 16x16 pixel tile and marches all 256 rays through the
+// volume in lock-step SLABS along the tile's major axis: per slab the CTA stages the sub-volume its rays traverse
+// (+ the -1..+2 voxel apron of the gradient footprint) into shared memory ONCE, already clamped to the volume and
+// already normalised to fp32 exactly as the sampler does (raw * 1/65535), and every tap of every sample in the slab
+// is then a 32-bit shared-memory load at a constant offset from one base address.  The arithmetic per sample -- sample
+// lattice, trilinear weights, classification, shading, compositing, early ray termination, empty-space skipping -- is
+// the same source as march.cuh, so images are identical to the per-ray kernel.
+//
+// A sample is taken from the staged region only if its whole 4x4x4 footprint lies inside it (exact integer test); rays
+// whose next sample is outside simply wait for a later slab.  The region always contains the footprint of the ray that
+// is furthest behind, so every round makes progress.
+#pragma once
+#include "march.cuh"
+
+#define SLAB_THREADS 256
+#define SLAB_TILE 16            // pixels per tile edge
+
+struct SlabShared {
+    int zmin;                   // min over rays of the direction-normalised major index of their next sample
+    int leader;                 // thread id of a ray attaining zmin
+    int lo[3], hi[3];           // bounding box (base indices) of the participating ray segments
+    int rlo[3], rn[3];          // staged region: origin (voxel index) and extent
+    int pitch;                  // floats per staged row (odd: conflict-free staging stores)
+    unsigned int tile;
+    int axis_vote[SLAB_THREADS / 32];
+};
+
+struct SlabArgs { int depth; int cap_floats; };
+
+__device__ __forceinline__ int pick3(int a, int b, int c, int axis) { return axis == 0 ? a : (axis == 1 ? b : c); }
+__device__ __forceinline__ float pick3f(float a, float b, float c, int axis) { return axis == 0 ? a : (axis == 1 ? b : c); }
+
+template <int DT>
+__device__ __forceinline__ float ld_norm_raw(const void* bricks, long long e, int rt_dtype) {
+    const int dt = DT ? DT : rt_dtype;
+    if (dt == B200RC_U16) return xmul((float)__ldg((const unsigned short*)bricks + e), 1.0f / 65535.0f);
+    if (dt == B200RC_U8) return xmul((float)__ldg((const unsigned char*)bricks + e), 1.0f / 255.0f);
+    return __ldg((const float*)bricks + e);
+}
+
+// exact u16 -> float on the integer + fma pipes: 0x4B000000 | v is the float 2^23 + v
+__device__ __forceinline__ float u16lo_norm(unsigned w) { return xmul(xsub(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)), 8388608.0f), 1.0f / 65535.0f); }
+__device__ __forceinline__ float u16hi_norm(unsigned w) { return xmul(xsub(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)), 8388608.0f), 1.0f / 65535.0f); }
+
+// Cooperative staging: region voxel (lx,ly,lz) <- normalised voxel clamp(rlo + l, clamp_lo, clamp_hi).
+// u16: one item = one 8-voxel brick row segment (a single 16-byte load); a warp takes 32 consecutive (ly,lz) rows of the
+// same x chunk, so 8 lanes share one 128-byte line of the brick pool and -- the row pitch being odd -- the eight
+// 32-bit stores of the warp hit 32 different banks.
+template <class C>
+__device__ __forceinline__ void slab_stage(const VolDev& v, const SlabShared& sh, float* __restrict__ S) {
+    const int nx = sh.rn[0], ny = sh.rn[1], nz = sh.rn[2], pitch = sh.pitch;
+    const int rows = ny * nz;
+    const int dt = C::DT ? C::DT : v.dtype;
+    if (dt == B200RC_U16) {
+        const int xr0 = sh.rlo[0] - v.res_lo[0];                    // resident x of region column 0
+        const int c_first = xr0 >> 3;                               // arithmetic shift: floor for negative x
+        const int nchunks = ((xr0 + nx - 1) >> 3) - c_first + 1;
+        const int rows_pad = (rows + 31) & ~31;
+        const int items = rows_pad * nchunks;
+        for (int it = threadIdx.x; it < items; it += SLAB_THREADS) {
+            const int c = it / rows_pad, r = it - c * rows_pad;
+            if (r >= rows) continue;
+            const int lz = r / ny, ly = r - lz * ny;
+            const int y = min(max(sh.rlo[1] + ly, v.clamp_lo[1]), v.clamp_hi[1]) - v.res_lo[1];
+            const int z = min(max(sh.rlo[2] + lz, v.clamp_lo[2]), v.clamp_hi[2]) - v.res_lo[2];
+            const int cx = c_first + c;
+            const int cxc = min(max(cx, 0), v.nbx - 1);
+            const long long e = (long long)cxc * 512 + brick_off_y(y, v.nbx) + brick_off_z(z, v.nbx, v.nby);
+            const uint4 q = __ldg((const uint4*)((const unsigned short*)v.bricks + e));
+            float f[8] = {u16lo_norm(q.x), u16hi_norm(q.x), u16lo_norm(q.y), u16hi_norm(q.y), u16lo_norm(q.z), u16hi_norm(q.z), u16lo_norm(q.w), u16hi_norm(q.w)};
+            // a chunk entirely left of the resident range replicates its first voxel (CLAMP_TO_EDGE / shard clamp); the pool
+            // itself replicates the last voxel of a row into the brick padding on the right
+            if (cx < 0) { for (int i = 1; i < 8; ++i) f[i] = f[0]; }
+            else if (cx > v.nbx - 1) { for (int i = 0; i < 7; ++i) f[i] = f[7]; }
+            // clamp_hi inside the last brick (sharded volumes whose resident range ends before the brick does not occur:
+            // the pool pads with the clamped voxel)
+            float* row = S + r * pitch;
+            const int lx0 = cx * 8 - xr0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int lx = lx0 + i;
+                if ((unsigned)lx < (unsigned)nx) row[lx] = f[i];
+            }
+        }
+    } else {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int r = warp; r < rows; r += SLAB_THREADS / 32) {
+            const int lz = r / ny, ly = r - lz * ny;
+            const int y = min(max(sh.rlo[1] + ly, v.clamp_lo[1]), v.clamp_hi[1]) - v.res_lo[1];
+            const int z = min(max(sh.rlo[2] + lz, v.clamp_lo[2]), v.clamp_hi[2]) - v.res_lo[2];
+            const long long oyz = brick_off_y(y, v.nbx) + brick_off_z(z, v.nbx, v.nby);
+            float* row = S + r * pitch;
+            for (int lx = lane; lx < nx; lx += 32) {
+                const int x = min(max(sh.rlo[0] + lx, v.clamp_lo[0]), v.clamp_hi[0]) - v.res_lo[0];
+                row[lx] = ld_norm_raw<C::DT>(v.bricks, brick_off_x(x) + oyz, v.dtype);
+            }
+        }
+    }
+}
+
+// jump over the empty cell the sample at t lies in: returns false when the cell is not empty
+__device__ __forceinline__ bool slab_skip_empty(const DevParams& p, const VolDev& V, float3 first, float3 dir, float tEnd, float step,
+                                                float& t, float& t_last, int& loop, bool& finished, RayStats& st) {
+    const float3 sp = f3(xadd(first.x, xmul(t, dir.x)), xadd(first.y, xmul(t, dir.y)), xadd(first.z, xmul(t, dir.z)));
+    float t_exit = 0.f;
+    if (!ess_empty_cell(V, sp, dir, t, t_exit)) return false;
+    if (t_exit > tEnd) { st.skipped += (unsigned)floorf((tEnd - t) / step) + 1u; finished = true; return true; }
+    int n = 1; float tn;
+    if (p.lattice_exact) {
+        int k1 = max(loop + 1, __float2int_ru(t_exit / step));
+        while ((float)k1 * step < t_exit) ++k1;
+        while (k1 - 1 > loop && (float)(k1 - 1) * step >= t_exit) --k1;
+        n = k1 - loop; tn = (float)k1 * step;
+        t_last = (float)(k1 - 1) * step;
+    } else {
+        t_last = t;
+        tn = xadd(t, step);
+        while (tn < t_exit && tn <= tEnd) { t_last = tn; tn = xadd(tn, step); ++n; }
+    }
+    st.skipped += n; loop += n; t = tn;
+    finished = (t > tEnd) || loop >= 256 * 256;
+    return true;
+}
+
+template <class C>
+__global__ void __launch_bounds__(SLAB_THREADS, 2) march_slab_kernel(const __grid_constant__ DevParams p, const SlabArgs sa) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ SlabShared sh;
+    float* S = (float*)smem_raw;
+    SmemTables sm;
+    {   // 1D TF + opacity LUT behind the region (TF classification only; pre-integration reads its 2D table)
+        sm.tf[0] = nullptr; sm.lut[0] = nullptr;
+        const ClsDev& cd = p.cls[0];
+        if (C::CLS == B200RC_CLASS_TF && cd.tf) {
+            uchar4* dst = (uchar4*)(smem_raw + (size_t)sa.cap_floats * sizeof(float));
+            for (int i = threadIdx.x; i < cd.tf_width; i += blockDim.x) dst[i] = cd.tf[i];
+            float* l = (float*)(dst + cd.tf_width);
+            for (int i = threadIdx.x; i < 256; i += blockDim.x) l[i] = cd.corr_lut[i];
+            sm.tf[0] = dst; sm.lut[0] = l;
+        }
+        if (threadIdx.x == 0) { sh.zmin = INT_MAX; sh.leader = INT_MAX; for (int a = 0; a < 3; ++a) { sh.lo[a] = INT_MAX; sh.hi[a] = INT_MIN; } }
+        __syncthreads();
+    }
+    const VolDev& V = p.vol[0];
+    constexpr int cmode = C::CLS;
+    constexpr int comp = C::COMP;
+    constexpr bool pi_mode = (cmode == B200RC_CLASS_PREINT);
+    const int smode = C::SHADE >= 0 ? C::SHADE : p.shading[0];
+    const float step = p.step;
+    const int DEPTH = sa.depth;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    RayStats st = {0u, 0u, 0u, 0u, 0ull};
+    const unsigned ntiles = (unsigned)p.tiles_x * (unsigned)p.tiles_y;      // 16x16 tiles, padded to 8x8 super-tiles
+    const unsigned super_x = (unsigned)p.tiles_x >> 3;
+
+    for (;;) {
+        if (threadIdx.x == 0) sh.tile = atomicAdd(p.tile_counter, 1u);
+        __syncthreads();
+        const unsigned tile = sh.tile;
+        if (tile >= ntiles) break;
+        const unsigned sup = tile >> 6, loc = tile & 63u;
+        const unsigned tx = (sup % super_x) * 8u + compact1by1(loc), ty = (sup / super_x) * 8u + compact1by1(loc >> 1);
+        // warp w covers the 8x4 sub-tile (w & 1, w >> 1) of the 16x16 tile
+        const int px = (int)(tx * SLAB_TILE + (warp & 1u) * 8u + (lane & 7u)), py = (int)(ty * SLAB_TILE + (warp >> 1) * 4u + (lane >> 3));
+        const bool inside = px < p.W && py < p.H;
+        const size_t pix = inside ? (size_t)py * p.W + px : 0;
+        float3 first = f3(0.f, 0.f, 0.f), dir = f3(0.f, 0.f, 1.f);
+        float tEnd = 0.f;
+        bool cast = false;
+        if (inside) {
+            const float4 e4 = p.entry[pix], x4 = p.exitp[pix];
+            first = f3(e4.x, e4.y, e4.z);
+            const float3 last = f3(x4.x, x4.y, x4.z);
+            cast = !(first.x == last.x && first.y == last.y && first.z == last.z);
+            if (cast) {
+                const float3 d = f3(xsub(last.x, first.x), xsub(last.y, first.y), xsub(last.z, first.z));
+                tEnd = __fsqrt_rn(xadd(xadd(xmul(d.x, d.x), xmul(d.y, d.y)), xmul(d.z, d.z)));
+                dir = f3(xdiv(d.x, tEnd), xdiv(d.y, tEnd), xdiv(d.z, tEnd));
+                st.rays++;
+                st.nominal += (unsigned long long)floorf(xdiv(tEnd, step)) + 1ull;
+            }
+        }
+        float4 result = make_float4(0.f, 0.f, 0.f, 0.f);
+        float t = 0.0f, t_last = 0.0f, tDepth = -1.0f, lastI = 0.f, maxI = 0.f;
+        int loop = 0;
+        bool finished = !cast;
+        bool prev_empty = false;       // pre-integration: the previous lattice sample lay in an empty cell
+        bool lastI_stale = false;      // ... and lastIntensity has to be re-fetched at t_last before the next classification
+        int cell_cached = -1;          // level-0 ESS cell known to be non-empty
+        const float vx = dir.x * V.dimf[0], vy = dir.y * V.dimf[1], vz = dir.z * V.dimf[2];
+        // slab orientation: major axis + travel direction of the tile's first casting ray, uniform over the CTA
+        int axis; float sgn;
+        {
+            const float ax_ = fabsf(vx), ay_ = fabsf(vy), az_ = fabsf(vz);
+            const int my_axis = (ax_ >= ay_ && ax_ >= az_) ? 0 : (ay_ >= az_ ? 1 : 2);
+            const unsigned m = __ballot_sync(0xffffffffu, cast);
+            const int mine = my_axis | (pick3f(vx, vy, vz, my_axis) < 0.f ? 4 : 0);
+            const int wa = m ? __shfl_sync(0xffffffffu, mine, __ffs(m) - 1) : 8;
+            if (lane == 0) sh.axis_vote[warp] = wa;
+            __syncthreads();
+            int a = 8;
+#pragma unroll
+            for (int w = 0; w < SLAB_THREADS / 32; ++w) if (a == 8 && sh.axis_vote[w] != 8) a = sh.axis_vote[w];
+            if (a == 8) a = 2;
+            axis = a & 3;
+            sgn = (a & 4) ? -1.f : 1.f;
+        }
+        const float vmaj = fabsf(pick3f(vx, vy, vz, axis));
+        // cached plan of the next sample (recomputed only after the ray moved)
+        bool stale = true;
+        int i0x = 0, i0y = 0, i0z = 0, zc = INT_MAX; float ux = 0.f, uy = 0.f, uz = 0.f;
+
+        // ---- rounds ---------------------------------------------------------------------------------------------------
+        for (;;) {
+            // (1) direction-normalised major index of this ray's next sample, after jumping over empty cells so that no
+            //     slab is staged where the ray would only skip
+            if (stale) {
+                if (V.ess && (!pi_mode || prev_empty))
+                    while (!finished && slab_skip_empty(p, V, first, dir, tEnd, step, t, t_last, loop, finished, st)) { if (pi_mode) lastI_stale = true; }
+                zc = INT_MAX;
+                if (!finished) {
+                    const float3 sp = f3(xadd(first.x, xmul(t, dir.x)), xadd(first.y, xmul(t, dir.y)), xadd(first.z, xmul(t, dir.z)));
+                    ux = xsub(xmul(sp.x, V.dimf[0]), 0.5f); uy = xsub(xmul(sp.y, V.dimf[1]), 0.5f); uz = xsub(xmul(sp.z, V.dimf[2]), 0.5f);
+                    i0x = (int)floorf(ux); i0y = (int)floorf(uy); i0z = (int)floorf(uz);
+                    const int im = pick3(i0x, i0y, i0z, axis);
+                    zc = sgn > 0.f ? im : -im;
+                }
+                stale = false;
+            }
+            {
+                const int wmin = __reduce_min_sync(0xffffffffu, zc);
+                if (lane == 0 && wmin != INT_MAX) atomicMin(&sh.zmin, wmin);
+            }
+            __syncthreads();
+            const int zmin = sh.zmin;
+            if (zmin == INT_MAX) break;                     // every ray of the tile is done (uniform)
+            // (2) bounding box of the participating segments
+            const bool part = !finished && zc < zmin + DEPTH;
+            {
+                int lo0 = INT_MAX, lo1 = INT_MAX, lo2 = INT_MAX, hi0 = INT_MIN, hi1 = INT_MIN, hi2 = INT_MIN;
+                if (part) {
+                    // ray parameter at which the major coordinate leaves the slab
+                    const float um = pick3f(ux, uy, uz, axis);
+                    const float dist = (float)(zmin + DEPTH) - (sgn > 0.f ? um : -um);     // > 0, in voxels
+                    const float dt = fminf(dist / fmaxf(vmaj, 1e-20f), tEnd - t);
+                    const int jx = __float2int_rd(ux + dt * vx), jy = __float2int_rd(uy + dt * vy), jz = __float2int_rd(uz + dt * vz);
+                    lo0 = min(i0x, jx); hi0 = max(i0x, jx); lo1 = min(i0y, jy); hi1 = max(i0y, jy); lo2 = min(i0z, jz); hi2 = max(i0z, jz);
+                }
+                lo0 = __reduce_min_sync(0xffffffffu, lo0); lo1 = __reduce_min_sync(0xffffffffu, lo1); lo2 = __reduce_min_sync(0xffffffffu, lo2);
+                hi0 = __reduce_max_sync(0xffffffffu, hi0); hi1 = __reduce_max_sync(0xffffffffu, hi1); hi2 = __reduce_max_sync(0xffffffffu, hi2);
+                if (lane == 0 && lo0 != INT_MAX) {
+                    atomicMin(&sh.lo[0], lo0); atomicMin(&sh.lo[1], lo1); atomicMin(&sh.lo[2], lo2);
+                    atomicMax(&sh.hi[0], hi0); atomicMax(&sh.hi[1], hi1); atomicMax(&sh.hi[2], hi2);
+                }
+                if (!finished && zc == zmin) atomicMin(&sh.leader, (int)threadIdx.x);
+            }
+            __syncthreads();
+            // (3) the leader fixes the region (footprint apron -1..+2, one voxel of slack) and resets the scratch
+            if ((int)threadIdx.x == sh.leader) {
+                const int li[3] = {i0x, i0y, i0z};
+                int lo[3], hi[3];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    lo[a] = sh.lo[a] - 2; hi[a] = sh.hi[a] + 3;
+                    if (a == axis) {        // the slab itself: base planes [zmin, zmin + DEPTH) in travel direction
+                        if (sgn > 0.f) { lo[a] = zmin - 1; hi[a] = zmin + DEPTH - 1 + 2; }
+                        else { lo[a] = -(zmin + DEPTH - 1) - 1; hi[a] = -zmin + 2; }
+                    }
+                    sh.lo[a] = INT_MAX; sh.hi[a] = INT_MIN;
+                }
+                // capacity: shrink the wider lateral axis around the leader's footprint until the region fits
+                const int a1 = (axis + 1) % 3, a2 = (axis + 2) % 3;
+                const int nmaj = hi[axis] - lo[axis] + 1;
+                for (int iter = 0; iter < 4; ++iter) {
+                    const int n1 = hi[a1] - lo[a1] + 1, n2 = hi[a2] - lo[a2] + 1;
+                    const int p1 = (a1 == 0) ? (n1 | 1) : n1, p2 = (a2 == 0) ? (n2 | 1) : n2, pm = (axis == 0) ? (nmaj | 1) : nmaj;
+                    if ((long long)p1 * p2 * pm <= sa.cap_floats) break;
+                    const int as = n1 >= n2 ? a1 : a2, other = n1 >= n2 ? p2 : p1;
+                    int cap = sa.cap_floats / (other * pm);
+                    if (as == 0) cap -= 1;      // the odd pitch (n | 1) must still fit
+                    cap = max(cap, 8);
+                    int l2 = li[as] - cap / 2;
+                    l2 = max(l2, lo[as]); l2 = min(l2, hi[as] - cap + 1);
+                    lo[as] = l2; hi[as] = l2 + cap - 1;
+                }
+#pragma unroll
+                for (int a = 0; a < 3; ++a) { sh.rlo[a] = lo[a]; sh.rn[a] = hi[a] - lo[a] + 1; }
+                sh.pitch = (hi[0] - lo[0] + 1) | 1;
+                sh.zmin = INT_MAX; sh.leader = INT_MAX;
+            }
+            __syncthreads();
+            // (4) stage
+            slab_stage<C>(V, sh, S);
+            __syncthreads();
+            // (5) march while the footprint of the next sample lies inside the region
+            if (part) {
+                const int rx = sh.rlo[0], ry = sh.rlo[1], rz = sh.rlo[2];
+                const int nx = sh.rn[0], ny = sh.rn[1], nz = sh.rn[2];
+                const int pitch = sh.pitch, slice = pitch * ny;
+                while (!finished) {
+                    const float3 sp = f3(xadd(first.x, xmul(t, dir.x)), xadd(first.y, xmul(t, dir.y)), xadd(first.z, xmul(t, dir.z)));
+                    const float sux = xsub(xmul(sp.x, V.dimf[0]), 0.5f), suy = xsub(xmul(sp.y, V.dimf[1]), 0.5f), suz = xsub(xmul(sp.z, V.dimf[2]), 0.5f);
+                    const float fx = floorf(sux), fy = floorf(suy), fz = floorf(suz);
+                    const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
+                    // ---- empty-space skipping ----
+                    bool empty = false;
+                    if (V.ess) {
+                        const int cid = (min(max(x0, 0), V.dims[0] - 1) >> 3) | ((min(max(y0, 0), V.dims[1] - 1) >> 3) << 10) | ((min(max(z0, 0), V.dims[2] - 1) >> 3) << 20);
+                        if (cid != cell_cached) {
+                            float t_exit;
+                            empty = ess_empty_cell(V, sp, dir, t, t_exit);
+                            if (!empty) cell_cached = cid;
+                            else if (!pi_mode || prev_empty) {
+                                // every lattice sample inside this cell classifies to alpha 0 without side effects.  With
+                                // pre-integration that also needs the PREVIOUS sample to lie in an empty cell: the value
+                                // ranges of the two (adjacent, overlapping) cells then form one interval on which the
+                                // transfer function is transparent, so the table entry (cur, prev) is transparent too.
+                                slab_skip_empty(p, V, first, dir, tEnd, step, t, t_last, loop, finished, st);
+                                if (pi_mode) lastI_stale = true;
+                                stale = true;
+                                continue;
+                            }
+                        }
+                    }
+                    // ---- is the 4x4x4 footprint staged? ----
+                    const int lx = x0 - rx, ly = y0 - ry, lz = z0 - rz;
+                    if ((unsigned)(lx - 1) >= (unsigned)(nx - 3) || (unsigned)(ly - 1) >= (unsigned)(ny - 3) || (unsigned)(lz - 1) >= (unsigned)(nz - 3)) break;
+                    stale = true;
+                    const float ax = xsub(sux, fx), ay = xsub(suy, fy), az = xsub(suz, fz);
+                    const float* b = S + (lz * ny + ly) * pitch + lx;
+                    if (pi_mode && lastI_stale) {
+                        // lastIntensity of the sample just before this one (it was skipped): its 2x2x2 taps lie within one
+                        // voxel of this sample's and therefore inside the staged footprint (sampling rate >= 1, checked by the launcher)
+                        const float3 q = f3(xadd(first.x, xmul(t_last, dir.x)), xadd(first.y, xmul(t_last, dir.y)), xadd(first.z, xmul(t_last, dir.z)));
+                        const float qx = xsub(xmul(q.x, V.dimf[0]), 0.5f), qy = xsub(xmul(q.y, V.dimf[1]), 0.5f), qz = xsub(xmul(q.z, V.dimf[2]), 0.5f);
+                        const float gx = floorf(qx), gy = floorf(qy), gz = floorf(qz);
+                        const int jx = min(max((int)gx - rx, 0), nx - 2), jy = min(max((int)gy - ry, 0), ny - 2), jz = min(max((int)gz - rz, 0), nz - 2);
+                        const float bx = xsub(qx, gx), by = xsub(qy, gy), bz = xsub(qz, gz);
+                        const float* c = S + (jz * ny + jy) * pitch + jx;
+                        const float d00 = xlerp(c[0], c[1], bx), d10 = xlerp(c[pitch], c[pitch + 1], bx);
+                        const float d01 = xlerp(c[slice], c[slice + 1], bx), d11 = xlerp(c[slice + pitch], c[slice + pitch + 1], bx);
+                        lastI = xadd(xmul(xlerp(xlerp(d00, d10, by), xlerp(d01, d11, by), bz), V.rwm_scale), V.rwm_offset);
+                        lastI_stale = false;
+                    }
+                    // ---- getVoxel: trilinear from the staged taps (GL float weights, identical to lerp_taps) ----
+                    const float c000 = b[0], c100 = b[1], c010 = b[pitch], c110 = b[pitch + 1];
+                    const float c001 = b[slice], c101 = b[slice + 1], c011 = b[slice + pitch], c111 = b[slice + pitch + 1];
+                    const float c00 = xlerp(c000, c100, ax), c10 = xlerp(c010, c110, ax), c01 = xlerp(c001, c101, ax), c11 = xlerp(c011, c111, ax);
+                    const float tex = xlerp(xlerp(c00, c10, ay), xlerp(c01, c11, ay), az);
+                    const float intensity = xadd(xmul(tex, V.rwm_scale), V.rwm_offset);
+                    st.classified++;
+                    int a8;
+                    const float4 color0 = classify<C>(cmode, p.cls[0], sm.tf[0], f3(0.f, 0.f, 0.f), intensity, lastI, a8);
+                    if (color0.w > 0.f) {
+                        st.shaded++;
+                        float3 gradient;
+                        if (t == 0.0f) gradient = fix_clip_border_gradient(p, sp, dir, px, py);
+                        else {
+                            // calcGradientA from the 32 distinct voxels its six offset fetches share (see grad_central_shared)
+                            auto L = [&](int i, int j, int k) -> float { return b[(i - 1) + (j - 1) * pitch + (k - 1) * slice]; };
+                            float dxq[2][2], dyq[2][2], dzq[2][2];
+                            const float cen[2][2][2] = {{{c000, c001}, {c010, c011}}, {{c100, c101}, {c110, c111}}};
+#pragma unroll
+                            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                                for (int k = 0; k < 2; ++k) {
+                                    const float A = L(0, j + 1, k + 1), B = cen[0][j][k], Cc = cen[1][j][k], D = L(3, j + 1, k + 1);
+                                    dxq[j][k] = (A - Cc) + ax * ((B - D) - (A - Cc));
+                                }
+#pragma unroll
+                            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                                for (int k = 0; k < 2; ++k) {
+                                    const float A = L(i + 1, 0, k + 1), D = L(i + 1, 3, k + 1), B = cen[i][0][k], Cc = cen[i][1][k];
+                                    dyq[i][k] = (A - Cc) + ay * ((B - D) - (A - Cc));
+                                }
+#pragma unroll
+                            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                                for (int j = 0; j < 2; ++j) {
+                                    const float A = L(i + 1, j + 1, 0), D = L(i + 1, j + 1, 3), B = cen[i][j][0], Cc = cen[i][j][1];
+                                    dzq[i][j] = (A - Cc) + az * ((B - D) - (A - Cc));
+                                }
+                            auto bil = [](const float q[2][2], float s, float tt) -> float {
+                                const float q0 = q[0][0] + s * (q[1][0] - q[0][0]), q1 = q[0][1] + s * (q[1][1] - q[0][1]);
+                                return q0 + tt * (q1 - q0);
+                            };
+                            gradient = f3(bil(dxq, ay, az), bil(dyq, ax, az), bil(dzq, ax, ay));
+                            gradient = gradient * f3(V.spacing_rcp[0] * 0.5f, V.spacing_rcp[1] * 0.5f, V.spacing_rcp[2] * 0.5f);
+                            gradient = gradient * V.rwm_scale;
+                        }
+                        const float3 posPhys = f3((sp.x * V.dimf[0] - 0.5f) * V.spacing[0] + V.offset[0], (sp.y * V.dimf[1] - 0.5f) * V.spacing[1] + V.offset[1],
+                                                  (sp.z * V.dimf[2] - 0.5f) * V.spacing[2] + V.offset[2]);
+                        float4 color = color0;
+                        const float3 rgb = f3(color.x, color.y, color.z);
+                        const float3 shd = apply_shading(smode, p.light, gradient, posPhys, ld3(V.light_phys), ld3(V.cam_phys), rgb, rgb, f3(1.f, 1.f, 1.f));
+                        color.x = shd.x; color.y = shd.y; color.z = shd.z;
+                        result = apply_compositing(comp, 1, p.preint_comp, result, intensity, color, a8, sm.lut[0], sp, gradient, t, step, tDepth, maxI, p.gamma[0], p.iso);
+                    }
+                    if (p.collect_stats && p.touched) {
+                        const int cx = min(max(x0, 0), V.dims[0] - 1) / B200RC_STAT_CELL, cy = min(max(y0, 0), V.dims[1] - 1) / B200RC_STAT_CELL,
+                                  cz = min(max(z0, 0), V.dims[2] - 1) / B200RC_STAT_CELL;
+                        p.touched[((size_t)cz * p.touched_dims[1] + cy) * p.touched_dims[0] + cx] = 1;
+                    }
+                    lastI = intensity;
+                    prev_empty = empty;
+                    if (p.ert && result.w >= 0.95f) {
+                        if (p.ert_snap) result.w = 1.0f;
+                        finished = true;
+                    }
+                    ++loop;
+                    t_last = t;
+                    t = p.lattice_exact ? (float)loop * step : xadd(t, step);
+                    finished = finished || (t > tEnd) || loop >= 256 * 256;
+                }
+            }
+        }
+        // ---- outputs ------------------------------------------------------------------------------------------------------
+        if (inside) {
+            float depth = 1.0f;
+            if (cast) depth = get_depth_value(tDepth, tEnd, p.entry_depth[pix], p.exit_depth[pix], p.near_d, p.far_d);
+            store_color(p, 0, pix, result);
+            if (p.out_depth) p.out_depth[pix] = p.quantize_depth24 ? depth24_roundtrip(depth) : depth;
+        }
+    }
+    if (p.collect_stats && p.stats) {
+        unsigned long long vals[5] = {st.rays, st.classified, st.shaded, st.nominal, st.skipped};
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            unsigned long long v = vals[i];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+            if (lane == 0 && v) atomicAdd(p.stats + i, v);
+        }
+    }
+}

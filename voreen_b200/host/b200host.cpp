@@ -1,0 +1,305 @@
+// b200host.cpp -- C++ host-side mirror of the reference's processor interface for the ray-casting path
+// (include/b200rc_host.h).  Plays Voreen's role outside Voreen: camera, transfer-function texture generation, property
+// handling, invalidation (what has to be re-uploaded / rebuilt before the next process()), then calls the C ABI of
+// include/b200rc.h.  No rendering arithmetic lives here -- every pixel comes out of libb200rc.so (sm_100a CUDA).
+//
+// V/ = /root/reference/voreen/
+#include "../../include/b200rc_host.h"
+#include "rc_properties.hpp"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace {
+
+// ---- tgt::mat4 / vec3 arithmetic the camera needs (row-major, column vectors; V/ext/tgt/matrix.h, vector.h) ----
+struct V3 { float x, y, z; };
+inline V3 sub(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline V3 cross(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+// tgt::normalize multiplies by the reciprocal length; lengthSq accumulates from 0 (vector.h:802-820)
+inline V3 normalize(V3 v) {
+    float l2 = 0.f; l2 += v.x * v.x; l2 += v.y * v.y; l2 += v.z * v.z;
+    const float r = 1.f / std::sqrt(l2);
+    return {v.x * r, v.y * r, v.z * r};
+}
+void mat_mul(const float a[16], const float b[16], float out[16]) {
+    float r[16];
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            float s = 0.f;
+            for (int k = 0; k < 4; ++k) s += a[i * 4 + k] * b[k * 4 + j];
+            r[i * 4 + j] = s;
+        }
+    std::memcpy(out, r, sizeof r);
+}
+// mat4::createLookAt (matrix.h:1196-1210): rotation rows (strafe, up, -look) times translate(-eye)
+void look_at(V3 eye, V3 focus, V3 up, float out[16]) {
+    const V3 look = normalize(sub(focus, eye));
+    const V3 strafe = normalize(cross(look, normalize(up)));
+    const V3 up2 = cross(strafe, look);
+    const float rot[16] = {strafe.x, strafe.y, strafe.z, 0.f, up2.x, up2.y, up2.z, 0.f, -look.x, -look.y, -look.z, 0.f, 0.f, 0.f, 0.f, 1.f};
+    const float tr[16] = {1.f, 0.f, 0.f, -eye.x, 0.f, 1.f, 0.f, -eye.y, 0.f, 0.f, 1.f, -eye.z, 0.f, 0.f, 0.f, 1.f};
+    mat_mul(rot, tr, out);
+}
+// mat4::createPerspective (matrix.h:1230-1248)
+void perspective(float fov_rad, float aspect, float n, float f, float out[16]) {
+    const float c = 1.f / std::tan(fov_rad / 2.f);
+    const float m[16] = {c / aspect, 0.f, 0.f, 0.f, 0.f, c, 0.f, 0.f, 0.f, 0.f, (n + f) / (n - f), (2.f * f * n) / (n - f), 0.f, 0.f, -1.f, 0.f};
+    std::memcpy(out, m, sizeof m);
+}
+// Camera::getProjectionMatrix, PERSPECTIVE (camera.cpp:188-217)
+void camera_projection(float fovy_deg, float frustum_ratio, float n, float f, float window_ratio, float out[16]) {
+    const float PIf = 3.14159265358979323846f;
+    float fovy = fovy_deg < 6.f ? 6.f : (fovy_deg > 175.f ? 175.f : fovy_deg);
+    if (window_ratio >= 1.0f) perspective((PIf / 180.f) * fovy, frustum_ratio * window_ratio, n, f, out);
+    else perspective(std::atan(std::tan((PIf / 180.f) * (fovy / 2.f)) / (window_ratio * frustum_ratio)) * 2.f, frustum_ratio * window_ratio, n, f, out);
+}
+
+inline int iround(float f) { return (int)std::floor(f + 0.5f); }     // tgt::iround (tgt_math.h:213-225)
+
+// TransFunc1DKeys::getMappingForValueUByte (transfunc1dkeys.cpp:119-154): the interpolation happens in GLubyte += float,
+// i.e. a float sum converted back with truncation
+void keys_mapping(const b200host_tf_key* keys, int n, float value, uint8_t out[4]) {
+    if (n == 0) { out[0] = out[1] = out[2] = out[3] = 0; return; }
+    value = value < 0.f ? 0.f : (value > 1.f ? 1.f : value);
+    int it = 0;
+    while (it != n && value > keys[it].intensity) ++it;
+    if (it == 0) { std::memcpy(out, keys[0].color_l, 4); return; }
+    if (it == n) { std::memcpy(out, keys[n - 1].color_r, 4); return; }
+    const b200host_tf_key& l = keys[it - 1]; const b200host_tf_key& r = keys[it];
+    const float fraction = (value - l.intensity) / (r.intensity - l.intensity);
+    for (int c = 0; c < 4; ++c) {
+        const float sum = (float)l.color_r[c] + (float)((int)r.color_l[c] - (int)l.color_r[c]) * fraction;
+        out[c] = (uint8_t)(int)sum;
+    }
+}
+
+struct TransFunc {
+    std::vector<b200host_tf_key> keys;
+    float domain[2] = {0.f, 1.f}, threshold[2] = {0.f, 1.f}, gamma = 1.f;
+    bool set = false, dirty = true;
+};
+
+}  // namespace
+
+// ---- flat C API -------------------------------------------------------------------------------------------------------
+extern "C" int b200host_camera(const float position[3], const float focus[3], const float up[3], float fovy_deg, float frustum_ratio,
+                               float near_dist, float far_dist, int width, int height, b200rc_camera* out) {
+    if (!position || !focus || !up || !out || width < 1 || height < 1) return B200RC_ERR_INVALID;
+    look_at({position[0], position[1], position[2]}, {focus[0], focus[1], focus[2]}, {up[0], up[1], up[2]}, out->view);
+    camera_projection(fovy_deg, frustum_ratio, near_dist, far_dist, (float)width / (float)height, out->proj);
+    for (int i = 0; i < 3; ++i) out->position[i] = position[i];
+    out->near_dist = near_dist; out->far_dist = far_dist;
+    return B200RC_OK;
+}
+
+extern "C" int b200host_tf1d_keys_texture(const b200host_tf_key* keys, int n_keys, const float threshold[2], float gamma, int alpha_mode,
+                                          int width, uint8_t* out) {
+    if ((!keys && n_keys > 0) || n_keys < 0 || width < 2 || !out) return B200RC_ERR_INVALID;
+    const float thr0 = threshold ? threshold[0] : 0.f, thr1 = threshold ? threshold[1] : 1.f;
+    // TransFunc1D::createTextureData (transfunc1d.cpp:85-116); quirk kept: threshold compared against round(thr * width)
+    const int front_end = iround(thr0 * (float)width), back_start = iround(thr1 * (float)width);
+    for (int x = 0; x < width; ++x) {
+        uint8_t* px = out + 4 * x;
+        if (x < front_end || x > back_start) px[0] = px[1] = px[2] = px[3] = 0;
+        else {
+            float v = (float)x / (float)(width - 1);
+            if (gamma != 1.f) v = std::pow(v, gamma);            // applyGammaToIntensity (:144-149)
+            keys_mapping(keys, n_keys, v, px);
+        }
+        if (alpha_mode == 2) { if (px[3]) px[3] = 255; }        // TF_ONE_ALPHA (transfuncbase.cpp:177-210)
+        else if (alpha_mode == 0) px[3] = 0;                    // TF_ZERO_ALPHA
+    }
+    return B200RC_OK;
+}
+
+extern "C" int b200host_tf1d_width_for(int dtype, int* out_width) {
+    if (!out_width) return B200RC_ERR_INVALID;
+    // bits per channel, float handled as 16 bit, 1D TFs limited to 12 bit (transfuncpropertybase.cpp:155-165,
+    // transfunc1dkeysproperty.cpp:94-97)
+    *out_width = dtype == B200RC_U8 ? 256 : 4096;
+    return B200RC_OK;
+}
+
+extern "C" int b200host_volume_desc(const int32_t dims[3], int channels, const char* format, const float* spacing, const float* offset,
+                                    const float* phys_to_world, b200rc_volume_desc* out) {
+    if (!dims || !format || !out || channels < 1 || channels > 4) return B200RC_ERR_INVALID;
+    std::memset(out, 0, sizeof *out);
+    const std::string f(format);
+    if (f == "uint8") { out->dtype = B200RC_U8; out->rwm_scale = 255.f; }
+    else if (f == "uint16") { out->dtype = B200RC_U16; out->rwm_scale = 65535.f; }
+    else if (f == "float") { out->dtype = B200RC_F32; out->rwm_scale = 1.f; }
+    else return B200RC_ERR_INVALID;
+    out->rwm_offset = 0.f;
+    out->channels = channels;
+    int m = 1;
+    for (int a = 0; a < 3; ++a) { out->dims[a] = dims[a]; if (dims[a] > m) m = dims[a]; }
+    for (int a = 0; a < 3; ++a) {
+        out->spacing[a] = spacing ? spacing[a] : 2.0f / (float)m;
+        out->offset[a] = offset ? offset[a] : (float)(-(dims[a] - 1) * 0.5f) * out->spacing[a];
+    }
+    for (int i = 0; i < 16; ++i) out->phys_to_world[i] = phys_to_world ? phys_to_world[i] : ((i % 5 == 0) ? 1.f : 0.f);
+    return B200RC_OK;
+}
+
+// ---- SingleVolumeRaycaster mirror ------------------------------------------------------------------------------------------
+struct b200host_svrc {
+    b200rc_ctx* ctx = nullptr;
+    b200rc::RaycasterProperties props;
+    TransFunc tf[B200RC_MAX_CHANNELS];
+    b200rc_volume_desc desc{};
+    bool have_volume = false;
+    bool have_camera = false;
+    float cam_pos[3] = {0.f, 0.f, 3.5f}, cam_focus[3] = {0.f, 0.f, 0.f}, cam_up[3] = {0.f, 1.f, 0.f};   // CameraProperty default
+    float fovy = 45.f, near_d = 0.1f, far_d = 50.f;
+    // entry/exit handed over by the caller (image.entrypoints / image.exitpoints)
+    int eep_w = 0, eep_h = 0;
+    const float* entry = nullptr; const float* entry_depth = nullptr; const float* exitp = nullptr; const float* exit_depth = nullptr;
+    // what the last beforeProcess() built (INVALID_PROGRAM analogue)
+    int built_width = 0; std::string built_cls; float built_step = -1.f;
+    std::string error;
+    std::vector<uint8_t> tex;
+};
+
+static int fail(b200host_svrc* p, int rc, const std::string& what) {
+    p->error = what;
+    if (p->ctx && rc == B200RC_ERR_CUDA) p->error += std::string(": ") + b200rc_last_error(p->ctx);
+    return rc;
+}
+static int forward(b200host_svrc* p, int rc, const char* what) {
+    if (rc != B200RC_OK) p->error = std::string(what) + ": " + b200rc_last_error(p->ctx);
+    return rc;
+}
+
+extern "C" int b200host_svrc_create(int device, b200host_svrc** out) {
+    if (!out) return B200RC_ERR_INVALID;
+    *out = nullptr;
+    b200host_svrc* p = new (std::nothrow) b200host_svrc();
+    if (!p) return B200RC_ERR_OOM;
+    const int rc = b200rc_create(device, &p->ctx);      // Processor::initialize(): no device -> no processor, no fallback
+    if (rc != B200RC_OK) { delete p; return rc; }
+    *out = p;
+    return B200RC_OK;
+}
+extern "C" void b200host_svrc_destroy(b200host_svrc* p) {
+    if (!p) return;
+    b200rc_destroy(p->ctx);                             // Processor::deinitialize()
+    delete p;
+}
+extern "C" const char* b200host_svrc_last_error(const b200host_svrc* p) { return p ? p->error.c_str() : "null processor"; }
+extern "C" b200rc_ctx* b200host_svrc_context(b200host_svrc* p) { return p ? p->ctx : nullptr; }
+
+extern "C" int b200host_svrc_set_property(b200host_svrc* p, const char* id, const char* value) {
+    if (!p || !id || !value) return B200RC_ERR_INVALID;
+    if (!p->props.set(id, value)) return fail(p, B200RC_ERR_INVALID, std::string("property not found or invalid value: ") + id + "=" + value);
+    return B200RC_OK;
+}
+extern "C" int b200host_svrc_get_sampling_step(b200host_svrc* p, float* out) {
+    if (!p || !out) return B200RC_ERR_INVALID;
+    if (!p->have_volume) return fail(p, B200RC_ERR_NOT_READY, "no volume");
+    *out = b200rc::sampling_step_size(p->desc.dims, p->props);
+    return B200RC_OK;
+}
+extern "C" int b200host_svrc_set_volume(b200host_svrc* p, const void* data, const b200rc_volume_desc* desc) {
+    if (!p || !data || !desc) return B200RC_ERR_INVALID;
+    const int rc = forward(p, b200rc_upload_volume(p->ctx, 0, data, desc), "upload_volume");
+    if (rc) return rc;
+    p->desc = *desc; p->have_volume = true; p->built_width = 0;
+    return B200RC_OK;
+}
+extern "C" int b200host_svrc_set_synthetic_volume(b200host_svrc* p, const b200rc_volume_desc* desc, uint64_t seed) {
+    if (!p || !desc) return B200RC_ERR_INVALID;
+    const int rc = forward(p, b200rc_synth_volume(p->ctx, 0, desc, seed), "synth_volume");
+    if (rc) return rc;
+    p->desc = *desc; p->have_volume = true; p->built_width = 0;
+    return B200RC_OK;
+}
+extern "C" int b200host_svrc_set_transfer_function(b200host_svrc* p, int channel, const b200host_tf_key* keys, int n_keys,
+                                                   float domain_lo, float domain_hi, const float threshold[2], float gamma) {
+    if (!p || channel < 0 || channel >= B200RC_MAX_CHANNELS || (!keys && n_keys > 0) || n_keys < 0) return B200RC_ERR_INVALID;
+    TransFunc& t = p->tf[channel];
+    t.keys.assign(keys, keys + n_keys);
+    t.domain[0] = domain_lo; t.domain[1] = domain_hi;
+    t.threshold[0] = threshold ? threshold[0] : 0.f; t.threshold[1] = threshold ? threshold[1] : 1.f;
+    t.gamma = gamma; t.set = true; t.dirty = true;
+    return B200RC_OK;
+}
+extern "C" int b200host_svrc_set_camera(b200host_svrc* p, const float position[3], const float focus[3], const float up[3],
+                                        float fovy_deg, float near_dist, float far_dist) {
+    if (!p || !position || !focus || !up) return B200RC_ERR_INVALID;
+    for (int i = 0; i < 3; ++i) { p->cam_pos[i] = position[i]; p->cam_focus[i] = focus[i]; p->cam_up[i] = up[i]; }
+    p->fovy = fovy_deg; p->near_d = near_dist; p->far_d = far_dist; p->have_camera = true;
+    return B200RC_OK;
+}
+extern "C" int b200host_svrc_connect_output(b200host_svrc* p, int port, int connected) {
+    if (!p || port < 0 || port >= B200RC_MAX_OUTPUTS) return B200RC_ERR_INVALID;
+    p->props.outputConnected[port] = connected != 0;
+    return B200RC_OK;
+}
+extern "C" int b200host_svrc_set_entry_exit(b200host_svrc* p, int width, int height, const float* entry_rgba, const float* entry_depth,
+                                            const float* exit_rgba, const float* exit_depth) {
+    if (!p) return B200RC_ERR_INVALID;
+    p->eep_w = width; p->eep_h = height;
+    p->entry = entry_rgba; p->entry_depth = entry_depth; p->exitp = exit_rgba; p->exit_depth = exit_depth;
+    return B200RC_OK;
+}
+extern "C" int b200host_svrc_is_ready(b200host_svrc* p) {
+    if (!p || !p->have_volume) return 0;
+    if (!p->props.outputConnected[0] && !p->props.outputConnected[1] && !p->props.outputConnected[2]) return 0;
+    for (int c = 0; c < p->desc.channels; ++c)
+        if (!p->tf[c].set) return 0;
+    return 1;
+}
+
+// beforeProcess(): (re)build TF textures / pre-integration tables the current properties need
+static int before_process(b200host_svrc* p, const b200rc_params& P, int builder) {
+    int width = 0;
+    b200host_tf1d_width_for(p->desc.dtype, &width);
+    const std::string cls = b200rc::effective_classification(p->props, false);
+    const bool rebuild_all = width != p->built_width || cls != p->built_cls || (builder >= 0 && P.sampling_step != p->built_step);
+    for (int c = 0; c < p->desc.channels; ++c) {
+        TransFunc& t = p->tf[c];
+        if (!t.dirty && !rebuild_all) continue;
+        if (builder >= 0) {
+            // PreIntegrationTableMap: resolution min(tfWidth, 1024) (preintegrationtablemap.cpp:66-67).  The CPU builders
+            // index the TF at table resolution, the GPU shader samples the full-width texture (preintegration.frag:64).
+            const int res = width < 1024 ? width : 1024;
+            const int w_build = builder == B200RC_PI_GPU ? width : res;
+            p->tex.resize((size_t)w_build * 4);
+            b200host_tf1d_keys_texture(t.keys.data(), (int)t.keys.size(), t.threshold, t.gamma, 1, w_build, p->tex.data());
+            int rc = forward(p, b200rc_set_tf1d(p->ctx, c, p->tex.data(), w_build, t.domain[0], t.domain[1]), "set_tf1d");
+            if (rc) return rc;
+            rc = forward(p, b200rc_build_preint(p->ctx, c, res, P.sampling_step, builder), "build_preint");
+            if (rc) return rc;
+        }
+        p->tex.resize((size_t)width * 4);
+        b200host_tf1d_keys_texture(t.keys.data(), (int)t.keys.size(), t.threshold, t.gamma, 1, width, p->tex.data());
+        const int rc = forward(p, b200rc_set_tf1d(p->ctx, c, p->tex.data(), width, t.domain[0], t.domain[1]), "set_tf1d");
+        if (rc) return rc;
+        t.dirty = false;
+    }
+    p->built_width = width; p->built_cls = cls; p->built_step = P.sampling_step;
+    return B200RC_OK;
+}
+
+extern "C" int b200host_svrc_process(b200host_svrc* p, int width, int height, void* out_color[B200RC_MAX_OUTPUTS], float* out_depth) {
+    if (!p || width < 1 || height < 1) return B200RC_ERR_INVALID;
+    if (!b200host_svrc_is_ready(p)) return fail(p, B200RC_ERR_NOT_READY, "processor not ready (volume, transfer function or outport missing)");
+    b200rc_params P; int builder = -1; std::string err;
+    if (!b200rc::to_params(p->props, p->desc.dims, false, &P, &builder, &err)) return fail(p, B200RC_ERR_INVALID, err);
+    int rc = before_process(p, P, builder);
+    if (rc) return rc;
+    b200rc_camera cam;
+    b200host_camera(p->cam_pos, p->cam_focus, p->cam_up, p->fovy, 1.f, p->near_d, p->far_d, width, height, &cam);
+    if (p->entry && p->exitp && p->entry_depth && p->exit_depth) {
+        if (p->eep_w != width || p->eep_h != height) return fail(p, B200RC_ERR_INVALID, "entry/exit size differs from the output size");
+        return forward(p, b200rc_render(p->ctx, &P, &cam, width, height, p->entry, p->entry_depth, p->exitp, p->exit_depth, out_color, out_depth), "render");
+    }
+    b200rc_eep_params E;
+    b200rc::to_eep_params(p->props, &E);
+    return forward(p, b200rc_render_camera(p->ctx, &P, &E, &cam, width, height, out_color, out_depth), "render_camera");
+}
