@@ -20,6 +20,7 @@
 
 #define SLAB_THREADS 256
 #define SLAB_TILE 16            // pixels per tile edge
+#define SLAB_OCC_WORDS 160      // (max lateral extent / 8 + 2)^2 occupancy words per region
 
 struct SlabShared {
     int zmin;                   // min over rays of the direction-normalised major index of their next sample
@@ -29,6 +30,10 @@ struct SlabShared {
     int pitch;                  // floats per staged row (odd: conflict-free staging stores)
     unsigned int tile;
     int axis_vote[SLAB_THREADS / 32];
+    // occupancy bits of the level-0 ESS cells overlapping the region: word (jz * occ_ny + jy), bit jx, where
+    // j = (l + occ_off) >> 3 for the region-local voxel index l
+    int occ_off[3], occ_ny;
+    unsigned int occ[SLAB_OCC_WORDS];
 };
 
 struct SlabArgs { int depth; int cap_floats; };
@@ -61,12 +66,10 @@ __device__ __forceinline__ void slab_stage(const VolDev& v, const SlabShared& sh
         const int xr0 = sh.rlo[0] - v.res_lo[0];                    // resident x of region column 0
         const int c_first = xr0 >> 3;                               // arithmetic shift: floor for negative x
         const int nchunks = ((xr0 + nx - 1) >> 3) - c_first + 1;
-        const int rows_pad = (rows + 31) & ~31;
-        const int items = rows_pad * nchunks;
-        for (int it = threadIdx.x; it < items; it += SLAB_THREADS) {
-            const int c = it / rows_pad, r = it - c * rows_pad;
-            if (r >= rows) continue;
-            const int lz = r / ny, ly = r - lz * ny;
+        const float rcp_ny = 1.0f / (float)ny;
+        for (int c = 0; c < nchunks; ++c)
+        for (int r = threadIdx.x; r < rows; r += SLAB_THREADS) {
+            const int lz = __float2int_rd(((float)r + 0.5f) * rcp_ny), ly = r - lz * ny;   // r / ny (exact: (r + .5) / ny is never near an integer)
             const int y = min(max(sh.rlo[1] + ly, v.clamp_lo[1]), v.clamp_hi[1]) - v.res_lo[1];
             const int z = min(max(sh.rlo[2] + lz, v.clamp_lo[2]), v.clamp_hi[2]) - v.res_lo[2];
             const int cx = c_first + c;
@@ -101,6 +104,30 @@ __device__ __forceinline__ void slab_stage(const VolDev& v, const SlabShared& sh
                 row[lx] = ld_norm_raw<C::DT>(v.bricks, brick_off_x(x) + oyz, v.dtype);
             }
         }
+    }
+}
+
+// occupancy bits of the region's level-0 cells -> shared memory (one word per (jy, jz) row of cells)
+__device__ __forceinline__ void slab_stage_occ(const VolDev& v, SlabShared& sh) {
+    int off[3], n[3], c0[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        off[a] = sh.rlo[a] & 7;                                     // table cell j covers voxels rlo - off + 8 j .. + 7
+        n[a] = (sh.rn[a] - 1 + off[a]) / 8 + 1;
+        c0[a] = (sh.rlo[a] - off[a]) >> 3;                          // (possibly negative) cell index of table cell 0
+    }
+    if (threadIdx.x == 0) { sh.occ_off[0] = off[0]; sh.occ_off[1] = off[1]; sh.occ_off[2] = off[2]; sh.occ_ny = n[1]; }
+    const int words = n[1] * n[2];
+    for (int w = threadIdx.x; w < words && w < SLAB_OCC_WORDS; w += SLAB_THREADS) {
+        const int jz = w / n[1], jy = w - jz * n[1];
+        const int cy = min(max(c0[1] + jy, 0), v.occ0_dims[1] - 1), cz = min(max(c0[2] + jz, 0), v.occ0_dims[2] - 1);
+        const uint32_t* rowp = v.occ0 + ((size_t)cz * v.occ0_dims[1] + cy) * v.occ0_wpr;
+        unsigned bits = 0;
+        for (int jx = 0; jx < n[0] && jx < 32; ++jx) {
+            const int cx = min(max(c0[0] + jx, 0), v.occ0_dims[0] - 1);
+            bits |= ((__ldg(rowp + (cx >> 5)) >> (cx & 31)) & 1u) << jx;
+        }
+        sh.occ[w] = bits;
     }
 }
 
@@ -192,7 +219,6 @@ __global__ void __launch_bounds__(SLAB_THREADS, 2) march_slab_kernel(const __gri
         bool finished = !cast;
         bool prev_empty = false;       // pre-integration: the previous lattice sample lay in an empty cell
         bool lastI_stale = false;      // ... and lastIntensity has to be re-fetched at t_last before the next classification
-        int cell_cached = -1;          // level-0 ESS cell known to be non-empty
         const float vx = dir.x * V.dimf[0], vy = dir.y * V.dimf[1], vz = dir.z * V.dimf[2];
         // slab orientation: major axis + travel direction of the tile's first casting ray, uniform over the CTA
         int axis; float sgn;
@@ -277,6 +303,14 @@ __global__ void __launch_bounds__(SLAB_THREADS, 2) march_slab_kernel(const __gri
                 // capacity: shrink the wider lateral axis around the leader's footprint until the region fits
                 const int a1 = (axis + 1) % 3, a2 = (axis + 2) % 3;
                 const int nmaj = hi[axis] - lo[axis] + 1;
+                for (int k = 0; k < 2; ++k) {       // no lateral extent beyond 64 voxels (occupancy table, odd pitch)
+                    const int as = k ? a2 : a1;
+                    if (hi[as] - lo[as] + 1 > 64) {
+                        int l2 = li[as] - 32;
+                        l2 = max(l2, lo[as]); l2 = min(l2, hi[as] - 63);
+                        lo[as] = l2; hi[as] = l2 + 63;
+                    }
+                }
                 for (int iter = 0; iter < 4; ++iter) {
                     const int n1 = hi[a1] - lo[a1] + 1, n2 = hi[a2] - lo[a2] + 1;
                     const int p1 = (a1 == 0) ? (n1 | 1) : n1, p2 = (a2 == 0) ? (n2 | 1) : n2, pm = (axis == 0) ? (nmaj | 1) : nmaj;
@@ -295,129 +329,136 @@ __global__ void __launch_bounds__(SLAB_THREADS, 2) march_slab_kernel(const __gri
                 sh.zmin = INT_MAX; sh.leader = INT_MAX;
             }
             __syncthreads();
-            // (4) stage
+            // (4) stage voxels + occupancy bits
             slab_stage<C>(V, sh, S);
+            if (V.ess) slab_stage_occ(V, sh);
             __syncthreads();
-            // (5) march while the footprint of the next sample lies inside the region
-            if (part) {
+            // (5) march while the footprint of the next sample lies inside the region.  The loop is warp-synchronous
+            //     (one __any_sync per iteration) so that the lanes of a warp take their samples together.
+            {
                 const int rx = sh.rlo[0], ry = sh.rlo[1], rz = sh.rlo[2];
                 const int nx = sh.rn[0], ny = sh.rn[1], nz = sh.rn[2];
                 const int pitch = sh.pitch, slice = pitch * ny;
-                while (!finished) {
-                    const float3 sp = f3(xadd(first.x, xmul(t, dir.x)), xadd(first.y, xmul(t, dir.y)), xadd(first.z, xmul(t, dir.z)));
-                    const float sux = xsub(xmul(sp.x, V.dimf[0]), 0.5f), suy = xsub(xmul(sp.y, V.dimf[1]), 0.5f), suz = xsub(xmul(sp.z, V.dimf[2]), 0.5f);
-                    const float fx = floorf(sux), fy = floorf(suy), fz = floorf(suz);
-                    const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
-                    // ---- empty-space skipping ----
-                    bool empty = false;
-                    if (V.ess) {
-                        const int cid = (min(max(x0, 0), V.dims[0] - 1) >> 3) | ((min(max(y0, 0), V.dims[1] - 1) >> 3) << 10) | ((min(max(z0, 0), V.dims[2] - 1) >> 3) << 20);
-                        if (cid != cell_cached) {
-                            float t_exit;
-                            empty = ess_empty_cell(V, sp, dir, t, t_exit);
-                            if (!empty) cell_cached = cid;
-                            else if (!pi_mode || prev_empty) {
-                                // every lattice sample inside this cell classifies to alpha 0 without side effects.  With
+                const int ox = sh.occ_off[0], oy = sh.occ_off[1], oz = sh.occ_off[2], ony = sh.occ_ny;
+                bool run = part;
+                while (__any_sync(0xffffffffu, run)) {
+                    if (run) {
+                        const float3 sp = f3(xadd(first.x, xmul(t, dir.x)), xadd(first.y, xmul(t, dir.y)), xadd(first.z, xmul(t, dir.z)));
+                        const float sux = xsub(xmul(sp.x, V.dimf[0]), 0.5f), suy = xsub(xmul(sp.y, V.dimf[1]), 0.5f), suz = xsub(xmul(sp.z, V.dimf[2]), 0.5f);
+                        const float fx = floorf(sux), fy = floorf(suy), fz = floorf(suz);
+                        const int lx = (int)fx - rx, ly = (int)fy - ry, lz = (int)fz - rz;
+                        // ---- is the 4x4x4 footprint staged? ----
+                        if ((unsigned)(lx - 1) >= (unsigned)(nx - 3) || (unsigned)(ly - 1) >= (unsigned)(ny - 3) || (unsigned)(lz - 1) >= (unsigned)(nz - 3)) run = false;
+                        else {
+                            // ---- empty-space skipping: occupancy bit of the sample's level-0 cell (staged) ----
+                            bool empty = false;
+                            if (V.ess) empty = !((sh.occ[((lz + oz) >> 3) * ony + ((ly + oy) >> 3)] >> ((lx + ox) >> 3)) & 1u);
+                            if (empty && (!pi_mode || prev_empty)) {
+                                // Every lattice sample inside this cell classifies to alpha 0 without side effects.  With
                                 // pre-integration that also needs the PREVIOUS sample to lie in an empty cell: the value
                                 // ranges of the two (adjacent, overlapping) cells then form one interval on which the
                                 // transfer function is transparent, so the table entry (cur, prev) is transparent too.
-                                slab_skip_empty(p, V, first, dir, tEnd, step, t, t_last, loop, finished, st);
-                                if (pi_mode) lastI_stale = true;
+                                if (!slab_skip_empty(p, V, first, dir, tEnd, step, t, t_last, loop, finished, st)) {
+                                    // (cannot happen: the staged bit and the global grid agree) -- take the sample instead
+                                    empty = false;
+                                } else {
+                                    if (pi_mode) lastI_stale = true;
+                                    stale = true;
+                                    run = !finished;
+                                }
+                            }
+                            if (!(empty && (!pi_mode || prev_empty))) {
                                 stale = true;
-                                continue;
+                                const float ax = xsub(sux, fx), ay = xsub(suy, fy), az = xsub(suz, fz);
+                                const float* b = S + (lz * ny + ly) * pitch + lx;
+                                if (pi_mode && lastI_stale) {
+                                    // lastIntensity of the (skipped) sample just before this one: its 2x2x2 taps lie within one voxel
+                                    // of this sample's, i.e. inside the staged footprint (sampling rate >= 1, checked by the launcher)
+                                    const float3 q = f3(xadd(first.x, xmul(t_last, dir.x)), xadd(first.y, xmul(t_last, dir.y)), xadd(first.z, xmul(t_last, dir.z)));
+                                    const float qx = xsub(xmul(q.x, V.dimf[0]), 0.5f), qy = xsub(xmul(q.y, V.dimf[1]), 0.5f), qz = xsub(xmul(q.z, V.dimf[2]), 0.5f);
+                                    const float gx = floorf(qx), gy = floorf(qy), gz = floorf(qz);
+                                    const int jx = min(max((int)gx - rx, 0), nx - 2), jy = min(max((int)gy - ry, 0), ny - 2), jz = min(max((int)gz - rz, 0), nz - 2);
+                                    const float bx = xsub(qx, gx), by = xsub(qy, gy), bz = xsub(qz, gz);
+                                    const float* c = S + (jz * ny + jy) * pitch + jx;
+                                    const float d00 = xlerp(c[0], c[1], bx), d10 = xlerp(c[pitch], c[pitch + 1], bx);
+                                    const float d01 = xlerp(c[slice], c[slice + 1], bx), d11 = xlerp(c[slice + pitch], c[slice + pitch + 1], bx);
+                                    lastI = xadd(xmul(xlerp(xlerp(d00, d10, by), xlerp(d01, d11, by), bz), V.rwm_scale), V.rwm_offset);
+                                    lastI_stale = false;
+                                }
+                                // ---- getVoxel: trilinear from the staged taps (GL float weights, identical to lerp_taps) ----
+                                const float c000 = b[0], c100 = b[1], c010 = b[pitch], c110 = b[pitch + 1];
+                                const float c001 = b[slice], c101 = b[slice + 1], c011 = b[slice + pitch], c111 = b[slice + pitch + 1];
+                                const float c00 = xlerp(c000, c100, ax), c10 = xlerp(c010, c110, ax), c01 = xlerp(c001, c101, ax), c11 = xlerp(c011, c111, ax);
+                                const float tex = xlerp(xlerp(c00, c10, ay), xlerp(c01, c11, ay), az);
+                                const float intensity = xadd(xmul(tex, V.rwm_scale), V.rwm_offset);
+                                st.classified++;
+                                int a8;
+                                const float4 color0 = classify<C>(cmode, p.cls[0], sm.tf[0], f3(0.f, 0.f, 0.f), intensity, lastI, a8);
+                                if (color0.w > 0.f) {
+                                    st.shaded++;
+                                    float3 gradient;
+                                    if (t == 0.0f) gradient = fix_clip_border_gradient(p, sp, dir, px, py);
+                                    else {
+                                        // calcGradientA from the 32 distinct voxels its six offset fetches share (see grad_central_shared)
+                                        auto L = [&](int i, int j, int k) -> float { return b[(i - 1) + (j - 1) * pitch + (k - 1) * slice]; };
+                                        float dxq[2][2], dyq[2][2], dzq[2][2];
+                                        const float cen[2][2][2] = {{{c000, c001}, {c010, c011}}, {{c100, c101}, {c110, c111}}};
+#pragma unroll
+                                        for (int j = 0; j < 2; ++j)
+#pragma unroll
+                                            for (int k = 0; k < 2; ++k) {
+                                                const float A = L(0, j + 1, k + 1), B = cen[0][j][k], Cc = cen[1][j][k], D = L(3, j + 1, k + 1);
+                                                dxq[j][k] = (A - Cc) + ax * ((B - D) - (A - Cc));
+                                            }
+#pragma unroll
+                                        for (int i = 0; i < 2; ++i)
+#pragma unroll
+                                            for (int k = 0; k < 2; ++k) {
+                                                const float A = L(i + 1, 0, k + 1), D = L(i + 1, 3, k + 1), B = cen[i][0][k], Cc = cen[i][1][k];
+                                                dyq[i][k] = (A - Cc) + ay * ((B - D) - (A - Cc));
+                                            }
+#pragma unroll
+                                        for (int i = 0; i < 2; ++i)
+#pragma unroll
+                                            for (int j = 0; j < 2; ++j) {
+                                                const float A = L(i + 1, j + 1, 0), D = L(i + 1, j + 1, 3), B = cen[i][j][0], Cc = cen[i][j][1];
+                                                dzq[i][j] = (A - Cc) + az * ((B - D) - (A - Cc));
+                                            }
+                                        auto bil = [](const float q[2][2], float s_, float tt) -> float {
+                                            const float q0 = q[0][0] + s_ * (q[1][0] - q[0][0]), q1 = q[0][1] + s_ * (q[1][1] - q[0][1]);
+                                            return q0 + tt * (q1 - q0);
+                                        };
+                                        gradient = f3(bil(dxq, ay, az), bil(dyq, ax, az), bil(dzq, ax, ay));
+                                        gradient = gradient * f3(V.spacing_rcp[0] * 0.5f, V.spacing_rcp[1] * 0.5f, V.spacing_rcp[2] * 0.5f);
+                                        gradient = gradient * V.rwm_scale;
+                                    }
+                                    const float3 posPhys = f3((sp.x * V.dimf[0] - 0.5f) * V.spacing[0] + V.offset[0], (sp.y * V.dimf[1] - 0.5f) * V.spacing[1] + V.offset[1],
+                                                              (sp.z * V.dimf[2] - 0.5f) * V.spacing[2] + V.offset[2]);
+                                    float4 color = color0;
+                                    const float3 rgb = f3(color.x, color.y, color.z);
+                                    const float3 shd = apply_shading(smode, p.light, gradient, posPhys, ld3(V.light_phys), ld3(V.cam_phys), rgb, rgb, f3(1.f, 1.f, 1.f));
+                                    color.x = shd.x; color.y = shd.y; color.z = shd.z;
+                                    result = apply_compositing(comp, 1, p.preint_comp, result, intensity, color, a8, sm.lut[0], sp, gradient, t, step, tDepth, maxI, p.gamma[0], p.iso);
+                                }
+                                if (p.collect_stats && p.touched) {
+                                    const int cx = min(max((int)fx, 0), V.dims[0] - 1) / B200RC_STAT_CELL, cy = min(max((int)fy, 0), V.dims[1] - 1) / B200RC_STAT_CELL,
+                                              cz = min(max((int)fz, 0), V.dims[2] - 1) / B200RC_STAT_CELL;
+                                    p.touched[((size_t)cz * p.touched_dims[1] + cy) * p.touched_dims[0] + cx] = 1;
+                                }
+                                lastI = intensity;
+                                prev_empty = empty;
+                                if (p.ert && result.w >= 0.95f) {
+                                    if (p.ert_snap) result.w = 1.0f;
+                                    finished = true;
+                                }
+                                ++loop;
+                                t_last = t;
+                                t = p.lattice_exact ? (float)loop * step : xadd(t, step);
+                                finished = finished || (t > tEnd) || loop >= 256 * 256;
+                                run = !finished;
                             }
                         }
                     }
-                    // ---- is the 4x4x4 footprint staged? ----
-                    const int lx = x0 - rx, ly = y0 - ry, lz = z0 - rz;
-                    if ((unsigned)(lx - 1) >= (unsigned)(nx - 3) || (unsigned)(ly - 1) >= (unsigned)(ny - 3) || (unsigned)(lz - 1) >= (unsigned)(nz - 3)) break;
-                    stale = true;
-                    const float ax = xsub(sux, fx), ay = xsub(suy, fy), az = xsub(suz, fz);
-                    const float* b = S + (lz * ny + ly) * pitch + lx;
-                    if (pi_mode && lastI_stale) {
-                        // lastIntensity of the sample just before this one (it was skipped): its 2x2x2 taps lie within one
-                        // voxel of this sample's and therefore inside the staged footprint (sampling rate >= 1, checked by the launcher)
-                        const float3 q = f3(xadd(first.x, xmul(t_last, dir.x)), xadd(first.y, xmul(t_last, dir.y)), xadd(first.z, xmul(t_last, dir.z)));
-                        const float qx = xsub(xmul(q.x, V.dimf[0]), 0.5f), qy = xsub(xmul(q.y, V.dimf[1]), 0.5f), qz = xsub(xmul(q.z, V.dimf[2]), 0.5f);
-                        const float gx = floorf(qx), gy = floorf(qy), gz = floorf(qz);
-                        const int jx = min(max((int)gx - rx, 0), nx - 2), jy = min(max((int)gy - ry, 0), ny - 2), jz = min(max((int)gz - rz, 0), nz - 2);
-                        const float bx = xsub(qx, gx), by = xsub(qy, gy), bz = xsub(qz, gz);
-                        const float* c = S + (jz * ny + jy) * pitch + jx;
-                        const float d00 = xlerp(c[0], c[1], bx), d10 = xlerp(c[pitch], c[pitch + 1], bx);
-                        const float d01 = xlerp(c[slice], c[slice + 1], bx), d11 = xlerp(c[slice + pitch], c[slice + pitch + 1], bx);
-                        lastI = xadd(xmul(xlerp(xlerp(d00, d10, by), xlerp(d01, d11, by), bz), V.rwm_scale), V.rwm_offset);
-                        lastI_stale = false;
-                    }
-                    // ---- getVoxel: trilinear from the staged taps (GL float weights, identical to lerp_taps) ----
-                    const float c000 = b[0], c100 = b[1], c010 = b[pitch], c110 = b[pitch + 1];
-                    const float c001 = b[slice], c101 = b[slice + 1], c011 = b[slice + pitch], c111 = b[slice + pitch + 1];
-                    const float c00 = xlerp(c000, c100, ax), c10 = xlerp(c010, c110, ax), c01 = xlerp(c001, c101, ax), c11 = xlerp(c011, c111, ax);
-                    const float tex = xlerp(xlerp(c00, c10, ay), xlerp(c01, c11, ay), az);
-                    const float intensity = xadd(xmul(tex, V.rwm_scale), V.rwm_offset);
-                    st.classified++;
-                    int a8;
-                    const float4 color0 = classify<C>(cmode, p.cls[0], sm.tf[0], f3(0.f, 0.f, 0.f), intensity, lastI, a8);
-                    if (color0.w > 0.f) {
-                        st.shaded++;
-                        float3 gradient;
-                        if (t == 0.0f) gradient = fix_clip_border_gradient(p, sp, dir, px, py);
-                        else {
-                            // calcGradientA from the 32 distinct voxels its six offset fetches share (see grad_central_shared)
-                            auto L = [&](int i, int j, int k) -> float { return b[(i - 1) + (j - 1) * pitch + (k - 1) * slice]; };
-                            float dxq[2][2], dyq[2][2], dzq[2][2];
-                            const float cen[2][2][2] = {{{c000, c001}, {c010, c011}}, {{c100, c101}, {c110, c111}}};
-#pragma unroll
-                            for (int j = 0; j < 2; ++j)
-#pragma unroll
-                                for (int k = 0; k < 2; ++k) {
-                                    const float A = L(0, j + 1, k + 1), B = cen[0][j][k], Cc = cen[1][j][k], D = L(3, j + 1, k + 1);
-                                    dxq[j][k] = (A - Cc) + ax * ((B - D) - (A - Cc));
-                                }
-#pragma unroll
-                            for (int i = 0; i < 2; ++i)
-#pragma unroll
-                                for (int k = 0; k < 2; ++k) {
-                                    const float A = L(i + 1, 0, k + 1), D = L(i + 1, 3, k + 1), B = cen[i][0][k], Cc = cen[i][1][k];
-                                    dyq[i][k] = (A - Cc) + ay * ((B - D) - (A - Cc));
-                                }
-#pragma unroll
-                            for (int i = 0; i < 2; ++i)
-#pragma unroll
-                                for (int j = 0; j < 2; ++j) {
-                                    const float A = L(i + 1, j + 1, 0), D = L(i + 1, j + 1, 3), B = cen[i][j][0], Cc = cen[i][j][1];
-                                    dzq[i][j] = (A - Cc) + az * ((B - D) - (A - Cc));
-                                }
-                            auto bil = [](const float q[2][2], float s, float tt) -> float {
-                                const float q0 = q[0][0] + s * (q[1][0] - q[0][0]), q1 = q[0][1] + s * (q[1][1] - q[0][1]);
-                                return q0 + tt * (q1 - q0);
-                            };
-                            gradient = f3(bil(dxq, ay, az), bil(dyq, ax, az), bil(dzq, ax, ay));
-                            gradient = gradient * f3(V.spacing_rcp[0] * 0.5f, V.spacing_rcp[1] * 0.5f, V.spacing_rcp[2] * 0.5f);
-                            gradient = gradient * V.rwm_scale;
-                        }
-                        const float3 posPhys = f3((sp.x * V.dimf[0] - 0.5f) * V.spacing[0] + V.offset[0], (sp.y * V.dimf[1] - 0.5f) * V.spacing[1] + V.offset[1],
-                                                  (sp.z * V.dimf[2] - 0.5f) * V.spacing[2] + V.offset[2]);
-                        float4 color = color0;
-                        const float3 rgb = f3(color.x, color.y, color.z);
-                        const float3 shd = apply_shading(smode, p.light, gradient, posPhys, ld3(V.light_phys), ld3(V.cam_phys), rgb, rgb, f3(1.f, 1.f, 1.f));
-                        color.x = shd.x; color.y = shd.y; color.z = shd.z;
-                        result = apply_compositing(comp, 1, p.preint_comp, result, intensity, color, a8, sm.lut[0], sp, gradient, t, step, tDepth, maxI, p.gamma[0], p.iso);
-                    }
-                    if (p.collect_stats && p.touched) {
-                        const int cx = min(max(x0, 0), V.dims[0] - 1) / B200RC_STAT_CELL, cy = min(max(y0, 0), V.dims[1] - 1) / B200RC_STAT_CELL,
-                                  cz = min(max(z0, 0), V.dims[2] - 1) / B200RC_STAT_CELL;
-                        p.touched[((size_t)cz * p.touched_dims[1] + cy) * p.touched_dims[0] + cx] = 1;
-                    }
-                    lastI = intensity;
-                    prev_empty = empty;
-                    if (p.ert && result.w >= 0.95f) {
-                        if (p.ert_snap) result.w = 1.0f;
-                        finished = true;
-                    }
-                    ++loop;
-                    t_last = t;
-                    t = p.lattice_exact ? (float)loop * step : xadd(t, step);
-                    finished = finished || (t > tEnd) || loop >= 256 * 256;
                 }
             }
         }
