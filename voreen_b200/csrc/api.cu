@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstring>
 #include <cstdlib>
+#include <cstdio>
 #include <cfloat>
 #include <new>
 
@@ -350,6 +351,7 @@ static int finish_frame(b200rc_ctx* ctx, const b200rc_params* P, bool had_eep) {
         RC_CHECK(cudaMemcpy(h, ctx->d_stats, sizeof h, cudaMemcpyDeviceToHost));
         ctx->stats.rays_cast = h[0]; ctx->stats.samples_classified = h[1]; ctx->stats.samples_shaded = h[2];
         ctx->stats.samples_nominal = h[3]; ctx->stats.samples_skipped = h[4]; ctx->stats.cells_touched = h[5];
+        if (getenv("B200RC_DEBUG")) fprintf(stderr, "[b200rc] slab ray-rounds with work %llu of %llu\n", h[6], h[7]);
     }
     return B200RC_OK;
 }

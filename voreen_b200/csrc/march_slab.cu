@@ -9,7 +9,7 @@ template <class C>
 static int launch_slab(b200rc_ctx* ctx, const DevParams& p0) {
     DevParams p = p0;
     p.tiles_x = (((p.W + SLAB_TILE - 1) / SLAB_TILE) + 7) / 8 * 8;
-    p.tiles_y = (((p.H + SLAB_TILE - 1) / SLAB_TILE) + 7) / 8 * 8;
+    p.tiles_y = (((p.H + SLAB_TILE_H - 1) / SLAB_TILE_H) + 7) / 8 * 8;
     // shared memory: two CTAs per SM (227 KB usable); the 1D TF (+ LUT) sits behind the staged region
     size_t tf_bytes = 0;
     if (C::CLS == B200RC_CLASS_TF && p.cls[0].tf) tf_bytes = (size_t)p.cls[0].tf_width * 4 + 1024;
@@ -17,7 +17,7 @@ static int launch_slab(b200rc_ctx* ctx, const DevParams& p0) {
     static int env_depth = -1, env_cap = -1;
     if (env_depth < 0) {
         const char* d = getenv("B200RC_SLAB_DEPTH"); env_depth = d ? atoi(d) : 8;
-        const char* c = getenv("B200RC_SLAB_KB"); env_cap = c ? atoi(c) : 88;
+        const char* c = getenv("B200RC_SLAB_KB"); env_cap = c ? atoi(c) : (SLAB_THREADS == 256 ? 88 : 52);
         if (env_depth < 2 || env_depth > 32) env_depth = 8;
         if (env_cap < 32 || env_cap > 200) env_cap = 88;
     }

@@ -18,8 +18,12 @@
 #pragma once
 #include "march.cuh"
 
-#define SLAB_THREADS 256
-#define SLAB_TILE 16            // pixels per tile edge
+#ifndef SLAB_THREADS
+#define SLAB_THREADS 256        // 256: 16x16-pixel tiles, 128: 16x8-pixel tiles
+#endif
+#define SLAB_TILE 16            // pixels per tile edge (x)
+#define SLAB_TILE_H (SLAB_THREADS / 16)     // tile rows: each warp owns an 8x4 sub-tile, two warps side by side
+#define SLAB_MIN_CTAS (512 / SLAB_THREADS)
 #define SLAB_OCC_WORDS 160      // (max lateral extent / 8 + 2)^2 occupancy words per region
 
 struct SlabShared {
@@ -156,7 +160,7 @@ __device__ __forceinline__ bool slab_skip_empty(const DevParams& p, const VolDev
 }
 
 template <class C>
-__global__ void __launch_bounds__(SLAB_THREADS, 2) march_slab_kernel(const __grid_constant__ DevParams p, const SlabArgs sa) {
+__global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel(const __grid_constant__ DevParams p, const SlabArgs sa) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ SlabShared sh;
     float* S = (float*)smem_raw;
@@ -183,6 +187,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, 2) march_slab_kernel(const __gri
     const int DEPTH = sa.depth;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     RayStats st = {0u, 0u, 0u, 0u, 0ull};
+    unsigned long long dbg_part = 0, dbg_rounds = 0;
     const unsigned ntiles = (unsigned)p.tiles_x * (unsigned)p.tiles_y;      // 16x16 tiles, padded to 8x8 super-tiles
     const unsigned super_x = (unsigned)p.tiles_x >> 3;
 
@@ -194,7 +199,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, 2) march_slab_kernel(const __gri
         const unsigned sup = tile >> 6, loc = tile & 63u;
         const unsigned tx = (sup % super_x) * 8u + compact1by1(loc), ty = (sup / super_x) * 8u + compact1by1(loc >> 1);
         // warp w covers the 8x4 sub-tile (w & 1, w >> 1) of the 16x16 tile
-        const int px = (int)(tx * SLAB_TILE + (warp & 1u) * 8u + (lane & 7u)), py = (int)(ty * SLAB_TILE + (warp >> 1) * 4u + (lane >> 3));
+        const int px = (int)(tx * SLAB_TILE + (warp & 1u) * 8u + (lane & 7u)), py = (int)(ty * SLAB_TILE_H + (warp >> 1) * 4u + (lane >> 3));
         const bool inside = px < p.W && py < p.H;
         const size_t pix = inside ? (size_t)py * p.W + px : 0;
         float3 first = f3(0.f, 0.f, 0.f), dir = f3(0.f, 0.f, 1.f);
@@ -214,7 +219,8 @@ __global__ void __launch_bounds__(SLAB_THREADS, 2) march_slab_kernel(const __gri
             }
         }
         float4 result = make_float4(0.f, 0.f, 0.f, 0.f);
-        float t = 0.0f, t_last = 0.0f, tDepth = -1.0f, lastI = 0.f, maxI = 0.f;
+        // pre-integration: lastI holds the TF texture coordinate of the previous sample's intensity (lastIntensity starts at 0)
+        float t = 0.0f, t_last = 0.0f, tDepth = -1.0f, lastI = pi_mode ? rw_to_tex(p.cls[0].dom_lo, p.cls[0].dom_hi, 0.f) : 0.f, maxI = 0.f;
         int loop = 0;
         bool finished = !cast;
         bool prev_empty = false;       // pre-integration: the previous lattice sample lay in an empty cell
@@ -341,6 +347,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, 2) march_slab_kernel(const __gri
                 const int pitch = sh.pitch, slice = pitch * ny;
                 const int ox = sh.occ_off[0], oy = sh.occ_off[1], oz = sh.occ_off[2], ony = sh.occ_ny;
                 bool run = part;
+                if (p.collect_stats) { dbg_part += part ? 1u : 0u; dbg_rounds += 1u; }
                 while (__any_sync(0xffffffffu, run)) {
                     if (run) {
                         const float3 sp = f3(xadd(first.x, xmul(t, dir.x)), xadd(first.y, xmul(t, dir.y)), xadd(first.z, xmul(t, dir.z)));
@@ -382,7 +389,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, 2) march_slab_kernel(const __gri
                                     const float* c = S + (jz * ny + jy) * pitch + jx;
                                     const float d00 = xlerp(c[0], c[1], bx), d10 = xlerp(c[pitch], c[pitch + 1], bx);
                                     const float d01 = xlerp(c[slice], c[slice + 1], bx), d11 = xlerp(c[slice + pitch], c[slice + pitch + 1], bx);
-                                    lastI = xadd(xmul(xlerp(xlerp(d00, d10, by), xlerp(d01, d11, by), bz), V.rwm_scale), V.rwm_offset);
+                                    lastI = rw_to_tex(p.cls[0].dom_lo, p.cls[0].dom_hi, xadd(xmul(xlerp(xlerp(d00, d10, by), xlerp(d01, d11, by), bz), V.rwm_scale), V.rwm_offset));
                                     lastI_stale = false;
                                 }
                                 // ---- getVoxel: trilinear from the staged taps (GL float weights, identical to lerp_taps) ----
@@ -392,8 +399,15 @@ __global__ void __launch_bounds__(SLAB_THREADS, 2) march_slab_kernel(const __gri
                                 const float tex = xlerp(xlerp(c00, c10, ay), xlerp(c01, c11, ay), az);
                                 const float intensity = xadd(xmul(tex, V.rwm_scale), V.rwm_offset);
                                 st.classified++;
-                                int a8;
-                                const float4 color0 = classify<C>(cmode, p.cls[0], sm.tf[0], f3(0.f, 0.f, 0.f), intensity, lastI, a8);
+                                int a8 = -1;
+                                float4 color0;
+                                if (pi_mode) {
+                                    // applyTFpi: texture(table, vec2(intensity, previous intensity)); the previous sample's texture
+                                    // coordinate is carried along instead of being mapped a second time (same value)
+                                    const float s_cur = rw_to_tex(p.cls[0].dom_lo, p.cls[0].dom_hi, intensity);
+                                    color0 = preint_lookup<C>(p.cls[0], s_cur, lastI);
+                                    lastI = s_cur;
+                                } else color0 = classify<C>(cmode, p.cls[0], sm.tf[0], f3(0.f, 0.f, 0.f), intensity, lastI, a8);
                                 if (color0.w > 0.f) {
                                     st.shaded++;
                                     float3 gradient;
@@ -445,7 +459,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, 2) march_slab_kernel(const __gri
                                               cz = min(max((int)fz, 0), V.dims[2] - 1) / B200RC_STAT_CELL;
                                     p.touched[((size_t)cz * p.touched_dims[1] + cy) * p.touched_dims[0] + cx] = 1;
                                 }
-                                lastI = intensity;
+                                if (!pi_mode) lastI = intensity;
                                 prev_empty = empty;
                                 if (p.ert && result.w >= 0.95f) {
                                     if (p.ert_snap) result.w = 1.0f;
@@ -471,12 +485,12 @@ __global__ void __launch_bounds__(SLAB_THREADS, 2) march_slab_kernel(const __gri
         }
     }
     if (p.collect_stats && p.stats) {
-        unsigned long long vals[5] = {st.rays, st.classified, st.shaded, st.nominal, st.skipped};
+        unsigned long long vals[7] = {st.rays, st.classified, st.shaded, st.nominal, st.skipped, dbg_part, dbg_rounds};
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
+        for (int i = 0; i < 7; ++i) {
             unsigned long long v = vals[i];
             for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-            if (lane == 0 && v) atomicAdd(p.stats + i, v);
+            if (lane == 0 && v) atomicAdd(p.stats + (i < 5 ? i : i + 1), v);      // [6] ray-rounds with work, [7] ray-rounds in total
         }
     }
 }
