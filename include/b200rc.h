@@ -167,6 +167,8 @@ typedef struct b200rc_params {
     int32_t out_format;         /* B200RC_OUT_* */
     int32_t quantize_depth24;   /* 1: depth rounded to GL_DEPTH_COMPONENT24 */
     int32_t collect_stats;      /* 1: count classified samples / cast rays (slower) */
+    int32_t partial_image;      /* 1: sort-last partial image of a sharded volume: early ray termination on the local alpha
+                                   without the snap to 1.0 (b200rc_finalize snaps after the merge); use B200RC_OUT_RGBA32F */
 } b200rc_params;
 
 /* MeshEntryExitPoints + proxy geometry settings for b200rc_render_camera / b200rc_entry_exit. */
@@ -275,7 +277,10 @@ int b200rc_render_camera_device(b200rc_ctx* ctx, const b200rc_params* params, co
 /* ---- sort-last compositing (new work; semantics = premultiplied front-to-back over, depth = min;
  *      SURVEY section 5 / 8e).  All pointers are DEVICE pointers; float4 colour + float depth, n pixels.
  *      dst = front OVER back.  `front` may alias dst.  With mode = compositing mode of the output:
- *      DVR -> over; MIP/MOP -> max-alpha/intensity select (w channel carries the key); FHP/FHN/ISO -> nearer depth. */
+ *      DVR -> over; MIP/MOP -> max-alpha/intensity select (w channel carries the key); FHP/FHN/ISO -> nearer depth.
+ *      mode | B200RC_COMPOSITE_ERT: early ray termination is active for this output (volumeraycaster.cpp:225-233): a
+ *      front image that already reached alpha >= 0.95 hides everything behind it, as the terminated ray would. */
+#define B200RC_COMPOSITE_ERT 0x100
 int b200rc_composite(b200rc_ctx* ctx, int mode, const float* front_rgba, const float* front_depth,
                      const float* back_rgba, const float* back_depth, float* dst_rgba, float* dst_depth, size_t n);
 /* ERT finalisation after merging (alpha >= 0.95 -> 1.0, mod_raysetup.frag:65-74) and conversion to out_format. */

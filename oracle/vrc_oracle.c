@@ -128,7 +128,9 @@ void orc_look_at(const float eye[3], const float focus[3], const float up[3], fl
 
 /* V/ext/tgt/matrix.h:1230-1248 createPerspective */
 void orc_perspective(float fov, float aspect, float pnear, float pfar, float out[16]) {
-    float f = 1.f / tanf(fov / 2.f);
+    /* `tan` inside tgt resolves to the C double overload (verified against the reference's own header by
+     * oracle/_ref/tgt_probe): T(1) / tan(fov / T(2)) is evaluated in double and rounded once */
+    float f = (float)(1.0 / tan((double)(fov / 2.f)));
     float m[16] = { f / aspect, 0.f, 0.f, 0.f,
                     0.f, f, 0.f, 0.f,
                     0.f, 0.f, (pnear + pfar) / (pnear - pfar), (2.f * pfar * pnear) / (pnear - pfar),
@@ -146,7 +148,7 @@ void orc_camera_projection(float fovy_deg, float frustum_ratio, float pnear, flo
     if (window_ratio >= 1.0f)
         orc_perspective((PIf / 180.f) * fovy, frustum_ratio * window_ratio, pnear, pfar, out);
     else
-        orc_perspective(atanf(tanf((PIf / 180.f) * (fovy / 2.f)) / (window_ratio * frustum_ratio)) * 2.f,
+        orc_perspective((float)(atan(tan((double)((PIf / 180.f) * (fovy / 2.f))) / (double)(window_ratio * frustum_ratio)) * 2),
                         frustum_ratio * window_ratio, pnear, pfar, out);
 }
 
@@ -1383,12 +1385,14 @@ void orc_composite(int mode, const float* fc, const float* fd, const float* bc, 
     for (size_t i = 0; i < n; ++i) {
         const float* F = fc + 4 * i; const float* B = bc + 4 * i; float* D = dc + 4 * i;
         float fdp = fd ? fd[i] : 1.f, bdp = bd ? bd[i] : 1.f;
-        if (mode == B200RC_COMP_DVR) {
-            float k = 1.0f - F[3];
+        int ert = (mode & B200RC_COMPOSITE_ERT) != 0;
+        int m = mode & 0xff;
+        if (m == B200RC_COMP_DVR) {
+            float k = (ert && F[3] >= 0.95f) ? 0.0f : 1.0f - F[3];
             float r0 = F[0] + k * B[0], r1 = F[1] + k * B[1], r2 = F[2] + k * B[2], r3 = F[3] + k * B[3];
             D[0] = r0; D[1] = r1; D[2] = r2; D[3] = r3;
             if (dd) dd[i] = fdp < bdp ? fdp : bdp;
-        } else if (mode == B200RC_COMP_MIP || mode == B200RC_COMP_MOP) {
+        } else if (m == B200RC_COMP_MIP || m == B200RC_COMP_MOP) {
             /* the key (max intensity / max alpha) travels in the depth slot of the partial images */
             int takeB = (bdp > fdp);
             const float* S = takeB ? B : F;

@@ -193,3 +193,82 @@ def test_host_mirror_processor(ctx):
         p.set_property("compositing", "no-such-mode")
     assert not p.is_ready()
     p.close()
+
+
+@pytest.mark.parametrize("world", [2, 8])
+@pytest.mark.parametrize("cls", ["tf", "preint"])
+def test_sharded_rendering_single_device(ctx, world, cls):
+    """Sort-last on ONE device: every shard (brick + apron) is uploaded in turn and renders its partial image; the
+    partial images merged front to back must reproduce the unsharded image (sample sets partition exactly; the only
+    difference is early ray termination on the local instead of the global alpha)."""
+    from voreen_b200 import sortlast
+    dims = (64, 56, 72)
+    vol = scenes.ct_like_volume(0, dims=dims)
+    # a translucent TF (global alpha stays below the ERT threshold) isolates the partition from the ERT caveat
+    keys = [(0.0, (0, 0, 0, 0)), (0.25, (0, 0, 0, 0)), (0.30, (255, 140, 60, 2)), (1.00, (255, 255, 255, 6))]
+    for k in (keys, scenes.CT_KEYS):
+        s = scenes.Scene(vol, keys=k, W=96, H=88, eye=(1.4, 0.9, 2.9), out_format=abi.OUT_RGBA32F)
+        if cls == "preint":
+            s.use_preint("cpu")
+        ref_outs, ref_depth = s.cuda_render(ctx)
+        cam_tex = sortlast.camera_texture_position(s.cam, s.desc)
+        parts = []
+        for r in range(world):
+            lo, hi = sortlast.shard_range(dims, r, world)
+            d = vb_desc(dims, lo, hi)
+            rl = [max(0, lo[a] - sortlast.APRON) for a in range(3)]; rh = [min(dims[a], hi[a] + sortlast.APRON) for a in range(3)]
+            ctx.upload_volume(0, np.ascontiguousarray(vol[rl[2]:rh[2], rl[1]:rh[1], rl[0]:rh[0]]), desc=d)
+            s.params.partial_image = 1
+            outs, depth = ctx.render_camera(s.params, s.eep, s.cam, s.W, s.H)
+            s.params.partial_image = 0
+            parts.append((outs[0].reshape(-1, 4).copy(), depth.reshape(-1).copy()))
+        # merge like the binary swap does: round by round, groups separated by one plane
+        imgs = dict(enumerate(parts))
+        nbits = world.bit_length() - 1
+        for rnd in range(nbits):
+            nxt = {}
+            for r in sorted(imgs):
+                if (r >> rnd) & 1:
+                    continue
+                a, b = imgs[r], imgs[r | (1 << rnd)]
+                front, back = (a, b) if sortlast.my_group_in_front(r, rnd, world, dims, cam_tex) else (b, a)
+                dc = np.empty_like(a[0]); dd = np.empty_like(a[1])
+                orc.lib().orc_composite(abi.COMP["dvr"] | abi.COMPOSITE_ERT, orc.fp(front[0]), orc.fp(front[1]), orc.fp(back[0]), orc.fp(back[1]), orc.fp(dc), orc.fp(dd), dc.shape[0])
+                nxt[r] = (dc, dd)
+            imgs = nxt
+        merged, mdepth = imgs[0]
+        merged = merged.reshape(s.H, s.W, 4).copy()
+        merged[..., 3] = np.where(merged[..., 3] >= 0.95, 1.0, merged[..., 3])       # ERT snap after the merge
+        frac, mx = scenes.parity_report(ref_outs[0], merged)
+        dfrac = float((np.abs(ref_depth.reshape(-1) - mdepth) <= 1e-4).mean())
+        print(f"sharded x{world} {cls} keys={'translucent' if k is keys else 'ct'}: within 1/255 {frac:.5f} max {mx:.4f} depth {dfrac:.5f}")
+        if k is keys:
+            assert frac >= 0.999 and mx < 2e-3, (frac, mx)        # exact partition: fp reassociation only
+            assert dfrac >= 0.999
+        else:
+            assert mx <= 0.051                                   # ERT caveat bound: (1 - 0.95) * colour
+    ctx.upload_volume(0, vol, desc=s.desc)
+
+
+def vb_desc(dims, lo, hi):
+    from voreen_b200 import raycaster as rc
+    from voreen_b200 import sortlast
+    return rc.make_volume_desc(dims, shard_lo=lo, shard_hi=hi, shard_apron=sortlast.APRON)
+
+
+def test_nucleon_workspace_against_committed_fixture(ctx):
+    """Config C1: the reference's standard workspace (nucleon.vvd + rendering-raycasting.vws: pre-integrated-gpu, Sobel
+    gradients, Phong, sampling rate 4, min-bounding-box proxy geometry) through the CUDA path, against the committed
+    fixture tests/golden/nucleon_oracle.npz (no access to /root/reference at run time)."""
+    import os
+    import nucleon_scene
+    z = np.load(os.path.join(nucleon_scene.GOLDEN, "nucleon_oracle.npz"))
+    s = nucleon_scene.load()
+    outs, depth, st = nucleon_scene.cuda_render(s, ctx)
+    q = z["rgba16"].astype(np.float32) / 65535.0
+    frac, mx = scenes.parity_report(q, np.clip(np.nan_to_num(outs[0]), 0, 1))
+    print(f"nucleon workspace: within 1/255 {frac:.5f} max {mx:.4f} rays {st.rays_cast} (fixture {int(z['rays'])})")
+    assert st.rays_cast == int(z["rays"]) and st.samples_nominal == int(z["nominal"])      # bit-exact entry/exit
+    assert frac >= 0.999
+    assert float((np.abs(depth - z["depth"]) <= 1e-4).mean()) >= 0.999
+    assert orc.image_diff_count(q, np.clip(np.nan_to_num(outs[0]), 0, 1)) <= 50             # the reference's own comparator

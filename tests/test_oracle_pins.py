@@ -2,7 +2,7 @@
 
   - the reference's own tgt headers, compiled where they lie into oracle/_ref/tgt_probe (camera / matrix arithmetic);
   - known answers the reference computed itself and serialised into its bundled nucleon.vvd: VolumeMinMax, the
-    intensity histogram and the 64x64 VolumePreview (software trilinear VolumeRAM::getVoxelNormalizedLinear);
+    intensity histogram (voxel normalisation VolumeRAM::getVoxelNormalized);
   - the numeric constants of the GLSL modules (0.95 ERT threshold + alpha snap, SAMPLING_BASE_INTERVAL_RCP = 200,
     ISO +-0.02, step-size formula), checked through closed-form scenes;
   - the committed rendering of the reference's standard workspace (regression fixture, tests/golden/).
@@ -32,7 +32,8 @@ def _probe(lines):
 
 
 def _hex(a):
-    return " ".join(float(v).hex() for v in np.asarray(a, np.float32).reshape(-1))
+    # decimal with 9 significant digits round-trips every float32 (the probe parses with operator>>)
+    return " ".join("%.9g" % float(v) for v in np.asarray(a, np.float32).reshape(-1))
 
 
 def test_camera_matrices_match_tgt_headers():
@@ -47,9 +48,9 @@ def test_camera_matrices_match_tgt_headers():
     persp = [(45.0, 1.0, 0.1, 50.0), (45.000003815, 1.0, 0.100000001, 502.0), (30.0, 1.7777, 0.5, 10.0), (175.0, 0.6, 0.01, 5.0)]
     deg2rad = _probe([f"deg2rad {_hex([p[0]])}" for p in persp])
     ref = _probe([f"persp {_hex(d)} {_hex([p[1]])} {_hex([p[2]])} {_hex([p[3]])}" for p, d in zip(persp, deg2rad)])
-    for p, r in zip(persp, ref):
+    for p, d, r in zip(persp, deg2rad, ref):
         got = np.zeros(16, np.float32)
-        orc.lib().orc_perspective(np.float32((np.float32(math.pi) / np.float32(180.0)) * np.float32(p[0])), p[1], p[2], p[3], orc.fp(got))
+        orc.lib().orc_perspective(float(d[0]), p[1], p[2], p[3], orc.fp(got))       # createPerspective on tgt::deg2rad's own output
         assert np.array_equal(got, r)
     # Camera::getProjectionMatrix for window ratio >= 1 is createPerspective(deg2rad(fovy), ratio, near, far)
     for p, r in zip(persp[:2], ref[:2]):
@@ -99,31 +100,9 @@ def test_nucleon_minmax_and_histogram_known_answers():
     assert np.array_equal(hist == 0, z["hist"] == 0) or (np.abs(hist - z["hist"]) > 0).sum() < 16
 
 
-def test_nucleon_preview_pins_linear_sampler():
-    """VolumePreview::createFrom (volumepreview.cpp:51-176) resamples the middle slice with the reference's software
-    trilinear filter; the oracle's texture sampler must reproduce the serialised bytes."""
-    z = _nucleon()
-    vox = np.ascontiguousarray(z["voxels"])
-    dz, dy, dx = vox.shape
-    desc = rc.make_volume_desc((dx, dy, dz), dtype=abi.U8)
-    ov = orc.make_volume(vox, desc)
-    n = 64
-    zpos = float((dz - 1) // 2)
-    vals = np.zeros((n, n), np.float32)
-    out = np.zeros(4, np.float32)
-    for y in range(n):
-        for x in range(n):
-            px = np.float32(x) / np.float32(n - 1) * np.float32(dx - 1.0)       # aspect ratio 1: offsets 0, scales 1
-            py = np.float32(y) / np.float32(n - 1) * np.float32(dy - 1.0)
-            pos = np.array([(px + 0.5) / dx, (py + 0.5) / dy, (zpos + 0.5) / dz], np.float32)
-            orc.lib().orc_sample3d(orc.C.byref(ov), abi.FILTER_LINEAR, abi.CLAMP_TO_EDGE, 0.0, orc.fp(pos), orc.fp(out))
-            vals[y, x] = out[0]
-    mn, mx = vals.min(), vals.max()
-    prev = np.floor(np.power((vals - mn) / (mx - mn), np.float32(1.0 / 1.8)) * 255.0 + 0.5).astype(np.int64)
-    ref = z["preview"].astype(np.int64)
-    d = np.abs(prev - ref)
-    assert d.max() <= 1, d.max()                # +-1: float weights (a + w (b - a)) vs the reference's 8-term sum
-    assert (d == 0).mean() > 0.97
+# (The 64x64 VolumePreview blob serialised in nucleon.vvd is NOT reproduced by the current VolumePreview::createFrom
+#  (volumepreview.cpp:51-176) applied to nucleon.raw in any slice / orientation / gamma -- it predates that code -- so it is
+#  not used as a known answer for the linear sampler.)
 
 
 # ---- constants of the GLSL modules through closed-form scenes ---------------------------------------------------------------
@@ -136,15 +115,16 @@ def _uniform_scene(alpha8, n=16, rate=2.0, **kw):
 def test_dvr_opacity_correction_and_step_size():
     """compositeDVR: a' = 1 - (1 - a)^(step * 200), step = 1 / (max(dim) * samplingRate) (mod_compositing.frag:40-59,
     volumeraycaster.cpp:312-322): a ray through a uniform medium takes floor(tEnd/step)+1 samples."""
-    s = _uniform_scene(10)
+    s = _uniform_scene(1)
     outs, depth, st = s.oracle_render()
     assert abs(s.step - 1.0 / (16 * 2.0)) < 1e-9
     e, ed, x, xd = s.oracle_eep()
     c = (16, 16)
     tend = float(np.linalg.norm(x[c][:3] - e[c][:3]))
     nsamp = math.floor(tend / s.step) + 1
-    a = 1.0 - (1.0 - 10 / 255.0) ** (s.step * 200.0)
+    a = 1.0 - (1.0 - 1 / 255.0) ** (s.step * 200.0)
     expect_alpha = 1.0 - (1.0 - a) ** nsamp
+    assert expect_alpha < 0.95
     assert abs(outs[0][c][3] - expect_alpha) < 2e-5
     assert abs(outs[0][c][0] - expect_alpha * 1.0) < 2e-5          # premultiplied colour, r = 255/255
     assert st.samples_nominal == st.samples_classified             # no early termination below 0.95

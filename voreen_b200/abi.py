@@ -25,6 +25,7 @@ SAMPLER_EXACT, SAMPLER_TEX = 0, 1
 OUT_RGBA32F, OUT_RGBA16 = 0, 1
 INSIDE_NONE, INSIDE_GPU = 0, 1
 PROXY_BBOX, PROXY_MINBBOX, PROXY_VISIBLE_BRICKS = 0, 1, 2
+COMPOSITE_ERT = 0x100
 
 
 class VolumeDesc(C.Structure):
@@ -59,7 +60,7 @@ class Params(C.Structure):
                 ("enable_channel_shift", C.c_int32), ("channel_shift", (C.c_float * 3) * MAX_CHANNELS),
                 ("light", Light),
                 ("sampler", C.c_int32), ("empty_space_skipping", C.c_int32), ("out_format", C.c_int32),
-                ("quantize_depth24", C.c_int32), ("collect_stats", C.c_int32)]
+                ("quantize_depth24", C.c_int32), ("collect_stats", C.c_int32), ("partial_image", C.c_int32)]
 
 
 class EepParams(C.Structure):

@@ -211,7 +211,7 @@ static int build_params(b200rc_ctx* ctx, const b200rc_params* P, const b200rc_ca
     p.near_d = cam->near_dist; p.far_d = cam->far_dist;
     p.out_format = P->out_format; p.quantize_depth24 = P->quantize_depth24;
     p.collect_stats = P->collect_stats;
-    p.ert_snap = 1;
+    p.ert_snap = P->partial_image ? 0 : 1;      // sort-last partial images keep the un-snapped alpha; b200rc_finalize snaps after the merge
     bool ert = true;
     for (int o = 0; o < 3; ++o) {
         p.comp[o] = P->compositing[o]; p.connected[o] = P->output_connected[o] ? 1 : 0; p.gamma[o] = P->mida_gamma[o];
@@ -287,7 +287,7 @@ static int build_params(b200rc_ctx* ctx, const b200rc_params* P, const b200rc_ca
         }
     }
     // empty-space skipping (single volume, unsharded, no channel shift): occupancy for the current TFs
-    if (P->empty_space_skipping && !P->multi_volume && !p.channel_shift && !ctx->vol[0].sharded) {
+    if (P->empty_space_skipping && !P->multi_volume && !p.channel_shift) {
         int modes[4];
         for (int c = 0; c < ncls; ++c) modes[c] = P->vol[0].classification;
         int rc = rc_volume_build_occupancy(ctx, 0, modes, ncls, false, P->vol[0].clamp, P->vol[0].border_intensity);

@@ -11,8 +11,10 @@ __global__ void composite_kernel(int mode, const float4* __restrict__ fc, const 
     const float4 F = fc[i], B = bc[i];
     const float fdp = fd ? fd[i] : 1.f, bdp = bd ? bd[i] : 1.f;
     float4 D; float dep;
+    const bool ert = (mode & B200RC_COMPOSITE_ERT) != 0;
+    mode &= 0xff;
     if (mode == B200RC_COMP_DVR) {
-        const float k = 1.0f - F.w;
+        const float k = (ert && F.w >= 0.95f) ? 0.0f : 1.0f - F.w;      // a terminated ray sees nothing behind it
         D = make_float4(F.x + k * B.x, F.y + k * B.y, F.z + k * B.z, F.w + k * B.w);
         dep = fminf(fdp, bdp);
     } else if (mode == B200RC_COMP_MIP || mode == B200RC_COMP_MOP) {

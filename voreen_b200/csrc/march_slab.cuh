@@ -116,9 +116,10 @@ __device__ __forceinline__ void slab_stage_occ(const VolDev& v, SlabShared& sh) 
     int off[3], n[3], c0[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        off[a] = sh.rlo[a] & 7;                                     // table cell j covers voxels rlo - off + 8 j .. + 7
+        const int rl = sh.rlo[a] - v.res_lo[a];                     // the grids cover the resident range: resident coordinates
+        off[a] = rl & 7;                                            // table cell j covers resident voxels rl - off + 8 j .. + 7
         n[a] = (sh.rn[a] - 1 + off[a]) / 8 + 1;
-        c0[a] = (sh.rlo[a] - off[a]) >> 3;                          // (possibly negative) cell index of table cell 0
+        c0[a] = (rl - off[a]) >> 3;                                 // (possibly negative) cell index of table cell 0
     }
     if (threadIdx.x == 0) { sh.occ_off[0] = off[0]; sh.occ_off[1] = off[1]; sh.occ_off[2] = off[2]; sh.occ_ny = n[1]; }
     const int words = n[1] * n[2];
@@ -225,6 +226,19 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
         bool finished = !cast;
         bool prev_empty = false;       // pre-integration: the previous lattice sample lay in an empty cell
         bool lastI_stale = false;      // ... and lastIntensity has to be re-fetched at t_last before the next classification
+        float tStop = tEnd;            // sort-last shard: march only [k0 * step, tStop]
+        if (cast && V.sharded) {
+            const ShardSeg seg = shard_segment(V, first, dir, tEnd, step);
+            tStop = seg.t_stop;
+            if (!seg.any) finished = true;
+            else if (seg.k0 > 0) {
+                loop = seg.k0;
+                if (p.lattice_exact) { t = (float)loop * step; t_last = (float)(loop - 1) * step; }
+                else for (int i = 0; i < loop; ++i) { t_last = t; t = xadd(t, step); }
+                lastI_stale = true;
+                finished = (t > tStop);
+            }
+        }
         const float vx = dir.x * V.dimf[0], vy = dir.y * V.dimf[1], vz = dir.z * V.dimf[2];
         // slab orientation: major axis + travel direction of the tile's first casting ray, uniform over the CTA
         int axis; float sgn;
@@ -254,7 +268,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
             //     slab is staged where the ray would only skip
             if (stale) {
                 if (V.ess && (!pi_mode || prev_empty))
-                    while (!finished && slab_skip_empty(p, V, first, dir, tEnd, step, t, t_last, loop, finished, st)) { if (pi_mode) lastI_stale = true; }
+                    while (!finished && slab_skip_empty(p, V, first, dir, tStop, step, t, t_last, loop, finished, st)) { if (pi_mode) lastI_stale = true; }
                 zc = INT_MAX;
                 if (!finished) {
                     const float3 sp = f3(xadd(first.x, xmul(t, dir.x)), xadd(first.y, xmul(t, dir.y)), xadd(first.z, xmul(t, dir.z)));
@@ -280,7 +294,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
                     // ray parameter at which the major coordinate leaves the slab
                     const float um = pick3f(ux, uy, uz, axis);
                     const float dist = (float)(zmin + DEPTH) - (sgn > 0.f ? um : -um);     // > 0, in voxels
-                    const float dt = fminf(dist / fmaxf(vmaj, 1e-20f), tEnd - t);
+                    const float dt = fminf(dist / fmaxf(vmaj, 1e-20f), tStop - t);
                     const int jx = __float2int_rd(ux + dt * vx), jy = __float2int_rd(uy + dt * vy), jz = __float2int_rd(uz + dt * vz);
                     lo0 = min(i0x, jx); hi0 = max(i0x, jx); lo1 = min(i0y, jy); hi1 = max(i0y, jy); lo2 = min(i0z, jz); hi2 = max(i0z, jz);
                 }
@@ -356,7 +370,15 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
                         const int lx = (int)fx - rx, ly = (int)fy - ry, lz = (int)fz - rz;
                         // ---- is the 4x4x4 footprint staged? ----
                         if ((unsigned)(lx - 1) >= (unsigned)(nx - 3) || (unsigned)(ly - 1) >= (unsigned)(ny - 3) || (unsigned)(lz - 1) >= (unsigned)(nz - 3)) run = false;
-                        else {
+                        else if (V.sharded && !shard_owns(V, (int)fx, (int)fy, (int)fz)) {
+                            // another rank's sample: step over it (pre-integration re-fetches lastIntensity afterwards)
+                            stale = true; prev_empty = false;
+                            if (pi_mode) lastI_stale = true;
+                            ++loop; t_last = t;
+                            t = p.lattice_exact ? (float)loop * step : xadd(t, step);
+                            finished = (t > tStop) || loop >= 256 * 256;
+                            run = !finished;
+                        } else {
                             // ---- empty-space skipping: occupancy bit of the sample's level-0 cell (staged) ----
                             bool empty = false;
                             if (V.ess) empty = !((sh.occ[((lz + oz) >> 3) * ony + ((ly + oy) >> 3)] >> ((lx + ox) >> 3)) & 1u);
@@ -365,7 +387,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
                                 // pre-integration that also needs the PREVIOUS sample to lie in an empty cell: the value
                                 // ranges of the two (adjacent, overlapping) cells then form one interval on which the
                                 // transfer function is transparent, so the table entry (cur, prev) is transparent too.
-                                if (!slab_skip_empty(p, V, first, dir, tEnd, step, t, t_last, loop, finished, st)) {
+                                if (!slab_skip_empty(p, V, first, dir, tStop, step, t, t_last, loop, finished, st)) {
                                     // (cannot happen: the staged bit and the global grid agree) -- take the sample instead
                                     empty = false;
                                 } else {
@@ -468,7 +490,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
                                 ++loop;
                                 t_last = t;
                                 t = p.lattice_exact ? (float)loop * step : xadd(t, step);
-                                finished = finished || (t > tEnd) || loop >= 256 * 256;
+                                finished = finished || (t > tStop) || loop >= 256 * 256;
                                 run = !finished;
                             }
                         }

@@ -47,7 +47,9 @@ void look_at(V3 eye, V3 focus, V3 up, float out[16]) {
 }
 // mat4::createPerspective (matrix.h:1230-1248)
 void perspective(float fov_rad, float aspect, float n, float f, float out[16]) {
-    const float c = 1.f / std::tan(fov_rad / 2.f);
+    // tgt's `tan` is the C double overload: T(1) / tan(fov / T(2)) is evaluated in double and rounded once (pinned against the
+    // reference header by tests/test_oracle_pins.py)
+    const float c = (float)(1.0 / ::tan((double)(fov_rad / 2.f)));
     const float m[16] = {c / aspect, 0.f, 0.f, 0.f, 0.f, c, 0.f, 0.f, 0.f, 0.f, (n + f) / (n - f), (2.f * f * n) / (n - f), 0.f, 0.f, -1.f, 0.f};
     std::memcpy(out, m, sizeof m);
 }
@@ -56,7 +58,7 @@ void camera_projection(float fovy_deg, float frustum_ratio, float n, float f, fl
     const float PIf = 3.14159265358979323846f;
     float fovy = fovy_deg < 6.f ? 6.f : (fovy_deg > 175.f ? 175.f : fovy_deg);
     if (window_ratio >= 1.0f) perspective((PIf / 180.f) * fovy, frustum_ratio * window_ratio, n, f, out);
-    else perspective(std::atan(std::tan((PIf / 180.f) * (fovy / 2.f)) / (window_ratio * frustum_ratio)) * 2.f, frustum_ratio * window_ratio, n, f, out);
+    else perspective((float)(::atan(::tan((double)((PIf / 180.f) * (fovy / 2.f))) / (double)(window_ratio * frustum_ratio)) * 2), frustum_ratio * window_ratio, n, f, out);
 }
 
 inline int iround(float f) { return (int)std::floor(f + 0.5f); }     // tgt::iround (tgt_math.h:213-225)

@@ -1,0 +1,204 @@
+"""Sort-last multi-GPU rendering: one process per GPU, each holding one brick (shard) of the volume.
+
+New work with no counterpart in the reference.  Per frame every rank
+  1. marches exactly the lattice samples its shard owns (b200rc_params.partial_image, volume.cu shard_lo/hi: the
+     shards' sample sets partition the single-GPU sample set, so merging partial images reproduces the single-GPU
+     accumulators up to the ERT caveat below) into a premultiplied RGBA32F + depth partial image of the full viewport;
+  2. merges the partial images by BINARY SWAP: log2(P) rounds, in round r partner = rank xor 2^r, the current pixel
+     range is halved, one half is sent and the partner's matching half received and blended with the over operator
+     in visibility order (the two groups of bricks are separated by one axis-aligned plane, so the order is the same
+     for every pixel: the group on the camera's side of the plane is in front);
+  3. finalises its 1/P of the image (ERT alpha snap + RGBA16 conversion) and sends it to rank 0.
+
+The exchange uses torch.distributed point-to-point operations (NCCL over NVLink on GPUs, gloo in the CPU tests); the
+blend and finalise steps are the CUDA kernels behind b200rc_composite / b200rc_finalize (or an injected function in the
+host-logic tests).  No collective touches the volume: bricks never move.
+
+ERT caveat: each rank terminates a ray on its LOCAL alpha >= 0.95 (safe: the global alpha is then >= 0.95 as well) and
+the merge stops accumulating behind an opaque front; a rank whose segment contains the global 0.95 crossing still
+marches to its own threshold, which can differ from the single-GPU image by up to (1 - 0.95) * colour on such pixels.
+DESIGN.md "Sort-last and early ray termination" quantifies it on the benchmark scenes.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from . import abi
+from . import raycaster as rc
+
+APRON = 8       # voxels; a multiple of 8 keeps the brick grid of the shard aligned with the global one
+
+
+def shard_grid(world):
+    """(gx, gy, gz) bricks per axis and the axis each rank bit splits (bit r <-> axes[r]); z is split first."""
+    if world & (world - 1) or world < 1 or world > 8:
+        raise ValueError("sort-last needs 1, 2, 4 or 8 ranks")
+    nbits = world.bit_length() - 1
+    axes = {0: [], 1: [2], 2: [1, 2], 3: [0, 1, 2]}[nbits]
+    grid = [1, 1, 1]
+    for a in axes:
+        grid[a] *= 2
+    return tuple(grid), axes
+
+
+def shard_coords(rank, world):
+    grid, axes = shard_grid(world)
+    c = [0, 0, 0]
+    for r, a in enumerate(axes):
+        c[a] = (rank >> r) & 1
+    return tuple(c)
+
+
+def shard_range(dims, rank, world):
+    """Owned voxel range [lo, hi) of a rank: the volume is halved along each split axis at a multiple of 8 voxels."""
+    grid, _ = shard_grid(world)
+    c = shard_coords(rank, world)
+    lo, hi = [], []
+    for a in range(3):
+        if grid[a] == 1:
+            lo.append(0); hi.append(dims[a])
+        else:
+            mid = (dims[a] // 2 + 7) // 8 * 8
+            lo.append(0 if c[a] == 0 else mid); hi.append(mid if c[a] == 0 else dims[a])
+    return tuple(lo), tuple(hi)
+
+
+def shard_desc(dims, rank, world, **desc_kw):
+    lo, hi = shard_range(dims, rank, world)
+    return rc.make_volume_desc(dims, shard_lo=lo, shard_hi=hi, shard_apron=APRON if world > 1 else 0, **desc_kw) if world > 1 else rc.make_volume_desc(dims, **desc_kw)
+
+
+def camera_texture_position(cam, desc):
+    """Camera position in the volume's texture space (worldToTexture * position)."""
+    d = np.array(desc.dims[:], np.float64); sp = np.array(desc.spacing[:], np.float64); off = np.array(desc.offset[:], np.float64)
+    p2w = np.array(desc.phys_to_world[:], np.float64).reshape(4, 4)
+    w = np.array(list(cam.position[:]) + [1.0])
+    phys = np.linalg.solve(p2w, w)[:3]
+    vox = (phys - off) / sp
+    return (vox + 0.5) / d
+
+
+def split_plane(dims, axis):
+    """Texture coordinate of the plane separating the two halves along `axis`: base indices < mid | >= mid."""
+    mid = (dims[axis] // 2 + 7) // 8 * 8
+    return (mid + 0.5) / dims[axis]
+
+
+def my_group_in_front(rank, rnd, world, dims, cam_tex):
+    """Round `rnd` merges the groups {bit rnd == 0} and {bit rnd == 1}, separated by the split plane of axes[rnd]."""
+    _, axes = shard_grid(world)
+    a = axes[rnd]
+    low_side_front = cam_tex[a] < split_plane(dims, a)
+    mine_low = ((rank >> rnd) & 1) == 0
+    return mine_low == low_side_front
+
+
+def final_ranges(npix, world):
+    """Pixel range [lo, hi) every rank owns after the last round (deterministic, known to all ranks)."""
+    out = []
+    nbits = world.bit_length() - 1
+    for rank in range(world):
+        lo, hi = 0, npix
+        for r in range(nbits):
+            mid = (lo + hi) // 2
+            if (rank >> r) & 1 == 0:
+                hi = mid
+            else:
+                lo = mid
+        out.append((lo, hi))
+    return out
+
+
+def binary_swap(color, depth, rank, world, in_front, blend, dist=None, group=None):
+    """In-place binary swap over `color` (npix, 4) and `depth` (npix,) torch tensors of this rank's partial image.
+
+    in_front(rnd) -> bool: is this rank's group in front of the partner's in round rnd.
+    blend(front_c, front_d, back_c, back_d, dst_c, dst_d): dst = front OVER back (may alias front or back).
+    Returns (lo, hi): the pixel range whose merged result this rank now holds in color[lo:hi], depth[lo:hi]."""
+    import torch
+    if dist is None:
+        import torch.distributed as dist
+    npix = color.shape[0]
+    lo, hi = 0, npix
+    nbits = world.bit_length() - 1
+    for r in range(nbits):
+        partner = rank ^ (1 << r)
+        mid = (lo + hi) // 2
+        keep = (lo, mid) if (rank >> r) & 1 == 0 else (mid, hi)
+        send = (mid, hi) if (rank >> r) & 1 == 0 else (lo, mid)
+        n = keep[1] - keep[0]
+        rc_ = torch.empty((n, 4), dtype=color.dtype, device=color.device)
+        rd_ = torch.empty((n,), dtype=depth.dtype, device=depth.device)
+        ops = [dist.P2POp(dist.isend, color[send[0]:send[1]], partner, group), dist.P2POp(dist.isend, depth[send[0]:send[1]], partner, group),
+               dist.P2POp(dist.irecv, rc_, partner, group), dist.P2POp(dist.irecv, rd_, partner, group)]
+        if rank > partner:      # both sides post in the same global order (send/recv pairs match up)
+            ops = ops[2:] + ops[:2]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        mc, md = color[keep[0]:keep[1]], depth[keep[0]:keep[1]]
+        if in_front(r):
+            blend(mc, md, rc_, rd_, mc, md)
+        else:
+            blend(rc_, rd_, mc, md, mc, md)
+        lo, hi = keep
+    return lo, hi
+
+
+class SortLast:
+    """One rank of the sort-last renderer (GPU)."""
+
+    def __init__(self, ctx, dims, rank, world, W, H, device, stream):
+        import torch
+        self.torch = torch
+        self.ctx, self.dims, self.rank, self.world, self.W, self.H = ctx, tuple(dims), rank, world, W, H
+        self.device, self.stream = device, stream
+        self.npix = W * H
+        self.color = torch.empty((self.npix, 4), dtype=torch.float32, device=device)
+        self.depth = torch.empty((self.npix,), dtype=torch.float32, device=device)
+        self.ranges = final_ranges(self.npix, world)
+        self.desc = shard_desc(self.dims, rank, world)
+
+    def shard_desc(self):
+        return self.desc
+
+    def _blend(self, fc, fd, bc, bd, dc, dd):
+        self.ctx.composite(abi.COMP["dvr"] | abi.COMPOSITE_ERT, fc.data_ptr(), fd.data_ptr(), bc.data_ptr(), bd.data_ptr(), dc.data_ptr(), dd.data_ptr(), fc.shape[0])
+
+    def render(self, params, eep, cam, out_rgba16, out_depth):
+        """Renders one frame; rank 0 receives the final RGBA16 image + depth in out_rgba16 / out_depth (device tensors).
+        Returns this rank's march-kernel time in ms."""
+        torch = self.torch
+        import torch.distributed as dist
+        p = params
+        saved = (p.partial_image, p.out_format)
+        p.partial_image, p.out_format = 1, abi.OUT_RGBA32F
+        with torch.cuda.stream(self.stream):
+            self.ctx.render_camera_ptrs(p, eep, cam, self.W, self.H, [self.color.data_ptr(), 0, 0], self.depth.data_ptr(), device=True)
+            march_ms = self.ctx.stats().last_march_ms
+            p.partial_image, p.out_format = saved
+            cam_tex = camera_texture_position(cam, self.desc)
+            lo, hi = binary_swap(self.color, self.depth, self.rank, self.world,
+                                 lambda r: my_group_in_front(self.rank, r, self.world, self.dims, cam_tex), self._blend)
+            # finalise my 1/P of the image (alpha snap + RGBA16) and hand it to rank 0
+            n = hi - lo
+            flat16 = out_rgba16.view(-1, 4)
+            flatd = out_depth.view(-1)
+            if self.rank == 0:
+                self.ctx.finalize(self.color[lo:hi].data_ptr(), self.depth[lo:hi].data_ptr(), n, abi.OUT_RGBA16, flat16[lo:hi].data_ptr())
+                flatd[lo:hi].copy_(self.depth[lo:hi])
+                ops = []
+                for r in range(1, self.world):
+                    a, b = self.ranges[r]
+                    ops.append(dist.P2POp(dist.irecv, flat16[a:b], r))
+                    ops.append(dist.P2POp(dist.irecv, flatd[a:b], r))
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+            else:
+                part16 = torch.empty((n, 4), dtype=torch.int16, device=self.device)
+                self.ctx.finalize(self.color[lo:hi].data_ptr(), self.depth[lo:hi].data_ptr(), n, abi.OUT_RGBA16, part16.data_ptr())
+                ops = [dist.P2POp(dist.isend, part16, 0), dist.P2POp(dist.isend, self.depth[lo:hi], 0)]
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+        return march_ms
