@@ -260,7 +260,7 @@ def run_b200(args, rank, world, local_rank):
     else:
         desc = vb.make_volume_desc(dims)
     t0 = time.perf_counter()
-    ctx.synth_volume(0, desc, args.seed)
+    ctx.synth_volume(0, vb.make_volume_desc(dims) if (world > 1 and rank == 0) else desc, args.seed)
     ctx.synchronize()
     t_synth = time.perf_counter() - t0
 
@@ -289,18 +289,33 @@ def run_b200(args, rank, world, local_rank):
         torch.cuda.synchronize(dev)
 
     # ---- statistics pass (outside the timed region): reference-equivalent samples and touched macro-cells per view ----
-    params.collect_stats = 1
-    ref_samples, classified, cells16, nominal = [], [], [], []
-    for k in range(N_VIEWS):
-        frame(k)
-        st = ctx.stats()
-        ref_samples.append(st.samples_classified + st.samples_skipped); classified.append(st.samples_classified)
-        cells16.append(st.cells_touched); nominal.append(st.samples_nominal)
-    params.collect_stats = 0
+    # N > 1: the sample counts that define the metric are those of the UNSHARDED frame (what the reference executes), so
+    # rank 0 first renders the whole volume once per view, then every rank loads its shard.
+    def stats_pass(render):
+        params.collect_stats = 1
+        out = []
+        for k in range(N_VIEWS):
+            render(k)
+            st = ctx.stats()
+            out.append((st.samples_classified + st.samples_skipped, st.samples_classified, st.cells_touched, st.samples_nominal))
+        params.collect_stats = 0
+        return [list(c) for c in zip(*out)]
+
+    def frame_unsharded(k):
+        ctx.render_camera_ptrs(params, eep, cams[k % N_VIEWS], W, H, [out_rgba.data_ptr(), 0, 0], out_depth.data_ptr(), device=True)
+
     if world > 1:
+        ref_samples = classified = nominal = [0.0] * N_VIEWS
+        if rank == 0:
+            ref_samples, classified, _, nominal = stats_pass(frame_unsharded)
         t = torch.tensor([ref_samples, classified, nominal], dtype=torch.float64, device=dev)
-        dist.all_reduce(t)
+        dist.broadcast(t, 0)
         ref_samples, classified, nominal = (t[i].tolist() for i in range(3))
+        ctx.synth_volume(0, desc, args.seed)            # now the shard
+        ctx.synchronize()
+        _, _, cells16, _ = stats_pass(frame)             # this rank's touched macro-cells (roofline of its own kernel)
+    else:
+        ref_samples, classified, cells16, nominal = stats_pass(frame)
 
     # ---- timed region -------------------------------------------------------------------------------------------------
     for k in range(args.warmup):

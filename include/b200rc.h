@@ -283,6 +283,19 @@ int b200rc_render_camera_device(b200rc_ctx* ctx, const b200rc_params* params, co
 #define B200RC_COMPOSITE_ERT 0x100
 int b200rc_composite(b200rc_ctx* ctx, int mode, const float* front_rgba, const float* front_depth,
                      const float* back_rgba, const float* back_depth, float* dst_rgba, float* dst_depth, size_t n);
+/* Exact early ray termination across shards (optional second pass between rendering and merging).
+ * b200rc_ert_plan: alphas_dev holds the alpha planes of ALL ranks' first-pass partial images (world x n floats, rank major),
+ * front_mask the ranks whose brick lies in front of this context's brick (camera side of every differing split plane).
+ * Erases this rank's pixels behind a terminated ray, and flags (2) those whose ray crosses the global 0.95 threshold inside
+ * this shard; prefix_dev receives the alpha in front of the shard.  remarch_count (host, may be NULL) returns the number of
+ * flagged pixels (synchronises).  b200rc_remarch_device re-marches exactly the flagged pixels with the alpha accumulator
+ * started at the prefix -- mod_raysetup.frag:65-74 then fires on the GLOBAL alpha -- reusing the entry/exit images of the
+ * preceding b200rc_render_camera_device call, and overwrites those pixels of the partial image. */
+int b200rc_ert_plan(b200rc_ctx* ctx, const float* alphas_dev, int world, uint32_t front_mask, float* color_dev, float* depth_dev, size_t n,
+                    float* prefix_dev, uint8_t* flags_dev, uint64_t* remarch_count);
+int b200rc_remarch_device(b200rc_ctx* ctx, const b200rc_params* params, const b200rc_camera* cam, int width, int height,
+                          const float* prefix_dev, const uint8_t* flags_dev, void* out_color_dev[B200RC_MAX_OUTPUTS], float* out_depth_dev);
+
 /* ERT finalisation after merging (alpha >= 0.95 -> 1.0, mod_raysetup.frag:65-74) and conversion to out_format. */
 int b200rc_finalize(b200rc_ctx* ctx, const float* rgba_dev, const float* depth_dev, size_t n, int out_format,
                     void* out_color_dev);

@@ -33,13 +33,13 @@ def test_shard_partition(world):
 
 def test_visibility_order():
     dims = (64, 64, 64)
-    # 2 ranks split along z at texture coordinate (32 + 0.5) / 64
-    assert sortlast.my_group_in_front(0, 0, 2, dims, (0.5, 0.5, -1.0))
-    assert not sortlast.my_group_in_front(1, 0, 2, dims, (0.5, 0.5, -1.0))
-    assert sortlast.my_group_in_front(1, 0, 2, dims, (0.5, 0.5, 2.0))
-    # 8 ranks: bit 0 <-> x, bit 1 <-> y, bit 2 <-> z
-    assert sortlast.shard_coords(5, 8) == (1, 0, 1)
-    assert sortlast.my_group_in_front(5, 0, 8, dims, (2.0, 0.0, 0.0)) and not sortlast.my_group_in_front(5, 1, 8, dims, (0.0, 2.0, 0.0))
+    # 2 ranks split along y at texture coordinate (32 + 0.5) / 64
+    assert sortlast.my_group_in_front(0, 0, 2, dims, (0.5, -1.0, 0.5))
+    assert not sortlast.my_group_in_front(1, 0, 2, dims, (0.5, -1.0, 0.5))
+    assert sortlast.my_group_in_front(1, 0, 2, dims, (0.5, 2.0, 0.5))
+    # 8 ranks: bit 0 <-> y, bit 1 <-> z, bit 2 <-> x
+    assert sortlast.shard_coords(5, 8) == (1, 1, 0)
+    assert sortlast.my_group_in_front(5, 0, 8, dims, (0.0, 2.0, 0.0)) and not sortlast.my_group_in_front(5, 1, 8, dims, (0.0, 0.0, 2.0))
 
 
 @pytest.mark.parametrize("world", [2, 4])

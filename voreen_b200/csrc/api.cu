@@ -440,8 +440,8 @@ extern "C" int b200rc_render(b200rc_ctx* ctx, const b200rc_params* P, const b200
 }
 
 static int render_camera_impl(b200rc_ctx* ctx, const b200rc_params* P, const b200rc_eep_params* eep, const b200rc_camera* cam, int W, int H,
-                              void* out_color[3], float* out_depth, bool device_out) {
-    if (!eep) { ctx->set_error("render_camera: eep params missing"); return B200RC_ERR_INVALID; }
+                              void* out_color[3], float* out_depth, bool device_out, const float* prefix = nullptr, const unsigned char* flags = nullptr) {
+    if (!eep && !flags) { ctx->set_error("render_camera: eep params missing"); return B200RC_ERR_INVALID; }
     if (P && P->multi_volume) { ctx->set_error("render_camera: multi-volume rendering takes explicit entry/exit buffers (b200rc_render)"); return B200RC_ERR_INVALID; }
     DevParams p; int nch = 1, dtype = 0;
     int rc = build_params(ctx, P, cam, W, H, p, &nch, &dtype);
@@ -449,8 +449,14 @@ static int render_camera_impl(b200rc_ctx* ctx, const b200rc_params* P, const b20
     const size_t px = (size_t)W * H;
     rc = ensure_frame_buffers(ctx, px, 1);
     if (rc) return rc;
-    rc = run_eep(ctx, eep, cam, W, H);
-    if (rc) return rc;
+    if (flags) {        // second pass: the entry/exit images of the first pass are still resident
+        if (ctx->eep_w != W || ctx->eep_h != H) { ctx->set_error("remarch: no entry/exit images of this size (call b200rc_render_camera_device first)"); return B200RC_ERR_NOT_READY; }
+        p.prefix = prefix; p.flags = flags;
+    } else {
+        rc = run_eep(ctx, eep, cam, W, H);
+        if (rc) return rc;
+        ctx->eep_w = W; ctx->eep_h = H;
+    }
     p.entry = ctx->d_entry; p.exitp = ctx->d_exit; p.entry_depth = ctx->d_entry_depth; p.exit_depth = ctx->d_exit_depth;
     for (int o = 0; o < 3; ++o) {
         if (!(p.connected[o] && out_color && out_color[o])) p.out[o] = nullptr;
@@ -463,7 +469,7 @@ static int render_camera_impl(b200rc_ctx* ctx, const b200rc_params* P, const b20
         rc = copy_outputs(ctx, P, px, out_color, out_depth, cudaMemcpyDeviceToHost, p);
         if (rc) return rc;
     }
-    return finish_frame(ctx, P, true);
+    return finish_frame(ctx, P, !flags);
 }
 
 extern "C" int b200rc_render_camera(b200rc_ctx* ctx, const b200rc_params* P, const b200rc_eep_params* eep, const b200rc_camera* cam, int W, int H,
@@ -490,4 +496,29 @@ extern "C" int b200rc_finalize(b200rc_ctx* ctx, const float* rgba_dev, const flo
     CTX_GUARD();
     if (!rgba_dev || !out_color_dev) { ctx->set_error("finalize: null image"); return B200RC_ERR_INVALID; }
     return rc_finalize_launch(ctx, rgba_dev, depth_dev, n, out_format, out_color_dev);
+}
+
+extern "C" int b200rc_ert_plan(b200rc_ctx* ctx, const float* alphas_dev, int world, uint32_t front_mask, float* color_dev, float* depth_dev, size_t n,
+                               float* prefix_dev, uint8_t* flags_dev, uint64_t* remarch_count) {
+    CTX_GUARD();
+    if (!alphas_dev || !color_dev || !depth_dev || !prefix_dev || !flags_dev || world < 1 || world > 32) { ctx->set_error("ert_plan: bad arguments"); return B200RC_ERR_INVALID; }
+    unsigned long long* counter = nullptr;
+    if (remarch_count) { counter = ctx->d_stats + 7; RC_CHECK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), ctx->stream)); }
+    const int rc = rc_ert_plan_launch(ctx, alphas_dev, world, front_mask, color_dev, depth_dev, n, prefix_dev, flags_dev, counter);
+    if (rc) return rc;
+    if (remarch_count) {
+        unsigned long long h = 0;
+        RC_CHECK(cudaMemcpyAsync(&h, counter, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+        RC_CHECK(cudaStreamSynchronize(ctx->stream));
+        *remarch_count = h;
+    }
+    return B200RC_OK;
+}
+
+extern "C" int b200rc_remarch_device(b200rc_ctx* ctx, const b200rc_params* P, const b200rc_camera* cam, int W, int H, const float* prefix_dev,
+                                     const uint8_t* flags_dev, void* out_color_dev[B200RC_MAX_OUTPUTS], float* out_depth_dev) {
+    CTX_GUARD();
+    if (!prefix_dev || !flags_dev) { ctx->set_error("remarch: prefix / flags missing"); return B200RC_ERR_INVALID; }
+    if (!P || !P->partial_image) { ctx->set_error("remarch: needs partial_image rendering"); return B200RC_ERR_INVALID; }
+    return render_camera_impl(ctx, P, nullptr, cam, W, H, out_color_dev, out_depth_dev, true, prefix_dev, flags_dev);
 }

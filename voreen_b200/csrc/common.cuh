@@ -74,6 +74,9 @@ struct DevParams {
     unsigned long long* stats;      // [0] rays [1] classified [2] shaded [3] nominal [4] skipped
     unsigned char* touched;         // per 16^3 macro-cell flag (collect_stats only)
     int touched_dims[3];
+    // sort-last exact early ray termination (second pass): only pixels with flags[pix] == 2 are marched, their alpha
+    // accumulator starts at the alpha of everything in front of this shard (prefix), so the 0.95 test is the global one
+    const float* prefix; const unsigned char* flags;
     unsigned int* tile_counter;     // persistent tile scheduler
     int tiles_x, tiles_y;
 };

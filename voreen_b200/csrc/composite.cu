@@ -53,3 +53,42 @@ int rc_finalize_launch(b200rc_ctx* ctx, const float* rgba, const float* depth, s
     RC_CHECK(cudaGetLastError());
     return B200RC_OK;
 }
+
+// ---- exact early ray termination across shards (sort-last second pass planning) ------------------------------------
+// alphas: world x n (alpha of every rank's first-pass partial image).  front_mask: ranks whose brick lies in front of
+// this rank's along every ray that crosses both (axis-aligned grid: on the camera's side of each differing split plane).
+//   P >= 0.95                         -> the ray terminated in front of this shard: its contribution is erased
+//   0 < P, P + (1-P) A_local >= 0.95  -> the global 0.95 crossing lies inside this shard's segment: re-march (flag 2)
+//   otherwise                         -> the first-pass result stands (P == 0: local and global thresholds coincide)
+__global__ void ert_plan_kernel(const float* __restrict__ alphas, int world, unsigned front_mask, float4* __restrict__ color,
+                                float* __restrict__ depth, size_t n, float* __restrict__ prefix, unsigned char* __restrict__ flags,
+                                unsigned long long* __restrict__ counter) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned flag = 0;
+    if (i < n) {
+        float T = 1.0f;
+        for (int r = 0; r < world; ++r)
+            if ((front_mask >> r) & 1u) T *= 1.0f - alphas[(size_t)r * n + i];
+        const float P = 1.0f - T;
+        const float A = color[i].w;
+        if (P >= 0.95f) {
+            if (A != 0.f) { color[i] = make_float4(0.f, 0.f, 0.f, 0.f); depth[i] = 1.0f; }
+            flag = 1;
+        } else if (P > 0.f && A > 0.f && P + (1.0f - P) * A >= 0.95f) flag = 2;
+        prefix[i] = P;
+        flags[i] = (unsigned char)flag;
+    }
+    if (counter) {
+        const unsigned c = __reduce_add_sync(0xffffffffu, flag == 2 ? 1u : 0u);
+        if ((threadIdx.x & 31) == 0 && c) atomicAdd(counter, (unsigned long long)c);
+    }
+}
+
+int rc_ert_plan_launch(b200rc_ctx* ctx, const float* alphas, int world, unsigned front_mask, float* color, float* depth, size_t n,
+                       float* prefix, unsigned char* flags, unsigned long long* counter) {
+    if (!n) return B200RC_OK;
+    ert_plan_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(alphas, world, front_mask, (float4*)color, depth, n, prefix, flags, counter);
+    ctx->launches++;
+    RC_CHECK(cudaGetLastError());
+    return B200RC_OK;
+}

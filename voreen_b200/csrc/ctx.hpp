@@ -57,6 +57,7 @@ struct b200rc_ctx {
     // per-frame device buffers
     float4* d_entry = nullptr; float4* d_exit = nullptr; float* d_entry_depth = nullptr; float* d_exit_depth = nullptr;
     size_t eep_capacity = 0;        // pixels x images
+    int eep_w = 0, eep_h = 0;       // size of the entry/exit images currently held (b200rc_remarch_device reuses them)
     void* d_out[3] = {nullptr, nullptr, nullptr}; float* d_out_depth = nullptr; size_t out_capacity = 0;
     unsigned long long* d_stats = nullptr;
     unsigned int* d_tile_counter = nullptr;
@@ -94,6 +95,8 @@ int rc_march_launch(b200rc_ctx* ctx, const DevParams& p, int sampler, int nch, i
 // composite.cu
 int rc_composite_launch(b200rc_ctx* ctx, int mode, const float* fc, const float* fd, const float* bc, const float* bd, float* dc, float* dd, size_t n);
 int rc_finalize_launch(b200rc_ctx* ctx, const float* rgba, const float* depth, size_t n, int out_format, void* out);
+int rc_ert_plan_launch(b200rc_ctx* ctx, const float* alphas, int world, unsigned front_mask, float* color, float* depth, size_t n,
+                       float* prefix, unsigned char* flags, unsigned long long* counter);
 
 // host matrix helpers (api.cu), tgt semantics (V/ext/tgt/matrix.h)
 void rc_mat4_mul(const float a[16], const float b[16], float out[16]);

@@ -206,7 +206,10 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
         float3 first = f3(0.f, 0.f, 0.f), dir = f3(0.f, 0.f, 1.f);
         float tEnd = 0.f;
         bool cast = false;
-        if (inside) {
+        const bool second_pass = p.flags != nullptr;
+        const bool wanted = inside && (!second_pass || p.flags[pix] == 2);      // sort-last second pass: flagged pixels only
+        const float prefixA = (second_pass && wanted) ? p.prefix[pix] : 0.f;
+        if (wanted) {
             const float4 e4 = p.entry[pix], x4 = p.exitp[pix];
             first = f3(e4.x, e4.y, e4.z);
             const float3 last = f3(x4.x, x4.y, x4.z);
@@ -219,7 +222,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
                 st.nominal += (unsigned long long)floorf(xdiv(tEnd, step)) + 1ull;
             }
         }
-        float4 result = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 result = make_float4(0.f, 0.f, 0.f, prefixA);
         // pre-integration: lastI holds the TF texture coordinate of the previous sample's intensity (lastIntensity starts at 0)
         float t = 0.0f, t_last = 0.0f, tDepth = -1.0f, lastI = pi_mode ? rw_to_tex(p.cls[0].dom_lo, p.cls[0].dom_hi, 0.f) : 0.f, maxI = 0.f;
         int loop = 0;
@@ -499,9 +502,13 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
             }
         }
         // ---- outputs ------------------------------------------------------------------------------------------------------
-        if (inside) {
+        if (wanted) {
             float depth = 1.0f;
             if (cast) depth = get_depth_value(tDepth, tEnd, p.entry_depth[pix], p.exit_depth[pix], p.near_d, p.far_d);
+            if (second_pass) {      // back to the shard-local convention: C_local = dC / (1 - P), A_local = (A - P) / (1 - P)
+                const float k = 1.0f / (1.0f - prefixA);
+                result.x *= k; result.y *= k; result.z *= k; result.w = (result.w - prefixA) * k;
+            }
             store_color(p, 0, pix, result);
             if (p.out_depth) p.out_depth[pix] = p.quantize_depth24 ? depth24_roundtrip(depth) : depth;
         }

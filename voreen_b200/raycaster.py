@@ -268,3 +268,12 @@ class Context:
 
     def finalize(self, rgba, depth, n, out_format, out):
         self._check(self.lib.b200rc_finalize(self.h, rgba, depth, n, out_format, out), "finalize")
+
+    def ert_plan(self, alphas, world, front_mask, color, depth, n, prefix, flags, count=False):
+        c = C.c_uint64(0)
+        self._check(self.lib.b200rc_ert_plan(self.h, alphas, world, front_mask, color, depth, n, prefix, flags, C.byref(c) if count else None), "ert_plan")
+        return int(c.value)
+
+    def remarch_device(self, params, cam, W, H, prefix, flags, out_ptrs, depth_ptr):
+        ptrs = (C.c_void_p * 3)(*[C.c_void_p(p) if p else None for p in out_ptrs])
+        self._check(self.lib.b200rc_remarch_device(self.h, C.byref(params), C.byref(cam), W, H, prefix, flags, C.byref(ptrs), C.c_void_p(depth_ptr) if depth_ptr else None), "remarch_device")

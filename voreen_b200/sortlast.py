@@ -14,10 +14,12 @@ The exchange uses torch.distributed point-to-point operations (NCCL over NVLink 
 blend and finalise steps are the CUDA kernels behind b200rc_composite / b200rc_finalize (or an injected function in the
 host-logic tests).  No collective touches the volume: bricks never move.
 
-ERT caveat: each rank terminates a ray on its LOCAL alpha >= 0.95 (safe: the global alpha is then >= 0.95 as well) and
-the merge stops accumulating behind an opaque front; a rank whose segment contains the global 0.95 crossing still
-marches to its own threshold, which can differ from the single-GPU image by up to (1 - 0.95) * colour on such pixels.
-DESIGN.md "Sort-last and early ray termination" quantifies it on the benchmark scenes.
+Early ray termination: in the first pass each rank terminates a ray on its LOCAL alpha >= 0.95 (safe: the global alpha is
+then >= 0.95 as well).  That alone differs from the single-GPU image by up to (1 - 0.95) * colour where the global 0.95
+crossing lies inside a brick that has something in front of it.  The second pass (exact_ert, default on) removes the
+difference: an all-gather of the alpha planes (4 B/pixel/rank) gives every rank the alpha in front of its brick; pixels
+behind a terminated ray are erased, pixels whose crossing lies inside the brick are re-marched with the accumulator started
+at that prefix, so mod_raysetup.frag:65-74 fires on the global alpha exactly where the single-GPU march stops.
 """
 from __future__ import annotations
 
@@ -32,11 +34,15 @@ APRON = 8       # voxels; a multiple of 8 keeps the brick grid of the shard alig
 
 
 def shard_grid(world):
-    """(gx, gy, gz) bricks per axis and the axis each rank bit splits (bit r <-> axes[r]); z is split first."""
+    """(gx, gy, gz) bricks per axis and the axis each rank bit splits (bit r <-> axes[r]).
+
+    y is split first: for turntable views (the reference's own benchmark rotates the camera about +y,
+    V/resource/voreencore/scripts/benchmark.py:30-47) the two y halves always lie side by side on screen, so early ray
+    termination cannot starve one of them; z and x follow."""
     if world & (world - 1) or world < 1 or world > 8:
         raise ValueError("sort-last needs 1, 2, 4 or 8 ranks")
     nbits = world.bit_length() - 1
-    axes = {0: [], 1: [2], 2: [1, 2], 3: [0, 1, 2]}[nbits]
+    axes = {0: [], 1: [1], 2: [1, 2], 3: [1, 2, 0]}[nbits]
     grid = [1, 1, 1]
     for a in axes:
         grid[a] *= 2
@@ -93,6 +99,27 @@ def my_group_in_front(rank, rnd, world, dims, cam_tex):
     low_side_front = cam_tex[a] < split_plane(dims, a)
     mine_low = ((rank >> rnd) & 1) == 0
     return mine_low == low_side_front
+
+
+def front_mask(rank, world, dims, cam_tex):
+    """Bit f set: brick f lies in front of brick `rank` along every ray that crosses both, i.e. f differs from `rank` and
+    sits on the camera's side of every split plane in which they differ (rays are monotone in each axis)."""
+    _, axes = shard_grid(world)
+    mine = shard_coords(rank, world)
+    mask = 0
+    for f in range(world):
+        if f == rank:
+            continue
+        c = shard_coords(f, world)
+        ok = True
+        for a in set(axes):
+            if c[a] != mine[a]:
+                cam_low = cam_tex[a] < split_plane(dims, a)
+                if (c[a] == 0) != cam_low:
+                    ok = False
+        if ok:
+            mask |= 1 << f
+    return mask
 
 
 def final_ranges(npix, world):
@@ -159,6 +186,12 @@ class SortLast:
         self.depth = torch.empty((self.npix,), dtype=torch.float32, device=device)
         self.ranges = final_ranges(self.npix, world)
         self.desc = shard_desc(self.dims, rank, world)
+        self.exact_ert = True       # second pass: early ray termination on the global alpha (images match the single-GPU result)
+        self.alpha = torch.empty((self.npix,), dtype=torch.float32, device=device)
+        self.alphas = torch.empty((world * self.npix,), dtype=torch.float32, device=device)
+        self.prefix = torch.empty((self.npix,), dtype=torch.float32, device=device)
+        self.flags = torch.empty((self.npix,), dtype=torch.uint8, device=device)
+        self.last_remarch_ms = 0.0
 
     def shard_desc(self):
         return self.desc
@@ -177,8 +210,18 @@ class SortLast:
         with torch.cuda.stream(self.stream):
             self.ctx.render_camera_ptrs(p, eep, cam, self.W, self.H, [self.color.data_ptr(), 0, 0], self.depth.data_ptr(), device=True)
             march_ms = self.ctx.stats().last_march_ms
-            p.partial_image, p.out_format = saved
             cam_tex = camera_texture_position(cam, self.desc)
+            if self.exact_ert and self.world > 1:
+                # every rank learns the alpha of every partial image, erases what a terminated ray hides and re-marches the
+                # pixels whose ray crosses the global 0.95 threshold inside its own shard
+                self.alpha.copy_(self.color[:, 3])
+                dist.all_gather_into_tensor(self.alphas, self.alpha)
+                self.ctx.ert_plan(self.alphas.data_ptr(), self.world, front_mask(self.rank, self.world, self.dims, cam_tex),
+                                  self.color.data_ptr(), self.depth.data_ptr(), self.npix, self.prefix.data_ptr(), self.flags.data_ptr())
+                self.ctx.remarch_device(p, cam, self.W, self.H, self.prefix.data_ptr(), self.flags.data_ptr(), [self.color.data_ptr(), 0, 0], self.depth.data_ptr())
+                self.last_remarch_ms = self.ctx.stats().last_march_ms
+                march_ms += self.last_remarch_ms
+            p.partial_image, p.out_format = saved
             lo, hi = binary_swap(self.color, self.depth, self.rank, self.world,
                                  lambda r: my_group_in_front(self.rank, r, self.world, self.dims, cam_tex), self._blend)
             # finalise my 1/P of the image (alpha snap + RGBA16) and hand it to rank 0
@@ -191,14 +234,14 @@ class SortLast:
                 ops = []
                 for r in range(1, self.world):
                     a, b = self.ranges[r]
-                    ops.append(dist.P2POp(dist.irecv, flat16[a:b], r))
+                    ops.append(dist.P2POp(dist.irecv, flat16[a:b].view(torch.uint8), r))       # NCCL has no int16: ship bytes
                     ops.append(dist.P2POp(dist.irecv, flatd[a:b], r))
                 for w in dist.batch_isend_irecv(ops):
                     w.wait()
             else:
                 part16 = torch.empty((n, 4), dtype=torch.int16, device=self.device)
                 self.ctx.finalize(self.color[lo:hi].data_ptr(), self.depth[lo:hi].data_ptr(), n, abi.OUT_RGBA16, part16.data_ptr())
-                ops = [dist.P2POp(dist.isend, part16, 0), dist.P2POp(dist.isend, self.depth[lo:hi], 0)]
+                ops = [dist.P2POp(dist.isend, part16.view(torch.uint8), 0), dist.P2POp(dist.isend, self.depth[lo:hi], 0)]
                 for w in dist.batch_isend_irecv(ops):
                     w.wait()
         return march_ms
