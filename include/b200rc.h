@@ -228,6 +228,10 @@ int b200rc_download_volume(b200rc_ctx* ctx, int slot, void* host_dst, size_t byt
  * (V/modules/base/processors/proxygeometry/optimizedproxygeometry.cpp:894-987).  out_minmax holds, per cell
  * (x fastest) and channel, {min,max} in real-world units.  cells[] receives the grid size. */
 int b200rc_region_minmax(b200rc_ctx* ctx, int slot, int cell_size, int32_t cells[3], float* out_minmax, size_t out_floats);
+/* The empty-space-skipping grid itself, for tests: per 8^3 macro-cell (x fastest) and channel {min,max} of the NORMALISED
+ * texture values over the cell's tap region [8c-1, 8c+9] (clamped to the resident range).  cells[] receives the grid size;
+ * out_minmax may be NULL to query it.  build_ms (may be NULL) returns the device time of the last build. */
+int b200rc_download_minmax(b200rc_ctx* ctx, int slot, int32_t cells[3], float* out_minmax, size_t out_floats, double* build_ms);
 
 /* ---- transfer functions: replaces TransFuncBase::getTexture()->bind + TransFunc1D::setUniform
  *      (V/src/core/datastructures/transfunc/1d/transfunc1d.cpp:184-194) and ClassificationModes::bindTexture

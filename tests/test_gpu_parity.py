@@ -291,3 +291,103 @@ def test_nucleon_workspace_against_committed_fixture(ctx):
     assert frac >= 0.999
     assert float((np.abs(depth - z["depth"]) <= 1e-4).mean()) >= 0.999
     assert orc.image_diff_count(q, np.clip(np.nan_to_num(outs[0]), 0, 1)) <= 50             # the reference's own comparator
+
+
+# ---- MultiVolumeRaycaster: world-space rays, per-volume entry/exit, per-volume TF / classification / shading ------
+def _multi_scene(nvol, cls="tf", n=32, W=80, H=80, comp="dvr"):
+    """nvol co-registered-but-shifted volumes; entry/exit images = [global, vol1..volN] in WORLD coordinates, produced by
+    the oracle's MeshEntryExitPoints restatement over each volume's bounding box (MultiVolumeProxyGeometry semantics:
+    the global proxy is the union of the volume boxes, V/modules/base/processors/proxygeometry/multivolumeproxygeometry.cpp)."""
+    from voreen_b200 import raycaster as rc
+    vols, descs = [], []
+    for v in range(nvol):
+        vols.append(scenes.ct_like_volume(n, seed=100 + v))
+        p2w = np.eye(4, dtype=np.float32)
+        p2w[0, 3] = 0.15 * v; p2w[1, 3] = -0.1 * v            # shifted so that worldToTexture differs per volume
+        descs.append(rc.make_volume_desc((n, n, n), phys_to_world=p2w))
+    cam = orc.make_camera((1.0, 0.9, 3.3), W=W, H=H)
+    eep = rc.default_eep(world_coords=1)
+    planes = []
+    for v in range(nvol):
+        ov = orc.make_volume(vols[v], descs[v])
+        planes.append(orc.entry_exit(orc.bbox_boxes(ov, eep), orc.texture_to_world(descs[v]), eep, cam, W, H))
+    # global proxy: nearest entry / farthest exit over the volumes (union of the cubes rendered with GL_LESS / GL_GREATER)
+    ge = np.zeros((H, W, 4), np.float32); gx = np.zeros((H, W, 4), np.float32)
+    ged = np.ones((H, W), np.float32); gxd = np.zeros((H, W), np.float32)
+    for (e, ed, x, xd) in planes:
+        cov = e[..., 3] > 0
+        near = cov & ((ged >= 1.0) | (ed < ged)) & ((ge[..., 3] == 0) | (ed < ged))
+        ge[near] = e[near]; ged[near] = ed[near]
+        far = cov & ((gx[..., 3] == 0) | (xd > gxd))
+        gx[far] = x[far]; gxd[far] = xd[far]
+    gxd[gx[..., 3] == 0] = 1.0
+    entry = np.stack([ge] + [p[0] for p in planes]); exitp = np.stack([gx] + [p[2] for p in planes])
+    # world-space step (multivolumeraycaster.cpp:326-344): min over volumes of max(cubeSizeWorld / dim) / samplingRate
+    step_world = float(min(max(2.0 * 1.0 / n for _ in range(3)) for _ in range(nvol)) / 2.0)
+    step_tex = float(np.float32(1.0) / (np.float32(n) * np.float32(2.0)))
+    params = rc.default_params(step_world, compositing=[abi.COMP[comp]] * 3)
+    params.num_volumes = nvol; params.multi_volume = 1
+    params.mv_opacity_correction_factor = step_tex / step_world        # :352-357
+    params.collect_stats = 1
+    keys = [scenes.CT_KEYS, [(0.0, (0, 0, 0, 0)), (0.3, (0, 255, 0, 0)), (1.0, (0, 255, 0, 120))],
+            [(0.0, (0, 0, 0, 0)), (0.4, (0, 0, 255, 0)), (1.0, (0, 0, 255, 90))], [(0.0, (0, 0, 0, 0)), (0.5, (255, 0, 255, 0)), (1.0, (255, 0, 255, 60))]]
+    tfs = [orc.make_tf(keys[v], domain=(0.0, 65535.0)) for v in range(nvol)]
+    tex = [orc.tf1d_texture(t, 4096) for t in tfs]
+    pre = None
+    if cls == "preint":
+        pre = [orc.preint_cpu(t, 1024, step_tex) for t in tfs]      # per-volume tables use the voxel step (:221-223,366-378)
+        for v in range(nvol):
+            params.vol[v].classification = abi.CLASS_PREINT
+    return vols, descs, cam, params, entry, ged, exitp, gxd, tex, pre
+
+
+@pytest.mark.parametrize("nvol,cls,comp", [(2, "tf", "dvr"), (4, "tf", "dvr"), (2, "preint", "dvr"), (3, "tf", "mip")])
+def test_multivolume(ctx, nvol, cls, comp):
+    vols, descs, cam, params, entry, ged, exitp, gxd, tex, pre = _multi_scene(nvol, cls, comp=comp)
+    H, W = ged.shape
+    ovs = [orc.make_volume(vols[v], descs[v]) for v in range(nvol)]
+    ocls = [orc.make_classifier(tex[v], (0.0, 65535.0), preint=pre[v] if pre else None) for v in range(nvol)]
+    o_outs, o_depth, o_st = orc.raycast(ovs, ocls, params, cam, W, H, entry, ged, exitp, gxd)
+    for v in range(nvol):
+        ctx.upload_volume(v, vols[v], desc=descs[v])
+        ctx.set_tf1d(v, tex[v], (0.0, 65535.0))
+        if pre:
+            ctx.set_preint(v, pre[v])
+    c_outs, c_depth = ctx.render(params, cam, W, H, entry, ged, exitp, gxd)
+    st = ctx.stats()
+    frac, mx = scenes.parity_report(o_outs[0], c_outs[0])
+    print(f"multivolume x{nvol} {cls} {comp}: within-1/255 {frac:.5f} max|d| {mx:.2e} rays {st.rays_cast}/{o_st.rays_cast} "
+          f"classified {st.samples_classified}/{o_st.samples_classified} shaded {st.samples_shaded}/{o_st.samples_shaded}")
+    assert o_st.rays_cast > 1000 and o_st.samples_shaded > 0
+    assert st.rays_cast == o_st.rays_cast
+    assert frac >= 0.999, (frac, mx)
+    assert float((np.abs(o_depth - c_depth) <= 1e-4).mean()) >= 0.999
+    for v in range(1, nvol):
+        ctx.lib.b200rc_release_volume(ctx.h, v)
+
+
+# ---- empty-space-skipping grid: the streaming min/max build against numpy, and against the per-cell kernel it replaced ----
+def _minmax_numpy(vol):
+    dz, dy, dx = vol.shape
+    n = [(d + 7) // 8 for d in (dx, dy, dz)]
+    out = np.empty((n[2], n[1], n[0], 1, 2), np.float32)
+    for cz in range(n[2]):
+        for cy in range(n[1]):
+            for cx in range(n[0]):
+                sub = vol[max(cz * 8 - 1, 0):min(cz * 8 + 9, dz - 1) + 1, max(cy * 8 - 1, 0):min(cy * 8 + 9, dy - 1) + 1,
+                          max(cx * 8 - 1, 0):min(cx * 8 + 9, dx - 1) + 1]
+                out[cz, cy, cx, 0] = (sub.min(), sub.max())
+    return out * np.float32(1.0 / 65535.0)
+
+
+@pytest.mark.parametrize("dims", [(40, 33, 27), (64, 64, 64), (8, 8, 8), (17, 9, 70)])
+def test_minmax_grid_streaming_build(ctx, dims):
+    rng = np.random.default_rng(7)
+    vol = rng.integers(0, 65536, size=dims[::-1], dtype=np.uint16)
+    vol[::3, ::2, ::5] = 0; vol[1::7, 1::3, 7::8] = 65535          # extremes on brick faces
+    ctx.upload_volume(0, vol)
+    got, ms = ctx.download_minmax(0)
+    want = _minmax_numpy(vol)
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)
+    assert ms > 0.0

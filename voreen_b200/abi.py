@@ -89,7 +89,7 @@ LIB_PATH = os.path.join(_HERE, "libb200rc.so")
 SYMBOLS = [
     "b200rc_abi_version", "b200rc_device_count", "b200rc_create", "b200rc_destroy", "b200rc_last_error",
     "b200rc_set_stream", "b200rc_synchronize", "b200rc_get_stats", "b200rc_upload_volume", "b200rc_release_volume",
-    "b200rc_synth_volume", "b200rc_download_volume", "b200rc_region_minmax", "b200rc_set_tf1d", "b200rc_set_preint",
+    "b200rc_synth_volume", "b200rc_download_volume", "b200rc_region_minmax", "b200rc_download_minmax", "b200rc_set_tf1d", "b200rc_set_preint",
     "b200rc_build_preint", "b200rc_download_preint", "b200rc_set_tf2d", "b200rc_entry_exit", "b200rc_render",
     "b200rc_render_camera", "b200rc_render_camera_device", "b200rc_composite", "b200rc_finalize", "b200rc_ert_plan",
     "b200rc_remarch_device",
@@ -123,6 +123,7 @@ def load_library():
     lib.b200rc_synth_volume.argtypes = [vp, i32, C.POINTER(VolumeDesc), u64]
     lib.b200rc_download_volume.argtypes = [vp, i32, vp, sz]
     lib.b200rc_region_minmax.argtypes = [vp, i32, i32, C.POINTER(C.c_int32 * 3), pf, sz]
+    lib.b200rc_download_minmax.argtypes = [vp, i32, C.POINTER(C.c_int32 * 3), pf, sz, C.POINTER(C.c_double)]
     lib.b200rc_set_tf1d.argtypes = [vp, i32, vp, i32, f32, f32]
     lib.b200rc_set_preint.argtypes = [vp, i32, pf, i32]
     lib.b200rc_build_preint.argtypes = [vp, i32, i32, f32, i32]

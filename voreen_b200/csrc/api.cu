@@ -150,6 +150,19 @@ extern "C" int b200rc_download_volume(b200rc_ctx* ctx, int slot, void* host_dst,
 extern "C" int b200rc_region_minmax(b200rc_ctx* ctx, int slot, int cell_size, int32_t cells[3], float* out_minmax, size_t out_floats) {
     CTX_GUARD(); if (slot < 0 || slot >= B200RC_MAX_VOLUMES || !cells) return B200RC_ERR_INVALID; return rc_volume_region_minmax(ctx, slot, cell_size, cells, out_minmax, out_floats);
 }
+extern "C" int b200rc_download_minmax(b200rc_ctx* ctx, int slot, int32_t cells[3], float* out, size_t out_floats, double* build_ms) {
+    CTX_GUARD();
+    if (slot < 0 || slot >= B200RC_MAX_VOLUMES || !cells || !ctx->vol[slot].valid) { ctx->set_error("download_minmax: no such volume"); return B200RC_ERR_INVALID; }
+    const VolumeSlot& v = ctx->vol[slot];
+    for (int a = 0; a < 3; ++a) cells[a] = v.cells[a];
+    if (build_ms) *build_ms = v.minmax_build_ms;
+    if (!out) return B200RC_OK;
+    const size_t need = (size_t)v.cells[0] * v.cells[1] * v.cells[2] * v.desc.channels * 2;
+    if (out_floats < need) { ctx->set_error("download_minmax: output buffer too small"); return B200RC_ERR_INVALID; }
+    RC_CHECK(cudaMemcpyAsync(out, v.minmax, need * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    RC_CHECK(cudaStreamSynchronize(ctx->stream));
+    return B200RC_OK;
+}
 extern "C" int b200rc_set_tf1d(b200rc_ctx* ctx, int chan, const uint8_t* rgba8, int width, float lo, float hi) { CTX_GUARD(); return rc_tf_set_1d(ctx, chan, rgba8, width, lo, hi); }
 extern "C" int b200rc_set_preint(b200rc_ctx* ctx, int chan, const float* rgba32f, int res) { CTX_GUARD(); return rc_tf_set_preint(ctx, chan, rgba32f, res); }
 extern "C" int b200rc_build_preint(b200rc_ctx* ctx, int chan, int res, float step, int mode) { CTX_GUARD(); return rc_tf_build_preint(ctx, chan, res, step, mode); }

@@ -10,6 +10,7 @@
 // trilinear fetch touch two lines and a warp marching an 8x4 pixel tile touches a handful of lines per tap.
 #include "ctx.hpp"
 #include <cstring>
+#include <cstdlib>
 #include <cstdio>
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -163,6 +164,91 @@ __global__ void minmax_kernel(const T* __restrict__ bricks, float2* __restrict__
         // same normalisation as the sampler: raw * (1/65535) -- monotone, so min/max commute with it
         if (lane == 0) out[warp * nch + c] = make_float2(__fmul_rn(mn[c], norm), __fmul_rn(mx[c], norm));
     }
+}
+
+// ---- streaming fast path: 1-channel u16 -------------------------------------------------------------------------------
+// The cell region [c*8-1, c*8+9] per axis is brick c plus the LAST voxel plane of brick c-1 and the FIRST TWO planes of
+// brick c+1, so min/max over it is separable into 27 per-brick partial results, one per neighbour offset d in {-1,0,+1}^3:
+// per axis d=-1 reads the neighbour's sub-range H = {7}, d=0 reads A = {0..7}, d=+1 reads L = {0,1}.
+//   pass A (HBM-bound, reads every voxel exactly once, fully coalesced-by-line): one thread per 128-byte brick line (one
+//          xy-slab), 8 x LDG.128, packed 2xu16 SIMD min/max (__vminu2 / __vmaxu2) for the 9 (y,x) sub-ranges in registers,
+//          then the 3 z sub-ranges over the 8 lanes of the brick with shuffles; a partial result is the 32-bit word
+//          (min | (65535 - max) << 16) so that ONE __vminu2 folds both.  Output SoA: part[k][brick], k = (dz+1)*9+(dy+1)*3+(dx+1).
+//   pass B: one thread per cell folds its 27 neighbours' words (coalesced: consecutive cells read consecutive words).
+// Algorithmic bytes: 2 B read per voxel (+ 216 B per 1 KiB brick of partials written and read back, + 8 B per cell out).
+__device__ __forceinline__ unsigned mm_pack(unsigned mn2, unsigned mx2) {        // horizontal fold of packed pairs -> (min | ~max << 16)
+    const unsigned mn = min(mn2 & 0xffffu, mn2 >> 16), mx = max(mx2 & 0xffffu, mx2 >> 16);
+    return mn | ((65535u - mx) << 16);
+}
+
+__global__ void __launch_bounds__(256) brick_partials_u16_kernel(const uint4* __restrict__ bricks, unsigned* __restrict__ part, long long nbricks) {
+    const long long slab = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // 8 slabs per brick, lane & 7 = z inside the brick
+    const bool live = slab < nbricks * 8;
+    const uint4* src = bricks + (live ? slab : 0) * 8;
+    uint4 r[8];
+#pragma unroll
+    for (int y = 0; y < 8; ++y) r[y] = __ldg(src + y);                               // 128 B in flight per thread
+    // x sub-ranges: A = all four words, L = word 0 (x0,x1), H = high half of word 3 (x7); y accumulates over rows
+    unsigned An = 0xffffffffu, Ax = 0u, Ln = 0xffffffffu, Lx = 0u, Hn = 0xffffffffu, Hx = 0u;
+    unsigned yl[6] = {0, 0, 0, 0, 0, 0};
+    unsigned rn = 0, rx = 0, r0 = 0, r3 = 0;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) {
+        rn = __vminu2(__vminu2(r[y].x, r[y].y), __vminu2(r[y].z, r[y].w));
+        rx = __vmaxu2(__vmaxu2(r[y].x, r[y].y), __vmaxu2(r[y].z, r[y].w));
+        r0 = r[y].x; r3 = r[y].w;
+        An = __vminu2(An, rn); Ax = __vmaxu2(Ax, rx);
+        Ln = __vminu2(Ln, r0); Lx = __vmaxu2(Lx, r0);
+        Hn = __vminu2(Hn, r3); Hx = __vmaxu2(Hx, r3);
+        if (y == 1) { yl[0] = An; yl[1] = Ax; yl[2] = Ln; yl[3] = Lx; yl[4] = Hn; yl[5] = Hx; }   // y sub-range L = rows {0,1}
+    }
+    const unsigned h3n = Hn >> 16 | (Hn & 0xffff0000u), h3x = Hx >> 16 | (Hx & 0xffff0000u);        // x7 only: duplicate the high half
+    // v[sy*3 + sx], s = 0: H (d = -1), 1: A (d = 0), 2: L (d = +1)
+    unsigned v[9];
+    {   // y = H: row 7 alone (rn/rx/r0/r3 still hold row 7)
+        const unsigned t3 = r3 >> 16 | (r3 & 0xffff0000u);
+        v[0] = mm_pack(t3, t3); v[1] = mm_pack(rn, rx); v[2] = mm_pack(r0, r0);
+    }
+    v[3] = mm_pack(h3n, h3x); v[4] = mm_pack(An, Ax); v[5] = mm_pack(Ln, Lx);
+    {
+        const unsigned t3n = yl[4] >> 16 | (yl[4] & 0xffff0000u), t3x = yl[5] >> 16 | (yl[5] & 0xffff0000u);
+        v[6] = mm_pack(t3n, t3x); v[7] = mm_pack(yl[0], yl[1]); v[8] = mm_pack(yl[2], yl[3]);
+    }
+    const unsigned lane = threadIdx.x & 31u, base = lane & ~7u, z = lane & 7u;
+    const long long brick = slab >> 3;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const unsigned zh = __shfl_sync(0xffffffffu, v[k], base + 7);                                 // z = H: plane 7
+        const unsigned zl = __vminu2(__shfl_sync(0xffffffffu, v[k], base), __shfl_sync(0xffffffffu, v[k], base + 1));   // z = L: planes {0,1}
+        unsigned za = v[k];
+        za = __vminu2(za, __shfl_xor_sync(0xffffffffu, za, 1));
+        za = __vminu2(za, __shfl_xor_sync(0xffffffffu, za, 2));
+        za = __vminu2(za, __shfl_xor_sync(0xffffffffu, za, 4));
+        // three of the brick's eight lanes store (one word each per k): 4 consecutive bricks of a warp -> one 16-byte segment
+        if (live && z < 3) part[(size_t)(z * 9 + k) * nbricks + brick] = (z == 0) ? zh : (z == 1 ? za : zl);
+    }
+}
+
+__global__ void cell_fold_u16_kernel(const unsigned* __restrict__ part, float2* __restrict__ out, int ncx, int ncy, int ncz, float norm) {
+    const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long ncell = (long long)ncx * ncy * ncz;
+    if (cell >= ncell) return;
+    const int cx = (int)(cell % ncx), cy = (int)((cell / ncx) % ncy), cz = (int)(cell / ((long long)ncx * ncy));
+    unsigned acc = 0xffffffffu;
+#pragma unroll
+    for (int dz = -1; dz <= 1; ++dz)
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int x = cx + dx, y = cy + dy, z = cz + dz;
+                if ((unsigned)x < (unsigned)ncx && (unsigned)y < (unsigned)ncy && (unsigned)z < (unsigned)ncz) {
+                    const int k = (dz + 1) * 9 + (dy + 1) * 3 + (dx + 1);
+                    acc = __vminu2(acc, __ldg(part + (size_t)k * ncell + ((long long)z * ncy + y) * ncx + x));
+                }
+            }
+    // same normalisation as the sampler: raw * (1/65535) -- monotone, so min/max commute with it
+    out[cell] = make_float2(__fmul_rn((float)(acc & 0xffffu), norm), __fmul_rn((float)(65535u - (acc >> 16)), norm));
 }
 
 // reference-style region structure with arbitrary cell size (for b200rc_region_minmax / proxy geometry):
@@ -320,7 +406,21 @@ static int volume_build_minmax(b200rc_ctx* ctx, int slot) {
     const int threads = 256;
     const long long blocks = (ncell * 32 + threads - 1) / threads;
     const int nch = v.desc.channels;
-    if (v.desc.dtype == B200RC_U16)
+    RC_CHECK(cudaEventRecord(ctx->ev[4], ctx->stream));
+    static const bool slow_minmax = getenv("B200RC_MINMAX_SLOW") != nullptr;        // A/B switch for tests and measurements
+    if (v.desc.dtype == B200RC_U16 && nch == 1 && !slow_minmax) {
+        // streaming two-pass build (see brick_partials_u16_kernel); the partials are temporary (27 words per brick)
+        unsigned* part = nullptr;
+        if (cudaMalloc(&part, sizeof(unsigned) * 27 * (size_t)ncell) != cudaSuccess) { cudaGetLastError(); ctx->set_error("out of device memory for min/max partials"); return B200RC_ERR_OOM; }
+        const long long slabs = ncell * 8;
+        brick_partials_u16_kernel<<<(unsigned)((slabs + 255) / 256), 256, 0, ctx->stream>>>((const uint4*)v.bricks, part, ncell);
+        cell_fold_u16_kernel<<<(unsigned)((ncell + 255) / 256), 256, 0, ctx->stream>>>(part, v.minmax, v.cells[0], v.cells[1], v.cells[2], 1.0f / 65535.0f);
+        ctx->launches++;
+        RC_CHECK(cudaGetLastError());
+        RC_CHECK(cudaEventRecord(ctx->ev[5], ctx->stream));
+        RC_CHECK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(part);
+    } else if (v.desc.dtype == B200RC_U16)
         minmax_kernel<unsigned short><<<(unsigned)blocks, threads, 0, ctx->stream>>>((const unsigned short*)v.bricks, v.minmax, v.res_dims[0], v.res_dims[1], v.res_dims[2],
                                                                                     v.nbx, v.nby, v.cells[0], v.cells[1], v.cells[2], nch, v.stored_nch, 1.0f / 65535.0f);
     else if (v.desc.dtype == B200RC_U8)
@@ -331,6 +431,9 @@ static int volume_build_minmax(b200rc_ctx* ctx, int slot) {
                                                                            v.nbx, v.nby, v.cells[0], v.cells[1], v.cells[2], nch, v.stored_nch, 1.0f);
     ctx->launches++;
     RC_CHECK(cudaGetLastError());
+    if (!(v.desc.dtype == B200RC_U16 && nch == 1 && !slow_minmax)) RC_CHECK(cudaEventRecord(ctx->ev[5], ctx->stream));
+    RC_CHECK(cudaEventSynchronize(ctx->ev[5]));
+    { float ms = 0.f; cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); v.minmax_build_ms = ms; }
     v.occ0_wpr = (v.cells[0] + 31) / 32;
     for (int a = 0; a < 3; ++a) v.occ1_dims[a] = (v.cells[a] + 7) / 8;
     v.occ1_wpr = (v.occ1_dims[0] + 31) / 32;

@@ -195,6 +195,14 @@ class Context:
         self._check(self.lib.b200rc_region_minmax(self.h, slot, cell_size, C.byref(cells), _fp(out), out.size), "region_minmax")
         return out
 
+    def download_minmax(self, slot):
+        """The 8^3 macro-cell min/max grid (normalised values) and the device time of its build in ms."""
+        cells = (C.c_int32 * 3)(); ms = C.c_double(0.0)
+        self._check(self.lib.b200rc_download_minmax(self.h, slot, C.byref(cells), None, 0, C.byref(ms)), "download_minmax")
+        out = np.empty((cells[2], cells[1], cells[0], self.volume_desc[slot].channels, 2), np.float32)
+        self._check(self.lib.b200rc_download_minmax(self.h, slot, C.byref(cells), _fp(out), out.size, None), "download_minmax")
+        return out, float(ms.value)
+
     # -- transfer functions ----------------------------------------------------------------------------------------
     def set_tf1d(self, chan, rgba8, domain):
         rgba8 = np.ascontiguousarray(rgba8, np.uint8).reshape(-1, 4)
