@@ -238,6 +238,10 @@ def run_b200(args, rank, world, local_rank):
     import voreen_b200 as vb
     from voreen_b200 import abi, host
 
+    # NCCL and friends print to stdout ("NCCL version ..."): keep fd 1 for the one JSON line, send everything else to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -252,15 +256,27 @@ def run_b200(args, rank, world, local_rank):
     use_pi = args.classification == "preint"
     sampler = abi.SAMPLER_TEX if args.sampler == "tex" else abi.SAMPLER_EXACT
 
-    sl = None
+    # N > 1: "sort-last" shards the volume (what a volume larger than one GPU's HBM needs); "sort-first" replicates it and
+    # partitions the image (what a volume that fits should do: no occlusion is lost between ranks, no compositing).
+    # "auto" = sort-first when the whole volume + grids fit in 60 % of this GPU's memory, else sort-last.
+    sl = sf = None
+    mode = "single GPU"
     if world > 1:
         from voreen_b200 import sortlast
-        sl = sortlast.SortLast(ctx, dims, rank, world, W, H, device=dev, stream=stream)
-        desc = sl.shard_desc()
+        mode = args.parallelism
+        if mode == "auto":
+            need = int(np.prod(dims)) * 2 * 1.25
+            mode = "sort-first" if need < 0.6 * torch.cuda.get_device_properties(dev).total_memory else "sort-last"
+        if mode == "sort-last":
+            sl = sortlast.SortLast(ctx, dims, rank, world, W, H, device=dev, stream=stream)
+            desc = sl.shard_desc()
+        else:
+            sf = sortlast.SortFirst(ctx, rank, world, W, H, device=dev, stream=stream)
+            desc = vb.make_volume_desc(dims)
     else:
         desc = vb.make_volume_desc(dims)
     t0 = time.perf_counter()
-    ctx.synth_volume(0, vb.make_volume_desc(dims) if (world > 1 and rank == 0) else desc, args.seed)
+    ctx.synth_volume(0, vb.make_volume_desc(dims) if (sl is not None and rank == 0) else desc, args.seed)
     ctx.synchronize()
     t_synth = time.perf_counter() - t0
     # the empty-space-skipping min/max build (brick_partials_u16_kernel + cell_fold_u16_kernel): HBM streaming, one read of
@@ -285,6 +301,8 @@ def run_b200(args, rank, world, local_rank):
     def frame(k):
         if sl is not None:
             return sl.render(params, eep, cams[k % N_VIEWS], out_rgba, out_depth)
+        if sf is not None:
+            return sf.render(params, eep, cams[k % N_VIEWS], out_rgba, out_depth)
         ctx.render_camera_ptrs(params, eep, cams[k % N_VIEWS], W, H, [out_rgba.data_ptr(), 0, 0], out_depth.data_ptr(), device=True)
         return ctx.stats().last_march_ms
 
@@ -316,8 +334,9 @@ def run_b200(args, rank, world, local_rank):
         t = torch.tensor([ref_samples, classified, nominal], dtype=torch.float64, device=dev)
         dist.broadcast(t, 0)
         ref_samples, classified, nominal = (t[i].tolist() for i in range(3))
-        ctx.synth_volume(0, desc, args.seed)            # now the shard
-        ctx.synchronize()
+        if sl is not None:
+            ctx.synth_volume(0, desc, args.seed)        # now the shard
+            ctx.synchronize()
         _, _, cells16, _ = stats_pass(frame)             # this rank's touched macro-cells (roofline of its own kernel)
     else:
         ref_samples, classified, cells16, nominal = stats_pass(frame)
@@ -357,7 +376,7 @@ def run_b200(args, rank, world, local_rank):
                 "kernel_share_of_step": sum(march_ms) / ms_total,
                 "alg_bytes_per_launch_avg": sum(alg_bytes) / len(alg_bytes), "frac_min": min(ach) / peak, "frac_max": max(ach) / peak,
                 "whole_volume_bytes": int(np.prod(dims)) * 2 + img_bytes,
-                "whole_volume_frac": (int(np.prod(dims)) * 2 / world + img_bytes) / (sum(march_ms) / len(march_ms) * 1e-3) / 1e9 / peak}
+                "whole_volume_frac": (int(np.prod(dims)) * 2 / (world if sl is not None else 1) + img_bytes) / (sum(march_ms) / len(march_ms) * 1e-3) / 1e9 / peak}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
@@ -418,7 +437,7 @@ def run_b200(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": workload_name(args), "sampler": args.sampler, "parallelism": f"sort-last x{world}" if world > 1 else "single GPU",
+            "config": {"workload": workload_name(args), "sampler": args.sampler, "parallelism": f"{mode} x{world}" if world > 1 else "single GPU",
                        "l2": f"volume {int(np.prod(dims)) * 2 / 2**30:.1f} GiB >> 126 MB L2, a different view every step"},
             "ms_per_frame": ms_total / args.steps,
             "gsamples_classified_per_s": sum(classified[v] for v in steps_views) / (ms_total * 1e-3) / 1e9,
@@ -429,7 +448,7 @@ def run_b200(args, rank, world, local_rank):
                              "achieved": mm_bytes / (mm_ms * 1e-3) / 1e9 if mm_ms > 0 else None, "peak": peak, "unit": "GB/s",
                              "frac": (mm_bytes / (mm_ms * 1e-3) / 1e9 / peak) if mm_ms > 0 else None, "bound": "hbm"},
         }
-        print(json.dumps(line), flush=True)
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -448,6 +467,7 @@ def main():
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--classification", default="preint", choices=["preint", "tf"])
     ap.add_argument("--sampler", default="exact", choices=["exact", "tex"])
+    ap.add_argument("--parallelism", default="auto", choices=["auto", "sort-first", "sort-last"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define B200RC_ABI_VERSION 1
+#define B200RC_ABI_VERSION 2
 #define B200RC_MAX_VOLUMES 4   /* MultiVolumeRaycaster: volume1..4 (multivolumeraycaster.cpp:41-65) */
 #define B200RC_MAX_CHANNELS 4  /* SingleVolumeRaycaster: NUM_CHANNELS 1..4 (singlevolumeraycaster.cpp:440-445) */
 #define B200RC_MAX_OUTPUTS 3   /* image.output, image.output1, image.output2 (volumeraycaster.cpp:44-49) */
@@ -169,6 +169,11 @@ typedef struct b200rc_params {
     int32_t collect_stats;      /* 1: count classified samples / cast rays (slower) */
     int32_t partial_image;      /* 1: sort-last partial image of a sharded volume: early ray termination on the local alpha
                                    without the snap to 1.0 (b200rc_finalize snaps after the merge); use B200RC_OUT_RGBA32F */
+    /* Sort-first (image-space) partition for volumes replicated on several GPUs: only pixel rows whose 16-row band index
+     * (row / 16) satisfies band % image_band_modulus == image_band_remainder are rendered; all other pixels of the outputs
+     * are left untouched.  modulus 0 or 1 = the whole image. */
+    int32_t image_band_modulus;
+    int32_t image_band_remainder;
 } b200rc_params;
 
 /* MeshEntryExitPoints + proxy geometry settings for b200rc_render_camera / b200rc_entry_exit. */

@@ -25,7 +25,7 @@ def test_libb200rc_exports_every_declared_symbol():
     assert set(declared) == set(abi.SYMBOLS), set(declared) ^ set(abi.SYMBOLS)
     for s in declared:
         assert hasattr(lib, s), s
-    assert lib.b200rc_abi_version() == 1
+    assert lib.b200rc_abi_version() == 2
 
 
 def test_libb200rc_host_exports_every_declared_symbol():
@@ -44,7 +44,7 @@ def test_ctypes_layouts_match_the_header():
 int main(void) {
     printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(b200rc_volume_desc), sizeof(b200rc_light), sizeof(b200rc_camera), sizeof(b200rc_volume_params),
            sizeof(b200rc_params), sizeof(b200rc_eep_params), sizeof(b200rc_stats), sizeof(b200host_tf_key));
-    printf("%zu %zu %zu %zu\n", offsetof(b200rc_params, light), offsetof(b200rc_params, sampler), offsetof(b200rc_params, partial_image), offsetof(b200rc_eep_params, boxes));
+    printf("%zu %zu %zu %zu\n", offsetof(b200rc_params, light), offsetof(b200rc_params, sampler), offsetof(b200rc_params, image_band_remainder), offsetof(b200rc_eep_params, boxes));
     return 0;
 }'''
     with tempfile.TemporaryDirectory() as d:
@@ -55,7 +55,7 @@ int main(void) {
     assert sizes == [C.sizeof(abi.VolumeDesc), C.sizeof(abi.Light), C.sizeof(abi.Camera), C.sizeof(abi.VolumeParams), C.sizeof(abi.Params),
                      C.sizeof(abi.EepParams), C.sizeof(abi.Stats), C.sizeof(host.TFKey)]
     offs = [int(v) for v in out[1].split()]
-    assert offs == [abi.Params.light.offset, abi.Params.sampler.offset, abi.Params.partial_image.offset, abi.EepParams.boxes.offset]
+    assert offs == [abi.Params.light.offset, abi.Params.sampler.offset, abi.Params.image_band_remainder.offset, abi.EepParams.boxes.offset]
 
 
 def test_no_cpu_fallback():

@@ -391,3 +391,25 @@ def test_minmax_grid_streaming_build(ctx, dims):
     assert got.shape == want.shape
     assert np.array_equal(got, want)
     assert ms > 0.0
+
+
+# ---- sort-first: the image-band partition reassembles to exactly the unpartitioned image (slab marcher and per-ray kernel) ----
+@pytest.mark.parametrize("world", [2, 8])
+@pytest.mark.parametrize("grad", ["central-differences", "sobel"])      # central -> slab marcher, sobel -> per-ray kernel
+def test_image_band_partition(ctx, world, grad):
+    from voreen_b200 import sortlast
+    vol = scenes.ct_like_volume(48)
+    H = 16 * world * 2
+    s = scenes.Scene(vol, W=96, H=H, gradient=abi.GRAD[grad], out_format=abi.OUT_RGBA16)
+    full, full_d = s.cuda_render(ctx)
+    merged = np.zeros_like(full[0]); merged_d = np.zeros_like(full_d)
+    seen = np.zeros(H, np.int32)
+    for r in range(world):
+        s.params.image_band_modulus, s.params.image_band_remainder = world, r
+        part, part_d = s.cuda_render(ctx, upload=False)
+        rows = sortlast.band_owner_rows(H, r, world)
+        merged[rows] = part[0][rows]; merged_d[rows] = part_d[rows]
+        seen[rows] += 1
+    assert (seen == 1).all()
+    assert np.array_equal(merged, full[0]) and np.array_equal(merged_d, full_d)
+    assert int((full[0][..., 3] > 0).sum()) > 0.05 * H * 96

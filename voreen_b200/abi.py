@@ -60,7 +60,8 @@ class Params(C.Structure):
                 ("enable_channel_shift", C.c_int32), ("channel_shift", (C.c_float * 3) * MAX_CHANNELS),
                 ("light", Light),
                 ("sampler", C.c_int32), ("empty_space_skipping", C.c_int32), ("out_format", C.c_int32),
-                ("quantize_depth24", C.c_int32), ("collect_stats", C.c_int32), ("partial_image", C.c_int32)]
+                ("quantize_depth24", C.c_int32), ("collect_stats", C.c_int32), ("partial_image", C.c_int32),
+                ("image_band_modulus", C.c_int32), ("image_band_remainder", C.c_int32)]
 
 
 class EepParams(C.Structure):

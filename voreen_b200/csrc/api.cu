@@ -224,6 +224,9 @@ static int build_params(b200rc_ctx* ctx, const b200rc_params* P, const b200rc_ca
     p.near_d = cam->near_dist; p.far_d = cam->far_dist;
     p.out_format = P->out_format; p.quantize_depth24 = P->quantize_depth24;
     p.collect_stats = P->collect_stats;
+    p.band_mod = P->image_band_modulus > 1 ? P->image_band_modulus : 1;
+    p.band_rem = P->image_band_modulus > 1 ? P->image_band_remainder : 0;
+    if (p.band_rem < 0 || p.band_rem >= p.band_mod) { ctx->set_error("image_band_remainder out of range"); return B200RC_ERR_INVALID; }
     p.ert_snap = P->partial_image ? 0 : 1;      // sort-last partial images keep the un-snapped alpha; b200rc_finalize snaps after the merge
     bool ert = true;
     for (int o = 0; o < 3; ++o) {
@@ -334,7 +337,11 @@ __global__ void count_touched_kernel(const unsigned char* __restrict__ f, size_t
 
 int rc_march_launch(b200rc_ctx* ctx, const DevParams& p, int sampler, int nch, int dtype) {
     int rc = B200RC_OK;
-    if (ctx->use_slab && rc_march_slab(ctx, p, sampler, nch, dtype, &rc)) return rc;
+    // sort-last second pass (p.flags): ~2 % of the pixels along a band.  Measured at 2048^3 x2 (profiles/r1_pass9_*): slab
+    // marcher 2.4 ms, per-ray kernel 3.4 ms -> the slab marcher stays; B200RC_REMARCH=ray selects the per-ray kernel (A/B)
+    static const bool remarch_ray = getenv("B200RC_REMARCH") && !strcmp(getenv("B200RC_REMARCH"), "ray");
+    const bool slab_ok = ctx->use_slab && !(p.flags && remarch_ray);
+    if (slab_ok && rc_march_slab(ctx, p, sampler, nch, dtype, &rc)) return rc;
     if (rc_march_fast(ctx, p, sampler, nch, dtype, &rc)) return rc;
     return rc_march_generic(ctx, p, sampler, nch);
 }

@@ -199,6 +199,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
         if (tile >= ntiles) break;
         const unsigned sup = tile >> 6, loc = tile & 63u;
         const unsigned tx = (sup % super_x) * 8u + compact1by1(loc), ty = (sup / super_x) * 8u + compact1by1(loc >> 1);
+        if (p.band_mod > 1 && (int)((ty * SLAB_TILE_H / 16u) % (unsigned)p.band_mod) != p.band_rem) { __syncthreads(); continue; }   // another rank's band (uniform)
         // warp w covers the 8x4 sub-tile (w & 1, w >> 1) of the 16x16 tile
         const int px = (int)(tx * SLAB_TILE + (warp & 1u) * 8u + (lane & 7u)), py = (int)(ty * SLAB_TILE_H + (warp >> 1) * 4u + (lane >> 3));
         const bool inside = px < p.W && py < p.H;

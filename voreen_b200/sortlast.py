@@ -192,6 +192,8 @@ class SortLast:
         self.prefix = torch.empty((self.npix,), dtype=torch.float32, device=device)
         self.flags = torch.empty((self.npix,), dtype=torch.uint8, device=device)
         self.last_remarch_ms = 0.0
+        self.profile = False        # True: per-phase CUDA-event timings + flagged-pixel count of the last frame in self.phases
+        self.phases = {}
 
     def shard_desc(self):
         return self.desc
@@ -207,20 +209,34 @@ class SortLast:
         p = params
         saved = (p.partial_image, p.out_format)
         p.partial_image, p.out_format = 1, abi.OUT_RGBA32F
+        prof = self.profile
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if prof else None
         with torch.cuda.stream(self.stream):
+            if prof:
+                ev[0].record(self.stream)
             self.ctx.render_camera_ptrs(p, eep, cam, self.W, self.H, [self.color.data_ptr(), 0, 0], self.depth.data_ptr(), device=True)
             march_ms = self.ctx.stats().last_march_ms
+            if prof:
+                self.phases = {"first_pass_ms": march_ms}
+                ev[1].record(self.stream)
             cam_tex = camera_texture_position(cam, self.desc)
             if self.exact_ert and self.world > 1:
                 # every rank learns the alpha of every partial image, erases what a terminated ray hides and re-marches the
                 # pixels whose ray crosses the global 0.95 threshold inside its own shard
                 self.alpha.copy_(self.color[:, 3])
                 dist.all_gather_into_tensor(self.alphas, self.alpha)
-                self.ctx.ert_plan(self.alphas.data_ptr(), self.world, front_mask(self.rank, self.world, self.dims, cam_tex),
-                                  self.color.data_ptr(), self.depth.data_ptr(), self.npix, self.prefix.data_ptr(), self.flags.data_ptr())
+                n_flag = self.ctx.ert_plan(self.alphas.data_ptr(), self.world, front_mask(self.rank, self.world, self.dims, cam_tex),
+                                           self.color.data_ptr(), self.depth.data_ptr(), self.npix, self.prefix.data_ptr(), self.flags.data_ptr(), count=prof)
+                if prof:
+                    self.phases["flagged_pixels"] = n_flag
+                    ev[2].record(self.stream)
                 self.ctx.remarch_device(p, cam, self.W, self.H, self.prefix.data_ptr(), self.flags.data_ptr(), [self.color.data_ptr(), 0, 0], self.depth.data_ptr())
                 self.last_remarch_ms = self.ctx.stats().last_march_ms
                 march_ms += self.last_remarch_ms
+                if prof:
+                    self.phases["remarch_ms"] = self.last_remarch_ms
+            if prof:
+                ev[3].record(self.stream)
             p.partial_image, p.out_format = saved
             lo, hi = binary_swap(self.color, self.depth, self.rank, self.world,
                                  lambda r: my_group_in_front(self.rank, r, self.world, self.dims, cam_tex), self._blend)
@@ -244,4 +260,70 @@ class SortLast:
                 ops = [dist.P2POp(dist.isend, part16.view(torch.uint8), 0), dist.P2POp(dist.isend, self.depth[lo:hi], 0)]
                 for w in dist.batch_isend_irecv(ops):
                     w.wait()
+            if prof:
+                ev[4].record(self.stream)
+                torch.cuda.synchronize(self.device)
+                self.phases["render_ms"] = ev[0].elapsed_time(ev[1])
+                if self.exact_ert and self.world > 1:
+                    self.phases["allgather_plan_ms"] = ev[1].elapsed_time(ev[2])
+                    self.phases["remarch_total_ms"] = ev[2].elapsed_time(ev[3])
+                self.phases["swap_gather_ms"] = ev[3].elapsed_time(ev[4])
+                self.phases["frame_ms"] = ev[0].elapsed_time(ev[4])
+        return march_ms
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# sort-first: the volume is REPLICATED (it fits in one GPU's 180 GB), the image is partitioned
+# ---------------------------------------------------------------------------------------------------------------------
+BAND_ROWS = 16      # b200rc_params.image_band_modulus works on 16-pixel-row bands
+
+
+def band_owner_rows(H, rank, world):
+    """Pixel rows rank `rank` renders: bands b = row // 16 with b % world == rank."""
+    rows = np.arange(H)
+    return rows[(rows // BAND_ROWS) % world == rank]
+
+
+class SortFirst:
+    """One rank of the image-space partition: every rank holds the whole volume and renders the 16-row bands
+    b % world == rank (interleaved, so the load is balanced whatever the camera sees); rank 0 gathers the bands.
+    No partial images, no over-compositing, no occlusion lost between ranks: the pixels are exactly the single-GPU ones."""
+
+    def __init__(self, ctx, rank, world, W, H, device, stream):
+        import torch
+        self.torch = torch
+        self.ctx, self.rank, self.world, self.W, self.H = ctx, rank, world, W, H
+        self.device, self.stream = device, stream
+        if H % (BAND_ROWS * world):
+            raise ValueError(f"image height {H} must be a multiple of {BAND_ROWS} x {world}")
+        self.groups = H // (BAND_ROWS * world)
+        self.full16 = torch.empty((H, W, 4), dtype=torch.int16, device=device)
+        self.fulld = torch.empty((H, W), dtype=torch.float32, device=device)
+        # my bands packed: colour (8 B/pixel) followed by depth (4 B/pixel), as bytes (NCCL has no int16)
+        self.npix_mine = self.groups * BAND_ROWS * W
+        self.pack = torch.empty((self.npix_mine * 12,), dtype=torch.uint8, device=device)
+        self.gathered = torch.empty((world, self.npix_mine * 12), dtype=torch.uint8, device=device) if rank == 0 else None
+
+    def render(self, params, eep, cam, out_rgba16, out_depth):
+        """Rank 0 receives the complete RGBA16 image + depth in out_rgba16 (H, W, 4) int16 / out_depth (H, W) float32."""
+        torch = self.torch
+        import torch.distributed as dist
+        p = params
+        saved = (p.image_band_modulus, p.image_band_remainder)
+        p.image_band_modulus, p.image_band_remainder = self.world, self.rank
+        G, B, W, N = self.groups, BAND_ROWS, self.W, self.world
+        with torch.cuda.stream(self.stream):
+            self.ctx.render_camera_ptrs(p, eep, cam, self.W, self.H, [self.full16.data_ptr(), 0, 0], self.fulld.data_ptr(), device=True)
+            march_ms = self.ctx.stats().last_march_ms
+            p.image_band_modulus, p.image_band_remainder = saved
+            mine16 = self.full16.view(G, N, B, W, 4)[:, self.rank]
+            mined = self.fulld.view(G, N, B, W)[:, self.rank]
+            nc = self.npix_mine * 8
+            self.pack[:nc].view(torch.int16).view(G, B, W, 4).copy_(mine16)
+            self.pack[nc:].view(torch.float32).view(G, B, W).copy_(mined)
+            dist.gather(self.pack, list(self.gathered.unbind(0)) if self.rank == 0 else None, dst=0)
+            if self.rank == 0:
+                g = self.gathered
+                out_rgba16.view(G, N, B, W, 4).copy_(g[:, :nc].view(torch.int16).view(N, G, B, W, 4).permute(1, 0, 2, 3, 4))
+                out_depth.view(G, N, B, W).copy_(g[:, nc:].view(torch.float32).view(N, G, B, W).permute(1, 0, 2, 3))
         return march_ms
