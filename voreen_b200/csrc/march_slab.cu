@@ -10,18 +10,22 @@ static int launch_slab(b200rc_ctx* ctx, const DevParams& p0) {
     DevParams p = p0;
     p.tiles_x = (((p.W + SLAB_TILE - 1) / SLAB_TILE) + 7) / 8 * 8;
     p.tiles_y = (((p.H + SLAB_TILE_H - 1) / SLAB_TILE_H) + 7) / 8 * 8;
-    // shared memory: two CTAs per SM (227 KB usable); the 1D TF (+ LUT) sits behind the staged region
+    // shared memory: SLAB_MIN_CTAS CTAs per SM share 227 KB; the 1D TF (+ LUT) sits behind the staged region
     size_t tf_bytes = 0;
     if (C::CLS == B200RC_CLASS_TF && p.cls[0].tf) tf_bytes = (size_t)p.cls[0].tf_width * 4 + 1024;
     if (tf_bytes > 40 * 1024) return -1;            // TF too wide for the staged layout: caller falls back
     static int env_depth = -1, env_cap = -1;
     if (env_depth < 0) {
-        const char* d = getenv("B200RC_SLAB_DEPTH"); env_depth = d ? atoi(d) : 8;
-        const char* c = getenv("B200RC_SLAB_KB"); env_cap = c ? atoi(c) : (SLAB_THREADS == 256 ? 88 : 52);
-        if (env_depth < 2 || env_depth > 32) env_depth = 8;
+        const char* d = getenv("B200RC_SLAB_DEPTH"); env_depth = d ? atoi(d) : 6;
+        const char* c = getenv("B200RC_SLAB_KB"); env_cap = c ? atoi(c) : (SLAB_THREADS == 256 ? 72 : 52);
+        if (env_depth < 2 || env_depth > 32) env_depth = 6;
         if (env_cap < 32 || env_cap > 200) env_cap = 88;
     }
-    SlabArgs sa; sa.depth = env_depth; sa.cap_floats = env_cap * 256;
+    // SLAB_MIN_CTAS CTAs share the SM's 227 KB: the staged region takes what the TF (+ LUT) leaves of one CTA's share
+    int cap_kb = env_cap;
+    const int share_kb = (227 - SLAB_MIN_CTAS) / SLAB_MIN_CTAS;         // 1 KB per CTA reserved by the runtime + static shared memory
+    if (cap_kb + (int)((tf_bytes + 1023) / 1024) > share_kb) cap_kb = share_kb - (int)((tf_bytes + 1023) / 1024);
+    SlabArgs sa; sa.depth = env_depth; sa.cap_floats = cap_kb * 256;
     // pre-integration + empty-space skipping restores lastIntensity from the staged footprint: needs <= 1 voxel per step
     if (C::CLS == B200RC_CLASS_PREINT && p.vol[0].ess) {
         const float m = fmaxf(p.vol[0].dimf[0], fmaxf(p.vol[0].dimf[1], p.vol[0].dimf[2]));

@@ -23,7 +23,11 @@
 #endif
 #define SLAB_TILE 16            // pixels per tile edge (x)
 #define SLAB_TILE_H (SLAB_THREADS / 16)     // tile rows: each warp owns an 8x4 sub-tile, two warps side by side
-#define SLAB_MIN_CTAS (512 / SLAB_THREADS)
+// 3 CTAs (24 warps) per SM: ptxas fits the kernel into 80 registers with 16-40 bytes of spills; measured against 2 CTAs/SM
+// (123 registers, 88 KB regions) at 2048^3: TF 18.7 -> 16.2 ms, pre-integration 23.2 -> 20.7 ms (profiles/r1_pass11_occupancy.txt)
+#ifndef SLAB_MIN_CTAS
+#define SLAB_MIN_CTAS (768 / SLAB_THREADS)
+#endif
 #define SLAB_OCC_WORDS 160      // (max lateral extent / 8 + 2)^2 occupancy words per region
 
 struct SlabShared {
