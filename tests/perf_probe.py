@@ -14,6 +14,7 @@ from voreen_b200 import abi  # noqa: E402
 
 def main():
     sizes = [int(a) for a in sys.argv[1:] if not a.startswith('--')] or [512]
+    comp = next((a.split('=')[1] for a in sys.argv if a.startswith('--comp=')), 'dvr')
     ctx = vb.Context(0)
     for n in sizes:
         img = 1024 if n <= 512 else 2048
@@ -32,7 +33,7 @@ def main():
                 for ess in ((1, 0) if '--noess' in sys.argv else (1,)):
                     if n >= 2048 and ess == 0 and sampler == abi.SAMPLER_EXACT:
                         continue
-                    p = vb.default_params(step, sampler=sampler, empty_space_skipping=ess, out_format=abi.OUT_RGBA16)
+                    p = vb.default_params(step, sampler=sampler, empty_space_skipping=ess, out_format=abi.OUT_RGBA16, compositing=[abi.COMP[comp]] * 3)
                     if cls == "pi":
                         if pi is None:
                             tf1k = orc.tf1d_texture(tf, 1024)
@@ -55,7 +56,7 @@ def main():
                     ctx.render_camera(p, eep, cam, img, img)
                     s = ctx.stats()
                     m = np.median([a for a, _ in ms])
-                    print(f"[{n}^3 @{img}^2] cls={cls} sampler={'tex' if sampler else 'exact'} ess={ess}: march {m:.3f} ms (min {min(a for a,_ in ms):.3f} max {max(a for a,_ in ms):.3f}) "
+                    print(f"[{n}^3 @{img}^2] comp={comp} cls={cls} sampler={'tex' if sampler else 'exact'} ess={ess}: march {m:.3f} ms (min {min(a for a,_ in ms):.3f} max {max(a for a,_ in ms):.3f}) "
                           f"eep {np.median([b for _, b in ms]):.3f} ms | rays {s.rays_cast} classified {s.samples_classified} shaded {s.samples_shaded} nominal {s.samples_nominal} "
                           f"cells16 {s.cells_touched} -> {s.samples_classified / m / 1e6:.2f} Gsamples/s", flush=True)
 

@@ -341,9 +341,15 @@ def _multi_scene(nvol, cls="tf", n=32, W=80, H=80, comp="dvr"):
     return vols, descs, cam, params, entry, ged, exitp, gxd, tex, pre
 
 
-@pytest.mark.parametrize("nvol,cls,comp", [(2, "tf", "dvr"), (4, "tf", "dvr"), (2, "preint", "dvr"), (3, "tf", "mip")])
-def test_multivolume(ctx, nvol, cls, comp):
+@pytest.mark.parametrize("nvol,cls,comp,outputs", [(2, "tf", "dvr", 1), (4, "tf", "dvr", 1), (2, "preint", "dvr", 1), (3, "tf", "mip", 1),
+                                                   (3, "tf", "dvr", 2), (2, "preint", "dvr", 2)])
+def test_multivolume(ctx, nvol, cls, comp, outputs):
+    """outputs == 1: the specialised multi-volume kernel (march_multi.cu); outputs == 2: image.output1 connected as well ->
+    the run-time-switched generic kernel.  Each is rendered with and without empty-space skipping: the two images must be
+    identical bit for bit, and both match the oracle (which never skips)."""
     vols, descs, cam, params, entry, ged, exitp, gxd, tex, pre = _multi_scene(nvol, cls, comp=comp)
+    if outputs == 2:
+        params.output_connected[:] = [1, 1, 0]
     H, W = ged.shape
     ovs = [orc.make_volume(vols[v], descs[v]) for v in range(nvol)]
     ocls = [orc.make_classifier(tex[v], (0.0, 65535.0), preint=pre[v] if pre else None) for v in range(nvol)]
@@ -353,14 +359,28 @@ def test_multivolume(ctx, nvol, cls, comp):
         ctx.set_tf1d(v, tex[v], (0.0, 65535.0))
         if pre:
             ctx.set_preint(v, pre[v])
+    params.empty_space_skipping = 0
+    n_outs, n_depth = ctx.render(params, cam, W, H, entry, ged, exitp, gxd)
+    n_st = ctx.stats()
+    params.empty_space_skipping = 1
     c_outs, c_depth = ctx.render(params, cam, W, H, entry, ged, exitp, gxd)
     st = ctx.stats()
     frac, mx = scenes.parity_report(o_outs[0], c_outs[0])
-    print(f"multivolume x{nvol} {cls} {comp}: within-1/255 {frac:.5f} max|d| {mx:.2e} rays {st.rays_cast}/{o_st.rays_cast} "
-          f"classified {st.samples_classified}/{o_st.samples_classified} shaded {st.samples_shaded}/{o_st.samples_shaded}")
+    print(f"multivolume x{nvol} {cls} {comp} outputs {outputs}: within-1/255 {frac:.5f} max|d| {mx:.2e} rays {st.rays_cast}/{o_st.rays_cast} "
+          f"classified {st.samples_classified} (no ESS {n_st.samples_classified}) / {o_st.samples_classified} shaded {st.samples_shaded}/{o_st.samples_shaded} "
+          f"skipped {st.samples_skipped}")
     assert o_st.rays_cast > 1000 and o_st.samples_shaded > 0
     assert st.rays_cast == o_st.rays_cast
+    assert n_st.samples_classified == o_st.samples_classified and n_st.samples_shaded == o_st.samples_shaded
+    assert st.samples_shaded == o_st.samples_shaded                 # skipping never drops a sample with alpha > 0
+    assert st.samples_skipped > 0 and st.samples_classified < n_st.samples_classified
+    for o in range(outputs):
+        assert np.array_equal(np.asarray(c_outs[o]), np.asarray(n_outs[o]))
+    assert np.array_equal(c_depth, n_depth)
     assert frac >= 0.999, (frac, mx)
+    if outputs == 2:
+        frac1, mx1 = scenes.parity_report(o_outs[1], c_outs[1])
+        assert frac1 >= 0.999, (frac1, mx1)
     assert float((np.abs(o_depth - c_depth) <= 1e-4).mean()) >= 0.999
     for v in range(1, nvol):
         ctx.lib.b200rc_release_volume(ctx.h, v)

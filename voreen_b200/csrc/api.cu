@@ -302,13 +302,24 @@ static int build_params(b200rc_ctx* ctx, const b200rc_params* P, const b200rc_ca
             d.tf2d = k.tf2d; d.tf2d_w = k.tf2d_w; d.tf2d_h = k.tf2d_h;
         }
     }
-    // empty-space skipping (single volume, unsharded, no channel shift): occupancy for the current TFs
+    // empty-space skipping (no channel shift): occupancy for the current TFs
     if (P->empty_space_skipping && !P->multi_volume && !p.channel_shift) {
         int modes[4];
         for (int c = 0; c < ncls; ++c) modes[c] = P->vol[0].classification;
         int rc = rc_volume_build_occupancy(ctx, 0, modes, ncls, false, P->vol[0].clamp, P->vol[0].border_intensity);
         if (rc) return rc;
         p.vol[0].ess = 1;
+    }
+    // multi-volume: one occupancy grid per volume for its own classifier (rc_multivolume.frag reads voxel.a of every
+    // volume, i.e. the last channel; multi-channel volumes keep marching every sample)
+    if (P->empty_space_skipping && P->multi_volume) {
+        for (int v = 0; v < nv; ++v) {
+            if (ctx->vol[v].desc.channels != 1 || ctx->vol[v].sharded) continue;
+            int mode = P->vol[v].classification;
+            int rc = rc_volume_build_occupancy(ctx, v, &mode, 1, true, P->vol[v].clamp, P->vol[v].border_intensity);
+            if (rc) return rc;
+            p.vol[v].ess = 1;
+        }
     }
     p.lattice_exact = (!P->multi_volume && lattice_is_exact(P->sampling_step, 65536)) ? 1 : 0;
     p.stats = ctx->d_stats;
@@ -343,6 +354,8 @@ int rc_march_launch(b200rc_ctx* ctx, const DevParams& p, int sampler, int nch, i
     const bool slab_ok = ctx->use_slab && !(p.flags && remarch_ray);
     if (slab_ok && rc_march_slab(ctx, p, sampler, nch, dtype, &rc)) return rc;
     if (rc_march_fast(ctx, p, sampler, nch, dtype, &rc)) return rc;
+    if (rc_march_fast_multi(ctx, p, sampler, &rc)) return rc;
+    if (rc_march_fast_multi(ctx, p, sampler, &rc)) return rc;
     return rc_march_generic(ctx, p, sampler, nch);
 }
 
