@@ -55,8 +55,9 @@ def orbit_eye(k, n=N_VIEWS, radius=3.5):
 
 
 def workload_name(args):
+    img = f"{args.image}^2" if args.image_h in (0, args.image) else f"{args.image}x{args.image_h}"
     return (f"synthetic CT-like {args.size}^3 u16, {args.classification} classification, ESS, central-diff + Phong, "
-            f"DVR, rate {args.rate:g}, {args.image}^2, {N_VIEWS}-view orbit")
+            f"DVR, rate {args.rate:g}, {img}, {N_VIEWS}-view orbit")
 
 
 def peaks():
@@ -123,7 +124,7 @@ class CpuSample:
         from voreen_b200 import raycaster as rc
         self.orc, self.abi, self.rc = orc, abi, rc
         self.args, self.dims = args, tuple(dims)
-        self.W = self.H = args.image
+        self.W, self.H = args.image, (args.image_h or args.image)
         self.step = float(np.float32(1.0) / (np.float32(max(dims)) * np.float32(args.rate)))
         self.cores = os.cpu_count() or 1
         orc.lib().orc_set_threads(self.cores)
@@ -251,7 +252,7 @@ def run_b200(args, rank, world, local_rank):
     ctx.set_stream(stream.cuda_stream)
 
     dims = (args.size,) * 3
-    W = H = args.image
+    W, H = args.image, (args.image_h or args.image)
     step = float(np.float32(1.0) / (np.float32(max(dims)) * np.float32(args.rate)))
     use_pi = args.classification == "preint"
     sampler = abi.SAMPLER_TEX if args.sampler == "tex" else abi.SAMPLER_EXACT
@@ -261,12 +262,13 @@ def run_b200(args, rank, world, local_rank):
     # "auto" = sort-first when the whole volume + grids fit in 60 % of this GPU's memory, else sort-last.
     sl = sf = None
     mode = "single GPU"
+    need = int(np.prod(dims)) * 2 * 1.25
+    fits = need < 0.6 * torch.cuda.get_device_properties(dev).total_memory
     if world > 1:
         from voreen_b200 import sortlast
         mode = args.parallelism
         if mode == "auto":
-            need = int(np.prod(dims)) * 2 * 1.25
-            mode = "sort-first" if need < 0.6 * torch.cuda.get_device_properties(dev).total_memory else "sort-last"
+            mode = "sort-first" if fits else "sort-last"
         if mode == "sort-last":
             sl = sortlast.SortLast(ctx, dims, rank, world, W, H, device=dev, stream=stream)
             desc = sl.shard_desc()
@@ -275,20 +277,36 @@ def run_b200(args, rank, world, local_rank):
             desc = vb.make_volume_desc(dims)
     else:
         desc = vb.make_volume_desc(dims)
+    if not fits and sl is None:
+        raise SystemExit(f"a {args.size}^3 u16 volume does not fit one GPU: run with --gpus N --parallelism sort-last")
+    # A volume that only fits sharded (C5: 4096^3 = 128 GiB) cannot be rendered unsharded for the reference-equivalent sample
+    # count; rank 0 measures the ratio (reference-equivalent / nominal) per view on the half-resolution rendering of the same
+    # procedural volume (same geometry, same optical depth per unit length) and applies it to the exact nominal count.
+    stats_dims = dims if fits else tuple(d // 2 for d in dims)
+    stats_step = float(np.float32(1.0) / (np.float32(max(stats_dims)) * np.float32(args.rate)))
+
+    def setup_classifier(st_):
+        if use_pi:
+            ctx.set_tf1d(0, host.tf1d_texture(CT_KEYS, 1024), (0.0, 65535.0))
+            ctx.build_preint(0, 1024, st_, abi.PI_CPU)      # PreIntegrationTable::computeTable on the device
+        ctx.set_tf1d(0, host.tf1d_texture(CT_KEYS, 4096), (0.0, 65535.0))
+
     t0 = time.perf_counter()
-    ctx.synth_volume(0, vb.make_volume_desc(dims) if (sl is not None and rank == 0) else desc, args.seed)
-    ctx.synchronize()
+    first_desc = desc
+    if sl is not None:
+        first_desc = vb.make_volume_desc(stats_dims) if rank == 0 else None
+    mm_ms, mm_vox = 0.0, 1
+    if first_desc is not None:
+        ctx.synth_volume(0, first_desc, args.seed)
+        ctx.synchronize()
+        # the empty-space-skipping min/max build (brick_partials_u16_kernel + cell_fold_u16_kernel): HBM streaming, one read of
+        # the volume; timed by the library with CUDA events on its stream during the upload above
+        _, mm_ms = ctx.download_minmax(0)
+        mm_vox = int(np.prod(stats_dims if sl is not None else dims))
     t_synth = time.perf_counter() - t0
-    # the empty-space-skipping min/max build (brick_partials_u16_kernel + cell_fold_u16_kernel): HBM streaming, one read of
-    # the volume; timed by the library with CUDA events on its stream during the upload above
-    _, mm_ms = ctx.download_minmax(0)
-    mm_vox = int(np.prod(dims))          # rank 0 (the reporting rank) always generates the whole volume first
     mm_bytes = mm_vox * 2 + (mm_vox // 512) * (27 * 4 * 2 + 8)
 
-    if use_pi:
-        ctx.set_tf1d(0, host.tf1d_texture(CT_KEYS, 1024), (0.0, 65535.0))
-        ctx.build_preint(0, 1024, step, abi.PI_CPU)      # PreIntegrationTable::computeTable on the device
-    ctx.set_tf1d(0, host.tf1d_texture(CT_KEYS, 4096), (0.0, 65535.0))
+    setup_classifier(stats_step if sl is not None else step)
     params = vb.default_params(step, classification=abi.CLASS_PREINT if use_pi else abi.CLASS_TF, sampler=sampler,
                                empty_space_skipping=1, out_format=abi.OUT_RGBA16)
     eep = vb.default_eep()
@@ -330,14 +348,24 @@ def run_b200(args, rank, world, local_rank):
     if world > 1:
         ref_samples = classified = nominal = [0.0] * N_VIEWS
         if rank == 0:
+            params.sampling_step = stats_step
             ref_samples, classified, _, nominal = stats_pass(frame_unsharded)
+            params.sampling_step = step
         t = torch.tensor([ref_samples, classified, nominal], dtype=torch.float64, device=dev)
         dist.broadcast(t, 0)
         ref_samples, classified, nominal = (t[i].tolist() for i in range(3))
         if sl is not None:
             ctx.synth_volume(0, desc, args.seed)        # now the shard
+            setup_classifier(step)
             ctx.synchronize()
-        _, _, cells16, _ = stats_pass(frame)             # this rank's touched macro-cells (roofline of its own kernel)
+            sl.exact_ert = False                         # statistics of the FIRST pass (the re-march resets the counters)
+        _, _, cells16, nominal_run = stats_pass(frame)   # this rank's touched macro-cells (roofline of its own kernel)
+        if sl is not None:
+            sl.exact_ert = True
+            if not fits:                                 # nominal is exact (every rank counts every cast ray); the rest is scaled
+                ref_samples = [n1 * r / max(n0, 1.0) for n1, r, n0 in zip(nominal_run, ref_samples, nominal)]
+                classified = [n1 * c / max(n0, 1.0) for n1, c, n0 in zip(nominal_run, classified, nominal)]
+                nominal = [float(n1) for n1 in nominal_run]
     else:
         ref_samples, classified, cells16, nominal = stats_pass(frame)
 
@@ -438,7 +466,9 @@ def run_b200(args, rank, world, local_rank):
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": workload_name(args), "sampler": args.sampler, "parallelism": f"{mode} x{world}" if world > 1 else "single GPU",
-                       "l2": f"volume {int(np.prod(dims)) * 2 / 2**30:.1f} GiB >> 126 MB L2, a different view every step"},
+                       "l2": f"volume {int(np.prod(dims)) * 2 / 2**30:.1f} GiB >> 126 MB L2, a different view every step",
+                       "samples": "exact (unsharded rendering of the same frames)" if fits else
+                                  f"nominal exact; reference-equivalent = nominal x ratio measured on the {stats_dims[0]}^3 rendering of the same procedural volume"},
             "ms_per_frame": ms_total / args.steps,
             "gsamples_classified_per_s": sum(classified[v] for v in steps_views) / (ms_total * 1e-3) / 1e9,
             "gsamples_nominal_per_s": sum(nominal[v] for v in steps_views) / (ms_total * 1e-3) / 1e9,
@@ -462,7 +492,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=2048)
-    ap.add_argument("--image", type=int, default=2048)
+    ap.add_argument("--image", type=int, default=2048, help="image width (and height unless --image-h)")
+    ap.add_argument("--image-h", type=int, default=0)
     ap.add_argument("--rate", type=float, default=2.0)
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--classification", default="preint", choices=["preint", "tf"])

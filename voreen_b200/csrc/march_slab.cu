@@ -65,6 +65,7 @@ bool rc_march_slab(b200rc_ctx* ctx, const DevParams& p, int sampler, int nch, in
     SLAB_CASE(B200RC_U16, B200RC_CLASS_TF, B200RC_COMP_DVR, B200RC_SHADE_PHONG)
     SLAB_CASE(B200RC_U16, B200RC_CLASS_TF, B200RC_COMP_MIP, B200RC_SHADE_PHONG)
     SLAB_CASE(B200RC_U16, B200RC_CLASS_TF, B200RC_COMP_ISO, B200RC_SHADE_PHONG)
+    SLAB_CASE(B200RC_U16, B200RC_CLASS_PREINT, B200RC_COMP_MIP, B200RC_SHADE_PHONG)
     SLAB_CASE(B200RC_U16, B200RC_CLASS_PREINT, B200RC_COMP_ISO, B200RC_SHADE_PHONG)
     SLAB_CASE(0, B200RC_CLASS_TF, B200RC_COMP_DVR, -1)
     SLAB_CASE(0, B200RC_CLASS_PREINT, B200RC_COMP_DVR, -1)

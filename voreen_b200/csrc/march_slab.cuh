@@ -438,8 +438,8 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
                                     color0 = preint_lookup<C>(p.cls[0], s_cur, lastI);
                                     lastI = s_cur;
                                 } else color0 = classify<C>(cmode, p.cls[0], sm.tf[0], f3(0.f, 0.f, 0.f), intensity, lastI, a8);
-                                if (color0.w > 0.f) {
-                                    st.shaded++;
+                                if (color0.w > 0.f) st.shaded++;
+                                if (color0.w > 0.f && compositing_takes_sample(comp, result, intensity, color0.w, maxI, p.iso)) {
                                     float3 gradient;
                                     if (t == 0.0f) gradient = fix_clip_border_gradient(p, sp, dir, px, py);
                                     else {
