@@ -263,17 +263,17 @@ def run_b200(args, rank, world, local_rank):
     sl = sf = None
     mode = "single GPU"
     need = int(np.prod(dims)) * 2 * 1.25
-    fits = need < 0.6 * torch.cuda.get_device_properties(dev).total_memory
+    fits = need < 0.6 * torch.cuda.get_device_properties(dev).total_memory and not args.treat_as_sharded_only
     if world > 1:
         from voreen_b200 import sortlast
         mode = args.parallelism
         if mode == "auto":
             mode = "sort-first" if fits else "sort-last"
         if mode == "sort-last":
-            sl = sortlast.SortLast(ctx, dims, rank, world, W, H, device=dev, stream=stream)
+            sl = sortlast.SortLast(ctx, dims, rank, world, W, H, device=dev, stream=stream, transport=args.transport)
             desc = sl.shard_desc()
         else:
-            sf = sortlast.SortFirst(ctx, rank, world, W, H, device=dev, stream=stream)
+            sf = sortlast.SortFirst(ctx, rank, world, W, H, device=dev, stream=stream, transport=args.transport)
             desc = vb.make_volume_desc(dims)
     else:
         desc = vb.make_volume_desc(dims)
@@ -466,6 +466,7 @@ def run_b200(args, rank, world, local_rank):
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": workload_name(args), "sampler": args.sampler, "parallelism": f"{mode} x{world}" if world > 1 else "single GPU",
+                       "transport": (sl or sf).transport if world > 1 else None,
                        "l2": f"volume {int(np.prod(dims)) * 2 / 2**30:.1f} GiB >> 126 MB L2, a different view every step",
                        "samples": "exact (unsharded rendering of the same frames)" if fits else
                                   f"nominal exact; reference-equivalent = nominal x ratio measured on the {stats_dims[0]}^3 rendering of the same procedural volume"},
@@ -499,6 +500,9 @@ def main():
     ap.add_argument("--classification", default="preint", choices=["preint", "tf"])
     ap.add_argument("--sampler", default="exact", choices=["exact", "tex"])
     ap.add_argument("--parallelism", default="auto", choices=["auto", "sort-first", "sort-last"])
+    ap.add_argument("--transport", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="N > 1: p2p = peer-memory loads/stores inside the kernels (symmetric memory), nccl = send/recv + gather")
+    ap.add_argument("--treat-as-sharded-only", action="store_true", help="testing: take the C5 code path (volume never rendered unsharded)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()

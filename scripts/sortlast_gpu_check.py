@@ -53,19 +53,35 @@ def main():
             ref[k] = (out.cpu().numpy().view(np.uint16).astype(np.float64) / 65535.0, depth.cpu().numpy().copy())
     dist.barrier()
     if mode == "sort-first":
-        sl = sortlast.SortFirst(ctx, rank, world, img, img, device=dev, stream=stream)
+        sl = sortlast.SortFirst(ctx, rank, world, img, img, device=dev, stream=stream, transport=os.environ.get("SL_TRANSPORT", "auto"))
         sl.phases = {}
         if rank != 0 or os.environ.get("SL_NOREF"):
             ctx.synth_volume(0, vb.make_volume_desc(dims), 1234)
             load_tf()
     else:
-        sl = sortlast.SortLast(ctx, dims, rank, world, img, img, device=dev, stream=stream)
+        sl = sortlast.SortLast(ctx, dims, rank, world, img, img, device=dev, stream=stream, transport=os.environ.get("SL_TRANSPORT", "auto"))
         ctx.synth_volume(0, sl.shard_desc(), 1234)
         load_tf()
         sl.profile = True
     ok = True
     for k in views:
         ms = sl.render(params, eep, cams[k], out, depth)          # first call of a view: warm-up
+        ms = sl.render(params, eep, cams[k], out, depth)
+        torch.cuda.synchronize(dev)
+        # whole-frame time (march + merge + gather), max over ranks, 5 frames back to back
+        prof_saved = getattr(sl, "profile", False)
+        sl.profile = False
+        dist.barrier(); torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(5):
+            sl.render(params, eep, cams[k], out, depth)
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        tt = torch.tensor([e0.elapsed_time(e1) / 5.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        frame_ms = float(tt.item())
+        sl.profile = prof_saved
         ms = sl.render(params, eep, cams[k], out, depth)
         torch.cuda.synchronize(dev)
         ph = [None] * world
@@ -81,7 +97,7 @@ def main():
             good = frac >= 0.999 and dfrac >= 0.999
             ok = ok and good
             print(f"{mode} x{world} {size}^3 @{img}^2 {cls} view {k}: within-1/255 {frac:.6f} max|d| {d.max():.4f} depth-ok {dfrac:.6f} "
-                  f"rank0 march {ms:.2f} ms {'OK' if good else 'FAIL'}", flush=True)
+                  f"rank0 march {ms:.2f} ms frame {frame_ms:.2f} ms transport {sl.transport} {'OK' if good else 'FAIL'}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     ctx.close()

@@ -89,7 +89,7 @@ extern "C" int b200rc_create(int device, b200rc_ctx** out_ctx) {
     ctx->stream = ctx->own_stream;
     for (int i = 0; i < 6; ++i) cudaEventCreate(&ctx->ev[i]);
     cudaMalloc(&ctx->d_stats, 8 * sizeof(unsigned long long));
-    cudaMalloc(&ctx->d_tile_counter, sizeof(unsigned int));
+    cudaMalloc(&ctx->d_tile_counter, 4 * sizeof(unsigned int));
     *out_ctx = ctx;
     return B200RC_OK;
 }
@@ -107,7 +107,7 @@ extern "C" int b200rc_destroy(b200rc_ctx* ctx) {
     }
     cudaFree(ctx->d_entry); cudaFree(ctx->d_exit); cudaFree(ctx->d_entry_depth); cudaFree(ctx->d_exit_depth);
     for (int o = 0; o < 3; ++o) cudaFree(ctx->d_out[o]);
-    cudaFree(ctx->d_out_depth); cudaFree(ctx->d_stats); cudaFree(ctx->d_tile_counter); cudaFree(ctx->d_boxes);
+    cudaFree(ctx->d_out_depth); cudaFree(ctx->d_stats); cudaFree(ctx->d_tile_counter); cudaFree(ctx->d_tile_cost); cudaFree(ctx->d_tile_order); cudaFree(ctx->d_boxes);
     for (int i = 0; i < 6; ++i) cudaEventDestroy(ctx->ev[i]);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;

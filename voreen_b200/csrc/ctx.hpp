@@ -60,7 +60,8 @@ struct b200rc_ctx {
     int eep_w = 0, eep_h = 0;       // size of the entry/exit images currently held (b200rc_remarch_device reuses them)
     void* d_out[3] = {nullptr, nullptr, nullptr}; float* d_out_depth = nullptr; size_t out_capacity = 0;
     unsigned long long* d_stats = nullptr;
-    unsigned int* d_tile_counter = nullptr;
+    unsigned int* d_tile_counter = nullptr;     // [0] scheduler counter, [1] number of tiles with work (slab marcher)
+    float* d_tile_cost = nullptr; unsigned int* d_tile_order = nullptr; size_t tile_capacity = 0;
     float* d_boxes = nullptr; int boxes_capacity = 0;
     b200rc_stats stats{};
     unsigned long long launches = 0;

@@ -41,7 +41,17 @@ static int launch_slab(b200rc_ctx* ctx, const DevParams& p0) {
     long long grid = (long long)ctx->num_sms * per_sm;      // persistent: one wave, a multiple of the SM count
     if (grid > tiles) grid = tiles;
     if (grid < 1) grid = 1;
-    RC_CHECK(cudaMemsetAsync(p.tile_counter, 0, sizeof(unsigned int), ctx->stream));
+    // tile order: most expensive first, tiles without work dropped (also resets the scheduler counter)
+    if (ctx->tile_capacity < (size_t)tiles) {
+        cudaFree(ctx->d_tile_cost); cudaFree(ctx->d_tile_order); ctx->d_tile_cost = nullptr; ctx->d_tile_order = nullptr; ctx->tile_capacity = 0;
+        RC_CHECK(cudaMalloc(&ctx->d_tile_cost, sizeof(float) * tiles));
+        RC_CHECK(cudaMalloc(&ctx->d_tile_order, sizeof(unsigned int) * tiles));
+        ctx->tile_capacity = (size_t)tiles;
+    }
+    slab_tile_cost_kernel<<<(unsigned)tiles, SLAB_THREADS, 0, ctx->stream>>>(p, ctx->d_tile_cost);
+    slab_tile_order_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_tile_cost, (unsigned)tiles, ctx->d_tile_order, p.tile_counter);
+    ctx->launches += 2;
+    sa.order = ctx->d_tile_order;
     kern<<<(unsigned)grid, SLAB_THREADS, smem, ctx->stream>>>(p, sa);
     ctx->launches++;
     RC_CHECK(cudaGetLastError());

@@ -44,7 +44,7 @@ struct SlabShared {
     unsigned int occ[SLAB_OCC_WORDS];
 };
 
-struct SlabArgs { int depth; int cap_floats; };
+struct SlabArgs { int depth; int cap_floats; const unsigned int* order; };   // order: tile ids, most expensive first; p.tile_counter[1] of them
 
 __device__ __forceinline__ int pick3(int a, int b, int c, int axis) { return axis == 0 ? a : (axis == 1 ? b : c); }
 __device__ __forceinline__ float pick3f(float a, float b, float c, int axis) { return axis == 0 ? a : (axis == 1 ? b : c); }
@@ -164,6 +164,95 @@ __device__ __forceinline__ bool slab_skip_empty(const DevParams& p, const VolDev
     return true;
 }
 
+// ---- tile scheduling: longest-processing-time first ---------------------------------------------------------------------
+// The persistent CTAs pull 16x16 tiles from a counter.  A tile whose rays cross the whole volume costs ~1 ms; handed out
+// last it leaves the other CTAs idle for that long (the tail grows relative to the frame when the image is split across
+// GPUs).  slab_tile_cost_kernel estimates every tile's work as the summed ray length (inside this rank's shard, of the
+// pixels this launch renders), slab_tile_order_kernel sorts the tiles by that estimate, most expensive first, and drops
+// the tiles that own no pixel of this launch (another rank's band, no flagged pixel in the second sort-last pass).  Tile ids keep the Z-order numbering of the marcher (8x8 super-tiles).
+__global__ void __launch_bounds__(SLAB_THREADS) slab_tile_cost_kernel(const __grid_constant__ DevParams p, float* __restrict__ cost) {
+    __shared__ float part[SLAB_THREADS / 32];
+    const unsigned tile = blockIdx.x;
+    const unsigned super_x = (unsigned)p.tiles_x >> 3;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned sup = tile >> 6, loc = tile & 63u;
+    const unsigned tx = (sup % super_x) * 8u + compact1by1(loc), ty = (sup / super_x) * 8u + compact1by1(loc >> 1);
+    float c = 0.f;
+    const bool mine = !(p.band_mod > 1 && (int)((ty * SLAB_TILE_H / 16u) % (unsigned)p.band_mod) != p.band_rem);
+    const int px = (int)(tx * SLAB_TILE + (warp & 1u) * 8u + (lane & 7u)), py = (int)(ty * SLAB_TILE_H + (warp >> 1) * 4u + (lane >> 3));
+    if (mine && px < p.W && py < p.H) {
+        const size_t pix = (size_t)py * p.W + px;
+        if (!p.flags || p.flags[pix] == 2) {
+            const float4 e4 = p.entry[pix], x4 = p.exitp[pix];
+            const float3 d = f3(x4.x - e4.x, x4.y - e4.y, x4.z - e4.z);
+            const float tEnd = sqrtf(dot3(d, d));
+            c = p.step;                             // every pixel this launch owns is written (background included): cost > 0
+            if (tEnd > 0.f) {
+                c = tEnd + 4.0f * p.step;
+                const VolDev& V = p.vol[0];
+                if (V.sharded) {
+                    const ShardSeg seg = shard_segment(V, f3(e4.x, e4.y, e4.z), d * (1.0f / tEnd), tEnd, p.step);
+                    c = seg.any ? fmaxf(seg.t_stop - (float)seg.k0 * p.step, 0.f) + 4.0f * p.step : p.step;
+                }
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if (lane == 0) part[warp] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int w = 0; w < SLAB_THREADS / 32; ++w) s += part[w];
+        cost[tile] = s;
+    }
+}
+
+#define SLAB_ORDER_BINS 1024
+__global__ void __launch_bounds__(1024) slab_tile_order_kernel(const float* __restrict__ cost, unsigned ntiles, unsigned int* __restrict__ order,
+                                                               unsigned int* __restrict__ counter) {
+    __shared__ unsigned hist[SLAB_ORDER_BINS];
+    __shared__ float wmax[32];
+    __shared__ unsigned carry;
+    float m = 0.f;
+    for (unsigned i = threadIdx.x; i < ntiles; i += blockDim.x) m = fmaxf(m, cost[i]);
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = m;
+    hist[threadIdx.x] = 0u;
+    if (threadIdx.x == 0) carry = 0u;
+    __syncthreads();
+    m = 0.f;
+    for (int w = 0; w < 32; ++w) m = fmaxf(m, wmax[w]);
+    const float scale = m > 0.f ? (float)(SLAB_ORDER_BINS - 1) / m : 0.f;
+    // bin 0 = most expensive
+    for (unsigned i = threadIdx.x; i < ntiles; i += blockDim.x) {
+        const float c = cost[i];
+        if (c > 0.f) atomicAdd(&hist[SLAB_ORDER_BINS - 1 - min((int)(c * scale), SLAB_ORDER_BINS - 1)], 1u);
+    }
+    __syncthreads();
+    // exclusive scan of the 1024 bins: warp scans + carry
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned v = hist[threadIdx.x];
+    unsigned inc = v;
+    for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (unsigned)o) inc += t; }
+    __shared__ unsigned wsum[32];
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned ws = wsum[lane], winc = ws;
+        for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= (unsigned)o) winc += t; }
+        wsum[lane] = winc - ws;
+        if (lane == 31) carry = winc;
+    }
+    __syncthreads();
+    hist[threadIdx.x] = wsum[warp] + inc - v;
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i < ntiles; i += blockDim.x) {
+        const float c = cost[i];
+        if (c > 0.f) order[atomicAdd(&hist[SLAB_ORDER_BINS - 1 - min((int)(c * scale), SLAB_ORDER_BINS - 1)], 1u)] = i;
+    }
+    if (threadIdx.x == 0) { counter[0] = 0u; counter[1] = carry; }
+}
+
 template <class C>
 __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel(const __grid_constant__ DevParams p, const SlabArgs sa) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -196,8 +285,12 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
     const unsigned ntiles = (unsigned)p.tiles_x * (unsigned)p.tiles_y;      // 16x16 tiles, padded to 8x8 super-tiles
     const unsigned super_x = (unsigned)p.tiles_x >> 3;
 
+    const unsigned n_active = min(__ldg(p.tile_counter + 1), ntiles);      // tiles with at least one ray to march (slab_tile_order_kernel)
     for (;;) {
-        if (threadIdx.x == 0) sh.tile = atomicAdd(p.tile_counter, 1u);
+        if (threadIdx.x == 0) {
+            const unsigned k = atomicAdd(p.tile_counter, 1u);
+            sh.tile = k < n_active ? __ldg(sa.order + k) : 0xffffffffu;
+        }
         __syncthreads();
         const unsigned tile = sh.tile;
         if (tile >= ntiles) break;

@@ -173,17 +173,107 @@ def binary_swap(color, depth, rank, world, in_front, blend, dist=None, group=Non
     return lo, hi
 
 
+def swap_schedule(npix, rank, world):
+    """[(partner, (keep_lo, keep_hi))] per round of the binary swap for `rank` (the range halves every round)."""
+    out = []
+    lo, hi = 0, npix
+    for r in range(world.bit_length() - 1):
+        mid = (lo + hi) // 2
+        lo, hi = (lo, mid) if (rank >> r) & 1 == 0 else (mid, hi)
+        out.append((rank ^ (1 << r), (lo, hi)))
+    return out
+
+
+def binary_swap_p2p_round(rnd, views, rank, world, in_front, blend):
+    """One round of the binary swap over PEER MEMORY: nothing is sent.  views(r) -> (color, depth) tensors that map rank r's
+    partial image (peer-mapped over NVLink for r != rank).  The blend kernel reads the partner's copy of the range this
+    rank keeps straight from the partner's HBM and blends it into the local copy in place -- transfer and over operator are
+    one kernel.  The caller synchronises the ranks before every round (the partner's range must be final) and after the
+    last one.  No hazard inside a round: a rank writes only the range it keeps, its partner reads only the other half."""
+    npix = views(rank)[0].shape[0]
+    partner, (a, b) = swap_schedule(npix, rank, world)[rnd]
+    mc, md = views(rank)
+    pc, pd = views(partner)
+    mc, md, pc, pd = mc[a:b], md[a:b], pc[a:b], pd[a:b]
+    if in_front(rnd):
+        blend(mc, md, pc, pd, mc, md)
+    else:
+        blend(pc, pd, mc, md, mc, md)
+    return a, b
+
+
+def binary_swap_p2p(views, rank, world, in_front, blend, barrier):
+    lo, hi = 0, views(rank)[0].shape[0]
+    for rnd in range(world.bit_length() - 1):
+        barrier()
+        lo, hi = binary_swap_p2p_round(rnd, views, rank, world, in_front, blend)
+    return lo, hi
+
+
+class PeerMemory:
+    """A buffer of `nbytes` on every rank, each mapped into every other rank's address space (torch symmetric memory:
+    cuMem allocations exchanged at rendezvous, NVLink/NVSwitch peer access).  ptr(r) is the device address of rank r's
+    buffer as seen from this process; kernels launched here may load from and store to it.  barrier() is a device-side
+    barrier enqueued on the current stream (signal pads in peer memory; no host round trip, no NCCL kernel)."""
+
+    def __init__(self, nbytes, device):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.torch = torch
+        self.nbytes = int(nbytes)
+        self.local = symm.empty((self.nbytes,), dtype=torch.uint8, device=device)
+        self.hdl = symm.rendezvous(self.local, dist.group.WORLD)
+        self.world, self.rank = self.hdl.world_size, self.hdl.rank
+        self.ptrs = [int(x) for x in self.hdl.buffer_ptrs]
+
+    def ptr(self, r, offset=0):
+        return self.ptrs[r] + int(offset)
+
+    def view(self, r, offset, shape, dtype):
+        """Tensor view of rank r's buffer at byte `offset`."""
+        esz = self.torch.empty((), dtype=dtype).element_size()
+        if r == self.rank:
+            n = int(np.prod(shape))
+            return self.local[offset:offset + n * esz].view(dtype).view(*shape)
+        return self.hdl.get_buffer(r, tuple(shape), dtype, offset // esz)
+
+    def barrier(self):
+        self.hdl.barrier(channel=0)
+
+
 class SortLast:
     """One rank of the sort-last renderer (GPU)."""
 
-    def __init__(self, ctx, dims, rank, world, W, H, device, stream):
+    def __init__(self, ctx, dims, rank, world, W, H, device, stream, transport="auto"):
         import torch
         self.torch = torch
         self.ctx, self.dims, self.rank, self.world, self.W, self.H = ctx, tuple(dims), rank, world, W, H
         self.device, self.stream = device, stream
         self.npix = W * H
-        self.color = torch.empty((self.npix, 4), dtype=torch.float32, device=device)
-        self.depth = torch.empty((self.npix,), dtype=torch.float32, device=device)
+        # transport "p2p": the partial image lives in peer-mapped memory, every binary-swap round is ONE kernel that reads the
+        # partner's half over NVLink and blends it in place, the finalise kernel stores each rank's 1/P straight into rank 0's
+        # output image.  transport "nccl": send/recv of the halves + a separate blend kernel (also what the gloo CPU tests run).
+        self.transport = "nccl"
+        self.peer = None
+        if world > 1 and transport in ("auto", "p2p"):
+            try:
+                # [colour npix x 16 B | depth npix x 4 B | final RGBA16 npix x 8 B | final depth npix x 4 B]
+                self.peer = PeerMemory(self.npix * 32, device)
+                self.transport = "p2p"
+            except Exception as e:      # symmetric memory unavailable on this box: NCCL point-to-point still works
+                if transport == "p2p":
+                    raise
+                import sys
+                print(f"[sortlast] peer memory unavailable ({type(e).__name__}: {e}); using NCCL send/recv", file=sys.stderr)
+        if self.peer is not None:
+            self.color = self.peer.view(rank, 0, (self.npix, 4), torch.float32)
+            self.depth = self.peer.view(rank, self.npix * 16, (self.npix,), torch.float32)
+            self._views = {r: (self.peer.view(r, 0, (self.npix, 4), torch.float32), self.peer.view(r, self.npix * 16, (self.npix,), torch.float32))
+                           for r in range(world)}
+        else:
+            self.color = torch.empty((self.npix, 4), dtype=torch.float32, device=device)
+            self.depth = torch.empty((self.npix,), dtype=torch.float32, device=device)
         self.ranges = final_ranges(self.npix, world)
         self.desc = shard_desc(self.dims, rank, world)
         self.exact_ert = True       # second pass: early ray termination on the global alpha (images match the single-GPU result)
@@ -238,28 +328,41 @@ class SortLast:
             if prof:
                 ev[3].record(self.stream)
             p.partial_image, p.out_format = saved
-            lo, hi = binary_swap(self.color, self.depth, self.rank, self.world,
-                                 lambda r: my_group_in_front(self.rank, r, self.world, self.dims, cam_tex), self._blend)
-            # finalise my 1/P of the image (alpha snap + RGBA16) and hand it to rank 0
-            n = hi - lo
             flat16 = out_rgba16.view(-1, 4)
             flatd = out_depth.view(-1)
-            if self.rank == 0:
-                self.ctx.finalize(self.color[lo:hi].data_ptr(), self.depth[lo:hi].data_ptr(), n, abi.OUT_RGBA16, flat16[lo:hi].data_ptr())
-                flatd[lo:hi].copy_(self.depth[lo:hi])
-                ops = []
-                for r in range(1, self.world):
-                    a, b = self.ranges[r]
-                    ops.append(dist.P2POp(dist.irecv, flat16[a:b].view(torch.uint8), r))       # NCCL has no int16: ship bytes
-                    ops.append(dist.P2POp(dist.irecv, flatd[a:b], r))
-                for w in dist.batch_isend_irecv(ops):
-                    w.wait()
+            if self.peer is not None:
+                in_front = lambda r: my_group_in_front(self.rank, r, self.world, self.dims, cam_tex)     # noqa: E731
+                lo, hi = binary_swap_p2p(lambda r: self._views[r], self.rank, self.world, in_front, self._blend, self.peer.barrier)
+                n = hi - lo
+                # finalise my 1/P (alpha snap + RGBA16) with the stores going to rank 0's image in peer memory
+                o16, od = self.npix * 20, self.npix * 28
+                self.ctx.finalize(self.color[lo:hi].data_ptr(), self.depth[lo:hi].data_ptr(), n, abi.OUT_RGBA16, self.peer.ptr(0, o16 + lo * 8))
+                self.peer.view(0, od, (self.npix,), torch.float32)[lo:hi].copy_(self.depth[lo:hi])
+                self.peer.barrier()         # every 1/P has landed; every read of this frame's partial images is done
+                if self.rank == 0:
+                    flat16.copy_(self.peer.view(0, o16, (self.npix, 4), torch.int16))
+                    flatd.copy_(self.peer.view(0, od, (self.npix,), torch.float32))
             else:
-                part16 = torch.empty((n, 4), dtype=torch.int16, device=self.device)
-                self.ctx.finalize(self.color[lo:hi].data_ptr(), self.depth[lo:hi].data_ptr(), n, abi.OUT_RGBA16, part16.data_ptr())
-                ops = [dist.P2POp(dist.isend, part16.view(torch.uint8), 0), dist.P2POp(dist.isend, self.depth[lo:hi], 0)]
-                for w in dist.batch_isend_irecv(ops):
-                    w.wait()
+                lo, hi = binary_swap(self.color, self.depth, self.rank, self.world,
+                                     lambda r: my_group_in_front(self.rank, r, self.world, self.dims, cam_tex), self._blend)
+                # finalise my 1/P of the image (alpha snap + RGBA16) and hand it to rank 0
+                n = hi - lo
+                if self.rank == 0:
+                    self.ctx.finalize(self.color[lo:hi].data_ptr(), self.depth[lo:hi].data_ptr(), n, abi.OUT_RGBA16, flat16[lo:hi].data_ptr())
+                    flatd[lo:hi].copy_(self.depth[lo:hi])
+                    ops = []
+                    for r in range(1, self.world):
+                        a, b = self.ranges[r]
+                        ops.append(dist.P2POp(dist.irecv, flat16[a:b].view(torch.uint8), r))       # NCCL has no int16: ship bytes
+                        ops.append(dist.P2POp(dist.irecv, flatd[a:b], r))
+                    for w in dist.batch_isend_irecv(ops):
+                        w.wait()
+                else:
+                    part16 = torch.empty((n, 4), dtype=torch.int16, device=self.device)
+                    self.ctx.finalize(self.color[lo:hi].data_ptr(), self.depth[lo:hi].data_ptr(), n, abi.OUT_RGBA16, part16.data_ptr())
+                    ops = [dist.P2POp(dist.isend, part16.view(torch.uint8), 0), dist.P2POp(dist.isend, self.depth[lo:hi], 0)]
+                    for w in dist.batch_isend_irecv(ops):
+                        w.wait()
             if prof:
                 ev[4].record(self.stream)
                 torch.cuda.synchronize(self.device)
@@ -289,11 +392,27 @@ class SortFirst:
     b % world == rank (interleaved, so the load is balanced whatever the camera sees); rank 0 gathers the bands.
     No partial images, no over-compositing, no occlusion lost between ranks: the pixels are exactly the single-GPU ones."""
 
-    def __init__(self, ctx, rank, world, W, H, device, stream):
+    def __init__(self, ctx, rank, world, W, H, device, stream, transport="auto"):
         import torch
         self.torch = torch
         self.ctx, self.rank, self.world, self.W, self.H = ctx, rank, world, W, H
         self.device, self.stream = device, stream
+        # transport "p2p": the marcher of every rank stores its bands straight into rank 0's image through peer-mapped memory
+        # (the RGBA16 / depth stores of the ray-marching kernel ARE the transfer; one device-side barrier ends the frame).
+        # transport "nccl": render locally, pack the bands, dist.gather, unpack on rank 0.
+        self.transport, self.peer, self.frame_no = "nccl", None, 0
+        self.npix = W * H
+        if world > 1 and transport in ("auto", "p2p"):
+            try:
+                self.peer = PeerMemory(2 * self.npix * 12, device)      # two frames of [RGBA16 | depth] (double-buffered)
+                self.transport = "p2p"
+            except Exception as e:
+                if transport == "p2p":
+                    raise
+                import sys
+                print(f"[sortfirst] peer memory unavailable ({type(e).__name__}: {e}); using NCCL gather", file=sys.stderr)
+        if self.peer is not None:
+            return
         if H % (BAND_ROWS * world):
             raise ValueError(f"image height {H} must be a multiple of {BAND_ROWS} x {world}")
         self.groups = H // (BAND_ROWS * world)
@@ -311,6 +430,21 @@ class SortFirst:
         p = params
         saved = (p.image_band_modulus, p.image_band_remainder)
         p.image_band_modulus, p.image_band_remainder = self.world, self.rank
+        if self.peer is not None:
+            # Frame k lands in half k & 1 of rank 0's buffer.  A rank can run at most one frame ahead of rank 0 (the barrier),
+            # and rank 0 enqueues its copy-out of frame k before it enters the barrier of frame k + 1, so the writes of frame
+            # k + 2 into the same half never overtake that copy.
+            base = (self.frame_no & 1) * self.npix * 12
+            self.frame_no += 1
+            with torch.cuda.stream(self.stream):
+                self.ctx.render_camera_ptrs(p, eep, cam, self.W, self.H, [self.peer.ptr(0, base), 0, 0], self.peer.ptr(0, base + self.npix * 8), device=True)
+                march_ms = self.ctx.stats().last_march_ms
+                p.image_band_modulus, p.image_band_remainder = saved
+                self.peer.barrier()
+                if self.rank == 0:
+                    out_rgba16.view(-1, 4).copy_(self.peer.view(0, base, (self.npix, 4), torch.int16))
+                    out_depth.view(-1).copy_(self.peer.view(0, base + self.npix * 8, (self.npix,), torch.float32))
+            return march_ms
         G, B, W, N = self.groups, BAND_ROWS, self.W, self.world
         with torch.cuda.stream(self.stream):
             self.ctx.render_camera_ptrs(p, eep, cam, self.W, self.H, [self.full16.data_ptr(), 0, 0], self.fulld.data_ptr(), device=True)
