@@ -389,6 +389,22 @@ def run_b200(args, rank, world, local_rank):
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
+    # sort-last: per-phase device times of a few frames outside the timed region (max over ranks of each phase)
+    sl_phases = None
+    if sl is not None:
+        sl.profile = True
+        acc = {}
+        pv = [0, 9, 18, 27]
+        for k in pv:
+            frame(k)
+            mine = {a: float(b) for a, b in sl.phases.items()}
+            allp = [None] * world
+            dist.all_gather_object(allp, mine)
+            for a in mine:
+                acc.setdefault(a, []).append(max(d_.get(a, 0.0) for d_ in allp))
+        sl.profile = False
+        sl_phases = {a: sum(v) / len(v) for a, v in acc.items()}
+        sl_phases["note"] = f"views {pv}, max over ranks per phase, mean over views; phases overlap across ranks, so they need not add up to frame_ms"
     steps_views = [(args.warmup + k) % N_VIEWS for k in range(args.steps)]
     S = sum(ref_samples[v] for v in steps_views)
     value = S / (ms_total * 1e-3) / 1e9
@@ -474,7 +490,7 @@ def run_b200(args, rank, world, local_rank):
             "gsamples_classified_per_s": sum(classified[v] for v in steps_views) / (ms_total * 1e-3) / 1e9,
             "gsamples_nominal_per_s": sum(nominal[v] for v in steps_views) / (ms_total * 1e-3) / 1e9,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
-            "synth_s": t_synth,
+            "synth_s": t_synth, "sortlast_phases": sl_phases,
             "minmax_build": {"kernel": "brick_partials_u16_kernel + cell_fold_u16_kernel", "ms": mm_ms, "alg_bytes": mm_bytes,
                              "achieved": mm_bytes / (mm_ms * 1e-3) / 1e9 if mm_ms > 0 else None, "peak": peak, "unit": "GB/s",
                              "frac": (mm_bytes / (mm_ms * 1e-3) / 1e9 / peak) if mm_ms > 0 else None, "bound": "hbm"},

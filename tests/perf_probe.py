@@ -14,6 +14,7 @@ from voreen_b200 import abi  # noqa: E402
 
 def main():
     sizes = [int(a) for a in sys.argv[1:] if not a.startswith('--')] or [512]
+    band = int(next((a.split('=')[1] for a in sys.argv if a.startswith('--band=')), '1'))
     comp = next((a.split('=')[1] for a in sys.argv if a.startswith('--comp=')), 'dvr')
     ctx = vb.Context(0)
     for n in sizes:
@@ -43,6 +44,7 @@ def main():
                             ctx.set_tf1d(0, tex, (0.0, 65535.0))
                             pi = True
                         p.vol[0].classification = abi.CLASS_PREINT
+                    p.image_band_modulus, p.image_band_remainder = band, 0
                     eep = vb.default_eep()
                     ms = []
                     for k in range(0, 36, 6):
@@ -56,7 +58,7 @@ def main():
                     ctx.render_camera(p, eep, cam, img, img)
                     s = ctx.stats()
                     m = np.median([a for a, _ in ms])
-                    print(f"[{n}^3 @{img}^2] comp={comp} cls={cls} sampler={'tex' if sampler else 'exact'} ess={ess}: march {m:.3f} ms (min {min(a for a,_ in ms):.3f} max {max(a for a,_ in ms):.3f}) "
+                    print(f"[{n}^3 @{img}^2] band 1/{band} comp={comp} cls={cls} sampler={'tex' if sampler else 'exact'} ess={ess}: march {m:.3f} ms (min {min(a for a,_ in ms):.3f} max {max(a for a,_ in ms):.3f}) "
                           f"eep {np.median([b for _, b in ms]):.3f} ms | rays {s.rays_cast} classified {s.samples_classified} shaded {s.samples_shaded} nominal {s.samples_nominal} "
                           f"cells16 {s.cells_touched} -> {s.samples_classified / m / 1e6:.2f} Gsamples/s", flush=True)
 

@@ -226,6 +226,9 @@ static int build_params(b200rc_ctx* ctx, const b200rc_params* P, const b200rc_ca
     p.collect_stats = P->collect_stats;
     p.band_mod = P->image_band_modulus > 1 ? P->image_band_modulus : 1;
     p.band_rem = P->image_band_modulus > 1 ? P->image_band_remainder : 0;
+    p.band_rows = 16;
+    { static const int env_rows = getenv("B200RC_BAND_ROWS") ? atoi(getenv("B200RC_BAND_ROWS")) : 0;      // experiments
+      if (env_rows >= 16 && env_rows % 16 == 0) p.band_rows = env_rows; }
     if (p.band_rem < 0 || p.band_rem >= p.band_mod) { ctx->set_error("image_band_remainder out of range"); return B200RC_ERR_INVALID; }
     p.ert_snap = P->partial_image ? 0 : 1;      // sort-last partial images keep the un-snapped alpha; b200rc_finalize snaps after the merge
     bool ert = true;

@@ -37,6 +37,8 @@ static int launch_slab(b200rc_ctx* ctx, const DevParams& p0) {
     int per_sm = 0;
     RC_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SLAB_THREADS, smem));
     if (per_sm < 1) per_sm = 1;
+    { static const int env_per_sm = getenv("B200RC_SLAB_CTAS_PER_SM") ? atoi(getenv("B200RC_SLAB_CTAS_PER_SM")) : 0;     // experiments
+      if (env_per_sm >= 1 && env_per_sm < per_sm) per_sm = env_per_sm; }
     const long long tiles = (long long)p.tiles_x * p.tiles_y;
     long long grid = (long long)ctx->num_sms * per_sm;      // persistent: one wave, a multiple of the SM count
     if (grid > tiles) grid = tiles;
@@ -49,7 +51,9 @@ static int launch_slab(b200rc_ctx* ctx, const DevParams& p0) {
         ctx->tile_capacity = (size_t)tiles;
     }
     slab_tile_cost_kernel<<<(unsigned)tiles, SLAB_THREADS, 0, ctx->stream>>>(p, ctx->d_tile_cost);
-    slab_tile_order_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_tile_cost, (unsigned)tiles, ctx->d_tile_order, p.tile_counter);
+    static const bool plain_order = getenv("B200RC_TILE_ORDER") && atoi(getenv("B200RC_TILE_ORDER")) == 0;     // A/B measurements
+    if (plain_order) slab_tile_order_plain_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_tile_cost, (unsigned)tiles, ctx->d_tile_order, p.tile_counter);
+    else slab_tile_order_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_tile_cost, (unsigned)tiles, ctx->d_tile_order, p.tile_counter);
     ctx->launches += 2;
     sa.order = ctx->d_tile_order;
     kern<<<(unsigned)grid, SLAB_THREADS, smem, ctx->stream>>>(p, sa);

@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(SLAB_THREADS) slab_tile_cost_kernel(const __gr
     const unsigned sup = tile >> 6, loc = tile & 63u;
     const unsigned tx = (sup % super_x) * 8u + compact1by1(loc), ty = (sup / super_x) * 8u + compact1by1(loc >> 1);
     float c = 0.f;
-    const bool mine = !(p.band_mod > 1 && (int)((ty * SLAB_TILE_H / 16u) % (unsigned)p.band_mod) != p.band_rem);
+    const bool mine = !(p.band_mod > 1 && (int)((ty * SLAB_TILE_H / (unsigned)p.band_rows) % (unsigned)p.band_mod) != p.band_rem);
     const int px = (int)(tx * SLAB_TILE + (warp & 1u) * 8u + (lane & 7u)), py = (int)(ty * SLAB_TILE_H + (warp >> 1) * 4u + (lane >> 3));
     if (mine && px < p.W && py < p.H) {
         const size_t pix = (size_t)py * p.W + px;
@@ -204,6 +204,15 @@ __global__ void __launch_bounds__(SLAB_THREADS) slab_tile_cost_kernel(const __gr
         float s = 0.f;
         for (int w = 0; w < SLAB_THREADS / 32; ++w) s += part[w];
         cost[tile] = s;
+    }
+}
+
+// A/B switch (B200RC_TILE_ORDER=0): Z-order numbering as is; only the tiles that own no pixel are dropped
+__global__ void slab_tile_order_plain_kernel(const float* __restrict__ cost, unsigned ntiles, unsigned int* __restrict__ order, unsigned int* __restrict__ counter) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        unsigned n = 0;
+        for (unsigned i = 0; i < ntiles; ++i) if (cost[i] > 0.f) order[n++] = i;
+        counter[0] = 0u; counter[1] = n;
     }
 }
 
@@ -296,7 +305,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
         if (tile >= ntiles) break;
         const unsigned sup = tile >> 6, loc = tile & 63u;
         const unsigned tx = (sup % super_x) * 8u + compact1by1(loc), ty = (sup / super_x) * 8u + compact1by1(loc >> 1);
-        if (p.band_mod > 1 && (int)((ty * SLAB_TILE_H / 16u) % (unsigned)p.band_mod) != p.band_rem) { __syncthreads(); continue; }   // another rank's band (uniform)
+        if (p.band_mod > 1 && (int)((ty * SLAB_TILE_H / (unsigned)p.band_rows) % (unsigned)p.band_mod) != p.band_rem) { __syncthreads(); continue; }   // another rank's band (uniform)
         // warp w covers the 8x4 sub-tile (w & 1, w >> 1) of the 16x16 tile
         const int px = (int)(tx * SLAB_TILE + (warp & 1u) * 8u + (lane & 7u)), py = (int)(ty * SLAB_TILE_H + (warp >> 1) * 4u + (lane >> 3));
         const bool inside = px < p.W && py < p.H;
