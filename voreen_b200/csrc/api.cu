@@ -107,7 +107,7 @@ extern "C" int b200rc_destroy(b200rc_ctx* ctx) {
     }
     cudaFree(ctx->d_entry); cudaFree(ctx->d_exit); cudaFree(ctx->d_entry_depth); cudaFree(ctx->d_exit_depth);
     for (int o = 0; o < 3; ++o) cudaFree(ctx->d_out[o]);
-    cudaFree(ctx->d_out_depth); cudaFree(ctx->d_stats); cudaFree(ctx->d_tile_counter); cudaFree(ctx->d_tile_cost); cudaFree(ctx->d_tile_order); cudaFree(ctx->d_boxes);
+    cudaFree(ctx->d_out_depth); cudaFree(ctx->d_stats); cudaFree(ctx->d_tile_counter); cudaFree(ctx->d_remarch_list); cudaFree(ctx->d_tile_cost); cudaFree(ctx->d_tile_order); cudaFree(ctx->d_boxes);
     for (int i = 0; i < 6; ++i) cudaEventDestroy(ctx->ev[i]);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -354,7 +354,7 @@ int rc_march_launch(b200rc_ctx* ctx, const DevParams& p, int sampler, int nch, i
     // sort-last second pass (p.flags): ~2 % of the pixels along a band.  Measured at 2048^3 x2 (profiles/r1_pass9_*): slab
     // marcher 2.4 ms, per-ray kernel 3.4 ms -> the slab marcher stays; B200RC_REMARCH=ray selects the per-ray kernel (A/B)
     static const bool remarch_ray = getenv("B200RC_REMARCH") && !strcmp(getenv("B200RC_REMARCH"), "ray");
-    const bool slab_ok = ctx->use_slab && !(p.flags && remarch_ray);
+    const bool slab_ok = ctx->use_slab && !(p.flags && (remarch_ray || p.pixel_list));
     if (slab_ok && rc_march_slab(ctx, p, sampler, nch, dtype, &rc)) return rc;
     if (rc_march_fast(ctx, p, sampler, nch, dtype, &rc)) return rc;
     if (rc_march_fast_multi(ctx, p, sampler, &rc)) return rc;
@@ -488,6 +488,13 @@ static int render_camera_impl(b200rc_ctx* ctx, const b200rc_params* P, const b20
     if (flags) {        // second pass: the entry/exit images of the first pass are still resident
         if (ctx->eep_w != W || ctx->eep_h != H) { ctx->set_error("remarch: no entry/exit images of this size (call b200rc_render_camera_device first)"); return B200RC_ERR_NOT_READY; }
         p.prefix = prefix; p.flags = flags;
+        // the flagged pixels were compacted by the b200rc_ert_plan call that wrote this flags buffer: march the list with
+        // the per-ray kernel (one warp per 32 flagged rays) instead of whole 16x16 tiles holding a handful of them each.
+        // B200RC_REMARCH=slab keeps the tile marcher (A/B measurements).
+        static const bool remarch_slab = getenv("B200RC_REMARCH") && !strcmp(getenv("B200RC_REMARCH"), "slab");
+        if (!remarch_slab && flags == ctx->plan_flags && px == ctx->plan_n && ctx->d_remarch_list) {
+            p.pixel_list = ctx->d_remarch_list; p.pixel_count = ctx->d_tile_counter + 2;
+        }
     } else {
         rc = run_eep(ctx, eep, cam, W, H);
         if (rc) return rc;

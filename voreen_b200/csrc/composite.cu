@@ -62,7 +62,7 @@ int rc_finalize_launch(b200rc_ctx* ctx, const float* rgba, const float* depth, s
 //   otherwise                         -> the first-pass result stands (P == 0: local and global thresholds coincide)
 __global__ void ert_plan_kernel(const float* __restrict__ alphas, int world, unsigned front_mask, float4* __restrict__ color,
                                 float* __restrict__ depth, size_t n, float* __restrict__ prefix, unsigned char* __restrict__ flags,
-                                unsigned long long* __restrict__ counter) {
+                                unsigned long long* __restrict__ counter, unsigned int* __restrict__ list, unsigned int* __restrict__ list_n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned flag = 0;
     if (i < n) {
@@ -78,6 +78,17 @@ __global__ void ert_plan_kernel(const float* __restrict__ alphas, int world, uns
         prefix[i] = P;
         flags[i] = (unsigned char)flag;
     }
+    if (list) {         // compact the pixels to re-march (warp-aggregated append: one atomic per warp, row neighbours stay together)
+        const unsigned m = __ballot_sync(0xffffffffu, flag == 2);
+        if (m) {
+            const unsigned lane = threadIdx.x & 31u;
+            const int leader = __ffs(m) - 1;
+            unsigned base = 0;
+            if ((int)lane == leader) base = atomicAdd(list_n, (unsigned)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (flag == 2) list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned int)i;
+        }
+    }
     if (counter) {
         const unsigned c = __reduce_add_sync(0xffffffffu, flag == 2 ? 1u : 0u);
         if ((threadIdx.x & 31) == 0 && c) atomicAdd(counter, (unsigned long long)c);
@@ -87,7 +98,20 @@ __global__ void ert_plan_kernel(const float* __restrict__ alphas, int world, uns
 int rc_ert_plan_launch(b200rc_ctx* ctx, const float* alphas, int world, unsigned front_mask, float* color, float* depth, size_t n,
                        float* prefix, unsigned char* flags, unsigned long long* counter) {
     if (!n) return B200RC_OK;
-    ert_plan_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(alphas, world, front_mask, (float4*)color, depth, n, prefix, flags, counter);
+    ctx->plan_flags = nullptr; ctx->plan_n = 0;
+    unsigned int* list = nullptr;
+    if (n < 0xffffffffull) {
+        if (ctx->remarch_capacity < n) {
+            cudaFree(ctx->d_remarch_list); ctx->d_remarch_list = nullptr; ctx->remarch_capacity = 0;
+            RC_CHECK(cudaMalloc(&ctx->d_remarch_list, sizeof(unsigned int) * n));
+            ctx->remarch_capacity = n;
+        }
+        list = ctx->d_remarch_list;
+        RC_CHECK(cudaMemsetAsync(ctx->d_tile_counter + 2, 0, sizeof(unsigned int), ctx->stream));
+    }
+    ert_plan_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(alphas, world, front_mask, (float4*)color, depth, n, prefix, flags, counter,
+                                                                         list, ctx->d_tile_counter + 2);
+    if (list) { ctx->plan_flags = flags; ctx->plan_n = n; }
     ctx->launches++;
     RC_CHECK(cudaGetLastError());
     return B200RC_OK;

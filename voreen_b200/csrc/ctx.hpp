@@ -61,6 +61,8 @@ struct b200rc_ctx {
     void* d_out[3] = {nullptr, nullptr, nullptr}; float* d_out_depth = nullptr; size_t out_capacity = 0;
     unsigned long long* d_stats = nullptr;
     unsigned int* d_tile_counter = nullptr;     // [0] scheduler counter, [1] number of tiles with work (slab marcher)
+    unsigned int* d_remarch_list = nullptr; size_t remarch_capacity = 0;   // pixels flagged by the last b200rc_ert_plan (count: d_tile_counter[2])
+    const void* plan_flags = nullptr; size_t plan_n = 0;                   // ... and the flags buffer / pixel count that call was made for
     float* d_tile_cost = nullptr; unsigned int* d_tile_order = nullptr; size_t tile_capacity = 0;
     float* d_boxes = nullptr; int boxes_capacity = 0;
     b200rc_stats stats{};

@@ -21,7 +21,7 @@ int rc_launch_march_cfg(b200rc_ctx* ctx, const DevParams& p) {
     const long long tiles = (long long)p.tiles_x * p.tiles_y;
     long long grid = (long long)ctx->num_sms * per_sm;       // persistent: one wave, multiple of the SM count
     const long long need = (tiles + (B200RC_MARCH_THREADS / 32) - 1) / (B200RC_MARCH_THREADS / 32);
-    if (grid > need) grid = need;
+    if (grid > need && !p.pixel_list) grid = need;
     if (grid < 1) grid = 1;
     RC_CHECK(cudaMemsetAsync(p.tile_counter, 0, sizeof(unsigned int), ctx->stream));
     kern<<<(unsigned)grid, B200RC_MARCH_THREADS, smem, ctx->stream>>>(p);
