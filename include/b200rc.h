@@ -224,6 +224,19 @@ int b200rc_get_stats(b200rc_ctx* ctx, b200rc_stats* out);
  *      (V/src/core/datastructures/volume/volumegl.cpp:106-139,336-381; V/src/core/utils/glsl.cpp:85-112).
  *      Builds the bricked pool (and the cudaArray for B200RC_SAMPLER_TEX) plus the min/max macro-cell grid. */
 int b200rc_upload_volume(b200rc_ctx* ctx, int slot, const void* data, const b200rc_volume_desc* desc);
+/* Streaming upload, for volumes that should not (or cannot) sit in host memory as a whole: begin allocates the pool, every
+ * slab call hands over planes [z0, z0 + nz) of the RESIDENT range (x fastest, channels interleaved; host memory, or device
+ * memory when desc->data_on_device) -- z0 a multiple of 8, nz a multiple of 8 except for the last slab -- and end builds the
+ * min/max grid.  The brick pool stores the 8-plane brick layers contiguously, so a slab lands in one contiguous range of it. */
+int b200rc_upload_volume_begin(b200rc_ctx* ctx, int slot, const b200rc_volume_desc* desc);
+int b200rc_upload_volume_slab(b200rc_ctx* ctx, int slot, int z0, int nz, const void* data);
+int b200rc_upload_volume_end(b200rc_ctx* ctx, int slot);
+/* Raw file -> HBM: replaces RawVolumeReader / VolumeDiskRaw::loadVolume (V/modules/core/io/rawvolumereader.cpp:460-560,
+ * V/src/core/datastructures/volume/volumedisk.cpp) for the formats of b200rc_volume_desc.  The file holds the WHOLE volume
+ * (desc->dims, x fastest, little endian) after `header_skip` bytes; only the resident range of desc is read (a sort-last
+ * rank streams just its shard + apron out of a volume no single GPU could hold).  Slabs of `slab_planes` planes (0 = about
+ * 64 MiB) go through two pinned buffers: the read of slab k+1 overlaps the host->device copy and bricking of slab k. */
+int b200rc_load_raw_file(b200rc_ctx* ctx, int slot, const char* path, const b200rc_volume_desc* desc, uint64_t header_skip, int slab_planes);
 int b200rc_release_volume(b200rc_ctx* ctx, int slot);
 /* Deterministic synthetic "CT-like" volume generated directly in HBM; u16, 1 channel. */
 int b200rc_synth_volume(b200rc_ctx* ctx, int slot, const b200rc_volume_desc* desc, uint64_t seed);

@@ -46,6 +46,20 @@ int b200host_tf1d_width_for(int dtype, int* out_width);
 int b200host_volume_desc(const int32_t dims[3], int channels, const char* format /* "uint8" "uint16" "float" */,
                          const float* spacing, const float* offset, const float* phys_to_world, b200rc_volume_desc* out);
 
+/* ---- .vvd volume descriptions (V/modules/core/io/vvdvolumereader.cpp:58-128, vvdformat.cpp:59-120,290-330): the XML
+ *      wrapper every bundled workspace loads.  Parses volume number `index` of the file: <RawData format x y z> with the raw
+ *      file either as the old `filename` attribute (relative to the .vvd) or as <Paths><paths><item value>, and the MetaData
+ *      items Offset, Spacing (Vec3MetaData), Transformation (Mat4MetaData, rows value.row0..3) and RealWorldMapping (scale,
+ *      offset); a volume without RealWorldMapping gets the denormalising one, as VvdVolumeReader::read does (:103-118).
+ *      DerivedData (hash, min/max, histogram, preview) is ignored: the library rebuilds what it needs on the device.
+ *      Formats: uint8 / uint16 / float and VectorN(<those>) for N = 2..4 channels; anything else (signed, 32/64-bit integer,
+ *      RawDataNoExternalFile, OctreeData) returns B200RC_ERR_INVALID with the reason in `error` (if given).
+ *      raw_path receives the absolute/relative path of the raw file (resolved against the directory of the .vvd). */
+int b200host_vvd_parse(const char* vvd_path, int index, b200rc_volume_desc* out_desc, char* raw_path, size_t raw_path_len,
+                       char* error, size_t error_len);
+/* Number of <Volume> entries in the file, or a negative status. */
+int b200host_vvd_count(const char* vvd_path);
+
 /* ---- SingleVolumeRaycaster mirror (V/modules/base/processors/render/singlevolumeraycaster.cpp:46-170,246-425) ---- */
 typedef struct b200host_svrc b200host_svrc;
 

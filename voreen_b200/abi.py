@@ -93,7 +93,7 @@ SYMBOLS = [
     "b200rc_synth_volume", "b200rc_download_volume", "b200rc_region_minmax", "b200rc_download_minmax", "b200rc_set_tf1d", "b200rc_set_preint",
     "b200rc_build_preint", "b200rc_download_preint", "b200rc_set_tf2d", "b200rc_entry_exit", "b200rc_render",
     "b200rc_render_camera", "b200rc_render_camera_device", "b200rc_composite", "b200rc_finalize", "b200rc_ert_plan",
-    "b200rc_remarch_device",
+    "b200rc_remarch_device", "b200rc_upload_volume_begin", "b200rc_upload_volume_slab", "b200rc_upload_volume_end", "b200rc_load_raw_file",
 ]
 
 _lib = None
@@ -121,6 +121,10 @@ def load_library():
     lib.b200rc_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.b200rc_upload_volume.argtypes = [vp, i32, vp, C.POINTER(VolumeDesc)]
     lib.b200rc_release_volume.argtypes = [vp, i32]
+    lib.b200rc_upload_volume_begin.argtypes = [vp, i32, C.POINTER(VolumeDesc)]
+    lib.b200rc_upload_volume_slab.argtypes = [vp, i32, i32, i32, vp]
+    lib.b200rc_upload_volume_end.argtypes = [vp, i32]
+    lib.b200rc_load_raw_file.argtypes = [vp, i32, C.c_char_p, C.POINTER(VolumeDesc), u64, i32]
     lib.b200rc_synth_volume.argtypes = [vp, i32, C.POINTER(VolumeDesc), u64]
     lib.b200rc_download_volume.argtypes = [vp, i32, vp, sz]
     lib.b200rc_region_minmax.argtypes = [vp, i32, i32, C.POINTER(C.c_int32 * 3), pf, sz]

@@ -142,6 +142,12 @@ extern "C" int b200rc_get_stats(b200rc_ctx* ctx, b200rc_stats* out) {
 
 // ---- volume / TF pass-throughs ---------------------------------------------------------------------------------------
 extern "C" int b200rc_upload_volume(b200rc_ctx* ctx, int slot, const void* data, const b200rc_volume_desc* desc) { CTX_GUARD(); return rc_volume_upload(ctx, slot, data, desc); }
+extern "C" int b200rc_upload_volume_begin(b200rc_ctx* ctx, int slot, const b200rc_volume_desc* desc) { CTX_GUARD(); return rc_volume_stream_begin(ctx, slot, desc); }
+extern "C" int b200rc_upload_volume_slab(b200rc_ctx* ctx, int slot, int z0, int nz, const void* data) { CTX_GUARD(); return rc_volume_stream_slab(ctx, slot, z0, nz, data); }
+extern "C" int b200rc_upload_volume_end(b200rc_ctx* ctx, int slot) { CTX_GUARD(); return rc_volume_stream_end(ctx, slot); }
+extern "C" int b200rc_load_raw_file(b200rc_ctx* ctx, int slot, const char* path, const b200rc_volume_desc* desc, uint64_t header_skip, int slab_planes) {
+    CTX_GUARD(); if (slot < 0 || slot >= B200RC_MAX_VOLUMES) return B200RC_ERR_INVALID; return rc_volume_load_raw(ctx, slot, path, desc, header_skip, slab_planes);
+}
 extern "C" int b200rc_release_volume(b200rc_ctx* ctx, int slot) { CTX_GUARD(); if (slot < 0 || slot >= B200RC_MAX_VOLUMES) return B200RC_ERR_INVALID; return rc_volume_release(ctx, slot); }
 extern "C" int b200rc_synth_volume(b200rc_ctx* ctx, int slot, const b200rc_volume_desc* desc, uint64_t seed) { CTX_GUARD(); return rc_volume_synth(ctx, slot, desc, seed); }
 extern "C" int b200rc_download_volume(b200rc_ctx* ctx, int slot, void* host_dst, size_t bytes) {
@@ -488,11 +494,13 @@ static int render_camera_impl(b200rc_ctx* ctx, const b200rc_params* P, const b20
     if (flags) {        // second pass: the entry/exit images of the first pass are still resident
         if (ctx->eep_w != W || ctx->eep_h != H) { ctx->set_error("remarch: no entry/exit images of this size (call b200rc_render_camera_device first)"); return B200RC_ERR_NOT_READY; }
         p.prefix = prefix; p.flags = flags;
-        // the flagged pixels were compacted by the b200rc_ert_plan call that wrote this flags buffer: march the list with
-        // the per-ray kernel (one warp per 32 flagged rays) instead of whole 16x16 tiles holding a handful of them each.
-        // B200RC_REMARCH=slab keeps the tile marcher (A/B measurements).
-        static const bool remarch_slab = getenv("B200RC_REMARCH") && !strcmp(getenv("B200RC_REMARCH"), "slab");
-        if (!remarch_slab && flags == ctx->plan_flags && px == ctx->plan_n && ctx->d_remarch_list) {
+        // B200RC_REMARCH=list (A/B measurements): the flagged pixels were compacted by the b200rc_ert_plan call that wrote this
+        // flags buffer; march that list with the per-ray kernel (one warp per 32 flagged rays).  Measured at 2048^3 x2 shards,
+        // 77 k flagged pixels (profiles/r1_pass20_remarch_2.txt): list 6.1 ms, slab marcher over the tiles that hold a flagged
+        // pixel 2.9 ms -- a warp of the per-ray kernel is a ~40-load dependency chain per sample, the staged tile is not, and
+        // the longest-first tile order already drops every tile without a flagged pixel.  The slab marcher stays the default.
+        static const bool remarch_list = getenv("B200RC_REMARCH") && !strcmp(getenv("B200RC_REMARCH"), "list");
+        if (remarch_list && flags == ctx->plan_flags && px == ctx->plan_n && ctx->d_remarch_list) {
             p.pixel_list = ctx->d_remarch_list; p.pixel_count = ctx->d_tile_counter + 2;
         }
     } else {

@@ -76,6 +76,10 @@ struct b200rc_ctx {
 int rc_volume_upload(b200rc_ctx* ctx, int slot, const void* data, const b200rc_volume_desc* desc);
 int rc_volume_synth(b200rc_ctx* ctx, int slot, const b200rc_volume_desc* desc, uint64_t seed);
 int rc_volume_release(b200rc_ctx* ctx, int slot);
+int rc_volume_stream_begin(b200rc_ctx* ctx, int slot, const b200rc_volume_desc* desc);
+int rc_volume_stream_slab(b200rc_ctx* ctx, int slot, int z0, int nz, const void* data);
+int rc_volume_stream_end(b200rc_ctx* ctx, int slot);
+int rc_volume_load_raw(b200rc_ctx* ctx, int slot, const char* path, const b200rc_volume_desc* desc, uint64_t header_skip, int slab_planes);
 int rc_volume_download(b200rc_ctx* ctx, int slot, void* host_dst, size_t bytes);
 int rc_volume_ensure_texture(b200rc_ctx* ctx, int slot, int filter, int clamp, float border);
 int rc_volume_region_minmax(b200rc_ctx* ctx, int slot, int cell_size, int32_t cells[3], float* out, size_t out_floats);

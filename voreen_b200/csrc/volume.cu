@@ -47,6 +47,40 @@ __global__ void brick_rows_u16x8_kernel(const uint4* __restrict__ lin, uint4* __
     bricks[row] = __ldg(lin + ((long long)z * dy + y) * dx8 + bx);
 }
 
+// slab variants: `lin` holds planes [z0, z0 + nz) of the resident range; the launch covers the brick layers [bz0, bz0 + nbz_slab)
+template <typename T>
+__global__ void brick_rows_slab_kernel(const T* __restrict__ lin, T* __restrict__ bricks, int dx, int dy, int dz, int nbx, int nby, int z0, int nz,
+                                       int bz0, int nbz_slab, int nch_in, int nch_st, T pad_value) {
+    const long long lrow = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nrows = (long long)nbx * nby * nbz_slab * 64;
+    if (lrow >= nrows) return;
+    const long long row = lrow + (long long)bz0 * nbx * nby * 64;
+    const long long brick = row >> 6;
+    const int within = (int)(row & 63);
+    const int bx = (int)(brick % nbx), by = (int)((brick / nbx) % nby), bz = (int)(brick / ((long long)nbx * nby));
+    const int y = min(by * 8 + (within & 7), dy - 1);
+    const int z = min(min(bz * 8 + (within >> 3), dz - 1), z0 + nz - 1) - z0;
+    const T* src = lin + ((long long)z * dy + y) * dx * nch_in;
+    T* dst = bricks + row * 8 * nch_st;
+    for (int i = 0; i < 8; ++i) {
+        const int x = min(bx * 8 + i, dx - 1);
+        for (int c = 0; c < nch_st; ++c) dst[i * nch_st + c] = (c < nch_in) ? src[(long long)x * nch_in + c] : pad_value;
+    }
+}
+__global__ void brick_rows_slab_u16x8_kernel(const uint4* __restrict__ lin, uint4* __restrict__ bricks, int dx8, int dy, int dz, int nbx, int nby, int z0, int nz,
+                                             int bz0, int nbz_slab) {
+    const long long lrow = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nrows = (long long)nbx * nby * nbz_slab * 64;
+    if (lrow >= nrows) return;
+    const long long row = lrow + (long long)bz0 * nbx * nby * 64;
+    const long long brick = row >> 6;
+    const int within = (int)(row & 63);
+    const int bx = (int)(brick % nbx), by = (int)((brick / nbx) % nby), bz = (int)(brick / ((long long)nbx * nby));
+    const int y = min(by * 8 + (within & 7), dy - 1);
+    const int z = min(min(bz * 8 + (within >> 3), dz - 1), z0 + nz - 1) - z0;
+    bricks[row] = __ldg(lin + ((long long)z * dy + y) * dx8 + bx);
+}
+
 template <typename T>
 __global__ void debrick_kernel(const T* __restrict__ bricks, T* __restrict__ lin, int dx, int dy, int dz, int nbx, int nby, int nch_out, int nch_st) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -474,6 +508,124 @@ int rc_volume_upload(b200rc_ctx* ctx, int slot, const void* data, const b200rc_v
     ctx->launches++;
     RC_CHECK(cudaGetLastError());
     if (staging) { RC_CHECK(cudaStreamSynchronize(ctx->stream)); cudaFree(staging); }
+    return volume_build_minmax(ctx, slot);
+}
+
+// ---- streaming upload ------------------------------------------------------------------------------------------------------
+int rc_volume_stream_begin(b200rc_ctx* ctx, int slot, const b200rc_volume_desc* desc) {
+    int rc = volume_prepare(ctx, slot, desc);
+    if (rc) return rc;
+    ctx->vol[slot].valid = false;           // not renderable before rc_volume_stream_end
+    return B200RC_OK;
+}
+
+// d_lin: planes [z0, z0 + nz) of the resident range in DEVICE memory
+static int volume_brick_slab(b200rc_ctx* ctx, VolumeSlot& v, int z0, int nz, const void* d_lin) {
+    const int dx = v.res_dims[0], dy = v.res_dims[1], dz = v.res_dims[2];
+    if (z0 < 0 || nz < 1 || z0 + nz > dz || (z0 & 7) || ((nz & 7) && z0 + nz != dz)) { ctx->set_error("upload slab: z0 / nz must be multiples of 8 (last slab excepted) inside the resident range"); return B200RC_ERR_INVALID; }
+    const int bz0 = z0 >> 3, nbz_slab = (nz + 7) >> 3;
+    const long long nrows = (long long)v.nbx * v.nby * nbz_slab * 64;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((nrows + threads - 1) / threads);
+    const b200rc_volume_desc& d = v.desc;
+    if (d.dtype == B200RC_U16 && d.channels == 1 && dx % 8 == 0 && ((uintptr_t)d_lin % 16) == 0)
+        brick_rows_slab_u16x8_kernel<<<blocks, threads, 0, ctx->stream>>>((const uint4*)d_lin, (uint4*)v.bricks, dx / 8, dy, dz, v.nbx, v.nby, z0, nz, bz0, nbz_slab);
+    else if (d.dtype == B200RC_U16)
+        brick_rows_slab_kernel<unsigned short><<<blocks, threads, 0, ctx->stream>>>((const unsigned short*)d_lin, (unsigned short*)v.bricks, dx, dy, dz, v.nbx, v.nby, z0, nz, bz0, nbz_slab, d.channels, v.stored_nch, (unsigned short)65535);
+    else if (d.dtype == B200RC_U8)
+        brick_rows_slab_kernel<unsigned char><<<blocks, threads, 0, ctx->stream>>>((const unsigned char*)d_lin, (unsigned char*)v.bricks, dx, dy, dz, v.nbx, v.nby, z0, nz, bz0, nbz_slab, d.channels, v.stored_nch, (unsigned char)255);
+    else
+        brick_rows_slab_kernel<float><<<blocks, threads, 0, ctx->stream>>>((const float*)d_lin, (float*)v.bricks, dx, dy, dz, v.nbx, v.nby, z0, nz, bz0, nbz_slab, d.channels, v.stored_nch, 1.0f);
+    ctx->launches++;
+    RC_CHECK(cudaGetLastError());
+    return B200RC_OK;
+}
+
+int rc_volume_stream_slab(b200rc_ctx* ctx, int slot, int z0, int nz, const void* data) {
+    if (slot < 0 || slot >= B200RC_MAX_VOLUMES || !data) { ctx->set_error("upload slab: bad arguments"); return B200RC_ERR_INVALID; }
+    VolumeSlot& v = ctx->vol[slot];
+    if (!v.bricks) { ctx->set_error("upload slab: call b200rc_upload_volume_begin first"); return B200RC_ERR_NOT_READY; }
+    if (v.desc.data_on_device) return volume_brick_slab(ctx, v, z0, nz, data);
+    if (nz < 1 || z0 < 0 || z0 + nz > v.res_dims[2]) { ctx->set_error("upload slab: planes outside the resident range"); return B200RC_ERR_INVALID; }
+    const size_t bytes = (size_t)v.res_dims[0] * v.res_dims[1] * nz * v.desc.channels * v.elem_bytes;
+    void* staging = nullptr;
+    if (cudaMalloc(&staging, bytes) != cudaSuccess) { cudaGetLastError(); ctx->set_error("out of device memory for upload staging"); return B200RC_ERR_OOM; }
+    int rc = B200RC_OK;
+    if (cudaMemcpyAsync(staging, data, bytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { ctx->set_error("upload slab: host to device copy failed"); rc = B200RC_ERR_CUDA; }
+    if (!rc) rc = volume_brick_slab(ctx, v, z0, nz, staging);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(staging);
+    return rc;
+}
+
+int rc_volume_stream_end(b200rc_ctx* ctx, int slot) {
+    if (slot < 0 || slot >= B200RC_MAX_VOLUMES || !ctx->vol[slot].bricks) { ctx->set_error("upload end: no upload in progress"); return B200RC_ERR_NOT_READY; }
+    return volume_build_minmax(ctx, slot);
+}
+
+// Raw file -> brick pool through two pinned buffers (see include/b200rc.h).
+int rc_volume_load_raw(b200rc_ctx* ctx, int slot, const char* path, const b200rc_volume_desc* desc, uint64_t header_skip, int slab_planes) {
+    if (!path || !desc) { ctx->set_error("load raw: bad arguments"); return B200RC_ERR_INVALID; }
+    if (desc->data_on_device) { ctx->set_error("load raw: data_on_device makes no sense for a file"); return B200RC_ERR_INVALID; }
+    FILE* f = fopen(path, "rb");
+    if (!f) { ctx->set_error(std::string("Failed to open file '") + path + "' for reading."); return B200RC_ERR_INVALID; }
+    int rc = rc_volume_stream_begin(ctx, slot, desc);
+    if (rc) { fclose(f); return rc; }
+    VolumeSlot& v = ctx->vol[slot];
+    const size_t vox = (size_t)desc->channels * v.elem_bytes;
+    const size_t row_bytes = (size_t)v.res_dims[0] * vox, plane_bytes = row_bytes * v.res_dims[1];
+    // the file must hold the whole volume
+    {
+        fseeko(f, 0, SEEK_END);
+        const unsigned long long have = (unsigned long long)ftello(f);
+        const unsigned long long need = header_skip + (unsigned long long)desc->dims[0] * desc->dims[1] * desc->dims[2] * vox;
+        if (have < need) { fclose(f); rc_volume_release(ctx, slot); ctx->set_error("load raw: file is shorter than the volume it should hold"); return B200RC_ERR_INVALID; }
+    }
+    int S = slab_planes > 0 ? (slab_planes + 7) / 8 * 8 : (int)(((size_t)64 << 20) / (plane_bytes ? plane_bytes : 1)) / 8 * 8;
+    if (S < 8) S = 8;
+    if (S > (v.res_dims[2] + 7) / 8 * 8) S = (v.res_dims[2] + 7) / 8 * 8;
+    const size_t slab_bytes = plane_bytes * S;
+    void* pinned[2] = {nullptr, nullptr}; void* dstage[2] = {nullptr, nullptr}; cudaEvent_t done[2] = {nullptr, nullptr};
+    bool used[2] = {false, false};
+    auto cleanup = [&]() {
+        cudaStreamSynchronize(ctx->stream);
+        for (int k = 0; k < 2; ++k) { if (pinned[k]) cudaFreeHost(pinned[k]); if (dstage[k]) cudaFree(dstage[k]); if (done[k]) cudaEventDestroy(done[k]); }
+        fclose(f);
+    };
+    for (int k = 0; k < 2; ++k) {
+        if (cudaHostAlloc(&pinned[k], slab_bytes, cudaHostAllocDefault) != cudaSuccess || cudaMalloc(&dstage[k], slab_bytes) != cudaSuccess ||
+            cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError(); cleanup(); rc_volume_release(ctx, slot); ctx->set_error("load raw: out of memory for the staging buffers"); return B200RC_ERR_OOM;
+        }
+    }
+    const bool full_rows = v.res_dims[0] == desc->dims[0], full_planes = full_rows && v.res_dims[1] == desc->dims[1];
+    int k = 0;
+    for (int z0 = 0; z0 < v.res_dims[2] && !rc; z0 += S, k ^= 1) {
+        const int nz = (z0 + S <= v.res_dims[2]) ? S : v.res_dims[2] - z0;
+        if (used[k]) cudaEventSynchronize(done[k]);         // the copy out of this pinned buffer has finished
+        unsigned char* dst = (unsigned char*)pinned[k];
+        bool ok = true;
+        if (full_planes) {
+            const unsigned long long off = header_skip + (unsigned long long)(v.res_lo[2] + z0) * desc->dims[1] * desc->dims[0] * vox;
+            ok = fseeko(f, (off_t)off, SEEK_SET) == 0 && fread(dst, 1, plane_bytes * nz, f) == plane_bytes * nz;
+        } else {
+            for (int z = 0; z < nz && ok; ++z)
+                for (int y = 0; y < v.res_dims[1] && ok; ++y) {
+                    const unsigned long long off = header_skip + ((((unsigned long long)(v.res_lo[2] + z0 + z) * desc->dims[1]) + (v.res_lo[1] + y)) * desc->dims[0] + v.res_lo[0]) * vox;
+                    if (y == 0 || !full_rows) ok = fseeko(f, (off_t)off, SEEK_SET) == 0;
+                    const size_t want = full_rows ? row_bytes * v.res_dims[1] : row_bytes;
+                    ok = ok && fread(dst + ((size_t)z * v.res_dims[1] + y) * row_bytes, 1, want, f) == want;
+                    if (full_rows) break;           // the whole plane's resident rows are contiguous
+                }
+        }
+        if (!ok) { ctx->set_error("load raw: read failed"); rc = B200RC_ERR_INVALID; break; }
+        if (cudaMemcpyAsync(dstage[k], pinned[k], plane_bytes * nz, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { ctx->set_error("load raw: host to device copy failed"); rc = B200RC_ERR_CUDA; break; }
+        rc = volume_brick_slab(ctx, v, z0, nz, dstage[k]);
+        cudaEventRecord(done[k], ctx->stream);
+        used[k] = true;
+    }
+    cleanup();
+    if (rc) { rc_volume_release(ctx, slot); return rc; }
     return volume_build_minmax(ctx, slot);
 }
 

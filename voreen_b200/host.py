@@ -16,7 +16,7 @@ SYMBOLS = [
     "b200host_svrc_destroy", "b200host_svrc_last_error", "b200host_svrc_context", "b200host_svrc_set_property",
     "b200host_svrc_get_sampling_step", "b200host_svrc_set_volume", "b200host_svrc_set_synthetic_volume",
     "b200host_svrc_set_transfer_function", "b200host_svrc_set_camera", "b200host_svrc_connect_output",
-    "b200host_svrc_set_entry_exit", "b200host_svrc_is_ready", "b200host_svrc_process",
+    "b200host_svrc_set_entry_exit", "b200host_svrc_is_ready", "b200host_svrc_process", "b200host_vvd_parse", "b200host_vvd_count",
 ]
 
 
@@ -41,6 +41,8 @@ def load_library():
     lib.b200host_tf1d_width_for.argtypes = [i32, C.POINTER(i32)]
     lib.b200host_volume_desc.argtypes = [C.POINTER(C.c_int32 * 3), i32, C.c_char_p, pf, pf, pf, C.POINTER(abi.VolumeDesc)]
     lib.b200host_svrc_create.argtypes = [i32, C.POINTER(vp)]
+    lib.b200host_vvd_parse.argtypes = [C.c_char_p, i32, C.POINTER(abi.VolumeDesc), C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
+    lib.b200host_vvd_count.argtypes = [C.c_char_p]
     lib.b200host_svrc_destroy.argtypes = [vp]
     lib.b200host_svrc_destroy.restype = None
     lib.b200host_svrc_last_error.argtypes = [vp]
@@ -72,6 +74,21 @@ def make_camera(eye, focus=(0, 0, 0), up=(0, 1, 0), fovy=45.0, near=0.1, far=50.
     if rc:
         raise abi.B200RCError(f"b200host_camera: status {rc}")
     return cam
+
+
+def parse_vvd(path, index=0):
+    """VvdVolumeReader::read for one volume of a .vvd file -> (b200rc_volume_desc, path of the raw file)."""
+    desc = abi.VolumeDesc()
+    raw = C.create_string_buffer(4096)
+    err = C.create_string_buffer(512)
+    rc = load_library().b200host_vvd_parse(os.fsencode(path), index, C.byref(desc), raw, len(raw), err, len(err))
+    if rc:
+        raise abi.B200RCError(f"b200host_vvd_parse: {err.value.decode(errors='replace') or rc}")
+    return desc, os.fsdecode(raw.value)
+
+
+def vvd_count(path):
+    return load_library().b200host_vvd_count(os.fsencode(path))
 
 
 def make_keys(keys):

@@ -7,7 +7,10 @@
 #include "../../include/b200rc_host.h"
 #include "rc_properties.hpp"
 
+#include <cctype>
 #include <cmath>
+#include <cstdlib>
+#include <utility>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -145,6 +148,167 @@ extern "C" int b200host_volume_desc(const int32_t dims[3], int channels, const c
         out->offset[a] = offset ? offset[a] : (float)(-(dims[a] - 1) * 0.5f) * out->spacing[a];
     }
     for (int i = 0; i < 16; ++i) out->phys_to_world[i] = phys_to_world ? phys_to_world[i] : ((i % 5 == 0) ? 1.f : 0.f);
+    return B200RC_OK;
+}
+
+// ---- .vvd (V/modules/core/io/vvdvolumereader.cpp:58-128, vvdformat.cpp:59-120,290-330) ---------------------------------------
+// A deliberately small reader for the subset of XML the XmlSerializer writes with setUseAttributes(true): elements, attributes
+// in double quotes, no CDATA, no entities in the values we read except the five predefined ones.
+namespace {
+struct XmlTag { std::string name; std::vector<std::pair<std::string, std::string>> attr; bool closing = false, self = false; size_t end = 0; };
+
+std::string xml_unescape(const std::string& s) {
+    std::string o; o.reserve(s.size());
+    for (size_t i = 0; i < s.size(); ++i) {
+        if (s[i] != '&') { o += s[i]; continue; }
+        if (!s.compare(i, 5, "&amp;")) { o += '&'; i += 4; }
+        else if (!s.compare(i, 4, "&lt;")) { o += '<'; i += 3; }
+        else if (!s.compare(i, 4, "&gt;")) { o += '>'; i += 3; }
+        else if (!s.compare(i, 6, "&quot;")) { o += '"'; i += 5; }
+        else if (!s.compare(i, 6, "&apos;")) { o += '\''; i += 5; }
+        else o += s[i];
+    }
+    return o;
+}
+
+// next tag at or after `pos` (comments, processing instructions and doctype skipped); false at the end of the text
+bool xml_next(const std::string& t, size_t pos, XmlTag& tag) {
+    for (;;) {
+        const size_t lt = t.find('<', pos);
+        if (lt == std::string::npos) return false;
+        if (!t.compare(lt, 4, "<!--")) { const size_t e = t.find("-->", lt + 4); if (e == std::string::npos) return false; pos = e + 3; continue; }
+        if (lt + 1 < t.size() && (t[lt + 1] == '?' || t[lt + 1] == '!')) { const size_t e = t.find('>', lt); if (e == std::string::npos) return false; pos = e + 1; continue; }
+        size_t i = lt + 1;
+        tag = XmlTag();
+        if (i < t.size() && t[i] == '/') { tag.closing = true; ++i; }
+        const size_t n0 = i;
+        while (i < t.size() && !isspace((unsigned char)t[i]) && t[i] != '>' && t[i] != '/') ++i;
+        tag.name = t.substr(n0, i - n0);
+        for (;;) {
+            while (i < t.size() && isspace((unsigned char)t[i])) ++i;
+            if (i >= t.size()) return false;
+            if (t[i] == '>') { tag.end = i + 1; return true; }
+            if (t[i] == '/') { tag.self = true; ++i; continue; }
+            const size_t k0 = i;
+            while (i < t.size() && t[i] != '=' && !isspace((unsigned char)t[i]) && t[i] != '>') ++i;
+            const std::string key = t.substr(k0, i - k0);
+            while (i < t.size() && (isspace((unsigned char)t[i]) || t[i] == '=')) ++i;
+            if (i >= t.size() || (t[i] != '"' && t[i] != '\'')) return false;
+            const char q = t[i++];
+            const size_t v0 = i;
+            while (i < t.size() && t[i] != q) ++i;
+            if (i >= t.size()) return false;
+            tag.attr.emplace_back(key, xml_unescape(t.substr(v0, i - v0)));
+            ++i;
+        }
+    }
+}
+const std::string* xml_attr(const XmlTag& t, const char* k) {
+    for (const auto& a : t.attr) if (a.first == k) return &a.second;
+    return nullptr;
+}
+bool xml_float(const XmlTag& t, const char* k, float& out) {
+    const std::string* s = xml_attr(t, k);
+    if (!s) return false;
+    char* e = nullptr;
+    const double v = strtod(s->c_str(), &e);
+    if (e == s->c_str()) return false;
+    out = (float)v;
+    return true;
+}
+bool read_text_file(const char* path, std::string& out) {
+    FILE* f = fopen(path, "rb");
+    if (!f) return false;
+    char buf[65536]; size_t n;
+    while ((n = fread(buf, 1, sizeof buf, f)) > 0) out.append(buf, n);
+    fclose(f);
+    return true;
+}
+void set_err(char* error, size_t n, const std::string& s) { if (error && n) { snprintf(error, n, "%s", s.c_str()); } }
+}  // namespace
+
+extern "C" int b200host_vvd_count(const char* vvd_path) {
+    std::string t;
+    if (!vvd_path || !read_text_file(vvd_path, t)) return -B200RC_ERR_INVALID;
+    int n = 0; size_t pos = 0; XmlTag tag;
+    while (xml_next(t, pos, tag)) { pos = tag.end; if (!tag.closing && tag.name == "Volume") ++n; }
+    return n;
+}
+
+extern "C" int b200host_vvd_parse(const char* vvd_path, int index, b200rc_volume_desc* out, char* raw_path, size_t raw_path_len,
+                                  char* error, size_t error_len) {
+    if (!vvd_path || !out || index < 0) { set_err(error, error_len, "vvd: bad arguments"); return B200RC_ERR_INVALID; }
+    std::string t;
+    if (!read_text_file(vvd_path, t)) { set_err(error, error_len, std::string("Failed to open file '") + vvd_path + "' for reading."); return B200RC_ERR_INVALID; }
+    // walk to <Volume> number `index`
+    size_t pos = 0; XmlTag tag; int seen = -1; bool in_volume = false;
+    std::string format, file, meta_name;
+    int dims[3] = {0, 0, 0};
+    bool have_raw = false, in_raw = false, in_paths = false, in_meta = false, other_repr = false;
+    bool have_sp = false, have_off = false, have_tf = false, have_rwm = false;
+    float sp[3] = {1.f, 1.f, 1.f}, off[3] = {0.f, 0.f, 0.f}, tf[16], rwm[2] = {1.f, 0.f};
+    for (int i = 0; i < 16; ++i) tf[i] = (i % 5 == 0) ? 1.f : 0.f;
+    while (xml_next(t, pos, tag)) {
+        pos = tag.end;
+        if (tag.name == "Volume") {
+            if (!tag.closing) { ++seen; in_volume = (seen == index); }
+            else if (in_volume) break;
+            continue;
+        }
+        if (!in_volume) continue;
+        if (tag.name == "RawData" && !tag.closing) {
+            have_raw = true; in_raw = !tag.self;
+            if (const std::string* s = xml_attr(tag, "format")) format = *s;
+            if (const std::string* s = xml_attr(tag, "filename")) file = *s;       // old files (vvdformat.cpp:76-80)
+            const char* names[3] = {"x", "y", "z"};
+            for (int a = 0; a < 3; ++a) if (const std::string* s = xml_attr(tag, names[a])) dims[a] = atoi(s->c_str());
+        } else if (tag.name == "RawData") in_raw = false;
+        else if (tag.name == "RawDataNoExternalFile" || tag.name == "OctreeData") other_repr = true;
+        else if (in_raw && tag.name == "paths") in_paths = !tag.closing && !tag.self;
+        else if (in_raw && in_paths && tag.name == "item" && file.empty()) { if (const std::string* s = xml_attr(tag, "value")) file = *s; }
+        else if (tag.name == "MetaItem") {
+            if (tag.closing) { in_meta = false; continue; }
+            in_meta = !tag.self;
+            const std::string* n = xml_attr(tag, "name");
+            meta_name = n ? *n : std::string();
+        } else if (in_meta && tag.name == "value" && !tag.closing) {
+            if (meta_name == "Spacing") have_sp = xml_float(tag, "x", sp[0]) && xml_float(tag, "y", sp[1]) && xml_float(tag, "z", sp[2]);
+            else if (meta_name == "Offset") have_off = xml_float(tag, "x", off[0]) && xml_float(tag, "y", off[1]) && xml_float(tag, "z", off[2]);
+            else if (meta_name == "RealWorldMapping") have_rwm = xml_float(tag, "scale", rwm[0]) && xml_float(tag, "offset", rwm[1]);
+        } else if (in_meta && !tag.closing && !tag.name.compare(0, 9, "value.row") && tag.name.size() == 10 &&
+                   (meta_name == "Transformation" || meta_name == "transformation")) {      // renamed from old files (vvdformat.cpp:317-318)
+            const int r = tag.name[9] - '0';
+            if (r >= 0 && r < 4) have_tf = (xml_float(tag, "x", tf[r * 4]) && xml_float(tag, "y", tf[r * 4 + 1]) && xml_float(tag, "z", tf[r * 4 + 2]) && xml_float(tag, "w", tf[r * 4 + 3])) || have_tf;
+        }
+    }
+    if (seen < index) { set_err(error, error_len, "vvd: no such volume in file"); return B200RC_ERR_INVALID; }
+    if (!have_raw) { set_err(error, error_len, other_repr ? "vvd: only RawData volumes are supported (RawDataNoExternalFile / OctreeData found)" : "vvd: no RawData element"); return B200RC_ERR_INVALID; }
+    if (dims[0] < 1 || dims[1] < 1 || dims[2] < 1) { set_err(error, error_len, "vvd: bad dimensions"); return B200RC_ERR_INVALID; }
+    // format: base type or VectorN(base)
+    int channels = 1; std::string base = format;
+    if (!format.compare(0, 6, "Vector") && format.size() > 9 && format[7] == '(' && format.back() == ')') {
+        channels = format[6] - '0';
+        base = format.substr(8, format.size() - 9);
+    }
+    if (channels < 1 || channels > 4 || b200host_volume_desc(dims, channels, base.c_str(), have_sp ? sp : nullptr, have_off ? off : nullptr, tf, out) != B200RC_OK) {
+        set_err(error, error_len, "vvd: unsupported format '" + format + "' (uint8, uint16, float and their Vector2-4 forms are)");
+        return B200RC_ERR_INVALID;
+    }
+    if (!have_sp) for (int a = 0; a < 3; ++a) out->spacing[a] = 1.f;           // Volume default meta data (volumebase.cpp getSpacing/getOffset)
+    if (!have_off) for (int a = 0; a < 3; ++a) out->offset[a] = 0.f;
+    if (have_rwm) { out->rwm_scale = rwm[0]; out->rwm_offset = rwm[1]; }       // else the denormalising mapping set by b200host_volume_desc
+    (void)have_tf;
+    if (raw_path && raw_path_len) {
+        std::string p = file;
+        if (p.empty()) { set_err(error, error_len, "vvd: RawData without a file name"); return B200RC_ERR_INVALID; }
+        if (p[0] != '/') {
+            const std::string v(vvd_path);
+            const size_t slash = v.find_last_of('/');
+            if (slash != std::string::npos) p = v.substr(0, slash + 1) + p;
+        }
+        if (p.size() + 1 > raw_path_len) { set_err(error, error_len, "vvd: raw path buffer too small"); return B200RC_ERR_INVALID; }
+        snprintf(raw_path, raw_path_len, "%s", p.c_str());
+    }
     return B200RC_OK;
 }
 

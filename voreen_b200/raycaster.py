@@ -5,6 +5,7 @@ Everything here is a direct call into libb200rc.so; no rendering arithmetic live
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -171,6 +172,34 @@ class Context:
         self._check(self.lib.b200rc_upload_volume(self.h, slot, C.c_void_p(device_ptr), C.byref(desc)), "upload_volume")
         self.volume_desc[slot] = desc
         return desc
+
+    def upload_volume_slabs(self, slot, data, desc, slab_planes=8):
+        """Streaming upload (b200rc_upload_volume_begin / _slab / _end): `data` is the resident range, handed over in z slabs."""
+        data = np.ascontiguousarray(data)
+        self._check(self.lib.b200rc_upload_volume_begin(self.h, slot, C.byref(desc)), "upload_volume_begin")
+        for z0 in range(0, data.shape[0], slab_planes):
+            part = np.ascontiguousarray(data[z0:z0 + slab_planes])
+            self._check(self.lib.b200rc_upload_volume_slab(self.h, slot, z0, part.shape[0], part.ctypes.data_as(C.c_void_p)), "upload_volume_slab")
+        self._check(self.lib.b200rc_upload_volume_end(self.h, slot), "upload_volume_end")
+        self.volume_desc[slot] = desc
+        return desc
+
+    def load_raw(self, slot, path, desc, header_skip=0, slab_planes=0):
+        """Raw file -> HBM through two pinned slab buffers (b200rc_load_raw_file); reads only the resident range of desc."""
+        self._check(self.lib.b200rc_load_raw_file(self.h, slot, os.fsencode(path), C.byref(desc), header_skip, slab_planes), "load_raw_file")
+        self.volume_desc[slot] = desc
+        return desc
+
+    def load_vvd(self, slot, path, index=0, slab_planes=0, **shard):
+        """A Voreen .vvd volume (host.parse_vvd) streamed into the brick pool; shard_lo / shard_hi / shard_apron select a shard."""
+        from . import host
+        desc, raw = host.parse_vvd(path, index)
+        for k, val in shard.items():
+            if k in ("shard_lo", "shard_hi"):
+                getattr(desc, k)[:] = list(val)
+            else:
+                setattr(desc, k, val)
+        return self.load_raw(slot, raw, desc, 0, slab_planes)
 
     def synth_volume(self, slot, desc, seed=1234):
         self._check(self.lib.b200rc_synth_volume(self.h, slot, C.byref(desc), seed), "synth_volume")
