@@ -1,4 +1,4 @@
-# Voreen module "b200raycast": drop-in SingleVolumeRaycaster backed by libb200rc.so (hand-written sm_100a CUDA).
+# Voreen module "b200raycast": drop-in SingleVolumeRaycaster + MultiVolumeRaycaster backed by libb200rc.so (hand-written sm_100a CUDA).
 # Consumed by V/cmake/commonconf.cmake:456-497 exactly like V/modules/sample/sample.cmake; enable with
 #   cmake -DVRN_CUSTOM_MODULEDIR=<repo>/custommodules -DVRN_MODULE_B200RAYCAST=ON -DB200RC_ROOT=<repo> ...
 # The module links only the C ABI (include/b200rc.h); no CUDA headers or nvcc are needed to build Voreen.
@@ -11,9 +11,11 @@ SET(MOD_CORE_MODULECLASS B200RaycastModule)
 
 SET(MOD_CORE_SOURCES
     ${MOD_DIR}/processors/b200singlevolumeraycaster.cpp
+    ${MOD_DIR}/processors/b200multivolumeraycaster.cpp
 )
 SET(MOD_CORE_HEADERS
     ${MOD_DIR}/processors/b200singlevolumeraycaster.h
+    ${MOD_DIR}/processors/b200multivolumeraycaster.h
 )
 
 SET(MOD_INCLUDE_DIRECTORIES ${B200RC_ROOT}/include)

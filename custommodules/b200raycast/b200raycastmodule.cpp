@@ -1,4 +1,4 @@
-// Registers the CUDA-backed raycaster.  Two registrations (SURVEY.md 8b "Running unchanged workspaces"):
+// Registers the CUDA-backed raycasters (single- and multi-volume).  Two registrations each (SURVEY.md 8b "Running unchanged workspaces"):
 //   - under its own class name "B200SingleVolumeRaycaster" (always);
 //   - under the reference's type name "SingleVolumeRaycaster" so that existing .vws files deserialise onto it
 //     (VoreenModule::registerSerializableType(typeName, obj), V/src/core/voreenmodule.cpp:169-176).  Type lookup is
@@ -8,6 +8,7 @@
 //     NetworkConverter::changeProcessorType(elem, "SingleVolumeRaycaster", "B200SingleVolumeRaycaster").
 #include "b200raycastmodule.h"
 #include "processors/b200singlevolumeraycaster.h"
+#include "processors/b200multivolumeraycaster.h"
 
 namespace voreen {
 
@@ -18,6 +19,8 @@ B200RaycastModule::B200RaycastModule(const std::string& modulePath)
     setGuiName("B200 Raycasting (CUDA sm_100a)");
     registerProcessor(new B200SingleVolumeRaycaster());
     registerSerializableType("SingleVolumeRaycaster", new B200SingleVolumeRaycaster());
+    registerProcessor(new B200MultiVolumeRaycaster());
+    registerSerializableType("MultiVolumeRaycaster", new B200MultiVolumeRaycaster());
 }
 
 std::string B200RaycastModule::getDescription() const {
