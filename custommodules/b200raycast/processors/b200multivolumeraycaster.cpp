@@ -271,7 +271,7 @@ void B200MultiVolumeRaycaster::process() {
     p.light.shininess = materialShininess_.get();
     p.light.apply_attenuation = applyLightAttenuation_.get() ? 1 : 0;
     p.sampler = B200RC_SAMPLER_EXACT;
-    p.empty_space_skipping = 1;
+    p.empty_space_skipping = 1;         // per-volume skipping of TF-transparent cells (pixels identical)
     p.out_format = B200RC_OUT_RGBA16;
     p.quantize_depth24 = 1;
 

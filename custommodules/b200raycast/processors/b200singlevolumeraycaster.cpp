@@ -225,7 +225,7 @@ void B200SingleVolumeRaycaster::fillParams(b200rc_params& p, b200rc_camera& cam,
     p.light.shininess = materialShininess_.get();
     p.light.apply_attenuation = applyLightAttenuation_.get() ? 1 : 0;
     p.sampler = B200RC_SAMPLER_EXACT;
-    p.empty_space_skipping = 1;
+    p.empty_space_skipping = 2;                                             // TF-transparent cells, and for MIP cells that cannot beat the running maximum
     p.out_format = B200RC_OUT_RGBA16;                                        // RenderPort default (renderport.h:116)
     p.quantize_depth24 = 1;
 

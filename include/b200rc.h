@@ -163,7 +163,10 @@ typedef struct b200rc_params {
     b200rc_light light;
     /* implementation knobs (no reference counterpart; never change pixels beyond the stated tolerance) */
     int32_t sampler;            /* B200RC_SAMPLER_* */
-    int32_t empty_space_skipping;   /* 0/1: macro-cell skipping inside [entry,exit]; result-identical */
+    int32_t empty_space_skipping;   /* 0: off.  1: macro-cells the TF maps to alpha 0 are skipped inside [entry,exit]; pixels AND sample
+                                       counters identical.  2: additionally, with MIP on a single connected output, cells whose maximum cannot
+                                       exceed the ray's running maximum are skipped; pixels identical, samples_shaded counts only the samples
+                                       actually classified */
     int32_t out_format;         /* B200RC_OUT_* */
     int32_t quantize_depth24;   /* 1: depth rounded to GL_DEPTH_COMPONENT24 */
     int32_t collect_stats;      /* 1: count classified samples / cast rays (slower) */

@@ -14,6 +14,7 @@ from voreen_b200 import abi  # noqa: E402
 
 def main():
     sizes = [int(a) for a in sys.argv[1:] if not a.startswith('--')] or [512]
+    essmode = int(next((a.split('=')[1] for a in sys.argv if a.startswith('--ess=')), '1'))
     band = int(next((a.split('=')[1] for a in sys.argv if a.startswith('--band=')), '1'))
     comp = next((a.split('=')[1] for a in sys.argv if a.startswith('--comp=')), 'dvr')
     ctx = vb.Context(0)
@@ -34,7 +35,7 @@ def main():
                 for ess in ((1, 0) if '--noess' in sys.argv else (1,)):
                     if n >= 2048 and ess == 0 and sampler == abi.SAMPLER_EXACT:
                         continue
-                    p = vb.default_params(step, sampler=sampler, empty_space_skipping=ess, out_format=abi.OUT_RGBA16, compositing=[abi.COMP[comp]] * 3)
+                    p = vb.default_params(step, sampler=sampler, empty_space_skipping=(essmode if ess else 0), out_format=abi.OUT_RGBA16, compositing=[abi.COMP[comp]] * 3)
                     if cls == "pi":
                         if pi is None:
                             tf1k = orc.tf1d_texture(tf, 1024)

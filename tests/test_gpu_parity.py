@@ -77,6 +77,24 @@ def test_compositing_modes(ctx, comp):
             check(s, ctx, label=f"mida gamma={g}")
 
 
+def test_mip_culling_matches_oracle_and_plain_mip(ctx):
+    """empty_space_skipping = 2: MIP additionally skips cells whose maximum cannot exceed the running maximum."""
+    vol = scenes.ct_like_volume(64)
+    s = scenes.Scene(vol, W=160, H=160, compositing=[abi.COMP["mip"]] * 3)
+    s.params.collect_stats = 1
+    plain, plain_d = s.cuda_render(ctx)
+    st1 = ctx.stats()
+    s.params.empty_space_skipping = 2
+    culled, culled_d = s.cuda_render(ctx, upload=False)
+    st2 = ctx.stats()
+    assert np.array_equal(np.asarray(plain[0]), np.asarray(culled[0])) and np.array_equal(plain_d, culled_d)
+    assert st2.samples_classified < st1.samples_classified and st2.samples_classified + st2.samples_skipped == st1.samples_classified + st1.samples_skipped
+    o_outs, o_depth, _ = s.oracle_render()
+    frac, mx = scenes.parity_report(o_outs[0], culled[0])
+    assert frac >= 0.999 and float((np.abs(o_depth - culled_d) <= 1e-4).mean()) >= 0.999
+    print(f"MIP culling 64^3: classified {st1.samples_classified} -> {st2.samples_classified}, within 1/255 {frac:.5f}")
+
+
 @pytest.mark.parametrize("grad", ["none", "forward-differences", "sobel", "filtered"])
 def test_gradient_modes(ctx, grad):
     vol = scenes.ct_like_volume(40)
@@ -540,6 +558,12 @@ def test_full_size_properties(n, img, cls, comp):
             assert np.all(alpha[~cast] == 0) and np.all(ad[~cast] == 1.0)
             if comp != "iso":
                 assert (alpha[cast] > 0).mean() > 0.2
+            if comp == "mip":       # mode 2: cells that cannot beat the running maximum are skipped as well -- same pixels, less work
+                c2, cd2, st2c = render(slab, k, ess=2)
+                assert np.array_equal(a, c2) and np.array_equal(ad, cd2)
+                assert st2c.samples_classified + st2c.samples_skipped == stn.samples_classified
+                assert st2c.samples_classified < 0.5 * st.samples_classified
+                print(f"   MIP culling view {k}: classified {st.samples_classified} -> {st2c.samples_classified}")
             ref[k] = (a, ad, st)
         # the image-band partition (sort-first) reassembles to the very same frame
         k = views[0]
@@ -564,5 +588,8 @@ def test_full_size_properties(n, img, cls, comp):
                   f"rays {st.rays_cast} classified {st.samples_classified} skipped {st.samples_skipped} shaded {st.samples_shaded}")
             assert frac >= 0.999
             assert float((np.abs(ad - bd) <= 1e-4).mean()) >= 0.999
+            if comp == "mip":
+                c2, cd2, _ = render(ray, k, ess=2)
+                assert np.array_equal(b, c2) and np.array_equal(bd, cd2)
     finally:
         ray.close()

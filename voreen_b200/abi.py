@@ -84,7 +84,7 @@ class B200RCError(RuntimeError):
 
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200rc.so")
+LIB_PATH = os.environ.get("B200RC_LIBRARY") or os.path.join(_HERE, "libb200rc.so")     # override: A/B builds of the same ABI (developer knob)
 
 # every symbol include/b200rc.h declares
 SYMBOLS = [

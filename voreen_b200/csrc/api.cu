@@ -274,6 +274,7 @@ static int build_params(b200rc_ctx* ctx, const b200rc_params* P, const b200rc_ca
         d.rwm_scale = vs.desc.rwm_scale; d.rwm_offset = vs.desc.rwm_offset;
         d.filter = vp.filter; d.clamp = vp.clamp; d.border = vp.border_intensity;
         d.occ0 = vs.occ0; d.occ1 = vs.occ1; d.occ0_wpr = vs.occ0_wpr; d.occ1_wpr = vs.occ1_wpr;
+        d.minmax = vs.minmax; d.max1 = vs.max1; d.mip_cull = 0;
         p.classification[v] = vp.classification; p.shading[v] = vp.shading;
         if (vp.classification < B200RC_CLASS_TF || vp.classification > B200RC_CLASS_TF2D || vp.shading < 0 || vp.shading > B200RC_SHADE_WARD) { ctx->set_error("render: unknown classification/shading mode"); return B200RC_ERR_INVALID; }
         if (P->sampler == B200RC_SAMPLER_TEX) {
@@ -318,6 +319,11 @@ static int build_params(b200rc_ctx* ctx, const b200rc_params* P, const b200rc_ca
         int rc = rc_volume_build_occupancy(ctx, 0, modes, ncls, false, P->vol[0].clamp, P->vol[0].border_intensity);
         if (rc) return rc;
         p.vol[0].ess = 1;
+        // MIP culling (mode 2): cells whose maximum cannot beat the running maximum are skipped like transparent ones.  One
+        // channel, un-bordered sampling, increasing real-world mapping, only image.output connected and compositing MIP.
+        if (P->empty_space_skipping >= 2 && ncls == 1 && p.comp[0] == B200RC_COMP_MIP && p.connected[0] && !p.connected[1] && !p.connected[2] &&
+            P->vol[0].clamp == B200RC_CLAMP_TO_EDGE && ctx->vol[0].desc.rwm_scale > 0.f && ctx->vol[0].max1)
+            p.vol[0].mip_cull = 1;
     }
     // multi-volume: one occupancy grid per volume for its own classifier (rc_multivolume.frag reads voxel.a of every
     // volume, i.e. the last channel; multi-channel volumes keep marching every sample)

@@ -36,6 +36,8 @@ struct VolDev {
     int occ0_dims[3], occ1_dims[3]; // cells per axis
     int occ0_wpr, occ1_wpr;         // 32-bit words per x-row
     int ess;                        // occupancy valid for this render
+    // MIP culling (b200rc_params.empty_space_skipping == 2): level-0 {min,max} per cell and level-1 max, normalised texture values
+    const float2* minmax; const float* max1; int mip_cull;
 };
 
 struct ClsDev {

@@ -28,6 +28,7 @@ struct VolumeSlot {
     cudaTextureObject_t tex = 0; int tex_filter = -1, tex_clamp = -1; float tex_border = 0.f;
     // min/max grid, level-0 cells (B200RC_ESS_CELL voxels): float2 per cell and channel, normalised texture values
     float2* minmax = nullptr; int cells[3] = {0, 0, 0}; double minmax_build_ms = 0.0;
+    float* max1 = nullptr;      // level-1 (64^3 voxels) maximum of the level-0 cell maxima, channel 0 (MIP culling)
     uint32_t* occ0 = nullptr; uint32_t* occ1 = nullptr;
     int occ0_wpr = 0, occ1_wpr = 0, occ1_dims[3] = {0, 0, 0};
     unsigned long long occ_key = 0;     // (tf generation, classification) the occupancy was built for

@@ -23,7 +23,11 @@ static int launch_slab(b200rc_ctx* ctx, const DevParams& p0) {
     }
     // SLAB_MIN_CTAS CTAs share the SM's 227 KB: the staged region takes what the TF (+ LUT) leaves of one CTA's share
     int cap_kb = env_cap;
-    const int share_kb = (227 - SLAB_MIN_CTAS) / SLAB_MIN_CTAS;         // 1 KB per CTA reserved by the runtime + static shared memory
+    // per CTA: 1 KB reserved by the runtime + this instantiation's static shared memory (scheduling scratch, MIP cell maxima)
+    auto kern = march_slab_kernel<C>;
+    cudaFuncAttributes fa;
+    RC_CHECK(cudaFuncGetAttributes(&fa, kern));
+    const int share_kb = (int)((227 * 1024 / SLAB_MIN_CTAS - 1024 - (long long)fa.sharedSizeBytes) / 1024);
     if (cap_kb + (int)((tf_bytes + 1023) / 1024) > share_kb) cap_kb = share_kb - (int)((tf_bytes + 1023) / 1024);
     SlabArgs sa; sa.depth = env_depth; sa.cap_floats = cap_kb * 256;
     // pre-integration + empty-space skipping restores lastIntensity from the staged footprint: needs <= 1 voxel per step
@@ -32,7 +36,6 @@ static int launch_slab(b200rc_ctx* ctx, const DevParams& p0) {
         if (p.step * m > 1.0f) return -1;
     }
     const size_t smem = (size_t)sa.cap_floats * sizeof(float) + tf_bytes;
-    auto kern = march_slab_kernel<C>;
     RC_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     RC_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SLAB_THREADS, smem));

@@ -29,6 +29,7 @@
 #define SLAB_MIN_CTAS (768 / SLAB_THREADS)
 #endif
 #define SLAB_OCC_WORDS 160      // (max lateral extent / 8 + 2)^2 occupancy words per region
+#define SLAB_CMAX 512           // staged level-0 cell maxima per region (MIP culling)
 
 struct SlabShared {
     int zmin;                   // min over rays of the direction-normalised major index of their next sample
@@ -41,6 +42,7 @@ struct SlabShared {
     // occupancy bits of the level-0 ESS cells overlapping the region: word (jz * occ_ny + jy), bit jx, where
     // j = (l + occ_off) >> 3 for the region-local voxel index l
     int occ_off[3], occ_ny;
+    int cm_nx, cm_ok;           // MIP culling: cells per x-row of the staged cell maxima; 0 when the region has more cells than the table
     unsigned int occ[SLAB_OCC_WORDS];
 };
 
@@ -116,7 +118,8 @@ __device__ __forceinline__ void slab_stage(const VolDev& v, const SlabShared& sh
 }
 
 // occupancy bits of the region's level-0 cells -> shared memory (one word per (jy, jz) row of cells)
-__device__ __forceinline__ void slab_stage_occ(const VolDev& v, SlabShared& sh) {
+template <bool CULL>
+__device__ __forceinline__ void slab_stage_occ(const VolDev& v, SlabShared& sh, float* __restrict__ cmax) {
     int off[3], n[3], c0[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
@@ -138,14 +141,25 @@ __device__ __forceinline__ void slab_stage_occ(const VolDev& v, SlabShared& sh) 
         }
         sh.occ[w] = bits;
     }
+    if (CULL && v.mip_cull) {       // level-0 cell maxima of the same cells (normalised texture values)
+        const int tot = n[0] * n[1] * n[2];
+        if (threadIdx.x == 0) { sh.cm_nx = n[0]; sh.cm_ok = (tot <= SLAB_CMAX && words <= SLAB_OCC_WORDS && n[0] <= 32) ? 1 : 0; }
+        if (tot <= SLAB_CMAX)
+            for (int i = threadIdx.x; i < tot; i += SLAB_THREADS) {
+                const int jx = i % n[0], jy = (i / n[0]) % n[1], jz = i / (n[0] * n[1]);
+                const int cx = min(max(c0[0] + jx, 0), v.occ0_dims[0] - 1), cy = min(max(c0[1] + jy, 0), v.occ0_dims[1] - 1), cz = min(max(c0[2] + jz, 0), v.occ0_dims[2] - 1);
+                cmax[i] = __ldg(&v.minmax[(((size_t)cz * v.occ0_dims[1] + cy) * v.occ0_dims[0] + cx) * v.nch].y);
+            }
+    }
 }
 
 // jump over the empty cell the sample at t lies in: returns false when the cell is not empty
+template <bool CULL>
 __device__ __forceinline__ bool slab_skip_empty(const DevParams& p, const VolDev& V, float3 first, float3 dir, float tEnd, float step,
-                                                float& t, float& t_last, int& loop, bool& finished, RayStats& st) {
+                                                float& t, float& t_last, int& loop, bool& finished, RayStats& st, float maxI) {
     const float3 sp = f3(xadd(first.x, xmul(t, dir.x)), xadd(first.y, xmul(t, dir.y)), xadd(first.z, xmul(t, dir.z)));
     float t_exit = 0.f;
-    if (!ess_empty_cell(V, sp, dir, t, t_exit)) return false;
+    if (!((CULL && V.mip_cull) ? ess_empty_cell_t<true>(V, sp, dir, t, maxI, t_exit) : ess_empty_cell(V, sp, dir, t, t_exit))) return false;
     if (t_exit > tEnd) { st.skipped += (unsigned)floorf((tEnd - t) / step) + 1u; finished = true; return true; }
     int n = 1; float tn;
     if (p.lattice_exact) {
@@ -266,6 +280,8 @@ template <class C>
 __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel(const __grid_constant__ DevParams p, const SlabArgs sa) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ SlabShared sh;
+    constexpr bool CULL = (C::COMP == B200RC_COMP_MIP && C::CLS == B200RC_CLASS_TF);      // MIP: skip cells that cannot beat the running maximum
+    __shared__ float sh_cmax[CULL ? SLAB_CMAX : 1];
     float* S = (float*)smem_raw;
     SmemTables sm;
     {   // 1D TF + opacity LUT behind the region (TF classification only; pre-integration reads its 2D table)
@@ -378,7 +394,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
             //     slab is staged where the ray would only skip
             if (stale) {
                 if (V.ess && (!pi_mode || prev_empty))
-                    while (!finished && slab_skip_empty(p, V, first, dir, tStop, step, t, t_last, loop, finished, st)) { if (pi_mode) lastI_stale = true; }
+                    while (!finished && slab_skip_empty<CULL>(p, V, first, dir, tStop, step, t, t_last, loop, finished, st, maxI)) { if (pi_mode) lastI_stale = true; }
                 zc = INT_MAX;
                 if (!finished) {
                     const float3 sp = f3(xadd(first.x, xmul(t, dir.x)), xadd(first.y, xmul(t, dir.y)), xadd(first.z, xmul(t, dir.z)));
@@ -461,7 +477,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
             __syncthreads();
             // (4) stage voxels + occupancy bits
             slab_stage<C>(V, sh, S);
-            if (V.ess) slab_stage_occ(V, sh);
+            if (V.ess) slab_stage_occ<CULL>(V, sh, sh_cmax);
             __syncthreads();
             // (5) march while the footprint of the next sample lies inside the region.  The loop is warp-synchronous
             //     (one __any_sync per iteration) so that the lanes of a warp take their samples together.
@@ -470,6 +486,8 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
                 const int nx = sh.rn[0], ny = sh.rn[1], nz = sh.rn[2];
                 const int pitch = sh.pitch, slice = pitch * ny;
                 const int ox = sh.occ_off[0], oy = sh.occ_off[1], oz = sh.occ_off[2], ony = sh.occ_ny;
+                const bool cull_on = CULL && V.mip_cull && V.ess && sh.cm_ok;
+                const int cm_nx = sh.cm_nx;
                 bool run = part;
                 if (p.collect_stats) { dbg_part += part ? 1u : 0u; dbg_rounds += 1u; }
                 while (__any_sync(0xffffffffu, run)) {
@@ -492,12 +510,13 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
                             // ---- empty-space skipping: occupancy bit of the sample's level-0 cell (staged) ----
                             bool empty = false;
                             if (V.ess) empty = !((sh.occ[((lz + oz) >> 3) * ony + ((ly + oy) >> 3)] >> ((lx + ox) >> 3)) & 1u);
+                            if (CULL && cull_on && !empty) empty = mip_cell_culled(V, sh_cmax[(((lz + oz) >> 3) * ony + ((ly + oy) >> 3)) * cm_nx + ((lx + ox) >> 3)], maxI);
                             if (empty && (!pi_mode || prev_empty)) {
                                 // Every lattice sample inside this cell classifies to alpha 0 without side effects.  With
                                 // pre-integration that also needs the PREVIOUS sample to lie in an empty cell: the value
                                 // ranges of the two (adjacent, overlapping) cells then form one interval on which the
                                 // transfer function is transparent, so the table entry (cur, prev) is transparent too.
-                                if (!slab_skip_empty(p, V, first, dir, tStop, step, t, t_last, loop, finished, st)) {
+                                if (!slab_skip_empty<CULL>(p, V, first, dir, tStop, step, t, t_last, loop, finished, st, maxI)) {
                                     // (cannot happen: the staged bit and the global grid agree) -- take the sample instead
                                     empty = false;
                                 } else {

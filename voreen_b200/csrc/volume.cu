@@ -338,6 +338,18 @@ __device__ __forceinline__ float occ_rw_to_tex(float lo, float hi, float v) {
     return __fdiv_rn(__fsub_rn(v, lo), __fsub_rn(hi, lo));
 }
 
+// level-1 maximum (MIP culling): max over the 8^3 level-0 cells of a 64^3-voxel cell, channel 0
+__global__ void cellmax1_kernel(const float2* __restrict__ minmax, float* __restrict__ max1, int ncx, int ncy, int ncz, int nch, int n1x, int n1y, int n1z) {
+    const long long c1 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c1 >= (long long)n1x * n1y * n1z) return;
+    const int x1 = (int)(c1 % n1x), y1 = (int)((c1 / n1x) % n1y), z1 = (int)(c1 / ((long long)n1x * n1y));
+    float m = -3.0e38f;
+    for (int z = z1 * 8; z < min(z1 * 8 + 8, ncz); ++z)
+        for (int y = y1 * 8; y < min(y1 * 8 + 8, ncy); ++y)
+            for (int x = x1 * 8; x < min(x1 * 8 + 8, ncx); ++x) m = fmaxf(m, minmax[(((long long)z * ncy + y) * ncx + x) * nch].y);
+    max1[c1] = m;
+}
+
 __global__ void occupancy0_kernel(const float2* __restrict__ minmax, uint32_t* __restrict__ occ, int ncx, int ncy, int ncz, int wpr,
                                   const __grid_constant__ OccArgs a) {
     // thread per cell, x padded to 32 so that one ballot = one occupancy word
@@ -398,7 +410,7 @@ int rc_volume_release(b200rc_ctx* ctx, int slot) {
     VolumeSlot& v = ctx->vol[slot];
     if (v.tex) cudaDestroyTextureObject(v.tex);
     if (v.array) cudaFreeArray(v.array);
-    cudaFree(v.bricks); cudaFree(v.minmax); cudaFree(v.occ0); cudaFree(v.occ1); cudaFree(v.touched);
+    cudaFree(v.bricks); cudaFree(v.minmax); cudaFree(v.max1); cudaFree(v.occ0); cudaFree(v.occ1); cudaFree(v.touched);
     v = VolumeSlot();
     return B200RC_OK;
 }
@@ -473,6 +485,14 @@ static int volume_build_minmax(b200rc_ctx* ctx, int slot) {
     v.occ1_wpr = (v.occ1_dims[0] + 31) / 32;
     RC_CHECK(cudaMalloc(&v.occ0, sizeof(uint32_t) * (size_t)v.occ0_wpr * v.cells[1] * v.cells[2]));
     RC_CHECK(cudaMalloc(&v.occ1, sizeof(uint32_t) * (size_t)v.occ1_wpr * v.occ1_dims[1] * v.occ1_dims[2]));
+    {
+        const long long n1 = (long long)v.occ1_dims[0] * v.occ1_dims[1] * v.occ1_dims[2];
+        RC_CHECK(cudaMalloc(&v.max1, sizeof(float) * n1));
+        cellmax1_kernel<<<(unsigned)((n1 + 127) / 128), 128, 0, ctx->stream>>>(v.minmax, v.max1, v.cells[0], v.cells[1], v.cells[2], v.desc.channels,
+                                                                              v.occ1_dims[0], v.occ1_dims[1], v.occ1_dims[2]);
+        ctx->launches++;
+        RC_CHECK(cudaGetLastError());
+    }
     v.occ_key = 0;
     for (int a = 0; a < 3; ++a) v.touched_dims[a] = (v.desc.dims[a] + B200RC_STAT_CELL - 1) / B200RC_STAT_CELL;
     v.valid = true;
