@@ -46,6 +46,26 @@ int b200host_tf1d_width_for(int dtype, int* out_width);
 int b200host_volume_desc(const int32_t dims[3], int channels, const char* format /* "uint8" "uint16" "float" */,
                          const float* spacing, const float* offset, const float* phys_to_world, b200rc_volume_desc* out);
 
+/* ---- OptimizedProxyGeometry, the transfer-function dependent modes (V/modules/base/processors/proxygeometry/
+ *      optimizedproxygeometry.cpp:878-880,1014-1116 "minboundingbox", :1119-1290 "visiblebricks"): the region structure comes
+ *      from the device (b200rc_region_minmax over cells of eep->proxy_cell_size voxels, [llf-1, urb+1] aprons, real-world units);
+ *      every region is classified with the 256^2 pre-integration table of its channel's transfer function at sampling step 1.0
+ *      (PreIntegrationTable::computeTable, preintegrationtable.cpp:67-133, alpha channel) and is empty iff
+ *      classify(min, max).a <= 1e-4 * eep->proxy_threshold; the non-empty regions give one bounding cube (MINBBOX) or one cube each
+ *      (VISIBLE_BRICKS; the reference merges neighbouring bricks into larger cubes, which covers the same union), clipped to
+ *      the clip region when enabled.  Cubes are written as (llf.xyz, urb.xyz) in texture space, ready for
+ *      b200rc_eep_params.boxes.  B200RC_PROXY_BBOX (or n_tfs == 0) yields the (clipped) bounding box.  *n_boxes receives the
+ *      number of cubes found (which may exceed max_boxes; only max_boxes are written). */
+typedef struct b200host_tf1d {
+    const b200host_tf_key* keys; int32_t n_keys;
+    float domain[2];            /* real-world units */
+    float threshold[2];         /* [0,1] */
+    float gamma;
+    int32_t alpha_mode;         /* 0 zero, 1 use, 2 one (TransFuncBase::AlphaMode) */
+} b200host_tf1d;
+int b200host_optimized_proxy_geometry(b200rc_ctx* ctx, int slot, const b200rc_volume_desc* desc, const b200rc_eep_params* eep,
+                                      const b200host_tf1d* tfs, int n_tfs, float* out_boxes, int max_boxes, int* n_boxes);
+
 /* ---- .vvd volume descriptions (V/modules/core/io/vvdvolumereader.cpp:58-128, vvdformat.cpp:59-120,290-330): the XML
  *      wrapper every bundled workspace loads.  Parses volume number `index` of the file: <RawData format x y z> with the raw
  *      file either as the old `filename` attribute (relative to the .vvd) or as <Paths><paths><item value>, and the MetaData

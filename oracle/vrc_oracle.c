@@ -1178,12 +1178,13 @@ int orc_proxy_boxes(const orc_volume* vol, const orc_tf1d* tfs, int n_tfs, const
                     defined = 1;
                 } else if (n < max_boxes) {
                     /* addCubeMesh (:480-491): tex = (coord + 0.5) / dim */
+                    int separated = 0;      /* checkBounds.intersects(cubeBounds) (:1205-1216; touching counts, bounds.h:162-170) */
                     for (int a = 0; a < 3; ++a) {
-                        if (eep->enable_clipping) { lo[a] = fmaxf(lo[a], coordLLF[a]); hi[a] = fminf(hi[a], coordURB[a]); }
+                        if (eep->enable_clipping) { lo[a] = fmaxf(lo[a], coordLLF[a]); hi[a] = fminf(hi[a], coordURB[a]); if (lo[a] > hi[a]) separated = 1; }
                         out[6 * n + a] = (lo[a] + 0.5f) / (float)dim[a];
                         out[6 * n + 3 + a] = (hi[a] + 0.5f) / (float)dim[a];
                     }
-                    n++;
+                    if (!separated) n++;
                 }
             }
     if (eep->proxy_mode == B200RC_PROXY_MINBBOX && defined && max_boxes >= 1) {

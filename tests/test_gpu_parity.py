@@ -593,3 +593,38 @@ def test_full_size_properties(n, img, cls, comp):
                 assert np.array_equal(b, c2) and np.array_equal(bd, cd2)
     finally:
         ray.close()
+
+
+# ---- OptimizedProxyGeometry, TF-dependent modes: the product's cubes (host mirror over the device region structure)
+#      against the oracle's restatement -- same cubes, hence bit-identical entry/exit images ------------------------------------------
+@pytest.mark.parametrize("mode", ["minboundingbox", "visiblebricks"])
+@pytest.mark.parametrize("clip", [False, True])
+@pytest.mark.parametrize("cell,threshold", [(4, 1.0), (7, 40.0)])
+def test_optimized_proxy_geometry_modes(ctx, mode, clip, cell, threshold):
+    from voreen_b200 import host
+    from voreen_b200 import raycaster as rc
+    vol = scenes.ct_like_volume(40)
+    vol[:, :, :6] = 0                                  # an empty slab so that the minimal box is smaller than the volume
+    desc = rc.make_volume_desc((40, 40, 40))
+    keys = [(0.0, (0, 0, 0, 0)), (0.3, (0, 0, 0, 0)), (0.35, (255, 120, 40, 3)), (0.7, (255, 255, 255, 120)), (1.0, (255, 255, 255, 255))]
+    dom, thr, gamma, amode = (0.0, 65535.0), (0.05, 0.95), 1.0, 1
+    eep = rc.default_eep(proxy_mode={"minboundingbox": abi.PROXY_MINBBOX, "visiblebricks": abi.PROXY_VISIBLE_BRICKS}[mode],
+                         proxy_cell_size=cell, proxy_threshold=threshold)
+    if clip:
+        eep.enable_clipping = 1
+        eep.clip_llf[:] = [3.0, 0.0, 5.0]; eep.clip_urb[:] = [30.0, 39.0, 33.0]
+    ctx.upload_volume(0, vol, desc=desc)
+    got = host.optimized_proxy_geometry(ctx, 0, desc, eep, [(keys, dom, thr, gamma, amode)])
+    want = orc.bbox_boxes(orc.make_volume(vol, desc), eep, [orc.make_tf(keys, domain=dom, threshold=thr, gamma=gamma, alpha_mode=amode)])
+    print(f"proxy geometry {mode} clip={clip} cell={cell} threshold={threshold}: {len(got)} cubes (oracle {len(want)})")
+    assert len(got) == len(want) and len(got) >= 1
+    assert np.array_equal(got, want)
+    if mode == "minboundingbox" and cell == 4 and not clip:
+        assert got[0, 0] > 0.05                         # (most of) the empty slab is outside the box
+    # ... and the entry/exit images they produce are the oracle's, bit for bit
+    cam = orc.make_camera((1.4, 0.8, 2.9), W=96, H=96)
+    eep2 = rc.default_eep(proxy_mode=eep.proxy_mode, proxy_cell_size=cell, proxy_threshold=threshold, enable_clipping=eep.enable_clipping,
+                          clip_llf=list(eep.clip_llf), clip_urb=list(eep.clip_urb), boxes=got)
+    e, ed, x, xd = ctx.entry_exit(eep2, cam, 96, 96)
+    oe, oed, ox, oxd = orc.entry_exit(want, orc.texture_to_world(desc), eep, cam, 96, 96)
+    assert np.array_equal(e, oe) and np.array_equal(x, ox) and np.array_equal(ed, oed) and np.array_equal(xd, oxd)

@@ -16,12 +16,17 @@ SYMBOLS = [
     "b200host_svrc_destroy", "b200host_svrc_last_error", "b200host_svrc_context", "b200host_svrc_set_property",
     "b200host_svrc_get_sampling_step", "b200host_svrc_set_volume", "b200host_svrc_set_synthetic_volume",
     "b200host_svrc_set_transfer_function", "b200host_svrc_set_camera", "b200host_svrc_connect_output",
-    "b200host_svrc_set_entry_exit", "b200host_svrc_is_ready", "b200host_svrc_process", "b200host_vvd_parse", "b200host_vvd_count",
+    "b200host_svrc_set_entry_exit", "b200host_svrc_is_ready", "b200host_svrc_process", "b200host_vvd_parse", "b200host_vvd_count", "b200host_optimized_proxy_geometry",
 ]
 
 
 class TFKey(C.Structure):
     _fields_ = [("intensity", C.c_float), ("color_l", C.c_uint8 * 4), ("color_r", C.c_uint8 * 4), ("split", C.c_int32)]
+
+
+class TF1D(C.Structure):
+    _fields_ = [("keys", C.POINTER(TFKey)), ("n_keys", C.c_int32), ("domain", C.c_float * 2), ("threshold", C.c_float * 2),
+                ("gamma", C.c_float), ("alpha_mode", C.c_int32)]
 
 
 _lib = None
@@ -43,6 +48,8 @@ def load_library():
     lib.b200host_svrc_create.argtypes = [i32, C.POINTER(vp)]
     lib.b200host_vvd_parse.argtypes = [C.c_char_p, i32, C.POINTER(abi.VolumeDesc), C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
     lib.b200host_vvd_count.argtypes = [C.c_char_p]
+    lib.b200host_optimized_proxy_geometry.argtypes = [vp, i32, C.POINTER(abi.VolumeDesc), C.POINTER(abi.EepParams), C.POINTER(TF1D), i32, pf, i32,
+                                                      C.POINTER(C.c_int)]
     lib.b200host_svrc_destroy.argtypes = [vp]
     lib.b200host_svrc_destroy.restype = None
     lib.b200host_svrc_last_error.argtypes = [vp]
@@ -74,6 +81,25 @@ def make_camera(eye, focus=(0, 0, 0), up=(0, 1, 0), fovy=45.0, near=0.1, far=50.
     if rc:
         raise abi.B200RCError(f"b200host_camera: status {rc}")
     return cam
+
+
+def optimized_proxy_geometry(ctx, slot, desc, eep, tfs, max_boxes=1 << 16):
+    """OptimizedProxyGeometry "minboundingbox" / "visiblebricks" for the volume in `slot` of `ctx` (a raycaster.Context):
+    tfs = [(keys, domain, threshold, gamma, alpha_mode)] per channel -> (n, 6) float32 cubes in texture space for eep.boxes."""
+    arr = (TF1D * max(1, len(tfs)))()
+    keep = []
+    for i, (keys, domain, threshold, gamma, alpha_mode) in enumerate(tfs):
+        k = make_keys(keys); keep.append(k)
+        arr[i].keys = k; arr[i].n_keys = len(keys)
+        arr[i].domain[:] = list(domain); arr[i].threshold[:] = list(threshold)
+        arr[i].gamma = gamma; arr[i].alpha_mode = alpha_mode
+    out = np.zeros((max_boxes, 6), np.float32)
+    n = C.c_int(0)
+    rc = load_library().b200host_optimized_proxy_geometry(ctx.h, slot, C.byref(desc), C.byref(eep), arr, len(tfs),
+                                                          out.ctypes.data_as(C.POINTER(C.c_float)), max_boxes, C.byref(n))
+    if rc:
+        raise abi.B200RCError(f"b200host_optimized_proxy_geometry: status {rc}: {ctx.last_error() if hasattr(ctx, 'last_error') else ''}")
+    return out[:min(n.value, max_boxes)].copy()
 
 
 def parse_vvd(path, index=0):

@@ -8,6 +8,7 @@
 #include "rc_properties.hpp"
 
 #include <cctype>
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <utility>
@@ -148,6 +149,124 @@ extern "C" int b200host_volume_desc(const int32_t dims[3], int channels, const c
         out->offset[a] = offset ? offset[a] : (float)(-(dims[a] - 1) * 0.5f) * out->spacing[a];
     }
     for (int i = 0; i < 16; ++i) out->phys_to_world[i] = phys_to_world ? phys_to_world[i] : ((i % 5 == 0) ? 1.f : 0.f);
+    return B200RC_OK;
+}
+
+// ---- OptimizedProxyGeometry: minboundingbox / visiblebricks ---------------------------------------------------------------------
+namespace {
+// alpha channel of PreIntegrationTable(tf, resolution 256, samplingStepSize 1.0).computeTable() (preintegrationtable.cpp:67-133);
+// table[sb * res + sf] composites the TF entries from sf towards sb
+void preint_alpha_table(const b200host_tf1d& tf, int res, float step, std::vector<float>& table) {
+    std::vector<float> a((size_t)res, 0.f);
+    const int front_end = iround(tf.threshold[0] * (float)res), back_start = iround(tf.threshold[1] * (float)res);
+    for (int i = std::max(front_end, 0); i < back_start && i < res; ++i) {
+        float v = (float)i / (float)(res - 1);
+        if (tf.gamma != 1.f) v = std::pow(v, tf.gamma);         // applyGammaToIntensity
+        uint8_t px[4];
+        keys_mapping(tf.keys, tf.n_keys, v, px);
+        float al = (float)px[3] / 255.f;
+        if (tf.alpha_mode == 2 && al != 0.f) al = 1.f;          // TF_ONE_ALPHA
+        else if (tf.alpha_mode == 0) al = 0.f;                  // TF_ZERO_ALPHA
+        a[i] = al;
+    }
+    table.assign((size_t)res * res, 0.f);
+    for (int sb = 0; sb < res; ++sb)
+        for (int sf = 0; sf < res; ++sf) {
+            float r;
+            if (sb != sf) {
+                const float scale = 1.0f / (std::fabs((float)(sb - sf)) + 1);
+                const int incr = sb < sf ? -1 : 1;
+                r = 0.f;
+                for (int s = sf; (incr == 1 ? s <= sb : s >= sb) && ((double)r < 0.95); s += incr) {
+                    float c = a[s];
+                    if (c > 0.0f) {
+                        c = 1.f - std::pow(1.f - c, step * 200.0f * scale);
+                        r = r + (1.0f - r) * c;
+                    }
+                }
+            } else {
+                r = std::min(std::max(a[sf], 0.f), 1.f);
+                r = 1.f - std::pow(1.f - r, step * 200.0f);
+            }
+            table[(size_t)sb * res + sf] = std::min(std::max(r, 0.f), 1.f);
+        }
+}
+// TransFuncBase::realWorldToNormalized (transfuncbase.cpp:244-259)
+float rw_to_normalized(float rw, const float dom[2]) {
+    if (rw < dom[0]) return 0.f;
+    if (rw > dom[1]) return 1.f;
+    if (dom[0] == dom[1]) return 0.f;
+    return (rw - dom[0]) / (dom[1] - dom[0]);
+}
+}  // namespace
+
+extern "C" int b200host_optimized_proxy_geometry(b200rc_ctx* ctx, int slot, const b200rc_volume_desc* desc, const b200rc_eep_params* eep,
+                                                 const b200host_tf1d* tfs, int n_tfs, float* out, int max_boxes, int* n_boxes) {
+    if (!ctx || !desc || !eep || !out || !n_boxes || max_boxes < 1 || (n_tfs > 0 && !tfs)) return B200RC_ERR_INVALID;
+    const int* dim = desc->dims;
+    float llf[3], urb[3];
+    for (int a = 0; a < 3; ++a) {           // the volume's cube incl. the half-voxel border, clipped (processCube :420-448)
+        llf[a] = -0.5f; urb[a] = (float)(dim[a] - 1) + 0.5f;
+        if (eep->enable_clipping) { llf[a] = std::max(llf[a], eep->clip_llf[a] - 0.5f); urb[a] = std::min(urb[a], eep->clip_urb[a] + 0.5f); }
+    }
+    auto emit = [&](int k, const float lo[3], const float hi[3]) {          // addCubeMesh (:480-491): tex = (coord + 0.5) / dim
+        for (int a = 0; a < 3; ++a) { out[6 * k + a] = (lo[a] + 0.5f) / (float)dim[a]; out[6 * k + 3 + a] = (hi[a] + 0.5f) / (float)dim[a]; }
+    };
+    if (eep->proxy_mode == B200RC_PROXY_BBOX || n_tfs <= 0) { emit(0, llf, urb); *n_boxes = 1; return B200RC_OK; }
+
+    const int step = eep->proxy_cell_size < 1 ? 1 : eep->proxy_cell_size;
+    int32_t cells[3] = {0, 0, 0};
+    int rc = b200rc_region_minmax(ctx, slot, step, cells, nullptr, 0);
+    if (rc) return rc;
+    const int nc = desc->channels;
+    const size_t ncell = (size_t)cells[0] * cells[1] * cells[2];
+    std::vector<float> mm(ncell * nc * 2);
+    rc = b200rc_region_minmax(ctx, slot, step, cells, mm.data(), mm.size());
+    if (rc) return rc;
+    std::vector<std::vector<float>> pi((size_t)std::min(nc, n_tfs));
+    for (size_t c = 0; c < pi.size(); ++c) preint_alpha_table(tfs[c], 256, 1.f, pi[c]);         // getPreIntegrationTable(1.f, 256) (:1051)
+    const double limit = 0.0001 * (double)eep->proxy_threshold;                                 // isRegionEmptyPi (:878-880)
+
+    float bmin[3] = {3.0e38f, 3.0e38f, 3.0e38f}, bmax[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    bool defined = false;
+    int n = 0;
+    for (int cz = 0; cz < cells[2]; ++cz)
+        for (int cy = 0; cy < cells[1]; ++cy)
+            for (int cx = 0; cx < cells[0]; ++cx) {
+                const size_t cell = ((size_t)cz * cells[1] + cy) * cells[0] + cx;
+                bool opaque = false;
+                for (size_t c = 0; c < pi.size() && !opaque; ++c) {
+                    const float fs = rw_to_normalized(mm[(cell * nc + c) * 2], tfs[c].domain), fe = rw_to_normalized(mm[(cell * nc + c) * 2 + 1], tfs[c].domain);
+                    const int i1 = std::min(std::max(iround(fs * 255.f), 0), 255), i2 = std::min(std::max(iround(fe * 255.f), 0), 255);      // classify (:256-280)
+                    opaque = !((double)pi[c][(size_t)i2 * 256 + i1] <= limit);
+                }
+                if (!opaque) continue;
+                const int pos[3] = {cx, cy, cz};
+                float lo[3], hi[3];
+                for (int a = 0; a < 3; ++a) {       // region bounds incl. the half-voxel border (:944-968)
+                    const int l = pos[a] * step, u = std::min((pos[a] + 1) * step - 1, dim[a] - 1);
+                    lo[a] = (float)l - 0.5f; hi[a] = (float)u + 0.5f;
+                }
+                if (eep->proxy_mode == B200RC_PROXY_MINBBOX) {
+                    for (int a = 0; a < 3; ++a) { bmin[a] = std::min(bmin[a], lo[a]); bmax[a] = std::max(bmax[a], hi[a]); }
+                    defined = true;
+                } else {
+                    if (eep->enable_clipping) {
+                        bool outside = false;
+                        for (int a = 0; a < 3; ++a) { lo[a] = std::max(lo[a], llf[a]); hi[a] = std::min(hi[a], urb[a]); outside = outside || lo[a] > hi[a]; }        // tgt::Bounds::intersects: touching still counts
+                        if (outside) continue;
+                    }
+                    if (n < max_boxes) emit(n, lo, hi);
+                    ++n;
+                }
+            }
+    if (eep->proxy_mode == B200RC_PROXY_MINBBOX && defined) {
+        bool outside = false;
+        if (eep->enable_clipping)           // addCubeMeshClip against the clip bounds (:1089-1102)
+            for (int a = 0; a < 3; ++a) { bmin[a] = std::max(bmin[a], llf[a]); bmax[a] = std::min(bmax[a], urb[a]); outside = outside || bmin[a] > bmax[a]; }
+        if (!outside) { emit(0, bmin, bmax); n = 1; }
+    }
+    *n_boxes = n;
     return B200RC_OK;
 }
 
