@@ -305,14 +305,25 @@ void B200MultiVolumeRaycaster::process() {
     for (int i = 0; i < 3; ++i) {
         if (!p.output_connected[i]) continue;
         if (i == 2 && !outport2_.isConnected()) continue;       // quirk: internalRenderPort3_ is copied only if outport2_ is connected (:412-413)
-        outp[i]->resize(size);
+        // rescaleRendering (volumeraycaster.cpp:348-377): internal size -> outport size with GL_LINEAR; the identity at equal size
+        const tgt::ivec2 outSize = outp[i]->getSize();
+        const uint16_t* colData = &hostColor_[i][0];
+        const float* depthData = &hostDepth_[0];
+        std::vector<uint16_t> up; std::vector<float> upDepth;
+        if (outSize != size) {
+            up.resize((size_t)outSize.x * outSize.y * 4);
+            if (i == 0) upDepth.resize((size_t)outSize.x * outSize.y);
+            failOn(b200rc_rescale(ctx_, colData, i == 0 ? depthData : 0, size.x, size.y, B200RC_OUT_RGBA16, &up[0], i == 0 ? &upDepth[0] : 0,
+                                  outSize.x, outSize.y, 0), "b200rc_rescale");
+            colData = &up[0]; depthData = i == 0 ? &upDepth[0] : 0;
+        }
         tgt::Texture* col = outp[i]->getColorTexture();
         col->bind();
-        glTexSubImage2D(GL_TEXTURE_2D, 0, 0, 0, size.x, size.y, GL_RGBA, GL_UNSIGNED_SHORT, &hostColor_[i][0]);
+        glTexSubImage2D(GL_TEXTURE_2D, 0, 0, 0, outSize.x, outSize.y, GL_RGBA, GL_UNSIGNED_SHORT, colData);
         if (i == 0) {
             tgt::Texture* dt = outp[i]->getDepthTexture();
             dt->bind();
-            glTexSubImage2D(GL_TEXTURE_2D, 0, 0, 0, size.x, size.y, GL_DEPTH_COMPONENT, GL_FLOAT, &hostDepth_[0]);
+            glTexSubImage2D(GL_TEXTURE_2D, 0, 0, 0, outSize.x, outSize.y, GL_DEPTH_COMPONENT, GL_FLOAT, depthData);
         }
         outp[i]->validateResult();
     }

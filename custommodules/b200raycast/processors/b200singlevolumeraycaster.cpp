@@ -247,7 +247,7 @@ void B200SingleVolumeRaycaster::beforeProcess() {
 void B200SingleVolumeRaycaster::writeOutport(RenderPort& port, const std::vector<uint16_t>& rgba16, const std::vector<float>* depth, const tgt::ivec2& size) {
     // non-sharing upload pattern of V/modules/opencl/processors/singleoctreeraycastercl.cpp:1765-1768; the port's render
     // target is RGBA16 + DEPTH24, the same formats the GLSL path writes (rescaleRendering is the identity at equal size).
-    port.resize(size);
+    // `size` is the port's own size here (process() rescales coarse renderings first), so the render target keeps its size
     tgt::Texture* col = port.getColorTexture();
     col->bind();
     glTexSubImage2D(GL_TEXTURE_2D, 0, 0, 0, size.x, size.y, GL_RGBA, GL_UNSIGNED_SHORT, &rgba16[0]);
@@ -288,9 +288,18 @@ void B200SingleVolumeRaycaster::process() {
                          reinterpret_cast<const float*>(exitp.get()), reinterpret_cast<const float*>(exitD.get()),
                          outColor, &hostDepth_[0]), "b200rc_render");
 
+    // rescaleRendering (volumeraycaster.cpp:348-377): internal size -> outport size with GL_LINEAR; the identity at equal size
     RenderPort* out[3] = {&outport1_, &outport2_, &outport3_};
-    for (int i = 0; i < 3; ++i)
-        if (params.output_connected[i]) writeOutport(*out[i], hostColor_[i], i == 0 ? &hostDepth_ : 0, size);
+    for (int i = 0; i < 3; ++i) {
+        if (!params.output_connected[i]) continue;
+        const tgt::ivec2 outSize = out[i]->getSize();
+        if (outSize == size) { writeOutport(*out[i], hostColor_[i], i == 0 ? &hostDepth_ : 0, size); continue; }
+        std::vector<uint16_t> up((size_t)outSize.x * outSize.y * 4);
+        std::vector<float> upDepth(i == 0 ? (size_t)outSize.x * outSize.y : 0);
+        failOn(b200rc_rescale(ctx_, &hostColor_[i][0], i == 0 ? &hostDepth_[0] : 0, size.x, size.y, B200RC_OUT_RGBA16,
+                              &up[0], i == 0 ? &upDepth[0] : 0, outSize.x, outSize.y, 0), "b200rc_rescale");
+        writeOutport(*out[i], up, i == 0 ? &upDepth : 0, outSize);
+    }
     tgt::TextureUnit::setZeroUnit();
     LGL_ERROR;
 }

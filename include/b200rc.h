@@ -321,6 +321,14 @@ int b200rc_ert_plan(b200rc_ctx* ctx, const float* alphas_dev, int world, uint32_
 int b200rc_remarch_device(b200rc_ctx* ctx, const b200rc_params* params, const b200rc_camera* cam, int width, int height,
                           const float* prefix_dev, const uint8_t* flags_dev, void* out_color_dev[B200RC_MAX_OUTPUTS], float* out_depth_dev);
 
+/* VolumeRaycaster::rescaleRendering (V/src/core/processors/volumeraycaster.cpp:348-377, copyimage.frag:37-55): the internal
+ * render targets (rendered at outport size / interactionCoarseness) are copied to the outports with GL_LINEAR filtering and
+ * CLAMP_TO_EDGE: destination pixel (x, y) fetches the source at ((x + 0.5) / dst_w, (y + 0.5) / dst_h), colour and depth alike;
+ * RGBA16 sources/destinations are unorm16 (B200RC_OUT_RGBA16) or float (B200RC_OUT_RGBA32F), depth is re-quantised to DEPTH24.
+ * Host buffers unless on_device != 0; src_depth / dst_depth may both be NULL. */
+int b200rc_rescale(b200rc_ctx* ctx, const void* src_color, const float* src_depth, int src_w, int src_h, int format,
+                   void* dst_color, float* dst_depth, int dst_w, int dst_h, int on_device);
+
 /* ERT finalisation after merging (alpha >= 0.95 -> 1.0, mod_raysetup.frag:65-74) and conversion to out_format. */
 int b200rc_finalize(b200rc_ctx* ctx, const float* rgba_dev, const float* depth_dev, size_t n, int out_format,
                     void* out_color_dev);

@@ -1505,3 +1505,33 @@ void orc_synth_volume(const int32_t dims[3], const int32_t lo[3], const int32_t 
         }
     }
 }
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* VolumeRaycaster::rescaleRendering (volumeraycaster.cpp:348-377) + copyimage.frag:37-55                         */
+/* ------------------------------------------------------------------------------------------------------------ */
+void orc_rescale_rgba16(const uint16_t* src, const float* src_depth, int sw, int sh, uint16_t* dst, float* dst_depth, int dw, int dh) {
+    #pragma omp parallel for schedule(static)
+    for (int y = 0; y < dh; ++y)
+        for (int x = 0; x < dw; ++x) {
+            /* fragCoord = gl_FragCoord.xy * screenDimRCP_ (copyimage.frag:43-47); GL_LINEAR: u = s * size - 0.5 */
+            float fx = ((float)x + 0.5f) * (1.0f / (float)dw), fy = ((float)y + 0.5f) * (1.0f / (float)dh);
+            float u = fx * (float)sw - 0.5f, v = fy * (float)sh - 0.5f;
+            float fu = floorf(u), fv = floorf(v);
+            float a = u - fu, b = v - fv;
+            int x0 = (int)fu, x1 = x0 + 1, y0 = (int)fv, y1 = y0 + 1;
+            x0 = x0 < 0 ? 0 : (x0 > sw - 1 ? sw - 1 : x0); x1 = x1 < 0 ? 0 : (x1 > sw - 1 ? sw - 1 : x1);
+            y0 = y0 < 0 ? 0 : (y0 > sh - 1 ? sh - 1 : y0); y1 = y1 < 0 ? 0 : (y1 > sh - 1 ? sh - 1 : y1);
+            size_t o = (size_t)y * dw + x;
+            for (int c = 0; c < 4; ++c) {
+                float c00 = (float)src[((size_t)y0 * sw + x0) * 4 + c] / 65535.f, c10 = (float)src[((size_t)y0 * sw + x1) * 4 + c] / 65535.f;
+                float c01 = (float)src[((size_t)y1 * sw + x0) * 4 + c] / 65535.f, c11 = (float)src[((size_t)y1 * sw + x1) * 4 + c] / 65535.f;
+                float r = lerp1(lerp1(c00, c10, a), lerp1(c01, c11, a), b);
+                r = r > 0.f ? (r > 1.f ? 1.f : r) : 0.f;
+                dst[o * 4 + c] = (uint16_t)floorf(r * 65535.f + 0.5f);          /* GL_RGBA16 store */
+            }
+            if (src_depth && dst_depth) {
+                float d00 = src_depth[(size_t)y0 * sw + x0], d10 = src_depth[(size_t)y0 * sw + x1], d01 = src_depth[(size_t)y1 * sw + x0], d11 = src_depth[(size_t)y1 * sw + x1];
+                dst_depth[o] = orc_depth24(lerp1(lerp1(d00, d10, a), lerp1(d01, d11, a), b));
+            }
+        }
+}

@@ -133,6 +133,10 @@ int64_t orc_image_diff_count(const float* a, const float* b, int width, int heig
  * Writes voxels [lo, lo+rdims) of a global volume of `dims` voxels, x fastest. --- */
 void orc_synth_volume(const int32_t dims[3], const int32_t lo[3], const int32_t rdims[3], uint64_t seed, uint16_t* out);
 
+/* VolumeRaycaster::rescaleRendering (volumeraycaster.cpp:348-377) with copyimage.frag:37-55: GL_LINEAR / CLAMP_TO_EDGE copy of an
+ * RGBA16-unorm colour image (as uint16) + DEPTH24 depth to another size. */
+void orc_rescale_rgba16(const uint16_t* src, const float* src_depth, int sw, int sh, uint16_t* dst, float* dst_depth, int dw, int dh);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,6 +64,8 @@ def lib():
         _lib.orc_preint_classify.argtypes = [pf, C.c_int, C.c_float, C.c_float, pf]
         _lib.orc_region_minmax.argtypes = [C.POINTER(Volume), C.c_int, C.POINTER(C.c_int32 * 3), pf]
         _lib.orc_proxy_boxes.argtypes = [C.POINTER(Volume), C.POINTER(TF1D), C.c_int, C.POINTER(abi.EepParams), pf, C.c_int]
+        _lib.orc_rescale_rgba16.argtypes = [C.c_void_p, pf, C.c_int, C.c_int, C.c_void_p, pf, C.c_int, C.c_int]
+        _lib.orc_rescale_rgba16.restype = None
         _lib.orc_proxy_boxes.restype = C.c_int
         _lib.orc_entry_exit.argtypes = [pf, C.c_int, pf, C.POINTER(abi.EepParams), C.POINTER(abi.Camera), C.c_int, C.c_int, pf, pf, pf, pf]
         _lib.orc_raycast.argtypes = [C.POINTER(Volume), C.POINTER(Classifier), C.POINTER(abi.Params), C.POINTER(abi.Camera), C.c_int, C.c_int,
@@ -224,3 +226,12 @@ def synth_volume(dims, seed=1234, lo=(0, 0, 0), rdims=None):
     a = (C.c_int32 * 3)(*dims); b = (C.c_int32 * 3)(*lo); c = (C.c_int32 * 3)(*rdims)
     lib().orc_synth_volume(C.byref(a), C.byref(b), C.byref(c), seed, out.ctypes.data_as(C.c_void_p))
     return out
+
+
+def rescale_rgba16(color, depth, dw, dh):
+    """VolumeRaycaster::rescaleRendering on an (H, W, 4) uint16 image + (H, W) float32 depth."""
+    color = np.ascontiguousarray(color, np.uint16); depth = np.ascontiguousarray(depth, np.float32)
+    sh, sw = color.shape[:2]
+    out = np.empty((dh, dw, 4), np.uint16); od = np.empty((dh, dw), np.float32)
+    lib().orc_rescale_rgba16(color.ctypes.data, fp(depth), sw, sh, out.ctypes.data, fp(od), dw, dh)
+    return out, od

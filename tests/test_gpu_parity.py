@@ -628,3 +628,21 @@ def test_optimized_proxy_geometry_modes(ctx, mode, clip, cell, threshold):
     e, ed, x, xd = ctx.entry_exit(eep2, cam, 96, 96)
     oe, oed, ox, oxd = orc.entry_exit(want, orc.texture_to_world(desc), eep, cam, 96, 96)
     assert np.array_equal(e, oe) and np.array_equal(x, ox) and np.array_equal(ed, oed) and np.array_equal(xd, oxd)
+
+
+# ---- VolumeRaycaster::rescaleRendering: the GL_LINEAR copy of the internal render targets to the outports ------------
+@pytest.mark.parametrize("dst", [(128, 96), (64, 48), (100, 77), (31, 17)])
+def test_rescale_rendering(ctx, dst):
+    vol = scenes.ct_like_volume(32)
+    s = scenes.Scene(vol, W=64, H=48, out_format=abi.OUT_RGBA16)
+    outs, depth = s.cuda_render(ctx)
+    src = np.asarray(outs[0]).view(np.uint16).reshape(48, 64, 4)
+    got, got_d = ctx.rescale(src, depth, dst[0], dst[1])
+    want, want_d = orc.rescale_rgba16(src, depth, dst[0], dst[1])
+    assert np.array_equal(got, want) and np.array_equal(got_d, want_d)         # integer outputs: bit-exact
+    if dst == (64, 48):
+        assert np.array_equal(got, src)                                          # identity at equal size (volumeraycaster.cpp:349)
+    assert int((got[..., 3] > 0).sum()) > 0.05 * dst[0] * dst[1]
+    f32 = src.astype(np.float32) / np.float32(65535.0)
+    gotf, _ = ctx.rescale(f32, depth, dst[0], dst[1])
+    assert np.abs(gotf - want.astype(np.float32) / 65535.0).max() <= 0.5 / 65535.0 + 1e-7

@@ -549,6 +549,30 @@ extern "C" int b200rc_composite(b200rc_ctx* ctx, int mode, const float* front_rg
     return rc_composite_launch(ctx, mode, front_rgba, front_depth, back_rgba, back_depth, dst_rgba, dst_depth, n);
 }
 
+extern "C" int b200rc_rescale(b200rc_ctx* ctx, const void* src_color, const float* src_depth, int sw, int sh, int format,
+                              void* dst_color, float* dst_depth, int dw, int dh, int on_device) {
+    CTX_GUARD();
+    if (!src_color || !dst_color || sw < 1 || sh < 1 || dw < 1 || dh < 1 || (format != B200RC_OUT_RGBA16 && format != B200RC_OUT_RGBA32F) ||
+        ((src_depth == nullptr) != (dst_depth == nullptr))) { ctx->set_error("rescale: bad arguments"); return B200RC_ERR_INVALID; }
+    if (on_device) return rc_rescale_launch(ctx, src_color, src_depth, sw, sh, format, dst_color, dst_depth, dw, dh);
+    const size_t pb = out_pixel_bytes(format), sp = (size_t)sw * sh, dp = (size_t)dw * dh;
+    void* d_src = nullptr; void* d_dst = nullptr; float* d_sd = nullptr; float* d_dd = nullptr;
+    int rc = B200RC_OK;
+    if (cudaMalloc(&d_src, sp * pb) != cudaSuccess || cudaMalloc(&d_dst, dp * pb) != cudaSuccess ||
+        (src_depth && (cudaMalloc(&d_sd, sp * sizeof(float)) != cudaSuccess || cudaMalloc(&d_dd, dp * sizeof(float)) != cudaSuccess))) {
+        cudaGetLastError(); ctx->set_error("rescale: out of device memory"); rc = B200RC_ERR_OOM;
+    }
+    if (!rc && cudaMemcpyAsync(d_src, src_color, sp * pb, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = B200RC_ERR_CUDA;
+    if (!rc && src_depth && cudaMemcpyAsync(d_sd, src_depth, sp * sizeof(float), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = B200RC_ERR_CUDA;
+    if (!rc) rc = rc_rescale_launch(ctx, d_src, d_sd, sw, sh, format, d_dst, d_dd, dw, dh);
+    if (!rc && cudaMemcpyAsync(dst_color, d_dst, dp * pb, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = B200RC_ERR_CUDA;
+    if (!rc && dst_depth && cudaMemcpyAsync(dst_depth, d_dd, dp * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = B200RC_ERR_CUDA;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && !rc) rc = B200RC_ERR_CUDA;
+    if (rc == B200RC_ERR_CUDA) ctx->set_error("rescale: copy failed");
+    cudaFree(d_src); cudaFree(d_dst); cudaFree(d_sd); cudaFree(d_dd);
+    return rc;
+}
+
 extern "C" int b200rc_finalize(b200rc_ctx* ctx, const float* rgba_dev, const float* depth_dev, size_t n, int out_format, void* out_color_dev) {
     CTX_GUARD();
     if (!rgba_dev || !out_color_dev) { ctx->set_error("finalize: null image"); return B200RC_ERR_INVALID; }

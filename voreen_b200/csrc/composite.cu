@@ -37,6 +37,47 @@ __global__ void finalize_kernel(const float4* __restrict__ rgba, size_t n, int o
     else ((float4*)out)[i] = r;
 }
 
+// rescaleRendering: bilinear (GL_LINEAR, CLAMP_TO_EDGE) copy of colour + depth to another size (copyimage.frag:37-55)
+__global__ void rescale_kernel(const void* __restrict__ src, const float* __restrict__ sdepth, int sw, int sh, int format,
+                               void* __restrict__ dst, float* __restrict__ ddepth, int dw, int dh) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= dw || y >= dh) return;
+    // fragCoord = gl_FragCoord.xy * screenDimRCP_;  u = s * size - 0.5 (GL 4.x 8.14)
+    const float fx = xmul(xadd((float)x, 0.5f), xdiv(1.0f, (float)dw)), fy = xmul(xadd((float)y, 0.5f), xdiv(1.0f, (float)dh));
+    const float u = xsub(xmul(fx, (float)sw), 0.5f), v = xsub(xmul(fy, (float)sh), 0.5f);
+    const float fu = floorf(u), fv = floorf(v);
+    const float a = xsub(u, fu), b = xsub(v, fv);
+    const int x0 = min(max((int)fu, 0), sw - 1), x1 = min(max((int)fu + 1, 0), sw - 1);
+    const int y0 = min(max((int)fv, 0), sh - 1), y1 = min(max((int)fv + 1, 0), sh - 1);
+    auto fetch = [&](int px, int py) -> float4 {
+        const size_t i = (size_t)py * sw + px;
+        if (format == B200RC_OUT_RGBA16) {
+            const ushort4 q = ((const ushort4*)src)[i];
+            return make_float4(xdiv((float)q.x, 65535.f), xdiv((float)q.y, 65535.f), xdiv((float)q.z, 65535.f), xdiv((float)q.w, 65535.f));
+        }
+        return ((const float4*)src)[i];
+    };
+    const float4 c00 = fetch(x0, y0), c10 = fetch(x1, y0), c01 = fetch(x0, y1), c11 = fetch(x1, y1);
+    float4 r;
+    r.x = xlerp(xlerp(c00.x, c10.x, a), xlerp(c01.x, c11.x, a), b); r.y = xlerp(xlerp(c00.y, c10.y, a), xlerp(c01.y, c11.y, a), b);
+    r.z = xlerp(xlerp(c00.z, c10.z, a), xlerp(c01.z, c11.z, a), b); r.w = xlerp(xlerp(c00.w, c10.w, a), xlerp(c01.w, c11.w, a), b);
+    const size_t o = (size_t)y * dw + x;
+    if (format == B200RC_OUT_RGBA16) ((ushort4*)dst)[o] = make_ushort4(to_unorm16(r.x), to_unorm16(r.y), to_unorm16(r.z), to_unorm16(r.w));
+    else ((float4*)dst)[o] = r;
+    if (sdepth && ddepth) {
+        const float d00 = sdepth[(size_t)y0 * sw + x0], d10 = sdepth[(size_t)y0 * sw + x1], d01 = sdepth[(size_t)y1 * sw + x0], d11 = sdepth[(size_t)y1 * sw + x1];
+        ddepth[o] = depth24_roundtrip(xlerp(xlerp(d00, d10, a), xlerp(d01, d11, a), b));
+    }
+}
+
+int rc_rescale_launch(b200rc_ctx* ctx, const void* src, const float* sdepth, int sw, int sh, int format, void* dst, float* ddepth, int dw, int dh) {
+    dim3 block(32, 8), grid((unsigned)((dw + 31) / 32), (unsigned)((dh + 7) / 8));
+    rescale_kernel<<<grid, block, 0, ctx->stream>>>(src, sdepth, sw, sh, format, dst, ddepth, dw, dh);
+    ctx->launches++;
+    RC_CHECK(cudaGetLastError());
+    return B200RC_OK;
+}
+
 int rc_composite_launch(b200rc_ctx* ctx, int mode, const float* fc, const float* fd, const float* bc, const float* bd, float* dc, float* dd, size_t n) {
     if (!n) return B200RC_OK;
     composite_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(mode, (const float4*)fc, fd, (const float4*)bc, bd, (float4*)dc, dd, n);

@@ -303,6 +303,18 @@ class Context:
     def composite(self, mode, front, front_depth, back, back_depth, dst, dst_depth, n):
         self._check(self.lib.b200rc_composite(self.h, mode, front, front_depth, back, back_depth, dst, dst_depth, n), "composite")
 
+    def rescale(self, color, depth, dw, dh):
+        """VolumeRaycaster::rescaleRendering: (H, W, 4) uint16 / float32 colour + (H, W) depth -> (dh, dw) with GL_LINEAR filtering."""
+        color = np.ascontiguousarray(color)
+        fmt = abi.OUT_RGBA16 if color.dtype == np.uint16 else abi.OUT_RGBA32F
+        sh, sw = color.shape[:2]
+        out = np.empty((dh, dw, 4), color.dtype)
+        od = np.empty((dh, dw), np.float32) if depth is not None else None
+        d = np.ascontiguousarray(depth, np.float32) if depth is not None else None
+        self._check(self.lib.b200rc_rescale(self.h, color.ctypes.data_as(C.c_void_p), _fp(d) if d is not None else None, sw, sh, fmt,
+                                            out.ctypes.data_as(C.c_void_p), _fp(od) if od is not None else None, dw, dh, 0), "rescale")
+        return out, od
+
     def finalize(self, rgba, depth, n, out_format, out):
         self._check(self.lib.b200rc_finalize(self.h, rgba, depth, n, out_format, out), "finalize")
 
