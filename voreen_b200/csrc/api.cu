@@ -88,7 +88,7 @@ extern "C" int b200rc_create(int device, b200rc_ctx** out_ctx) {
     }
     ctx->stream = ctx->own_stream;
     for (int i = 0; i < 6; ++i) cudaEventCreate(&ctx->ev[i]);
-    cudaMalloc(&ctx->d_stats, 8 * sizeof(unsigned long long));
+    cudaMalloc(&ctx->d_stats, 16 * sizeof(unsigned long long));     // [0..7] counters, [8..15] SLAB_PROFILE phase clocks
     cudaMalloc(&ctx->d_tile_counter, 4 * sizeof(unsigned int));
     *out_ctx = ctx;
     return B200RC_OK;
@@ -375,7 +375,7 @@ int rc_march_launch(b200rc_ctx* ctx, const DevParams& p, int sampler, int nch, i
 }
 
 static int run_march(b200rc_ctx* ctx, const b200rc_params* P, DevParams& p, int nch, int dtype) {
-    if (P->collect_stats) RC_CHECK(cudaMemsetAsync(ctx->d_stats, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    if (P->collect_stats) RC_CHECK(cudaMemsetAsync(ctx->d_stats, 0, 16 * sizeof(unsigned long long), ctx->stream));
     RC_CHECK(cudaEventRecord(ctx->ev[2], ctx->stream));
     int rc = rc_march_launch(ctx, p, P->sampler, nch, dtype);
     if (rc) return rc;
@@ -399,7 +399,14 @@ static int finish_frame(b200rc_ctx* ctx, const b200rc_params* P, bool had_eep) {
         RC_CHECK(cudaMemcpy(h, ctx->d_stats, sizeof h, cudaMemcpyDeviceToHost));
         ctx->stats.rays_cast = h[0]; ctx->stats.samples_classified = h[1]; ctx->stats.samples_shaded = h[2];
         ctx->stats.samples_nominal = h[3]; ctx->stats.samples_skipped = h[4]; ctx->stats.cells_touched = h[5];
-        if (getenv("B200RC_DEBUG")) fprintf(stderr, "[b200rc] slab ray-rounds with work %llu of %llu\n", h[6], h[7]);
+        if (getenv("B200RC_DEBUG")) {
+            fprintf(stderr, "[b200rc] slab ray-rounds with work %llu of %llu\n", h[6], h[7]);
+            unsigned long long ph[8];
+            RC_CHECK(cudaMemcpy(ph, ctx->d_stats + 8, sizeof ph, cudaMemcpyDeviceToHost));
+            if (ph[7])      // only a -DSLAB_PROFILE build fills these: clock cycles of warp 0 of every CTA, summed
+                fprintf(stderr, "[b200rc] slab phases (cycles of thread 0, summed over CTAs): skip+zmin %llu wait1 %llu bbox %llu wait2 %llu leader+wait3 %llu stage %llu march %llu rounds %llu\n",
+                        ph[0], ph[1], ph[2], ph[3], ph[4], ph[5], ph[6], ph[7]);
+        }
     }
     return B200RC_OK;
 }

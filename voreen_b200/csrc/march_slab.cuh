@@ -28,6 +28,9 @@
 #ifndef SLAB_MIN_CTAS
 #define SLAB_MIN_CTAS (768 / SLAB_THREADS)
 #endif
+#ifndef SLAB_STAGE_BATCH
+#define SLAB_STAGE_BATCH 4      // 16-byte loads in flight per thread while staging
+#endif
 #define SLAB_OCC_WORDS 160      // (max lateral extent / 8 + 2)^2 occupancy words per region
 #define SLAB_CMAX 512           // staged level-0 cell maxima per region (MIP culling)
 
@@ -77,28 +80,44 @@ __device__ __forceinline__ void slab_stage(const VolDev& v, const SlabShared& sh
         const int c_first = xr0 >> 3;                               // arithmetic shift: floor for negative x
         const int nchunks = ((xr0 + nx - 1) >> 3) - c_first + 1;
         const float rcp_ny = 1.0f / (float)ny;
-        for (int c = 0; c < nchunks; ++c)
-        for (int r = threadIdx.x; r < rows; r += SLAB_THREADS) {
-            const int lz = __float2int_rd(((float)r + 0.5f) * rcp_ny), ly = r - lz * ny;   // r / ny (exact: (r + .5) / ny is never near an integer)
-            const int y = min(max(sh.rlo[1] + ly, v.clamp_lo[1]), v.clamp_hi[1]) - v.res_lo[1];
-            const int z = min(max(sh.rlo[2] + lz, v.clamp_lo[2]), v.clamp_hi[2]) - v.res_lo[2];
-            const int cx = c_first + c;
-            const int cxc = min(max(cx, 0), v.nbx - 1);
-            const long long e = (long long)cxc * 512 + brick_off_y(y, v.nbx) + brick_off_z(z, v.nbx, v.nby);
-            const uint4 q = __ldg((const uint4*)((const unsigned short*)v.bricks + e));
-            float f[8] = {u16lo_norm(q.x), u16hi_norm(q.x), u16lo_norm(q.y), u16hi_norm(q.y), u16lo_norm(q.z), u16hi_norm(q.z), u16lo_norm(q.w), u16hi_norm(q.w)};
-            // a chunk entirely left of the resident range replicates its first voxel (CLAMP_TO_EDGE / shard clamp); the pool
-            // itself replicates the last voxel of a row into the brick padding on the right
-            if (cx < 0) { for (int i = 1; i < 8; ++i) f[i] = f[0]; }
-            else if (cx > v.nbx - 1) { for (int i = 0; i < 7; ++i) f[i] = f[7]; }
-            // clamp_hi inside the last brick (sharded volumes whose resident range ends before the brick does not occur:
-            // the pool pads with the clamped voxel)
-            float* row = S + r * pitch;
-            const int lx0 = cx * 8 - xr0;
+        // items = (x chunk, row) pairs, chunk-major; every thread takes SLAB_STAGE_BATCH items per trip and issues all their
+        // 16-byte loads before it converts and stores the first one (the loads of a trip are in flight together)
+        const int items = nchunks * rows;
+        const float rcp_rows = 1.0f / (float)rows;
+        for (int base = threadIdx.x; base < items; base += SLAB_THREADS * SLAB_STAGE_BATCH) {
+            uint4 q[SLAB_STAGE_BATCH]; int rr[SLAB_STAGE_BATCH], cxs[SLAB_STAGE_BATCH];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int lx = lx0 + i;
-                if ((unsigned)lx < (unsigned)nx) row[lx] = f[i];
+            for (int k = 0; k < SLAB_STAGE_BATCH; ++k) {
+                const int it = base + k * SLAB_THREADS;
+                rr[k] = -1; cxs[k] = 0; q[k] = make_uint4(0u, 0u, 0u, 0u);
+                if (it < items) {
+                    const int c = __float2int_rd(((float)it + 0.5f) * rcp_rows), r = it - c * rows;         // it / rows (exact: a half-integer over rows is never near an integer)
+                    const int lz = __float2int_rd(((float)r + 0.5f) * rcp_ny), ly = r - lz * ny;            // r / ny (exact: (r + .5) / ny is never near an integer)
+                    const int y = min(max(sh.rlo[1] + ly, v.clamp_lo[1]), v.clamp_hi[1]) - v.res_lo[1];
+                    const int z = min(max(sh.rlo[2] + lz, v.clamp_lo[2]), v.clamp_hi[2]) - v.res_lo[2];
+                    const int cx = c_first + c;
+                    const int cxc = min(max(cx, 0), v.nbx - 1);
+                    const long long e = (long long)cxc * 512 + brick_off_y(y, v.nbx) + brick_off_z(z, v.nbx, v.nby);
+                    q[k] = __ldg((const uint4*)((const unsigned short*)v.bricks + e));
+                    rr[k] = r; cxs[k] = cx;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < SLAB_STAGE_BATCH; ++k) {
+                if (rr[k] < 0) continue;
+                const int cx = cxs[k];
+                float f[8] = {u16lo_norm(q[k].x), u16hi_norm(q[k].x), u16lo_norm(q[k].y), u16hi_norm(q[k].y), u16lo_norm(q[k].z), u16hi_norm(q[k].z), u16lo_norm(q[k].w), u16hi_norm(q[k].w)};
+                // a chunk entirely left of the resident range replicates its first voxel (CLAMP_TO_EDGE / shard clamp); the pool
+                // itself replicates the last voxel of a row into the brick padding on the right
+                if (cx < 0) { for (int i = 1; i < 8; ++i) f[i] = f[0]; }
+                else if (cx > v.nbx - 1) { for (int i = 0; i < 7; ++i) f[i] = f[7]; }
+                float* row = S + rr[k] * pitch;
+                const int lx0 = cx * 8 - xr0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int lx = lx0 + i;
+                    if ((unsigned)lx < (unsigned)nx) row[lx] = f[i];
+                }
             }
         }
     } else {
@@ -307,6 +326,12 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     RayStats st = {0u, 0u, 0u, 0u, 0ull};
     unsigned long long dbg_part = 0, dbg_rounds = 0;
+#ifdef SLAB_PROFILE
+    long long pf_sched = 0, pf_stage = 0, pf_march = 0, pf_wait = 0, pf_setup = 0, pf_rounds = 0, pf_bbox = 0, pf_wait2 = 0, pf_leader = 0, pf_t = clock64();
+#define PF_MARK(acc) { const long long now_ = clock64(); acc += now_ - pf_t; pf_t = now_; }
+#else
+#define PF_MARK(acc)
+#endif
     const unsigned ntiles = (unsigned)p.tiles_x * (unsigned)p.tiles_y;      // 16x16 tiles, padded to 8x8 super-tiles
     const unsigned super_x = (unsigned)p.tiles_x >> 3;
 
@@ -388,6 +413,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
         bool stale = true;
         int i0x = 0, i0y = 0, i0z = 0, zc = INT_MAX; float ux = 0.f, uy = 0.f, uz = 0.f;
 
+        PF_MARK(pf_setup)
         // ---- rounds ---------------------------------------------------------------------------------------------------
         for (;;) {
             // (1) direction-normalised major index of this ray's next sample, after jumping over empty cells so that no
@@ -409,7 +435,9 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
                 const int wmin = __reduce_min_sync(0xffffffffu, zc);
                 if (lane == 0 && wmin != INT_MAX) atomicMin(&sh.zmin, wmin);
             }
+            PF_MARK(pf_sched)
             __syncthreads();
+            PF_MARK(pf_wait)
             const int zmin = sh.zmin;
             if (zmin == INT_MAX) break;                     // every ray of the tile is done (uniform)
             // (2) bounding box of the participating segments
@@ -430,9 +458,14 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
                     atomicMin(&sh.lo[0], lo0); atomicMin(&sh.lo[1], lo1); atomicMin(&sh.lo[2], lo2);
                     atomicMax(&sh.hi[0], hi0); atomicMax(&sh.hi[1], hi1); atomicMax(&sh.hi[2], hi2);
                 }
-                if (!finished && zc == zmin) atomicMin(&sh.leader, (int)threadIdx.x);
+                {   // leader = smallest thread id among the rays at the slab front: one shared-memory atomic per warp, not per ray
+                    const int cand = __reduce_min_sync(0xffffffffu, (!finished && zc == zmin) ? (int)threadIdx.x : INT_MAX);
+                    if (lane == 0 && cand != INT_MAX) atomicMin(&sh.leader, cand);
+                }
             }
+            PF_MARK(pf_bbox)
             __syncthreads();
+            PF_MARK(pf_wait2)
             // (3) the leader fixes the region (footprint apron -1..+2, one voxel of slack) and resets the scratch
             if ((int)threadIdx.x == sh.leader) {
                 const int li[3] = {i0x, i0y, i0z};
@@ -475,10 +508,12 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
                 sh.zmin = INT_MAX; sh.leader = INT_MAX;
             }
             __syncthreads();
+            PF_MARK(pf_leader)
             // (4) stage voxels + occupancy bits
             slab_stage<C>(V, sh, S);
             if (V.ess) slab_stage_occ<CULL>(V, sh, sh_cmax);
             __syncthreads();
+            PF_MARK(pf_stage)
             // (5) march while the footprint of the next sample lies inside the region.  The loop is warp-synchronous
             //     (one __any_sync per iteration) so that the lanes of a warp take their samples together.
             {
@@ -625,6 +660,10 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
                         }
                     }
                 }
+                PF_MARK(pf_march)
+#ifdef SLAB_PROFILE
+                pf_rounds++;
+#endif
             }
         }
         // ---- outputs ------------------------------------------------------------------------------------------------------
@@ -639,6 +678,13 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
             if (p.out_depth) p.out_depth[pix] = p.quantize_depth24 ? depth24_roundtrip(depth) : depth;
         }
     }
+#ifdef SLAB_PROFILE
+    if (p.collect_stats && p.stats && threadIdx.x == 0) {
+        atomicAdd(p.stats + 8, (unsigned long long)pf_sched); atomicAdd(p.stats + 9, (unsigned long long)pf_wait); atomicAdd(p.stats + 10, (unsigned long long)pf_bbox);
+        atomicAdd(p.stats + 11, (unsigned long long)pf_wait2); atomicAdd(p.stats + 12, (unsigned long long)pf_leader); atomicAdd(p.stats + 13, (unsigned long long)pf_stage);
+        atomicAdd(p.stats + 14, (unsigned long long)(pf_march + 0 * pf_setup)); atomicAdd(p.stats + 15, (unsigned long long)pf_rounds);
+    }
+#endif
     if (p.collect_stats && p.stats) {
         unsigned long long vals[7] = {st.rays, st.classified, st.shaded, st.nominal, st.skipped, dbg_part, dbg_rounds};
 #pragma unroll
