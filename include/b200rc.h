@@ -94,6 +94,7 @@ enum { B200RC_INSIDE_NONE = 0, B200RC_INSIDE_GPU = 1 };
 /* OptimizedProxyGeometry "modeString" (optimizedproxygeometry.cpp:107-114).  The library itself builds the
  * bounding-box cube (processCube :420-448); for the TF-dependent modes the host mirror classifies the min/max
  * regions (b200rc_region_minmax) with the TF keys and hands the resulting cubes over as explicit boxes. */
+enum { B200RC_RAYCASTER_SINGLE = 0, B200RC_RAYCASTER_SIMPLE = 1 };
 enum { B200RC_PROXY_BBOX = 0, B200RC_PROXY_MINBBOX = 1, B200RC_PROXY_VISIBLE_BRICKS = 2 };
 
 /* ---- PODs ------------------------------------------------------------------------------------ */
@@ -177,6 +178,11 @@ typedef struct b200rc_params {
      * are left untouched.  modulus 0 or 1 = the whole image. */
     int32_t image_band_modulus;
     int32_t image_band_remainder;
+    /* Which raycaster of the family (B200RC_RAYCASTER_*).  SIMPLE = voreen::SimpleRaycaster (rc_simple.frag:50-102): one output,
+     * 1D TF on voxel.a, no gradients / shading, DVR with opacity correction, first-hit depth at the first sample that leaves
+     * result.a > 0, early termination at alpha >= 1.0, at most 255*255 loop iterations.  gradient / shading / classification
+     * / compositing fields are ignored. */
+    int32_t raycaster;
 } b200rc_params;
 
 /* MeshEntryExitPoints + proxy geometry settings for b200rc_render_camera / b200rc_entry_exit. */

@@ -823,6 +823,59 @@ static inline v3 tex_to_physical(const vol_ctx* c, v3 p) {
 
 typedef struct { uint64_t rays, classified, shaded, nominal; } loc_stats;
 
+/* SimpleRaycaster (V/modules/base/glsl/rc_simple.frag:50-122; host side simpleraycaster.cpp:71-150) */
+static void raycast_simple(const orc_volume* vol, const orc_classifier* cls, const b200rc_params* P, const b200rc_camera* cam, int W, int H,
+                           const float* entry, const float* entryD, const float* exitp, const float* exitD,
+                           float* out_color[3], float* out_depth, b200rc_stats* stats) {
+    const float step = P->sampling_step;
+    uint64_t s_rays = 0, s_class = 0, s_shaded = 0, s_nominal = 0;
+#pragma omp parallel for schedule(dynamic, 2) reduction(+ : s_rays, s_class, s_shaded, s_nominal)
+    for (int py = 0; py < H; ++py)
+        for (int px = 0; px < W; ++px) {
+            size_t pix = (size_t)py * W + px;
+            v3 first = V3(entry[4 * pix], entry[4 * pix + 1], entry[4 * pix + 2]);
+            v3 last = V3(exitp[4 * pix], exitp[4 * pix + 1], exitp[4 * pix + 2]);
+            v4 result = V4(0, 0, 0, 0);
+            float depth = 1.0f;
+            if (!(first.x == last.x && first.y == last.y && first.z == last.z)) {      /* :113-116 */
+                s_rays++;
+                float depthT = -1.0f, t = 0.0f;
+                v3 dir = sub3(last, first);
+                float tend = length3(dir);
+                dir = V3(dir.x / tend, dir.y / tend, dir.z / tend);
+                s_nominal += (uint64_t)floorf(tend / step) + 1u;
+                int finished = 0;
+                for (int loop = 0; !finished && loop < 255 * 255; ++loop) {
+                    v3 samplePos = add3(first, scale3(dir, t));
+                    v4 voxel = get_voxel(vol, &P->vol[0], samplePos);
+                    s_class++;
+                    v4 color = classify(B200RC_CLASS_TF, &cls[0], V4(0, 0, 0, voxel.w), 0.f);      /* applyTF(tf, tex, vec4 voxel): voxel.a */
+                    if (color.w > 0.0f) {
+                        s_shaded++;
+                        color.w = 1.0f - powf(1.0f - color.w, step * 200.0f);
+                        result.x = result.x + (1.0f - result.w) * color.w * color.x;
+                        result.y = result.y + (1.0f - result.w) * color.w * color.y;
+                        result.z = result.z + (1.0f - result.w) * color.w * color.z;
+                        result.w = result.w + (1.0f - result.w) * color.w;
+                    }
+                    if (depthT < 0.0f && result.w > 0.0f) depthT = t;
+                    if (result.w >= 1.0f) { result.w = 1.0f; finished = 1; }
+                    t += step;
+                    finished = finished || (t > tend);
+                }
+                if (depthT >= 0.0f) depth = get_depth_value(depthT, tend, entryD[pix], exitD[pix], cam->near_dist, cam->far_dist);
+            }
+            if (out_color[0]) {
+                float* d = out_color[0] + 4 * pix;
+                v4 r = result;
+                if (P->out_format == B200RC_OUT_RGBA16) r = V4(orc_unorm16(r.x), orc_unorm16(r.y), orc_unorm16(r.z), orc_unorm16(r.w));
+                d[0] = r.x; d[1] = r.y; d[2] = r.z; d[3] = r.w;
+            }
+            if (out_depth) out_depth[pix] = P->quantize_depth24 ? orc_depth24(depth) : depth;
+        }
+    if (stats) { stats->rays_cast = s_rays; stats->samples_classified = s_class; stats->samples_shaded = s_shaded; stats->samples_nominal = s_nominal; }
+}
+
 static void raycast_single(const orc_volume* vol, const orc_classifier* cls, const b200rc_params* P,
                            const b200rc_camera* cam, int W, int H,
                            const float* entry, const float* entryD, const float* exitp, const float* exitD,
@@ -1055,7 +1108,9 @@ void orc_raycast(const orc_volume* vols, const orc_classifier* cls, const b200rc
                  const b200rc_camera* cam, int width, int height,
                  const float* entry_rgba, const float* entry_depth, const float* exit_rgba, const float* exit_depth,
                  float* out_color[B200RC_MAX_OUTPUTS], float* out_depth, b200rc_stats* stats) {
-    if (params->multi_volume)
+    if (!params->multi_volume && params->raycaster == B200RC_RAYCASTER_SIMPLE)
+        raycast_simple(vols, cls, params, cam, width, height, entry_rgba, entry_depth, exit_rgba, exit_depth, out_color, out_depth, stats);
+    else if (params->multi_volume)
         raycast_multi(vols, cls, params, cam, width, height, entry_rgba, entry_depth, exit_rgba, exit_depth, out_color, out_depth, stats);
     else
         raycast_single(vols, cls, params, cam, width, height, entry_rgba, entry_depth, exit_rgba, exit_depth, out_color, out_depth, stats);

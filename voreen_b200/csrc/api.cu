@@ -225,6 +225,8 @@ static int build_params(b200rc_ctx* ctx, const b200rc_params* P, const b200rc_ca
     p.nvol = nv; p.multi = P->multi_volume ? 1 : 0;
     p.step = P->sampling_step; p.mv_factor = P->mv_opacity_correction_factor;
     p.gradient = P->gradient;
+    p.simple = (!P->multi_volume && P->raycaster == B200RC_RAYCASTER_SIMPLE) ? 1 : 0;
+    if (P->raycaster != B200RC_RAYCASTER_SINGLE && P->raycaster != B200RC_RAYCASTER_SIMPLE) { ctx->set_error("render: unknown raycaster kind"); return B200RC_ERR_INVALID; }
     p.iso = P->iso_value;
     p.light = P->light;
     p.near_d = cam->near_dist; p.far_d = cam->far_dist;
@@ -292,11 +294,11 @@ static int build_params(b200rc_ctx* ctx, const b200rc_params* P, const b200rc_ca
         rc_texture_to_world(&vs.desc, t2w);
         if (!rc_mat4_invert(t2w, d.w2t)) { ctx->set_error("render: singular textureToWorld matrix"); return B200RC_ERR_INVALID; }
     }
-    // classifiers: per channel (single volume) or per volume (multi)
-    const int ncls = P->multi_volume ? nv : ctx->vol[0].desc.channels;
+    // classifiers: per channel (single volume) or per volume (multi); SimpleRaycaster: one 1D TF on voxel.a
+    const int ncls = P->multi_volume ? nv : (p.simple ? 1 : ctx->vol[0].desc.channels);
     for (int c = 0; c < ncls; ++c) {
         ClassifierSlot& k = ctx->cls[c];
-        const int mode = P->multi_volume ? P->vol[c].classification : P->vol[0].classification;
+        const int mode = p.simple ? B200RC_CLASS_TF : (P->multi_volume ? P->vol[c].classification : P->vol[0].classification);
         ClsDev& d = p.cls[c];
         d.dom_lo = k.dom[0]; d.dom_hi = k.dom[1]; d.domy_lo = k.domy[0]; d.domy_hi = k.domy[1];
         if (mode == B200RC_CLASS_TF) {
@@ -313,9 +315,10 @@ static int build_params(b200rc_ctx* ctx, const b200rc_params* P, const b200rc_ca
         }
     }
     // empty-space skipping (no channel shift): occupancy for the current TFs
-    if (P->empty_space_skipping && !P->multi_volume && !p.channel_shift) {
+    if (p.simple) { p.classification[0] = B200RC_CLASS_TF; p.channel_shift = 0; p.preint_comp = 0; }
+    if (P->empty_space_skipping && !P->multi_volume && !p.channel_shift && !(p.simple && ctx->vol[0].desc.channels != 1)) {
         int modes[4];
-        for (int c = 0; c < ncls; ++c) modes[c] = P->vol[0].classification;
+        for (int c = 0; c < ncls; ++c) modes[c] = p.simple ? B200RC_CLASS_TF : P->vol[0].classification;
         int rc = rc_volume_build_occupancy(ctx, 0, modes, ncls, false, P->vol[0].clamp, P->vol[0].border_intensity);
         if (rc) return rc;
         p.vol[0].ess = 1;
@@ -367,6 +370,7 @@ int rc_march_launch(b200rc_ctx* ctx, const DevParams& p, int sampler, int nch, i
     // marcher 2.4 ms, per-ray kernel 3.4 ms -> the slab marcher stays; B200RC_REMARCH=ray selects the per-ray kernel (A/B)
     static const bool remarch_ray = getenv("B200RC_REMARCH") && !strcmp(getenv("B200RC_REMARCH"), "ray");
     const bool slab_ok = ctx->use_slab && !(p.flags && (remarch_ray || p.pixel_list));
+    if (p.simple) return rc_march_generic(ctx, p, sampler, nch);      // SimpleRaycaster: the run-time-switched per-ray kernel
     if (slab_ok && rc_march_slab(ctx, p, sampler, nch, dtype, &rc)) return rc;
     if (rc_march_fast(ctx, p, sampler, nch, dtype, &rc)) return rc;
     if (rc_march_fast_multi(ctx, p, sampler, &rc)) return rc;
