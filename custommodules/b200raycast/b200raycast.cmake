@@ -12,10 +12,12 @@ SET(MOD_CORE_MODULECLASS B200RaycastModule)
 SET(MOD_CORE_SOURCES
     ${MOD_DIR}/processors/b200singlevolumeraycaster.cpp
     ${MOD_DIR}/processors/b200multivolumeraycaster.cpp
+    ${MOD_DIR}/processors/b200simpleraycaster.cpp
 )
 SET(MOD_CORE_HEADERS
     ${MOD_DIR}/processors/b200singlevolumeraycaster.h
     ${MOD_DIR}/processors/b200multivolumeraycaster.h
+    ${MOD_DIR}/processors/b200simpleraycaster.h
 )
 
 SET(MOD_INCLUDE_DIRECTORIES ${B200RC_ROOT}/include)

@@ -9,6 +9,7 @@
 #include "b200raycastmodule.h"
 #include "processors/b200singlevolumeraycaster.h"
 #include "processors/b200multivolumeraycaster.h"
+#include "processors/b200simpleraycaster.h"
 
 namespace voreen {
 
@@ -21,6 +22,8 @@ B200RaycastModule::B200RaycastModule(const std::string& modulePath)
     registerSerializableType("SingleVolumeRaycaster", new B200SingleVolumeRaycaster());
     registerProcessor(new B200MultiVolumeRaycaster());
     registerSerializableType("MultiVolumeRaycaster", new B200MultiVolumeRaycaster());
+    registerProcessor(new B200SimpleRaycaster());
+    registerSerializableType("SimpleRaycaster", new B200SimpleRaycaster());
 }
 
 std::string B200RaycastModule::getDescription() const {

@@ -646,3 +646,22 @@ def test_rescale_rendering(ctx, dst):
     f32 = src.astype(np.float32) / np.float32(65535.0)
     gotf, _ = ctx.rescale(f32, depth, dst[0], dst[1])
     assert np.abs(gotf - want.astype(np.float32) / 65535.0).max() <= 0.5 / 65535.0 + 1e-7
+
+
+# ---- the rest of the raycaster family: SimpleRaycaster (rc_simple.frag) ------------------------------------------
+@pytest.mark.parametrize("ess", [0, 1])
+@pytest.mark.parametrize("dtype", [np.uint16, np.uint8])
+def test_simple_raycaster(ctx, ess, dtype):
+    vol = scenes.ct_like_volume(48)
+    if dtype == np.uint8:
+        vol = (vol >> 8).astype(np.uint8)
+    s = scenes.Scene(vol, W=112, H=96, raycaster=abi.RAYCASTER_SIMPLE, empty_space_skipping=ess)
+    st, o_st = check(s, ctx, label=f"simple raycaster {np.dtype(dtype).name} ess={ess}")
+    assert st.samples_classified + st.samples_skipped == o_st.samples_classified
+    if ess:
+        assert st.samples_skipped > 0
+    # it really is a different renderer: no shading, termination at alpha 1.0 instead of 0.95
+    s2 = scenes.Scene(vol, W=112, H=96, shading=abi.SHADE["none"])
+    full, _ = s2.cuda_render(ctx)
+    simple, _ = s.cuda_render(ctx)
+    assert np.abs(np.asarray(full[0]) - np.asarray(simple[0])).max() > 1e-3
