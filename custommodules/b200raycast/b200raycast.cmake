@@ -13,11 +13,13 @@ SET(MOD_CORE_SOURCES
     ${MOD_DIR}/processors/b200singlevolumeraycaster.cpp
     ${MOD_DIR}/processors/b200multivolumeraycaster.cpp
     ${MOD_DIR}/processors/b200simpleraycaster.cpp
+    ${MOD_DIR}/processors/b200rgbraycaster.cpp
 )
 SET(MOD_CORE_HEADERS
     ${MOD_DIR}/processors/b200singlevolumeraycaster.h
     ${MOD_DIR}/processors/b200multivolumeraycaster.h
     ${MOD_DIR}/processors/b200simpleraycaster.h
+    ${MOD_DIR}/processors/b200rgbraycaster.h
 )
 
 SET(MOD_INCLUDE_DIRECTORIES ${B200RC_ROOT}/include)

@@ -10,6 +10,7 @@
 #include "processors/b200singlevolumeraycaster.h"
 #include "processors/b200multivolumeraycaster.h"
 #include "processors/b200simpleraycaster.h"
+#include "processors/b200rgbraycaster.h"
 
 namespace voreen {
 
@@ -24,6 +25,8 @@ B200RaycastModule::B200RaycastModule(const std::string& modulePath)
     registerSerializableType("MultiVolumeRaycaster", new B200MultiVolumeRaycaster());
     registerProcessor(new B200SimpleRaycaster());
     registerSerializableType("SimpleRaycaster", new B200SimpleRaycaster());
+    registerProcessor(new B200RGBRaycaster());
+    registerSerializableType("RGBRaycaster", new B200RGBRaycaster());
 }
 
 std::string B200RaycastModule::getDescription() const {

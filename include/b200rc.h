@@ -94,7 +94,7 @@ enum { B200RC_INSIDE_NONE = 0, B200RC_INSIDE_GPU = 1 };
 /* OptimizedProxyGeometry "modeString" (optimizedproxygeometry.cpp:107-114).  The library itself builds the
  * bounding-box cube (processCube :420-448); for the TF-dependent modes the host mirror classifies the min/max
  * regions (b200rc_region_minmax) with the TF keys and hands the resulting cubes over as explicit boxes. */
-enum { B200RC_RAYCASTER_SINGLE = 0, B200RC_RAYCASTER_SIMPLE = 1 };
+enum { B200RC_RAYCASTER_SINGLE = 0, B200RC_RAYCASTER_SIMPLE = 1, B200RC_RAYCASTER_RGB = 2 };
 enum { B200RC_PROXY_BBOX = 0, B200RC_PROXY_MINBBOX = 1, B200RC_PROXY_VISIBLE_BRICKS = 2 };
 
 /* ---- PODs ------------------------------------------------------------------------------------ */
@@ -183,6 +183,11 @@ typedef struct b200rc_params {
      * result.a > 0, early termination at alpha >= 1.0, at most 255*255 loop iterations.  gradient / shading / classification
      * / compositing fields are ignored. */
     int32_t raycaster;
+    /* B200RC_RAYCASTER_RGB = voreen::RGBRaycaster (rc_rgb.frag:65-140) for 3- or 4-channel volumes: the sample's colour is the
+     * un-mapped texture value, its alpha comes from the 1D TF looked up at the hue of that colour; rgb_color_modulation =
+     * the "applyColorModulation" property (colour *= TF colour).  Otherwise like SIMPLE.  No empty-space skipping (the alpha
+     * of a cell is not a function of a scalar range). */
+    int32_t rgb_color_modulation;
 } b200rc_params;
 
 /* MeshEntryExitPoints + proxy geometry settings for b200rc_render_camera / b200rc_entry_exit. */

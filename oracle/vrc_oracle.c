@@ -823,7 +823,21 @@ static inline v3 tex_to_physical(const vol_ctx* c, v3 p) {
 
 typedef struct { uint64_t rays, classified, shaded, nominal; } loc_stats;
 
-/* SimpleRaycaster (V/modules/base/glsl/rc_simple.frag:50-122; host side simpleraycaster.cpp:71-150) */
+/* rgb2hsv(...).r of rc_rgb.frag:44-63 */
+static float rgb_hue(v3 c) {
+    float mn = gl_min(c.x, gl_min(c.y, c.z)), mx = gl_max(c.x, gl_max(c.y, c.z));
+    float delta = mx - mn, sat = (mx != 0.0f) ? delta / mx : 0.0f, h = 0.0f;
+    if (sat == 0.0f) return 0.0f;
+    if (c.x == mx) h = (c.y - c.z) / delta;
+    else if (c.y == mx) h = 2 + (c.z - c.x) / delta;
+    else if (c.z == mx) h = 4 + (c.x - c.y) / delta;
+    h *= 60.0f;
+    if (h < 0.0f) h += 360.0f;
+    return h / 360.0f;
+}
+
+/* SimpleRaycaster (V/modules/base/glsl/rc_simple.frag:50-122; host side simpleraycaster.cpp:71-150) and
+ * RGBRaycaster (rc_rgb.frag:65-140, rgbraycaster.cpp:63-125): same loop, different sample colour */
 static void raycast_simple(const orc_volume* vol, const orc_classifier* cls, const b200rc_params* P, const b200rc_camera* cam, int W, int H,
                            const float* entry, const float* entryD, const float* exitp, const float* exitD,
                            float* out_color[3], float* out_depth, b200rc_stats* stats) {
@@ -847,9 +861,19 @@ static void raycast_simple(const orc_volume* vol, const orc_classifier* cls, con
                 int finished = 0;
                 for (int loop = 0; !finished && loop < 255 * 255; ++loop) {
                     v3 samplePos = add3(first, scale3(dir, t));
-                    v4 voxel = get_voxel(vol, &P->vol[0], samplePos);
+                    v4 color;
                     s_class++;
-                    v4 color = classify(B200RC_CLASS_TF, &cls[0], V4(0, 0, 0, voxel.w), 0.f);      /* applyTF(tf, tex, vec4 voxel): voxel.a */
+                    if (P->raycaster == B200RC_RAYCASTER_RGB) {
+                        /* texture(volume_, sampleVal): no real-world mapping; alpha from the TF at the colour's hue (:84-91) */
+                        v4 voxel = tex3d(vol, P->vol[0].filter, P->vol[0].clamp, P->vol[0].border_intensity, samplePos);
+                        v4 tfColor = classify(B200RC_CLASS_TF, &cls[0], V4(0, 0, 0, rgb_hue(V3(voxel.x, voxel.y, voxel.z))), 0.f);
+                        color = voxel;
+                        if (P->rgb_color_modulation) { color.x *= tfColor.x; color.y *= tfColor.y; color.z *= tfColor.z; }
+                        color.w = tfColor.w;
+                    } else {
+                        v4 voxel = get_voxel(vol, &P->vol[0], samplePos);
+                        color = classify(B200RC_CLASS_TF, &cls[0], V4(0, 0, 0, voxel.w), 0.f);      /* applyTF(tf, tex, vec4 voxel): voxel.a */
+                    }
                     if (color.w > 0.0f) {
                         s_shaded++;
                         color.w = 1.0f - powf(1.0f - color.w, step * 200.0f);
@@ -1108,7 +1132,7 @@ void orc_raycast(const orc_volume* vols, const orc_classifier* cls, const b200rc
                  const b200rc_camera* cam, int width, int height,
                  const float* entry_rgba, const float* entry_depth, const float* exit_rgba, const float* exit_depth,
                  float* out_color[B200RC_MAX_OUTPUTS], float* out_depth, b200rc_stats* stats) {
-    if (!params->multi_volume && params->raycaster == B200RC_RAYCASTER_SIMPLE)
+    if (!params->multi_volume && (params->raycaster == B200RC_RAYCASTER_SIMPLE || params->raycaster == B200RC_RAYCASTER_RGB))
         raycast_simple(vols, cls, params, cam, width, height, entry_rgba, entry_depth, exit_rgba, exit_depth, out_color, out_depth, stats);
     else if (params->multi_volume)
         raycast_multi(vols, cls, params, cam, width, height, entry_rgba, entry_depth, exit_rgba, exit_depth, out_color, out_depth, stats);

@@ -44,7 +44,7 @@ def orbit_eye(k, n=36, radius=3.5):
 class Scene:
     """One volume (or several) + TFs + params; renders through the oracle and through the C ABI."""
 
-    def __init__(self, vol, keys=CT_KEYS, W=128, H=128, eye=(1.2, 1.05, 3.1), tf_width=None, **param_kw):
+    def __init__(self, vol, keys=CT_KEYS, W=128, H=128, eye=(1.2, 1.05, 3.1), tf_width=None, tf_domain=None, **param_kw):
         self.vol = np.ascontiguousarray(vol)
         self.nch = vol.shape[3] if vol.ndim == 4 else 1
         dims = vol.shape[2::-1]
@@ -59,7 +59,8 @@ class Scene:
         scale = self.desc.rwm_scale
         self.tf_width = tf_width or {abi.U8: 256, abi.U16: 4096, abi.F32: 4096}[self.dtype]   # transfuncpropertybase.cpp:155-165
         keys_per_ch = keys if isinstance(keys[0], list) else [keys] * self.nch
-        self.tfs = [orc.make_tf(k, domain=(0.0, scale)) for k in keys_per_ch]
+        self.domain = tuple(tf_domain) if tf_domain is not None else (0.0, scale)
+        self.tfs = [orc.make_tf(k, domain=self.domain) for k in keys_per_ch]
         self.tf_tex = [orc.tf1d_texture(t, self.tf_width) for t in self.tfs]
         self.preint = None
 
@@ -86,14 +87,14 @@ class Scene:
         e, ed, x, xd = eep_images if eep_images is not None else self.oracle_eep()
         cls = []
         for c in range(self.nch):
-            cls.append(orc.make_classifier(self.tf_tex[c], (0.0, self.desc.rwm_scale), preint=self.preint[c] if self.preint else None))
+            cls.append(orc.make_classifier(self.tf_tex[c], self.domain, preint=self.preint[c] if self.preint else None))
         return orc.raycast([ov], cls, self.params, self.cam, self.W, self.H, e, ed, x, xd)
 
     # ---- CUDA (through the C ABI) ----------------------------------------------------------------------------------
     def upload(self, ctx):
         ctx.upload_volume(0, self.vol, desc=self.desc)
         for c in range(self.nch):
-            ctx.set_tf1d(c, self.tf_tex[c], (0.0, self.desc.rwm_scale))
+            ctx.set_tf1d(c, self.tf_tex[c], self.domain)
             if self.preint:
                 ctx.set_preint(c, self.preint[c])
 

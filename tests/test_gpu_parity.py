@@ -665,3 +665,16 @@ def test_simple_raycaster(ctx, ess, dtype):
     full, _ = s2.cuda_render(ctx)
     simple, _ = s.cuda_render(ctx)
     assert np.abs(np.asarray(full[0]) - np.asarray(simple[0])).max() > 1e-3
+
+
+@pytest.mark.parametrize("modulate", [0, 1])
+@pytest.mark.parametrize("nch", [3, 4])
+def test_rgb_raycaster(ctx, modulate, nch):
+    """RGBRaycaster (rc_rgb.frag): colour = the un-mapped texture value, alpha = 1D TF at the hue of that colour."""
+    chans = [scenes.ct_like_volume(40, seed=7 + c) for c in range(nch)]
+    vol = np.stack([np.roll((c >> 8).astype(np.uint8), 3 * i, axis=i % 3) for i, c in enumerate(chans)], axis=3)
+    keys = [(0.0, (255, 0, 0, 0)), (0.08, (255, 60, 0, 30)), (0.35, (0, 255, 0, 90)), (0.7, (0, 0, 255, 10)), (1.0, (255, 0, 255, 160))]
+    s = scenes.Scene(vol, keys=keys, W=104, H=88, tf_domain=(0.0, 1.0), tf_width=256, raycaster=abi.RAYCASTER_RGB, rgb_color_modulation=modulate)
+    st, o_st = check(s, ctx, label=f"rgb raycaster {nch} channels modulation={modulate}")
+    assert st.samples_classified == o_st.samples_classified and st.samples_skipped == 0
+    assert o_st.samples_shaded > 0.02 * o_st.samples_classified

@@ -24,7 +24,7 @@ CLAMP_TO_EDGE, CLAMP_TO_BORDER = 0, 1
 SAMPLER_EXACT, SAMPLER_TEX = 0, 1
 OUT_RGBA32F, OUT_RGBA16 = 0, 1
 INSIDE_NONE, INSIDE_GPU = 0, 1
-RAYCASTER_SINGLE, RAYCASTER_SIMPLE = 0, 1
+RAYCASTER_SINGLE, RAYCASTER_SIMPLE, RAYCASTER_RGB = 0, 1, 2
 PROXY_BBOX, PROXY_MINBBOX, PROXY_VISIBLE_BRICKS = 0, 1, 2
 COMPOSITE_ERT = 0x100
 
@@ -62,7 +62,7 @@ class Params(C.Structure):
                 ("light", Light),
                 ("sampler", C.c_int32), ("empty_space_skipping", C.c_int32), ("out_format", C.c_int32),
                 ("quantize_depth24", C.c_int32), ("collect_stats", C.c_int32), ("partial_image", C.c_int32),
-                ("image_band_modulus", C.c_int32), ("image_band_remainder", C.c_int32), ("raycaster", C.c_int32)]
+                ("image_band_modulus", C.c_int32), ("image_band_remainder", C.c_int32), ("raycaster", C.c_int32), ("rgb_color_modulation", C.c_int32)]
 
 
 class EepParams(C.Structure):

@@ -225,8 +225,10 @@ static int build_params(b200rc_ctx* ctx, const b200rc_params* P, const b200rc_ca
     p.nvol = nv; p.multi = P->multi_volume ? 1 : 0;
     p.step = P->sampling_step; p.mv_factor = P->mv_opacity_correction_factor;
     p.gradient = P->gradient;
-    p.simple = (!P->multi_volume && P->raycaster == B200RC_RAYCASTER_SIMPLE) ? 1 : 0;
-    if (P->raycaster != B200RC_RAYCASTER_SINGLE && P->raycaster != B200RC_RAYCASTER_SIMPLE) { ctx->set_error("render: unknown raycaster kind"); return B200RC_ERR_INVALID; }
+    p.simple = P->multi_volume ? 0 : (P->raycaster == B200RC_RAYCASTER_SIMPLE ? 1 : (P->raycaster == B200RC_RAYCASTER_RGB ? 2 : 0));
+    p.rgb_modulate = P->rgb_color_modulation ? 1 : 0;
+    if (p.simple == 2 && ctx->vol[0].valid && ctx->vol[0].desc.channels < 3) { ctx->set_error("render: RGBRaycaster needs a 3- or 4-channel volume"); return B200RC_ERR_INVALID; }
+    if (P->raycaster < B200RC_RAYCASTER_SINGLE || P->raycaster > B200RC_RAYCASTER_RGB) { ctx->set_error("render: unknown raycaster kind"); return B200RC_ERR_INVALID; }
     p.iso = P->iso_value;
     p.light = P->light;
     p.near_d = cam->near_dist; p.far_d = cam->far_dist;
@@ -316,7 +318,7 @@ static int build_params(b200rc_ctx* ctx, const b200rc_params* P, const b200rc_ca
     }
     // empty-space skipping (no channel shift): occupancy for the current TFs
     if (p.simple) { p.classification[0] = B200RC_CLASS_TF; p.channel_shift = 0; p.preint_comp = 0; }
-    if (P->empty_space_skipping && !P->multi_volume && !p.channel_shift && !(p.simple && ctx->vol[0].desc.channels != 1)) {
+    if (P->empty_space_skipping && !P->multi_volume && !p.channel_shift && !(p.simple && (p.simple == 2 || ctx->vol[0].desc.channels != 1))) {
         int modes[4];
         for (int c = 0; c < ncls; ++c) modes[c] = p.simple ? B200RC_CLASS_TF : P->vol[0].classification;
         int rc = rc_volume_build_occupancy(ctx, 0, modes, ncls, false, P->vol[0].clamp, P->vol[0].border_intensity);

@@ -81,7 +81,8 @@ struct DevParams {
     const float* prefix; const unsigned char* flags;
     // ... compacted by ert_plan_kernel: the per-ray kernel marches pixel_list[0 .. *pixel_count) instead of image tiles
     const unsigned int* pixel_list; const unsigned int* pixel_count;
-    int simple;                     // SimpleRaycaster semantics (rc_simple.frag), per-ray generic kernel
+    int simple;                     // 1: SimpleRaycaster (rc_simple.frag), 2: RGBRaycaster (rc_rgb.frag); per-ray generic kernel
+    int rgb_modulate;               // RGBRaycaster applyColorModulation
     int band_mod, band_rem;         // sort-first: render only the pixel-row bands with band % band_mod == band_rem (band_mod <= 1: all)
     int band_rows;                  // rows per band (a multiple of 16; b200rc_params.image_band_rows, default 16)
     unsigned int* tile_counter;     // persistent tile scheduler
