@@ -14,11 +14,14 @@ static int launch_slab(b200rc_ctx* ctx, const DevParams& p0) {
     size_t tf_bytes = 0;
     if (C::CLS == B200RC_CLASS_TF && p.cls[0].tf) tf_bytes = (size_t)p.cls[0].tf_width * 4 + 1024;
     if (tf_bytes > 40 * 1024) return -1;            // TF too wide for the staged layout: caller falls back
-    static int env_depth = -1, env_cap = -1;
+    static int env_depth = -1, env_cap = -1, env_depth_remarch = 6;
     if (env_depth < 0) {
         const char* d = getenv("B200RC_SLAB_DEPTH"); env_depth = d ? atoi(d) : 6;
         const char* c = getenv("B200RC_SLAB_KB"); env_cap = c ? atoi(c) : (SLAB_THREADS == 256 ? 72 : 52);
         if (env_depth < 2 || env_depth > 32) env_depth = 6;
+        // sort-last second pass: a handful of flagged rays per tile -> narrow regions, deeper slabs fit and mean fewer rounds
+        const char* dr = getenv("B200RC_SLAB_DEPTH_REMARCH"); env_depth_remarch = dr ? atoi(dr) : env_depth;
+        if (env_depth_remarch < 2 || env_depth_remarch > 32) env_depth_remarch = env_depth;
         if (env_cap < 32 || env_cap > 200) env_cap = 88;
     }
     // SLAB_MIN_CTAS CTAs share the SM's 227 KB: the staged region takes what the TF (+ LUT) leaves of one CTA's share
@@ -29,7 +32,7 @@ static int launch_slab(b200rc_ctx* ctx, const DevParams& p0) {
     RC_CHECK(cudaFuncGetAttributes(&fa, kern));
     const int share_kb = (int)((227 * 1024 / SLAB_MIN_CTAS - 1024 - (long long)fa.sharedSizeBytes) / 1024);
     if (cap_kb + (int)((tf_bytes + 1023) / 1024) > share_kb) cap_kb = share_kb - (int)((tf_bytes + 1023) / 1024);
-    SlabArgs sa; sa.depth = env_depth; sa.cap_floats = cap_kb * 256;
+    SlabArgs sa; sa.depth = p0.flags ? env_depth_remarch : env_depth; sa.cap_floats = cap_kb * 256;
     // pre-integration + empty-space skipping restores lastIntensity from the staged footprint: needs <= 1 voxel per step
     if (C::CLS == B200RC_CLASS_PREINT && p.vol[0].ess) {
         const float m = fmaxf(p.vol[0].dimf[0], fmaxf(p.vol[0].dimf[1], p.vol[0].dimf[2]));
