@@ -13,4 +13,4 @@ run bench_c5_n8 8 --size 4096 --image 3840 --image-h 2160 --parallelism sort-las
 run bench_n8 8 --steps 36 --warmup 5
 run bench_n8_sortlast 8 --steps 12 --warmup 3 --parallelism sort-last
 run bench_n4 4 --steps 36 --warmup 5
-run bench_n8_nccl 8 --steps 36 --warmup 5 --transport nccl
+run bench_n2 2 --steps 36 --warmup 5
