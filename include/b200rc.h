@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define B200RC_ABI_VERSION 2
+#define B200RC_ABI_VERSION 3     /* 3: b200rc_params grew (raycaster, rgb_color_modulation); streaming upload, rescale, raw loader */
 #define B200RC_MAX_VOLUMES 4   /* MultiVolumeRaycaster: volume1..4 (multivolumeraycaster.cpp:41-65) */
 #define B200RC_MAX_CHANNELS 4  /* SingleVolumeRaycaster: NUM_CHANNELS 1..4 (singlevolumeraycaster.cpp:440-445) */
 #define B200RC_MAX_OUTPUTS 3   /* image.output, image.output1, image.output2 (volumeraycaster.cpp:44-49) */

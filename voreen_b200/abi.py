@@ -24,6 +24,7 @@ CLAMP_TO_EDGE, CLAMP_TO_BORDER = 0, 1
 SAMPLER_EXACT, SAMPLER_TEX = 0, 1
 OUT_RGBA32F, OUT_RGBA16 = 0, 1
 INSIDE_NONE, INSIDE_GPU = 0, 1
+ABI_VERSION = 3          # include/b200rc.h B200RC_ABI_VERSION
 RAYCASTER_SINGLE, RAYCASTER_SIMPLE, RAYCASTER_RGB = 0, 1, 2
 PROXY_BBOX, PROXY_MINBBOX, PROXY_VISIBLE_BRICKS = 0, 1, 2
 COMPOSITE_ERT = 0x100
@@ -112,6 +113,8 @@ def load_library():
     vp, i32, f32, u64, sz = C.c_void_p, C.c_int, C.c_float, C.c_uint64, C.c_size_t
     pf = C.POINTER(C.c_float)
     lib.b200rc_abi_version.restype = i32
+    if lib.b200rc_abi_version() != ABI_VERSION:
+        raise B200RCError(f"{LIB_PATH} has ABI version {lib.b200rc_abi_version()}, this binding expects {ABI_VERSION}: rebuild (g.build())")
     lib.b200rc_device_count.restype = i32
     lib.b200rc_create.argtypes = [i32, C.POINTER(vp)]
     lib.b200rc_destroy.argtypes = [vp]

@@ -87,6 +87,10 @@ bool rc_march_slab(b200rc_ctx* ctx, const DevParams& p, int sampler, int nch, in
     SLAB_CASE(B200RC_U16, B200RC_CLASS_TF, B200RC_COMP_ISO, B200RC_SHADE_PHONG)
     SLAB_CASE(B200RC_U16, B200RC_CLASS_PREINT, B200RC_COMP_MIP, B200RC_SHADE_PHONG)
     SLAB_CASE(B200RC_U16, B200RC_CLASS_PREINT, B200RC_COMP_ISO, B200RC_SHADE_PHONG)
+    SLAB_CASE(B200RC_U16, B200RC_CLASS_TF, B200RC_COMP_MOP, B200RC_SHADE_PHONG)
+    SLAB_CASE(B200RC_U16, B200RC_CLASS_TF, B200RC_COMP_MIDA, B200RC_SHADE_PHONG)
+    SLAB_CASE(B200RC_U16, B200RC_CLASS_TF, B200RC_COMP_FHP, B200RC_SHADE_PHONG)
+    SLAB_CASE(B200RC_U16, B200RC_CLASS_TF, B200RC_COMP_FHN, B200RC_SHADE_PHONG)
     SLAB_CASE(0, B200RC_CLASS_TF, B200RC_COMP_DVR, -1)
     SLAB_CASE(0, B200RC_CLASS_PREINT, B200RC_COMP_DVR, -1)
     return false;

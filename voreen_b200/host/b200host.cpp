@@ -461,6 +461,7 @@ static int forward(b200host_svrc* p, int rc, const char* what) {
 }
 
 extern "C" int b200host_svrc_create(int device, b200host_svrc** out) {
+    if (b200rc_abi_version() != B200RC_ABI_VERSION) return B200RC_ERR_INVALID;      // built against another b200rc.h: struct layouts differ
     if (!out) return B200RC_ERR_INVALID;
     *out = nullptr;
     b200host_svrc* p = new (std::nothrow) b200host_svrc();
