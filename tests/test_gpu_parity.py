@@ -678,3 +678,52 @@ def test_rgb_raycaster(ctx, modulate, nch):
     st, o_st = check(s, ctx, label=f"rgb raycaster {nch} channels modulation={modulate}")
     assert st.samples_classified == o_st.samples_classified and st.samples_skipped == 0
     assert o_st.samples_shaded > 0.02 * o_st.samples_classified
+
+
+# ---- edge cases: ragged images, volumes smaller than a brick, camera inside the volume, degenerate transfer functions -------------
+@pytest.mark.parametrize("W,H", [(1, 1), (17, 3), (33, 65)])
+@pytest.mark.parametrize("dims", [(5, 7, 9), (8, 8, 8), (23, 3, 40)])
+def test_ragged_images_and_tiny_volumes(ctx, W, H, dims):
+    rng = np.random.default_rng(dims[0] * 100 + W)
+    vol = (rng.random(dims[::-1]) ** 2 * 65535).astype(np.uint16)
+    for ess in (0, 1):
+        s = scenes.Scene(vol, W=W, H=H, empty_space_skipping=ess)
+        check(s, ctx, frac_bar=0.999 if W * H >= 1000 else 0.99, label=f"{dims} @{W}x{H} ess={ess}")
+
+
+@pytest.mark.parametrize("cls", ["tf", "preint"])
+def test_camera_inside_the_volume(ctx, cls):
+    vol = scenes.ct_like_volume(48)
+    s = scenes.Scene(vol, W=96, H=80, eye=(0.1, 0.05, 0.35))       # inside the [-1,1]^3 cube: entry points come from the near plane
+    if cls == "preint":
+        s.use_preint("cpu")
+    st, o_st = check(s, ctx, label=f"camera inside, {cls}")
+    assert st.rays_cast == 96 * 80                                   # every pixel looks into the volume
+
+
+@pytest.mark.parametrize("mode", ["cpu", "gpu"])
+def test_fully_opaque_tf_entries_with_preintegration(ctx, mode):
+    """alpha 255 texels: 1 - 255 * (1/255.f) contracted into an fma is -5.9e-8 and pow() of it NaN -- the table must stay finite."""
+    vol = scenes.ct_like_volume(40)
+    keys = [(0.0, (0, 0, 0, 0)), (0.3, (0, 0, 0, 0)), (0.32, (255, 200, 100, 255)), (1.0, (255, 255, 255, 255))]
+    s = scenes.Scene(vol, keys=keys, W=72, H=72).use_preint(mode)
+    check(s, ctx, label=f"opaque keys, preint-{mode}")
+    outs, _ = s.cuda_render(ctx, upload=False)
+    assert np.isfinite(np.asarray(outs[0])).all()
+
+
+@pytest.mark.parametrize("kind", ["transparent", "opaque"])
+def test_degenerate_transfer_functions(ctx, kind):
+    vol = scenes.ct_like_volume(40)
+    keys = [(0.0, (10, 20, 30, 0)), (1.0, (200, 100, 50, 0))] if kind == "transparent" else [(0.0, (255, 255, 255, 255)), (1.0, (255, 255, 255, 255))]
+    s = scenes.Scene(vol, keys=keys, W=72, H=72)
+    s.params.collect_stats = 1
+    st, o_st = check(s, ctx, label=f"{kind} TF")
+    outs, depth = s.cuda_render(ctx, upload=False)
+    a = np.asarray(outs[0])[..., 3]
+    if kind == "transparent":
+        assert st.samples_shaded == 0 and float(a.max()) == 0.0 and np.all(depth == 1.0)
+        assert ctx.stats().samples_classified == 0 and ctx.stats().samples_skipped == o_st.samples_classified     # everything is skipped
+    else:
+        assert st.samples_shaded == st.rays_cast                       # the first sample of every ray saturates (alpha 1 -> ERT)
+        assert set(np.unique(a)) <= {0.0, 1.0}

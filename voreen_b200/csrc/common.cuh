@@ -96,7 +96,11 @@ __device__ __forceinline__ float3 operator-(float3 a, float3 b) { return f3(a.x 
 __device__ __forceinline__ float3 operator*(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
 __device__ __forceinline__ float3 operator*(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
 __device__ __forceinline__ float dot3(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-__device__ __forceinline__ float3 cross3(float3 a, float3 b) { return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+// un-contracted: cross(v, v) must be exactly zero (fixClipBorderGradient at the image border / next to uncovered pixels feeds two
+// identical vectors; an fma residue would turn the resulting NaN normal into an arbitrary unit vector)
+__device__ __forceinline__ float3 cross3(float3 a, float3 b) {
+    return f3(__fsub_rn(__fmul_rn(a.y, b.z), __fmul_rn(a.z, b.y)), __fsub_rn(__fmul_rn(a.z, b.x), __fmul_rn(a.x, b.z)), __fsub_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
+}
 // GLSL normalize: a zero vector gives NaN (0 * rsq(0)); max()/min() below drop NaNs like FMNMX / maxps do.
 __device__ __forceinline__ float3 normalize3(float3 a) { float r = rsqrtf(dot3(a, a)); return f3(a.x * r, a.y * r, a.z * r); }
 __device__ __forceinline__ float length3(float3 a) { return sqrtf(dot3(a, a)); }

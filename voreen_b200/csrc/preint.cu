@@ -29,7 +29,8 @@ __global__ void preint_build_kernel(const uchar4* __restrict__ tf, int tfw, int 
         } else i = s;
         i = min(max(i, 0), tfw - 1);
         const uchar4 q = tf[i];
-        return make_float4(q.x * k255, q.y * k255, q.z * k255, q.w * k255);
+        // rounded here, never contracted into the 1 - alpha below (255 * k255 must be exactly 1.0: pow(-6e-8, fraction) is NaN)
+        return make_float4(__fmul_rn(q.x, k255), __fmul_rn(q.y, k255), __fmul_rn(q.z, k255), __fmul_rn(q.w, k255));
     };
     if (x == y) {
         c = fetch(x, true);
@@ -113,7 +114,9 @@ __global__ void exclusive_scan_small_kernel(const int* __restrict__ in, int n, i
 
 __global__ void corr_lut_kernel(float* __restrict__ lut, float step) {
     const int i = threadIdx.x;
-    if (i < 256) lut[i] = 1.0f - powf(1.0f - (float)i * (1.0f / 255.0f), step * 200.0f);   // mod_compositing.frag:40,51
+    // mod_compositing.frag:40,51.  The texel alpha is rounded to float before the subtraction (255 -> exactly 1.0): contracted into an
+    // fma, 1 - 255 * (1/255.f) is -5.9e-8 and pow(negative, fraction) is NaN -- a fully opaque TF entry must give alpha 1
+    if (i < 256) lut[i] = 1.0f - powf(__fsub_rn(1.0f, __fmul_rn((float)i, 1.0f / 255.0f)), step * 200.0f);
 }
 
 // ---- host ---------------------------------------------------------------------------------------------------------
