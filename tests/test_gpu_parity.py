@@ -727,3 +727,47 @@ def test_degenerate_transfer_functions(ctx, kind):
     else:
         assert st.samples_shaded == st.rays_cast                       # the first sample of every ray saturates (alpha 1 -> ERT)
         assert set(np.unique(a)) <= {0.0, 1.0}
+
+
+# ---- less common switches of the path: entry-point jitter, clipped proxy cube, world-space entry/exit, light attenuation, channel shift ---
+@pytest.mark.parametrize("variant", ["jitter", "clip", "world", "jitter+world"])
+def test_entry_exit_variants_bit_exact(ctx, variant):
+    vol = scenes.ct_like_volume(32)
+    for eye in [(1.2, 1.05, 3.1), (0.3, 0.2, 0.6)]:
+        s = scenes.Scene(vol, W=96, H=80, eye=eye)
+        if "jitter" in variant:
+            s.eep.jitter = 1; s.eep.jitter_step_length = 0.02          # eep_jitter.frag:38-78
+        if "world" in variant:
+            s.eep.world_coords = 1                                      # RGBA16F entry/exit storage
+        if variant == "clip":
+            s.eep.enable_clipping = 1
+            s.eep.clip_llf[:] = [4.0, 0.0, 6.0]; s.eep.clip_urb[:] = [27.0, 31.0, 25.0]
+        s.upload(ctx)
+        oe = s.oracle_eep()
+        ce = ctx.entry_exit(s.eep, s.cam, s.W, s.H)
+        for a, b in zip(oe, ce):
+            assert np.array_equal(a, b), (variant, eye)
+        assert int(np.any(oe[0][..., :3] != oe[2][..., :3], axis=2).sum()) > 100
+    if variant in ("jitter", "clip"):
+        check(s, ctx, label=f"eep {variant}")
+
+
+def test_light_attenuation(ctx):
+    vol = scenes.ct_like_volume(48)
+    s = scenes.Scene(vol, W=96, H=96)
+    s.params.light.apply_attenuation = 1
+    s.params.light.attenuation[:] = [0.4, 0.3, 0.2]
+    check(s, ctx, label="light attenuation")
+
+
+@pytest.mark.parametrize("nch", [2, 4])
+def test_channel_shift(ctx, nch):
+    chans = [scenes.ct_like_volume(40, seed=21 + c) for c in range(nch)]
+    vol = np.stack(chans, axis=3)
+    keys = [scenes.CT_KEYS, [(0.0, (0, 0, 0, 0)), (0.3, (0, 255, 0, 0)), (1.0, (0, 255, 0, 120))],
+            [(0.0, (0, 0, 0, 0)), (0.4, (0, 0, 255, 0)), (1.0, (0, 0, 255, 90))], [(0.0, (0, 0, 0, 0)), (0.5, (255, 0, 255, 0)), (1.0, (255, 0, 255, 60))]][:nch]
+    s = scenes.Scene(vol, keys=keys, W=88, H=88)
+    s.params.enable_channel_shift = 1                                   # getVoxelChannelShift (rc_singlevolume.frag:96-113)
+    for c in range(nch):
+        s.params.channel_shift[c][:] = [0.03 * (c + 1), -0.02 * c, 0.01 * (c - 1)]
+    check(s, ctx, label=f"channel shift, {nch} channels")
