@@ -771,3 +771,48 @@ def test_channel_shift(ctx, nch):
     for c in range(nch):
         s.params.channel_shift[c][:] = [0.03 * (c + 1), -0.02 * c, 0.01 * (c - 1)]
     check(s, ctx, label=f"channel shift, {nch} channels")
+
+
+# ---- real-world mapping other than the denormalising default, and the 2D (intensity x gradient magnitude) transfer function --------
+@pytest.mark.parametrize("cls", ["tf", "preint"])
+@pytest.mark.parametrize("ess", [0, 1])
+def test_real_world_mapping(ctx, cls, ess):
+    """A CT-style mapping (scale 4095, offset -1024) with a TF domain in Hounsfield-like units (mod_sampler3d.frag:90-101,
+    mod_transfunc.frag:38-47): the empty-space grid must classify in the same units."""
+    vol = scenes.ct_like_volume(48)
+    s = scenes.Scene(vol, W=96, H=96, tf_domain=(-700.0, 2600.0), empty_space_skipping=ess)
+    s.desc.rwm_scale = 4095.0; s.desc.rwm_offset = -1024.0
+    if cls == "preint":
+        s.use_preint("cpu")
+    st, o_st = check(s, ctx, label=f"rwm 4095/-1024 {cls} ess={ess}")
+    assert o_st.samples_shaded > 1000
+    assert st.samples_classified + st.samples_skipped == o_st.samples_classified
+
+
+@pytest.mark.parametrize("grad", ["central-differences", "sobel"])
+def test_tf2d_classification(ctx, grad):
+    """TFT_2DPRIMITIVES: applyTF(tf, tex2D, intensity, |gradient|) (mod_transfunc.frag:80-95); the gradient is needed before
+    classification (CLASSIFICATION_REQUIRES_GRADIENT)."""
+    vol = scenes.ct_like_volume(48)
+    s = scenes.Scene(vol, W=96, H=96, gradient=abi.GRAD[grad], classification=abi.CLASS_TF2D)
+    rng = np.random.default_rng(3)
+    w, h = 64, 32
+    tf2d = np.zeros((h, w, 4), np.uint8)
+    tf2d[..., :3] = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+    xs = np.linspace(0.0, 1.0, w)[None, :]; ys = np.linspace(0.0, 1.0, h)[:, None]
+    tf2d[..., 3] = np.clip((xs - 0.3) * 300.0 * (0.2 + ys), 0, 255).astype(np.uint8)      # opacity grows with intensity and gradient magnitude
+    dom_x, dom_y = (0.0, s.desc.rwm_scale), (0.0, 0.6 * s.desc.rwm_scale)
+    ov = orc.make_volume(s.vol, s.desc)
+    e, ed, x, xd = s.oracle_eep()
+    s.params.collect_stats = 1
+    o_outs, o_depth, o_st = orc.raycast([ov], [orc.make_classifier(tf2d=tf2d, domain=dom_x, domain_y=dom_y)], s.params, s.cam, s.W, s.H, e, ed, x, xd)
+    ctx.upload_volume(0, s.vol, desc=s.desc)
+    ctx.set_tf2d(0, tf2d, dom_x, dom_y)
+    c_outs, c_depth = ctx.render_camera(s.params, s.eep, s.cam, s.W, s.H)
+    st = ctx.stats()
+    frac, mx = scenes.parity_report(o_outs[0], c_outs[0])
+    print(f"tf2d {grad}: within-1/255 {frac:.5f} max|d| {mx:.2e} classified {st.samples_classified}/{o_st.samples_classified} shaded {st.samples_shaded}/{o_st.samples_shaded}")
+    assert o_st.samples_shaded > 1000 and st.rays_cast == o_st.rays_cast
+    assert frac >= 0.999
+    assert abs(int(st.samples_shaded) - int(o_st.samples_shaded)) <= 0.001 * o_st.samples_shaded     # |gradient| feeds the lookup: not a bit-exact decision
+    assert float((np.abs(o_depth - c_depth) <= 1e-4).mean()) >= 0.999
