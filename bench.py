@@ -332,6 +332,8 @@ def run_b200(args, rank, world, local_rank):
     # ---- statistics pass (outside the timed region): reference-equivalent samples and touched macro-cells per view ----
     # N > 1: the sample counts that define the metric are those of the UNSHARDED frame (what the reference executes), so
     # rank 0 first renders the whole volume once per view, then every rank loads its shard.
+    shaded_by_view = {}
+
     def stats_pass(render):
         params.collect_stats = 1
         out = []
@@ -339,6 +341,7 @@ def run_b200(args, rank, world, local_rank):
             render(k)
             st = ctx.stats()
             out.append((st.samples_classified + st.samples_skipped, st.samples_classified, st.cells_touched, st.samples_nominal))
+            shaded_by_view[k % N_VIEWS] = st.samples_shaded
         params.collect_stats = 0
         return [list(c) for c in zip(*out)]
 
@@ -421,6 +424,16 @@ def run_b200(args, rank, world, local_rank):
                 "alg_bytes_per_launch_avg": sum(alg_bytes) / len(alg_bytes), "frac_min": min(ach) / peak, "frac_max": max(ach) / peak,
                 "whole_volume_bytes": int(np.prod(dims)) * 2 + img_bytes,
                 "whole_volume_frac": (int(np.prod(dims)) * 2 / (world if sl is not None else 1) + img_bytes) / (sum(march_ms) / len(march_ms) * 1e-3) / 1e9 / peak}
+    # second candidate bound: the tap rate.  The slab marcher reads 8 staged taps per classified sample and 24 more per
+    # shaded one from shared memory; peak = SMs x 32 banks x SM clock (4-byte words, no bank conflicts)
+    if world == 1 and shaded_by_view:
+        taps = sum(classified[v] * 8 + shaded_by_view.get(v, 0) * 24 for v in steps_views)
+        sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+        sm_clock_hz = (clk["sm_mhz"] if clk and clk.get("sm_mhz") else 1965.0) * 1e6
+        tap_peak = sm_count * 32 * sm_clock_hz
+        roofline["shared_memory_taps"] = {"achieved_gtaps_per_s": taps / (sum(march_ms) * 1e-3) / 1e9, "peak_gtaps_per_s": tap_peak / 1e9,
+                                          "frac": taps / (sum(march_ms) * 1e-3) / tap_peak,
+                                          "note": "32-bit shared-memory loads of the trilinear + central-difference footprints; data-dependent gathers replay ~2.4x on bank conflicts (ncu)"}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
