@@ -38,8 +38,8 @@ private:
     void failOn(int status, const char* what);
 
     ShaderProperty shader_;                         ///< inert; keeps "raycast.prg" deserialisable
-    BoolProperty applyColorModulation_;
     TransFunc1DKeysProperty transferFunc_;
+    BoolProperty applyColorModulation_;
     CameraProperty camera_;
 
     b200rc_ctx* ctx_;
