@@ -6,7 +6,7 @@ import math
 import numpy as np
 
 import orc
-from voreen_b200 import abi
+from voreen_b200 import abi, host
 from voreen_b200 import raycaster as rc
 
 # SURVEY 8d transfer function (intensity : rgba8)
@@ -60,6 +60,7 @@ class Scene:
         self.tf_width = tf_width or {abi.U8: 256, abi.U16: 4096, abi.F32: 4096}[self.dtype]   # transfuncpropertybase.cpp:155-165
         keys_per_ch = keys if isinstance(keys[0], list) else [keys] * self.nch
         self.domain = tuple(tf_domain) if tf_domain is not None else (0.0, scale)
+        self.keys_per_ch = keys_per_ch
         self.tfs = [orc.make_tf(k, domain=self.domain) for k in keys_per_ch]
         self.tf_tex = [orc.tf1d_texture(t, self.tf_width) for t in self.tfs]
         self.preint = None
@@ -94,7 +95,8 @@ class Scene:
     def upload(self, ctx):
         ctx.upload_volume(0, self.vol, desc=self.desc)
         for c in range(self.nch):
-            ctx.set_tf1d(c, self.tf_tex[c], self.domain)
+            # the product's own TransFunc1DKeys::getTexture (host mirror), not the oracle's texels (pinned equal in test_oracle_pins)
+            ctx.set_tf1d(c, host.tf1d_texture(self.keys_per_ch[c], self.tf_width), self.domain)
             if self.preint:
                 ctx.set_preint(c, self.preint[c])
 

@@ -191,3 +191,30 @@ def test_nucleon_workspace_fixture_reproduces():
     frac, mx = scenes.parity_report(q, np.clip(np.nan_to_num(outs[0]), 0, 1))
     assert frac >= 0.9999 and mx < 1e-3, (frac, mx)        # libm differences between machines stay far below 1/255
     assert float((np.abs(depth - z["depth"]) <= 1e-5).mean()) >= 0.9999
+
+
+def test_host_mirror_tf_texture_equals_the_oracle():
+    """The product's TransFunc1DKeys::getTexture (host mirror, C++) against the oracle's restatement: split keys, thresholds,
+    gamma, the three alpha modes, the widths the reference uses (256 for 8-bit data, 4096 for 16-bit, 1024 for the tables)."""
+    from voreen_b200 import host
+    rng = np.random.default_rng(11)
+    key_sets = [
+        [(0.0, (0, 0, 0, 0)), (1.0, (255, 255, 255, 255))],
+        [(0.0, (0, 0, 0, 0)), (0.25, (0, 0, 0, 0)), (0.30, (255, 140, 60, 8)), (0.55, (255, 230, 200, 40)), (0.80, (255, 255, 255, 200)), (1.00, (255, 255, 255, 255))],
+        [(0.1, (10, 20, 30, 40), (200, 100, 50, 25)), (0.5, (0, 255, 0, 128)), (0.5001, (255, 0, 0, 3), (1, 2, 3, 250)), (0.9, (9, 8, 7, 6))],     # split keys, keys not at 0/1
+    ]
+    for _ in range(6):
+        n = int(rng.integers(2, 9))
+        xs = np.sort(rng.random(n))
+        key_sets.append([(float(x), tuple(int(v) for v in rng.integers(0, 256, 4))) for x in xs])
+    checked = 0
+    for keys in key_sets:
+        for width in (256, 1024, 4096, 37):
+            for thr in ((0.0, 1.0), (0.1, 0.9), (0.33, 0.34)):
+                for gamma in (1.0, 0.5, 2.2):
+                    for amode in (0, 1, 2):
+                        want = orc.tf1d_texture(orc.make_tf(keys, threshold=thr, gamma=gamma, alpha_mode=amode), width)
+                        got = host.tf1d_texture(keys, width, threshold=thr, gamma=gamma, alpha_mode=amode)
+                        assert np.array_equal(got, want), (keys, width, thr, gamma, amode)
+                        checked += 1
+    assert checked == len(key_sets) * 4 * 3 * 3 * 3
