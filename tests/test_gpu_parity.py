@@ -816,3 +816,27 @@ def test_tf2d_classification(ctx, grad):
     assert frac >= 0.999
     assert abs(int(st.samples_shaded) - int(o_st.samples_shaded)) <= 0.001 * o_st.samples_shaded     # |gradient| feeds the lookup: not a bit-exact decision
     assert float((np.abs(o_depth - c_depth) <= 1e-4).mean()) >= 0.999
+
+
+# ---- the product's own pre-integration table builders (b200rc_build_preint) against the oracle's tables, entry by entry ----------------
+@pytest.mark.parametrize("mode", ["cpu", "approx", "gpu"])
+@pytest.mark.parametrize("keyset", ["ct", "opaque"])
+def test_preintegration_table_builders(ctx, mode, keyset):
+    from voreen_b200 import host
+    keys = scenes.CT_KEYS if keyset == "ct" else [(0.0, (0, 0, 0, 0)), (0.3, (0, 0, 0, 0)), (0.32, (255, 200, 100, 255)), (1.0, (255, 255, 255, 255))]
+    res, step = 256, float(np.float32(1.0 / 96.0))
+    tf = orc.make_tf(keys, domain=(0.0, 65535.0))
+    if mode == "gpu":       # preintegration.frag:35-87 reads the TF *texture* (width 1024 here), RGBA16 render target
+        tex = host.tf1d_texture(keys, 1024)
+        want = orc.preint_gpu(orc.tf1d_texture(tf, 1024), res, step)
+    else:                   # PreIntegrationTable::computeTable reads the keys at the table resolution
+        tex = host.tf1d_texture(keys, res)
+        want = orc.preint_cpu(tf, res, step, mode == "approx")
+    ctx.set_tf1d(0, tex, (0.0, 65535.0))
+    ctx.build_preint(0, res, step, {"cpu": abi.PI_CPU, "approx": abi.PI_APPROX, "gpu": abi.PI_GPU}[mode])
+    got = ctx.download_preint(0, res)
+    assert np.isfinite(got).all()
+    err = float(np.abs(got - want).max())
+    print(f"preint table {mode} {keyset}: max |d| {err:.2e}")
+    # pow()/exp() differ in the last bits between libm and the device; RGBA16 rounds; the integral variant divides by max(alpha, 0.001)
+    assert err <= {"gpu": 1.0 / 65535.0 + 1e-6, "cpu": 2e-6, "approx": 1e-4}[mode]

@@ -64,7 +64,7 @@ __global__ void preint_integral_kernel(const uchar4* __restrict__ tf, int res, f
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int i = 0; i < res; ++i) {
         const uchar4 q = tf[i];
-        const float4 c = make_float4(q.x * k255, q.y * k255, q.z * k255, q.w * k255);
+        const float4 c = make_float4(__fmul_rn(q.x, k255), __fmul_rn(q.y, k255), __fmul_rn(q.z, k255), __fmul_rn(q.w, k255));
         if (c.w > 0.0f) {
             acc.x = __fadd_rn(acc.x, __fmul_rn(c.x, c.w)); acc.y = __fadd_rn(acc.y, __fmul_rn(c.y, c.w));
             acc.z = __fadd_rn(acc.z, __fmul_rn(c.z, c.w)); acc.w = __fadd_rn(acc.w, c.w);
@@ -87,8 +87,8 @@ __global__ void preint_approx_kernel(const uchar4* __restrict__ tf, const float4
     } else {
         const uchar4 q = tf[smin];
         const float k255 = 1.0f / 255.0f;
-        col = make_float4(q.x * k255, q.y * k255, q.z * k255, q.w * k255);
-        col.w = 1.f - powf(1.f - col.w, step * 200.0f);
+        col = make_float4(__fmul_rn(q.x, k255), __fmul_rn(q.y, k255), __fmul_rn(q.z, k255), __fmul_rn(q.w, k255));     // rounded: 255 -> exactly 1.0
+        col.w = 1.f - powf(__fsub_rn(1.f, col.w), step * 200.0f);
     }
     table[(size_t)sb * res + sf] = make_float4(fminf(fmaxf(col.x, 0.f), 1.f), fminf(fmaxf(col.y, 0.f), 1.f), fminf(fmaxf(col.z, 0.f), 1.f), fminf(fmaxf(col.w, 0.f), 1.f));
 }
