@@ -840,3 +840,24 @@ def test_preintegration_table_builders(ctx, mode, keyset):
     print(f"preint table {mode} {keyset}: max |d| {err:.2e}")
     # pow()/exp() differ in the last bits between libm and the device; RGBA16 rounds; the integral variant divides by max(alpha, 0.001)
     assert err <= {"gpu": 1.0 / 65535.0 + 1e-6, "cpu": 2e-6, "approx": 1e-4}[mode]
+
+
+def test_multivolume_fully_opaque_keys(ctx):
+    """mvOpacityCorrection = 1 - pow(1 - alpha, factor): alpha 255/255 must be exactly 1.0 there as well."""
+    vols, descs, cam, params, entry, ged, exitp, gxd, tex, pre = _multi_scene(2, "tf")
+    keys = [(0.0, (0, 0, 0, 0)), (0.3, (0, 0, 0, 0)), (0.32, (255, 200, 100, 255)), (1.0, (255, 255, 255, 255))]
+    tf = orc.make_tf(keys, domain=(0.0, 65535.0))
+    tex = [orc.tf1d_texture(tf, 4096)] * 2
+    H, W = ged.shape
+    ovs = [orc.make_volume(vols[v], descs[v]) for v in range(2)]
+    ocls = [orc.make_classifier(tex[v], (0.0, 65535.0)) for v in range(2)]
+    o_outs, o_depth, o_st = orc.raycast(ovs, ocls, params, cam, W, H, entry, ged, exitp, gxd)
+    for v in range(2):
+        ctx.upload_volume(v, vols[v], desc=descs[v])
+        ctx.set_tf1d(v, tex[v], (0.0, 65535.0))
+    c_outs, c_depth = ctx.render(params, cam, W, H, entry, ged, exitp, gxd)
+    st = ctx.stats()
+    assert np.isfinite(np.asarray(c_outs[0])).all()
+    frac, mx = scenes.parity_report(o_outs[0], c_outs[0])
+    assert frac >= 0.999 and st.samples_shaded == o_st.samples_shaded
+    ctx.lib.b200rc_release_volume(ctx.h, 1)
