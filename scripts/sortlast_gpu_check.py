@@ -31,6 +31,8 @@ def main():
     dims = (size,) * 3
     step = float(np.float32(1.0) / (np.float32(size) * np.float32(2.0)))
     params = vb.default_params(step, classification=abi.CLASS_PREINT if cls == "preint" else abi.CLASS_TF, out_format=abi.OUT_RGBA16)
+    if os.environ.get("SL_COMP"):         # e.g. iso / fhn / fhp: merged by "front-most hit wins"
+        params.compositing[:] = [abi.COMP[os.environ["SL_COMP"]]] * 3
     eep = vb.default_eep()
     views = [0, 5, 9, 14, 22, 31]
     cams = {k: host.make_camera(bench.orbit_eye(k), W=img, H=img) for k in views}

@@ -888,3 +888,44 @@ def test_transformed_anisotropic_volume(ctx, cls):
         assert np.array_equal(x, y)
     st, o_st = check(s, ctx, label=f"transformed anisotropic volume, {cls}")
     assert o_st.rays_cast > 1500 and o_st.samples_shaded > 1000
+
+
+@pytest.mark.parametrize("world", [2, 8])
+@pytest.mark.parametrize("comp", ["iso", "fhn", "fhp"])
+def test_sharded_first_hit_modes_single_device(ctx, world, comp):
+    """Sort-last for the first-hit family: every shard renders its own first hit; the front-most partial image that has one wins
+    (composite mode = the compositing mode).  Exact without a second pass."""
+    from voreen_b200 import sortlast
+    dims = (64, 56, 72)
+    vol = scenes.ct_like_volume(0, dims=dims)
+    s = scenes.Scene(vol, W=96, H=88, eye=(1.4, 0.9, 2.9), out_format=abi.OUT_RGBA32F, compositing=[abi.COMP[comp]] * 3, iso_value=0.5)
+    ref_outs, ref_depth = s.cuda_render(ctx)
+    cam_tex = sortlast.camera_texture_position(s.cam, s.desc)
+    s.params.partial_image = 1
+    parts = {}
+    for r in range(world):
+        lo, hi = sortlast.shard_range(dims, r, world)
+        rl = [max(0, lo[a] - sortlast.APRON) for a in range(3)]; rh = [min(dims[a], hi[a] + sortlast.APRON) for a in range(3)]
+        ctx.upload_volume(0, np.ascontiguousarray(vol[rl[2]:rh[2], rl[1]:rh[1], rl[0]:rh[0]]), desc=vb_desc(dims, lo, hi))
+        outs, depth = ctx.render_camera(s.params, s.eep, s.cam, s.W, s.H)
+        parts[r] = (np.asarray(outs[0]).reshape(-1, 4).copy(), depth.reshape(-1).copy())
+    s.params.partial_image = 0
+    imgs = parts
+    for rnd in range(world.bit_length() - 1):
+        nxt = {}
+        for r in sorted(imgs):
+            if (r >> rnd) & 1:
+                continue
+            a, b = imgs[r], imgs[r | (1 << rnd)]
+            front, back = (a, b) if sortlast.my_group_in_front(r, rnd, world, dims, cam_tex) else (b, a)
+            dc = np.empty_like(a[0]); dd = np.empty_like(a[1])
+            orc.lib().orc_composite(abi.COMP[comp], orc.fp(front[0]), orc.fp(front[1]), orc.fp(back[0]), orc.fp(back[1]), orc.fp(dc), orc.fp(dd), dc.shape[0])
+            nxt[r] = (dc, dd)
+        imgs = nxt
+    merged, mdepth = imgs[0]
+    frac, mx = scenes.parity_report(ref_outs[0], merged.reshape(s.H, s.W, 4))
+    dfrac = float((np.abs(ref_depth.reshape(-1) - mdepth) <= 1e-4).mean())
+    hits = int((np.asarray(ref_outs[0])[..., 3] > 0).sum())
+    print(f"sharded x{world} {comp}: within 1/255 {frac:.5f} max {mx:.4f} depth {dfrac:.5f} hit pixels {hits}")
+    assert hits > 200 and frac >= 0.999 and dfrac >= 0.999
+    ctx.upload_volume(0, vol, desc=s.desc)

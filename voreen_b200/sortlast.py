@@ -282,6 +282,7 @@ class SortLast:
         self.prefix = torch.empty((self.npix,), dtype=torch.float32, device=device)
         self.flags = torch.empty((self.npix,), dtype=torch.uint8, device=device)
         self.last_remarch_ms = 0.0
+        self._merge_mode = abi.COMP["dvr"] | abi.COMPOSITE_ERT
         self.profile = False        # True: per-phase CUDA-event timings + flagged-pixel count of the last frame in self.phases
         self.phases = {}
 
@@ -289,7 +290,7 @@ class SortLast:
         return self.desc
 
     def _blend(self, fc, fd, bc, bd, dc, dd):
-        self.ctx.composite(abi.COMP["dvr"] | abi.COMPOSITE_ERT, fc.data_ptr(), fd.data_ptr(), bc.data_ptr(), bd.data_ptr(), dc.data_ptr(), dd.data_ptr(), fc.shape[0])
+        self.ctx.composite(self._merge_mode, fc.data_ptr(), fd.data_ptr(), bc.data_ptr(), bd.data_ptr(), dc.data_ptr(), dd.data_ptr(), fc.shape[0])
 
     def render(self, params, eep, cam, out_rgba16, out_depth):
         """Renders one frame; rank 0 receives the final RGBA16 image + depth in out_rgba16 / out_depth (device tensors).
@@ -297,6 +298,16 @@ class SortLast:
         torch = self.torch
         import torch.distributed as dist
         p = params
+        # DVR: over operator + exact early ray termination (second pass).  ISO / FHP / FHN: the front-most partial image that has a hit
+        # wins (the first sample along the ray that satisfies the predicate lies in the front-most shard that has one) -- exact without
+        # a second pass.  MIP / MOP / MIDA on a sharded volume are not supported (the marcher does not export the key plane).
+        comp = int(p.compositing[0])
+        if comp == abi.COMP["dvr"]:
+            self._merge_mode, need_ert_pass = abi.COMP["dvr"] | abi.COMPOSITE_ERT, True
+        elif comp in (abi.COMP["iso"], abi.COMP["fhp"], abi.COMP["fhn"]):
+            self._merge_mode, need_ert_pass = comp, False
+        else:
+            raise abi.B200RCError("sort-last rendering supports dvr, iso, fhp and fhn compositing; use the image partition (SortFirst) for the others")
         saved = (p.partial_image, p.out_format)
         p.partial_image, p.out_format = 1, abi.OUT_RGBA32F
         prof = self.profile
@@ -310,7 +321,7 @@ class SortLast:
                 self.phases = {"first_pass_ms": march_ms}
                 ev[1].record(self.stream)
             cam_tex = camera_texture_position(cam, self.desc)
-            if self.exact_ert and self.world > 1:
+            if self.exact_ert and need_ert_pass and self.world > 1:
                 # every rank learns the alpha of every partial image, erases what a terminated ray hides and re-marches the
                 # pixels whose ray crosses the global 0.95 threshold inside its own shard
                 self.alpha.copy_(self.color[:, 3])
@@ -367,7 +378,7 @@ class SortLast:
                 ev[4].record(self.stream)
                 torch.cuda.synchronize(self.device)
                 self.phases["render_ms"] = ev[0].elapsed_time(ev[1])
-                if self.exact_ert and self.world > 1:
+                if self.exact_ert and need_ert_pass and self.world > 1:
                     self.phases["allgather_plan_ms"] = ev[1].elapsed_time(ev[2])
                     self.phases["remarch_total_ms"] = ev[2].elapsed_time(ev[3])
                 self.phases["swap_gather_ms"] = ev[3].elapsed_time(ev[4])
