@@ -929,3 +929,74 @@ def test_sharded_first_hit_modes_single_device(ctx, world, comp):
     print(f"sharded x{world} {comp}: within 1/255 {frac:.5f} max {mx:.4f} depth {dfrac:.5f} hit pixels {hits}")
     assert hits > 200 and frac >= 0.999 and dfrac >= 0.999
     ctx.upload_volume(0, vol, desc=s.desc)
+
+
+@pytest.mark.parametrize("cls", ["tf", "preint"])
+def test_multivolume_heterogeneous_volumes(ctx, cls):
+    """Two volumes of different size, spacing and placement (one rotated): per-volume worldToTexture, per-volume voxel step for
+    the pre-integration tables, per-volume empty-space grids with different cell geometry."""
+    from voreen_b200 import raycaster as rc
+    dims = [(32, 32, 32), (40, 28, 36)]
+    vols = [scenes.ct_like_volume(0, dims=dims[0], seed=5), scenes.ct_like_volume(0, dims=dims[1], seed=6)]
+    a = 0.5
+    rot = np.array([[np.cos(a), 0, np.sin(a), 0.2], [0, 1, 0, -0.1], [-np.sin(a), 0, np.cos(a), 0.05], [0, 0, 0, 1]], np.float32)
+    descs = [rc.make_volume_desc(dims[0]), rc.make_volume_desc(dims[1], spacing=(0.045, 0.06, 0.05), phys_to_world=rot)]
+    W, H = 88, 80
+    cam = orc.make_camera((1.0, 0.9, 3.3), W=W, H=H)
+    eep = rc.default_eep(world_coords=1)
+    planes = []
+    for v in range(2):
+        ov = orc.make_volume(vols[v], descs[v])
+        planes.append(orc.entry_exit(orc.bbox_boxes(ov, eep), orc.texture_to_world(descs[v]), eep, cam, W, H))
+    ge = np.zeros((H, W, 4), np.float32); gx = np.zeros((H, W, 4), np.float32)
+    ged = np.ones((H, W), np.float32); gxd = np.zeros((H, W), np.float32)
+    for (e, ed, x, xd) in planes:
+        cov = e[..., 3] > 0
+        near = cov & ((ged >= 1.0) | (ed < ged)) & ((ge[..., 3] == 0) | (ed < ged))
+        ge[near] = e[near]; ged[near] = ed[near]
+        far = cov & ((gx[..., 3] == 0) | (xd > gxd))
+        gx[far] = x[far]; gxd[far] = xd[far]
+    gxd[gx[..., 3] == 0] = 1.0
+    entry = np.stack([ge] + [p[0] for p in planes]); exitp = np.stack([gx] + [p[2] for p in planes])
+    # multivolumeraycaster.cpp:326-344: the finest volume (smallest max(cubeSizeWorld / dim)) sets the step
+    cube = [np.array(dims[v]) * np.array(descs[v].spacing[:]) for v in range(2)]
+    scl = [np.ones(3), np.ones(3)]
+    vsw = [float(np.max(cube[v] * scl[v] / np.array(dims[v]))) for v in range(2)]
+    fin = int(np.argmin(vsw))
+    step_world = vsw[fin] / 2.0
+    step_tex = float(np.max(1.0 / np.array(dims[fin], np.float32))) / 2.0
+    params = rc.default_params(step_world)
+    params.num_volumes = 2; params.multi_volume = 1
+    params.mv_opacity_correction_factor = step_tex / step_world
+    params.collect_stats = 1
+    keys = [scenes.CT_KEYS, [(0.0, (0, 0, 0, 0)), (0.3, (0, 255, 0, 0)), (1.0, (0, 255, 0, 120))]]
+    tfs = [orc.make_tf(keys[v], domain=(0.0, 65535.0)) for v in range(2)]
+    tex = [orc.tf1d_texture(t, 4096) for t in tfs]
+    pre = None
+    if cls == "preint":
+        # getVoxelSamplingStepSize (multivolumeraycaster.cpp:221-223): min(worldStep * physicalToTexture scaling)
+        vstep = [float(np.min(step_world / cube[v])) for v in range(2)]
+        pre = [orc.preint_cpu(tfs[v], 1024, vstep[v]) for v in range(2)]
+        for v in range(2):
+            params.vol[v].classification = abi.CLASS_PREINT
+    ovs = [orc.make_volume(vols[v], descs[v]) for v in range(2)]
+    ocls = [orc.make_classifier(tex[v], (0.0, 65535.0), preint=pre[v] if pre else None) for v in range(2)]
+    o_outs, o_depth, o_st = orc.raycast(ovs, ocls, params, cam, W, H, entry, ged, exitp, gxd)
+    for v in range(2):
+        ctx.upload_volume(v, vols[v], desc=descs[v])
+        ctx.set_tf1d(v, tex[v], (0.0, 65535.0))
+        if pre:
+            ctx.set_preint(v, pre[v])
+    res = {}
+    for ess in (0, 1):
+        params.empty_space_skipping = ess
+        res[ess] = ctx.render(params, cam, W, H, entry, ged, exitp, gxd) + (ctx.stats(),)
+    assert np.array_equal(np.asarray(res[0][0][0]), np.asarray(res[1][0][0])) and np.array_equal(res[0][1], res[1][1])
+    st = res[1][2]
+    frac, mx = scenes.parity_report(o_outs[0], res[1][0][0])
+    print(f"heterogeneous multi-volume {cls}: within-1/255 {frac:.5f} max|d| {mx:.2e} rays {st.rays_cast}/{o_st.rays_cast} shaded {st.samples_shaded}/{o_st.samples_shaded} "
+          f"classified {st.samples_classified} (no ESS {res[0][2].samples_classified}) skipped {st.samples_skipped}")
+    assert st.rays_cast == o_st.rays_cast and st.samples_shaded == o_st.samples_shaded and res[0][2].samples_classified == o_st.samples_classified
+    assert o_st.samples_shaded > 1000 and st.samples_skipped > 0
+    assert frac >= 0.999 and float((np.abs(o_depth - res[1][1]) <= 1e-4).mean()) >= 0.999
+    ctx.lib.b200rc_release_volume(ctx.h, 1)
