@@ -1000,3 +1000,18 @@ def test_multivolume_heterogeneous_volumes(ctx, cls):
     assert o_st.samples_shaded > 1000 and st.samples_skipped > 0
     assert frac >= 0.999 and float((np.abs(o_depth - res[1][1]) <= 1e-4).mean()) >= 0.999
     ctx.lib.b200rc_release_volume(ctx.h, 1)
+
+
+@pytest.mark.parametrize("rate", [0.5, 1.0, 3.0, 7.3])
+@pytest.mark.parametrize("cls", ["tf", "preint"])
+def test_sampling_rates(ctx, rate, cls):
+    """samplingRate (and with it the texture-space step 1 / (max(dim) * rate), volumeraycaster.cpp:312-322) from coarser than a voxel
+    to many samples per voxel; 7.3 makes the step a non-dyadic float, so the lattice is the shader's accumulated t += step."""
+    vol = scenes.ct_like_volume(40)
+    s = scenes.Scene(vol, W=88, H=80, sampling_rate=rate)
+    if cls == "preint":
+        s.use_preint("cpu")
+    for ess in (0, 1):
+        s.params.empty_space_skipping = ess
+        st, o_st = check(s, ctx, label=f"rate {rate} {cls} ess={ess}")
+        assert st.samples_classified + st.samples_skipped == o_st.samples_classified
