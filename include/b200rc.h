@@ -340,6 +340,13 @@ int b200rc_remarch_device(b200rc_ctx* ctx, const b200rc_params* params, const b2
 int b200rc_rescale(b200rc_ctx* ctx, const void* src_color, const float* src_depth, int src_w, int src_h, int format,
                    void* dst_color, float* dst_depth, int dst_w, int dst_h, int on_device);
 
+/* Max-key merge for sharded MIP / MOP: dst = the image with the larger key (front on ties); colour, key and depth planes move together.
+ * A partial MIP / MOP image is rendered with partial_image = 1 and out_color[1] (output 1 unconnected) pointing at a float-per-pixel
+ * key plane: the marcher stores the ray's maximum intensity (MIP) / maximum alpha (MOP) there.  All pointers are device pointers. */
+int b200rc_composite_keyed(b200rc_ctx* ctx, const float* front_rgba, const float* front_key, const float* front_depth,
+                           const float* back_rgba, const float* back_key, const float* back_depth,
+                           float* dst_rgba, float* dst_key, float* dst_depth, size_t n);
+
 /* ERT finalisation after merging (alpha >= 0.95 -> 1.0, mod_raysetup.frag:65-74) and conversion to out_format. */
 int b200rc_finalize(b200rc_ctx* ctx, const float* rgba_dev, const float* depth_dev, size_t n, int out_format,
                     void* out_color_dev);

@@ -1015,3 +1015,51 @@ def test_sampling_rates(ctx, rate, cls):
         s.params.empty_space_skipping = ess
         st, o_st = check(s, ctx, label=f"rate {rate} {cls} ess={ess}")
         assert st.samples_classified + st.samples_skipped == o_st.samples_classified
+
+
+@pytest.mark.parametrize("world", [2, 8])
+@pytest.mark.parametrize("comp", ["mip", "mop"])
+def test_sharded_max_key_modes_single_device(ctx, world, comp):
+    """Sort-last MIP / MOP: every shard exports colour, depth and the merge key (max intensity / max alpha) of its own samples;
+    the larger key wins, the front shard on ties (the reference keeps the FIRST sample that exceeds the running maximum)."""
+    import torch
+    from voreen_b200 import sortlast
+    dims = (64, 56, 72)
+    vol = scenes.ct_like_volume(0, dims=dims)
+    s = scenes.Scene(vol, W=96, H=88, eye=(1.4, 0.9, 2.9), out_format=abi.OUT_RGBA32F, compositing=[abi.COMP[comp]] * 3)
+    ref_outs, ref_depth = s.cuda_render(ctx)
+    cam_tex = sortlast.camera_texture_position(s.cam, s.desc)
+    dev = torch.device("cuda", 0)
+    npix = s.W * s.H
+    s.params.partial_image = 1
+    parts = {}
+    for r in range(world):
+        lo, hi = sortlast.shard_range(dims, r, world)
+        rl = [max(0, lo[a] - sortlast.APRON) for a in range(3)]; rh = [min(dims[a], hi[a] + sortlast.APRON) for a in range(3)]
+        ctx.upload_volume(0, np.ascontiguousarray(vol[rl[2]:rh[2], rl[1]:rh[1], rl[0]:rh[0]]), desc=vb_desc(dims, lo, hi))
+        col = torch.zeros((npix, 4), dtype=torch.float32, device=dev); key = torch.full((npix,), -1.0, dtype=torch.float32, device=dev)
+        dep = torch.zeros((npix,), dtype=torch.float32, device=dev)
+        ctx.render_camera_ptrs(s.params, s.eep, s.cam, s.W, s.H, [col.data_ptr(), key.data_ptr(), 0], dep.data_ptr(), device=True)
+        ctx.synchronize()
+        parts[r] = (col, key, dep)
+        assert float(key.min()) >= 0.0                       # every pixel's key was written
+    s.params.partial_image = 0
+    imgs = parts
+    for rnd in range(world.bit_length() - 1):
+        nxt = {}
+        for r in sorted(imgs):
+            if (r >> rnd) & 1:
+                continue
+            a, b = imgs[r], imgs[r | (1 << rnd)]
+            f, k = (a, b) if sortlast.my_group_in_front(r, rnd, world, dims, cam_tex) else (b, a)
+            dc = torch.empty_like(f[0]); dk = torch.empty_like(f[1]); dd = torch.empty_like(f[2])
+            ctx.composite_keyed(f[0].data_ptr(), f[1].data_ptr(), f[2].data_ptr(), k[0].data_ptr(), k[1].data_ptr(), k[2].data_ptr(),
+                                dc.data_ptr(), dk.data_ptr(), dd.data_ptr(), npix)
+            ctx.synchronize()
+            nxt[r] = (dc, dk, dd)
+        imgs = nxt
+    merged = imgs[0][0].cpu().numpy().reshape(s.H, s.W, 4); mdepth = imgs[0][2].cpu().numpy()
+    assert np.array_equal(merged, np.asarray(ref_outs[0]))                  # a selection, not a blend: bit-identical
+    assert np.array_equal(mdepth.reshape(s.H, s.W), ref_depth)
+    assert int((merged[..., 3] > 0).sum()) > 1000
+    ctx.upload_volume(0, vol, desc=s.desc)

@@ -95,7 +95,7 @@ SYMBOLS = [
     "b200rc_synth_volume", "b200rc_download_volume", "b200rc_region_minmax", "b200rc_download_minmax", "b200rc_set_tf1d", "b200rc_set_preint",
     "b200rc_build_preint", "b200rc_download_preint", "b200rc_set_tf2d", "b200rc_entry_exit", "b200rc_render",
     "b200rc_render_camera", "b200rc_render_camera_device", "b200rc_composite", "b200rc_finalize", "b200rc_ert_plan",
-    "b200rc_remarch_device", "b200rc_upload_volume_begin", "b200rc_upload_volume_slab", "b200rc_upload_volume_end", "b200rc_load_raw_file", "b200rc_rescale",
+    "b200rc_remarch_device", "b200rc_upload_volume_begin", "b200rc_upload_volume_slab", "b200rc_upload_volume_end", "b200rc_load_raw_file", "b200rc_rescale", "b200rc_composite_keyed",
 ]
 
 _lib = None
@@ -144,6 +144,7 @@ def load_library():
     lib.b200rc_render_camera_device.argtypes = [vp, C.POINTER(Params), C.POINTER(EepParams), C.POINTER(Camera), i32, i32, C.POINTER(vp * 3), vp]
     lib.b200rc_composite.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, sz]
     lib.b200rc_finalize.argtypes = [vp, vp, vp, sz, i32, vp]
+    lib.b200rc_composite_keyed.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz]
     lib.b200rc_rescale.argtypes = [vp, vp, pf, i32, i32, i32, vp, pf, i32, i32, i32]
     lib.b200rc_ert_plan.argtypes = [vp, vp, i32, C.c_uint32, vp, vp, sz, vp, vp, C.POINTER(C.c_uint64)]
     lib.b200rc_remarch_device.argtypes = [vp, C.POINTER(Params), C.POINTER(Camera), i32, i32, vp, vp, C.POINTER(vp * 3), vp]

@@ -533,6 +533,9 @@ static int render_camera_impl(b200rc_ctx* ctx, const b200rc_params* P, const b20
         else p.out[o] = device_out ? out_color[o] : ctx->d_out[o];
     }
     p.out_depth = out_depth ? (device_out ? out_depth : ctx->d_out_depth) : nullptr;
+    // sort-last partial MIP / MOP image: out_color[1] (unconnected) receives the merge key plane, one float per pixel
+    if (P->partial_image && device_out && !p.connected[1] && out_color && out_color[1] && (p.comp[0] == B200RC_COMP_MIP || p.comp[0] == B200RC_COMP_MOP))
+        p.out_key = (float*)out_color[1];
     rc = run_march(ctx, P, p, nch, dtype);
     if (rc) return rc;
     if (!device_out) {
@@ -584,6 +587,14 @@ extern "C" int b200rc_rescale(b200rc_ctx* ctx, const void* src_color, const floa
     if (rc == B200RC_ERR_CUDA) ctx->set_error("rescale: copy failed");
     cudaFree(d_src); cudaFree(d_dst); cudaFree(d_sd); cudaFree(d_dd);
     return rc;
+}
+
+extern "C" int b200rc_composite_keyed(b200rc_ctx* ctx, const float* front_rgba, const float* front_key, const float* front_depth,
+                                      const float* back_rgba, const float* back_key, const float* back_depth,
+                                      float* dst_rgba, float* dst_key, float* dst_depth, size_t n) {
+    CTX_GUARD();
+    if (!front_rgba || !back_rgba || !dst_rgba || !front_key || !back_key || !dst_key) { ctx->set_error("composite_keyed: null image"); return B200RC_ERR_INVALID; }
+    return rc_composite_keyed_launch(ctx, front_rgba, front_key, front_depth, back_rgba, back_key, back_depth, dst_rgba, dst_key, dst_depth, n);
 }
 
 extern "C" int b200rc_finalize(b200rc_ctx* ctx, const float* rgba_dev, const float* depth_dev, size_t n, int out_format, void* out_color_dev) {

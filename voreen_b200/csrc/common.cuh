@@ -56,6 +56,7 @@ struct DevParams {
     const float4* exitp; const float* exit_depth;
     void* out[3];
     float* out_depth;
+    float* out_key;                 // sort-last partial MIP / MOP image: the merge key (max intensity / max alpha) per pixel, or null
     int out_format, quantize_depth24;
     int nvol, multi;
     VolDev vol[B200RC_MAX_VOLUMES];

@@ -78,6 +78,31 @@ int rc_rescale_launch(b200rc_ctx* ctx, const void* src, const float* sdepth, int
     return B200RC_OK;
 }
 
+// max-key merge (sort-last MIP / MOP): the partial image with the larger key wins, the front one on ties -- the reference keeps the
+// FIRST sample whose intensity (alpha) exceeds the running maximum (mod_compositing.frag:85-106), and every sample of the front
+// shard precedes every sample of the back shard on the ray
+__global__ void composite_keyed_kernel(const float4* __restrict__ fc, const float* __restrict__ fk, const float* __restrict__ fd,
+                                       const float4* __restrict__ bc, const float* __restrict__ bk, const float* __restrict__ bd,
+                                       float4* __restrict__ dc, float* __restrict__ dk, float* __restrict__ dd, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float kf = fk[i], kb = bk[i];
+    const bool takeB = kb > kf;
+    const float4 c = takeB ? bc[i] : fc[i];
+    const float d = (fd && bd) ? (takeB ? bd[i] : fd[i]) : 1.0f;
+    dc[i] = c; dk[i] = takeB ? kb : kf;
+    if (dd) dd[i] = d;
+}
+
+int rc_composite_keyed_launch(b200rc_ctx* ctx, const float* fc, const float* fk, const float* fd, const float* bc, const float* bk, const float* bd,
+                              float* dc, float* dk, float* dd, size_t n) {
+    if (!n) return B200RC_OK;
+    composite_keyed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const float4*)fc, fk, fd, (const float4*)bc, bk, bd, (float4*)dc, dk, dd, n);
+    ctx->launches++;
+    RC_CHECK(cudaGetLastError());
+    return B200RC_OK;
+}
+
 int rc_composite_launch(b200rc_ctx* ctx, int mode, const float* fc, const float* fd, const float* bc, const float* bd, float* dc, float* dd, size_t n) {
     if (!n) return B200RC_OK;
     composite_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(mode, (const float4*)fc, fd, (const float4*)bc, bd, (float4*)dc, dd, n);

@@ -102,6 +102,8 @@ bool rc_march_fast_multi(b200rc_ctx* ctx, const DevParams& p, int sampler, int* 
 bool rc_march_slab(b200rc_ctx* ctx, const DevParams& p, int sampler, int nch, int dtype, int* rc_out);
 int rc_march_launch(b200rc_ctx* ctx, const DevParams& p, int sampler, int nch, int dtype);
 // composite.cu
+int rc_composite_keyed_launch(b200rc_ctx* ctx, const float* fc, const float* fk, const float* fd, const float* bc, const float* bk, const float* bd,
+                              float* dc, float* dk, float* dd, size_t n);
 int rc_rescale_launch(b200rc_ctx* ctx, const void* src, const float* sdepth, int sw, int sh, int format, void* dst, float* ddepth, int dw, int dh);
 int rc_composite_launch(b200rc_ctx* ctx, int mode, const float* fc, const float* fd, const float* bc, const float* bd, float* dc, float* dd, size_t n);
 int rc_finalize_launch(b200rc_ctx* ctx, const float* rgba, const float* depth, size_t n, int out_format, void* out);

@@ -315,6 +315,9 @@ class Context:
                                             out.ctypes.data_as(C.c_void_p), _fp(od) if od is not None else None, dw, dh, 0), "rescale")
         return out, od
 
+    def composite_keyed(self, fc, fk, fd, bc, bk, bd, dc, dk, dd, n):
+        self._check(self.lib.b200rc_composite_keyed(self.h, fc, fk, fd, bc, bk, bd, dc, dk, dd, n), "composite_keyed")
+
     def finalize(self, rgba, depth, n, out_format, out):
         self._check(self.lib.b200rc_finalize(self.h, rgba, depth, n, out_format, out), "finalize")
 

@@ -258,8 +258,8 @@ class SortLast:
         self.peer = None
         if world > 1 and transport in ("auto", "p2p"):
             try:
-                # [colour npix x 16 B | depth npix x 4 B | final RGBA16 npix x 8 B | final depth npix x 4 B]
-                self.peer = PeerMemory(self.npix * 32, device)
+                # [colour npix x 16 B | depth npix x 4 B | final RGBA16 npix x 8 B | final depth npix x 4 B | MIP/MOP key npix x 4 B]
+                self.peer = PeerMemory(self.npix * 36, device)
                 self.transport = "p2p"
             except Exception as e:      # symmetric memory unavailable on this box: NCCL point-to-point still works
                 if transport == "p2p":
@@ -271,6 +271,9 @@ class SortLast:
             self.depth = self.peer.view(rank, self.npix * 16, (self.npix,), torch.float32)
             self._views = {r: (self.peer.view(r, 0, (self.npix, 4), torch.float32), self.peer.view(r, self.npix * 16, (self.npix,), torch.float32))
                            for r in range(world)}
+            # max-key merges (MIP / MOP) swap on the key plane; the depth plane rides along at a fixed offset inside every rank's buffer
+            self.key = self.peer.view(rank, self.npix * 32, (self.npix,), torch.float32)
+            self._key_views = {r: (self._views[r][0], self.peer.view(r, self.npix * 32, (self.npix,), torch.float32)) for r in range(world)}
         else:
             self.color = torch.empty((self.npix, 4), dtype=torch.float32, device=device)
             self.depth = torch.empty((self.npix,), dtype=torch.float32, device=device)
@@ -289,6 +292,12 @@ class SortLast:
     def shard_desc(self):
         return self.desc
 
+    def _blend_keyed(self, fc, fk, bc, bk, dc, dk):
+        # fk / bk / dk are slices of key planes; the matching depth slices sit (16 n - 32 n) bytes before them in the same buffers
+        off = self.npix * 16 - self.npix * 32
+        self.ctx.composite_keyed(fc.data_ptr(), fk.data_ptr(), fk.data_ptr() + off, bc.data_ptr(), bk.data_ptr(), bk.data_ptr() + off,
+                                 dc.data_ptr(), dk.data_ptr(), dk.data_ptr() + off, fc.shape[0])
+
     def _blend(self, fc, fd, bc, bd, dc, dd):
         self.ctx.composite(self._merge_mode, fc.data_ptr(), fd.data_ptr(), bc.data_ptr(), bd.data_ptr(), dc.data_ptr(), dd.data_ptr(), fc.shape[0])
 
@@ -306,8 +315,11 @@ class SortLast:
             self._merge_mode, need_ert_pass = abi.COMP["dvr"] | abi.COMPOSITE_ERT, True
         elif comp in (abi.COMP["iso"], abi.COMP["fhp"], abi.COMP["fhn"]):
             self._merge_mode, need_ert_pass = comp, False
+        elif comp in (abi.COMP["mip"], abi.COMP["mop"]) and self.peer is not None:
+            self._merge_mode, need_ert_pass = comp, False      # max-key merge over peer memory (key plane exported by the marcher)
         else:
-            raise abi.B200RCError("sort-last rendering supports dvr, iso, fhp and fhn compositing; use the image partition (SortFirst) for the others")
+            raise abi.B200RCError("sort-last rendering supports dvr, iso, fhp, fhn (and mip, mop over peer memory); use the image partition (SortFirst) otherwise")
+        keyed = comp in (abi.COMP["mip"], abi.COMP["mop"])
         saved = (p.partial_image, p.out_format)
         p.partial_image, p.out_format = 1, abi.OUT_RGBA32F
         prof = self.profile
@@ -315,7 +327,7 @@ class SortLast:
         with torch.cuda.stream(self.stream):
             if prof:
                 ev[0].record(self.stream)
-            self.ctx.render_camera_ptrs(p, eep, cam, self.W, self.H, [self.color.data_ptr(), 0, 0], self.depth.data_ptr(), device=True)
+            self.ctx.render_camera_ptrs(p, eep, cam, self.W, self.H, [self.color.data_ptr(), self.key.data_ptr() if keyed else 0, 0], self.depth.data_ptr(), device=True)
             march_ms = self.ctx.stats().last_march_ms
             if prof:
                 self.phases = {"first_pass_ms": march_ms}
@@ -343,7 +355,10 @@ class SortLast:
             flatd = out_depth.view(-1)
             if self.peer is not None:
                 in_front = lambda r: my_group_in_front(self.rank, r, self.world, self.dims, cam_tex)     # noqa: E731
-                lo, hi = binary_swap_p2p(lambda r: self._views[r], self.rank, self.world, in_front, self._blend, self.peer.barrier)
+                if keyed:
+                    lo, hi = binary_swap_p2p(lambda r: self._key_views[r], self.rank, self.world, in_front, self._blend_keyed, self.peer.barrier)
+                else:
+                    lo, hi = binary_swap_p2p(lambda r: self._views[r], self.rank, self.world, in_front, self._blend, self.peer.barrier)
                 n = hi - lo
                 # finalise my 1/P (alpha snap + RGBA16) with the stores going to rank 0's image in peer memory
                 o16, od = self.npix * 20, self.npix * 28
