@@ -3,7 +3,7 @@
 
 #include "voreen/core/datastructures/volume/volumeram.h"
 #include "voreen/core/datastructures/transfunc/1d/transfunc1d.h"
-#include "voreen/core/datastructures/transfunc/preintegrationtable.h"
+#include "voreen/core/datastructures/transfunc/1d/preintegrationtable.h"
 #include "voreen/core/ports/conditions/portconditionvolumetype.h"
 #include "voreen/core/utils/classificationmodes.h"
 #include "voreen/core/utils/glsl.h"
@@ -155,6 +155,8 @@ void B200MultiVolumeRaycaster::beforeProcess() {
     if (volumeInport_.hasChanged() || volumeInport2_.hasChanged() || volumeInport3_.hasChanged() || volumeInport4_.hasChanged()) {
         tgt::Bounds b;
         const VolumePort* vp[kVolumes] = {&volumeInport_, &volumeInport2_, &volumeInport3_, &volumeInport4_};
+        for (int i = 0; i < kVolumes; ++i)
+            if (vp[i]->hasChanged()) resident_[i] = 0;     // new voxels (or a reused address), whatever the invalidation level
         for (int i = 0; i < kVolumes; ++i)
             if (vp[i]->hasData()) b.addVolume(vp[i]->getData()->getBoundingBox().getBoundingBox());
         if (length(b.diagonal()) != 0.0) camera_.adaptInteractionToScene(b);

@@ -49,6 +49,7 @@ void B200SimpleRaycaster::deinitialize() {
 void B200SimpleRaycaster::beforeProcess() {
     VolumeRaycaster::beforeProcess();
     transferFunc_.setVolume(volumeInport_.getData());
+    if (volumeInport_.hasChanged()) residentVolume_ = 0;       // new voxels (or a reused address), whatever the invalidation level
     if (volumeInport_.hasChanged() && volumeInport_.getData())
         camera_.adaptInteractionToScene(volumeInport_.getData()->getBoundingBox().getBoundingBox());
 }

@@ -3,7 +3,8 @@
 
 #include "voreen/core/datastructures/volume/volumeram.h"
 #include "voreen/core/datastructures/transfunc/1d/transfunc1d.h"
-#include "voreen/core/datastructures/transfunc/preintegrationtable.h"
+#include "voreen/core/datastructures/transfunc/1d/preintegrationtable.h"
+#include "voreen/core/datastructures/callback/memberfunctioncallback.h"
 #include "voreen/core/utils/classificationmodes.h"
 #include "voreen/core/utils/exception.h"
 #include "tgt/textureunit.h"
@@ -53,6 +54,8 @@ B200SingleVolumeRaycaster::B200SingleVolumeRaycaster()
     , ctx_(0)
     , residentVolume_(0)
 {
+    for (int c = 0; c < kChannels; ++c) residentPreint_[c] = 0;
+    volumeInport_.onChange(MemberFunctionCallback<B200SingleVolumeRaycaster>(this, &B200SingleVolumeRaycaster::volumeInportOnChange));
     addProperty(shaderProp_);
     addProperty(transFuncTypeProp_);
     for (int c = 0; c < kChannels; ++c) {
@@ -87,6 +90,59 @@ B200SingleVolumeRaycaster::B200SingleVolumeRaycaster()
     addProperty(enableChannelShift_); enableChannelShift_.setGroupID("channelShift");
     for (int c = 0; c < kChannels; ++c) { addProperty(*channelShift_[c]); channelShift_[c]->setGroupID("channelShift"); }
     setPropertyGroupGuiName("channelShift", "Channel Shift");
+
+    // same listeners as singlevolumeraycaster.cpp:160-168: GUI state and the classification rules follow these properties
+    const MemberFunctionCallback<B200SingleVolumeRaycaster> adjust(this, &B200SingleVolumeRaycaster::adjustPropertyVisibilities);
+    classificationMode_.onChange(adjust); shadeMode_.onChange(adjust);
+    compositingMode1_.onChange(adjust); compositingMode2_.onChange(adjust); compositingMode3_.onChange(adjust);
+    applyLightAttenuation_.onChange(adjust); transFuncTypeProp_.onChange(adjust); enableChannelShift_.onChange(adjust);
+    volumeInport_.onNewData(adjust);
+}
+
+// singlevolumeraycaster.cpp:531-557: camera interaction + light range follow the scene, every TF property learns the volume
+// (TransFunc1DKeysProperty::setVolume resizes the TF texture to 2^bits texels and fits the domain on first use,
+// transfunc1dkeysproperty.cpp:94-140) -- without this an unchanged workspace would classify through a texture of the wrong width
+void B200SingleVolumeRaycaster::volumeInportOnChange() {
+    if (volumeInport_.hasData()) {
+        const tgt::Bounds bb = volumeInport_.getData()->getBoundingBox().getBoundingBox();
+        camera_.adaptInteractionToScene(bb, tgt::min(volumeInport_.getData()->getSpacing()));
+        lightPosition_.setMaxDist(10.f * tgt::length(bb.diagonal()));       // LIGHT_POSITION_MAX_DIST_MULTIPLIER (:40)
+    }
+    const int channels = volumeInport_.hasData() ? (int)volumeInport_.getData()->getNumChannels() : 1;
+    for (int c = 0; c < kChannels; ++c) {
+        if (c > 0 && channels < c + 1) break;
+        tf1d_[c]->setVolume(volumeInport_.getData(), c);
+        tf2d_[c]->setVolume(volumeInport_.getData(), c);
+        tfGauss_[c]->setVolume(volumeInport_.getData(), c);
+    }
+    residentVolume_ = 0;        // whatever the invalidation level: a changed port means new voxels (or a reused address)
+}
+
+// singlevolumeraycaster.cpp:474-529
+void B200SingleVolumeRaycaster::adjustPropertyVisibilities() {
+    const int channels = volumeInport_.hasData() ? (int)volumeInport_.getData()->getNumChannels() : 1;
+    const bool tf1d = transFuncTypeProp_.getValue() == TFT_1DKEYS, tf2d = transFuncTypeProp_.getValue() == TFT_2DPRIMITIVES,
+               tfg = transFuncTypeProp_.getValue() == TFT_1DGAUSSIAN;
+    for (int c = 0; c < kChannels; ++c) {
+        tf1d_[c]->setVisibleFlag(channels >= c + 1 && tf1d);
+        tf2d_[c]->setVisibleFlag(channels >= c + 1 && tf2d);
+        tfGauss_[c]->setVisibleFlag(channels >= c + 1 && tfg);
+        channelShift_[c]->setVisibleFlag(enableChannelShift_.get() && channels >= c + 1);
+    }
+    lightAttenuation_.setVisibleFlag(applyLightAttenuation_.get());
+    gammaValue1_.setVisibleFlag(compositingMode1_.isSelected("mida"));
+    gammaValue2_.setVisibleFlag(compositingMode2_.isSelected("mida"));
+    gammaValue3_.setVisibleFlag(compositingMode3_.isSelected("mida"));
+    // the two rejection rules of the reference (:516-528): no pre-integration with 2D transfer functions or with MIP
+    if (tf2d && !(classificationMode_.get() == "transfer-function")) {
+        LWARNING("Pre-integration is not allowed with 2d transfer functions. Switching to normal transfer function mode.");
+        classificationMode_.select("transfer-function");
+    }
+    if ((compositingMode1_.get() == "mip" || compositingMode2_.get() == "mip" || compositingMode3_.get() == "mip")
+        && !(classificationMode_.get() == "transfer-function")) {
+        LWARNING("Pre-integration is not allowed with Mip rendering. Switching to normal transfer function mode.");
+        classificationMode_.select("transfer-function");
+    }
 }
 
 B200SingleVolumeRaycaster::~B200SingleVolumeRaycaster() {}
@@ -109,12 +165,14 @@ void B200SingleVolumeRaycaster::initialize() {
         ctx_ = 0;
         throw VoreenException("b200raycast: no usable B200 device (there is no CPU fallback)");
     }
+    adjustPropertyVisibilities();       // singlevolumeraycaster.cpp:173-178
 }
 
 void B200SingleVolumeRaycaster::deinitialize() {
     if (ctx_) b200rc_destroy(ctx_);
     ctx_ = 0;
     residentVolume_ = 0;
+    for (int c = 0; c < kChannels; ++c) residentPreint_[c] = 0;
     VolumeRaycaster::deinitialize();
 }
 
@@ -158,6 +216,7 @@ void B200SingleVolumeRaycaster::uploadTransferFunctions(float stepSize) {
         switch (transFuncTypeProp_.getValue()) {
             case TFT_1DKEYS:     tf = tf1d_[c]->get(); break;
             case TFT_1DGAUSSIAN: tf = tfGauss_[c]->get(); break;
+            default: break;
             case TFT_2DPRIMITIVES: {
                 if (c > 0) continue;                                        // the GLSL path binds channel 1 only (singlevolumeraycaster.cpp:376-386)
                 TransFunc2DPrimitives* t2 = tf2d_[0]->get();
@@ -177,14 +236,19 @@ void B200SingleVolumeRaycaster::uploadTransferFunctions(float stepSize) {
             // preintegration.frag:35-87 re-done on the device from the TF texels (RGBA16 quantisation included)
             failOn(b200rc_build_preint(ctx_, c, std::min(tex->getWidth(), 1024), stepSize, B200RC_PI_GPU), "b200rc_build_preint");
         } else if (cls == "pre-integrated-cpu" || cls == "pre-integrated-approximation") {
-            // Voreen's own table (preintegrationtable.cpp:67-204), handed over as is: bit-identical classification
+            // Voreen's own table (preintegrationtable.cpp:67-204), handed over as is: bit-identical classification.  The TF
+            // caches its tables per (step, dimension, mode) and drops them when its keys change (preintegrationtablemap.cpp:59-97),
+            // so an unchanged pointer is an unchanged table; the library compares content hashes on top of that
             const PreIntegrationTable* t = tf->getPreIntegrationTable(stepSize, 0, cls == "pre-integrated-approximation", false);
-            failOn(b200rc_set_preint(ctx_, c, reinterpret_cast<const float*>(t->getTable()), (int)t->getDimension()), "b200rc_set_preint");
+            if (residentPreint_[c] != t->getTable()) {
+                failOn(b200rc_set_preint(ctx_, c, reinterpret_cast<const float*>(t->getTable()), (int)t->getDimension()), "b200rc_set_preint");
+                residentPreint_[c] = t->getTable();
+            }
         }
     }
 }
 
-void B200SingleVolumeRaycaster::fillParams(b200rc_params& p, b200rc_camera& cam, const tgt::ivec2& size, float stepSize) const {
+void B200SingleVolumeRaycaster::fillParams(b200rc_params& p, b200rc_camera& cam, const tgt::ivec2& size, float stepSize) {
     std::memset(&p, 0, sizeof(p));
     p.num_volumes = 1;
     b200rc_volume_params& v = p.vol[0];
@@ -239,25 +303,36 @@ void B200SingleVolumeRaycaster::fillParams(b200rc_params& p, b200rc_camera& cam,
 
 void B200SingleVolumeRaycaster::beforeProcess() {
     VolumeRaycaster::beforeProcess();
-    // INVALID_PROGRAM in the GLSL path = recompile; here = re-upload what changed (volume, TFs); kernels are pre-built
+    // INVALID_PROGRAM in the GLSL path = recompile; here the kernels are pre-built.  A changed volume port -- whatever the
+    // invalidation level it arrived with -- means the voxels in HBM are stale
+    if (volumeInport_.hasChanged()) residentVolume_ = 0;
     if (getInvalidationLevel() >= Processor::INVALID_PROGRAM)
-        residentVolume_ = (volumeInport_.hasChanged() ? 0 : residentVolume_);
+        for (int c = 0; c < kChannels; ++c) residentPreint_[c] = 0;
 }
 
-void B200SingleVolumeRaycaster::writeOutport(RenderPort& port, const std::vector<uint16_t>& rgba16, const std::vector<float>* depth, const tgt::ivec2& size) {
+void B200SingleVolumeRaycaster::writeOutport(RenderPort& port, const uint16_t* rgba16, const float* depth, const tgt::ivec2& size) {
     // non-sharing upload pattern of V/modules/opencl/processors/singleoctreeraycastercl.cpp:1765-1768; the port's render
     // target is RGBA16 + DEPTH24, the same formats the GLSL path writes (rescaleRendering is the identity at equal size).
     // `size` is the port's own size here (process() rescales coarse renderings first), so the render target keeps its size
     tgt::Texture* col = port.getColorTexture();
     col->bind();
-    glTexSubImage2D(GL_TEXTURE_2D, 0, 0, 0, size.x, size.y, GL_RGBA, GL_UNSIGNED_SHORT, &rgba16[0]);
+    glTexSubImage2D(GL_TEXTURE_2D, 0, 0, 0, size.x, size.y, GL_RGBA, GL_UNSIGNED_SHORT, rgba16);
     if (depth) {
         tgt::Texture* dt = port.getDepthTexture();
         dt->bind();
-        glTexSubImage2D(GL_TEXTURE_2D, 0, 0, 0, size.x, size.y, GL_DEPTH_COMPONENT, GL_FLOAT, &(*depth)[0]);
+        glTexSubImage2D(GL_TEXTURE_2D, 0, 0, 0, size.x, size.y, GL_DEPTH_COMPONENT, GL_FLOAT, depth);
     }
     port.validateResult();
     LGL_ERROR;
+}
+
+namespace {
+// glGetTexImage straight into a page-locked buffer (what Texture::downloadTextureToBuffer does into heap memory,
+// V/ext/tgt/texture.cpp; pattern cpuraycaster.cpp:166-169)
+void downloadInto(tgt::Texture* tex, GLenum format, void* dst) {
+    tex->bind();
+    glGetTexImage(GL_TEXTURE_2D, 0, format, GL_FLOAT, dst);
+}
 }
 
 void B200SingleVolumeRaycaster::process() {
@@ -265,40 +340,47 @@ void B200SingleVolumeRaycaster::process() {
     const tgt::ivec2 size = coarse ? outport1_.getSize() / interactionCoarseness_.get() : outport1_.getSize();
     const float stepSize = getSamplingStepSize(volumeInport_.getData());                            // volumeraycaster.cpp:312-322
 
-    uploadVolume();
-    uploadTransferFunctions(stepSize);
+    uploadVolume();                         // no-op unless the volume port changed
+    uploadTransferFunctions(stepSize);      // hands the TFs over; the library skips whatever is unchanged (no per-frame allocation)
     b200rc_params params; b200rc_camera cam;
     fillParams(params, cam, size, stepSize);
 
-    // entry/exit RenderPorts -> host float buffers (download pattern: cpuraycaster.cpp:166-169); the entry/exit images
-    // have the size of the internal render targets because MeshEntryExitPoints follows the same coarseness rule
+    // entry/exit RenderPorts -> page-locked host buffers; the entry/exit images have the size of the internal render targets
+    // because MeshEntryExitPoints follows the same coarseness rule
     const size_t px = (size_t)size.x * size.y;
-    std::unique_ptr<GLubyte[]> entry(entryPort_.getColorTexture()->downloadTextureToBuffer(GL_RGBA, GL_FLOAT));
-    std::unique_ptr<GLubyte[]> exitp(exitPort_.getColorTexture()->downloadTextureToBuffer(GL_RGBA, GL_FLOAT));
-    std::unique_ptr<GLubyte[]> entryD(entryPort_.getDepthTexture()->downloadTextureToBuffer(GL_DEPTH_COMPONENT, GL_FLOAT));
-    std::unique_ptr<GLubyte[]> exitD(exitPort_.getDepthTexture()->downloadTextureToBuffer(GL_DEPTH_COMPONENT, GL_FLOAT));
+    float* entry = static_cast<float*>(pinEntry_.ensure(px * 16));
+    float* exitp = static_cast<float*>(pinExit_.ensure(px * 16));
+    float* entryD = static_cast<float*>(pinEntryDepth_.ensure(px * 4));
+    float* exitD = static_cast<float*>(pinExitDepth_.ensure(px * 4));
+    float* depth = static_cast<float*>(pinDepth_.ensure(px * 4));
+    if (!entry || !exitp || !entryD || !exitD || !depth) throw VoreenException("b200raycast: out of page-locked host memory");
+    downloadInto(entryPort_.getColorTexture(), GL_RGBA, entry);
+    downloadInto(exitPort_.getColorTexture(), GL_RGBA, exitp);
+    downloadInto(entryPort_.getDepthTexture(), GL_DEPTH_COMPONENT, entryD);
+    downloadInto(exitPort_.getDepthTexture(), GL_DEPTH_COMPONENT, exitD);
 
     void* outColor[B200RC_MAX_OUTPUTS] = {0, 0, 0};
     for (int i = 0; i < B200RC_MAX_OUTPUTS; ++i)
-        if (params.output_connected[i]) { hostColor_[i].resize(px * 4); outColor[i] = &hostColor_[i][0]; }
-    hostDepth_.resize(px);
+        if (params.output_connected[i]) {
+            outColor[i] = pinColor_[i].ensure(px * 8);
+            if (!outColor[i]) throw VoreenException("b200raycast: out of page-locked host memory");
+        }
 
-    failOn(b200rc_render(ctx_, &params, &cam, size.x, size.y,
-                         reinterpret_cast<const float*>(entry.get()), reinterpret_cast<const float*>(entryD.get()),
-                         reinterpret_cast<const float*>(exitp.get()), reinterpret_cast<const float*>(exitD.get()),
-                         outColor, &hostDepth_[0]), "b200rc_render");
+    failOn(b200rc_render(ctx_, &params, &cam, size.x, size.y, entry, entryD, exitp, exitD, outColor, depth), "b200rc_render");
 
     // rescaleRendering (volumeraycaster.cpp:348-377): internal size -> outport size with GL_LINEAR; the identity at equal size
     RenderPort* out[3] = {&outport1_, &outport2_, &outport3_};
     for (int i = 0; i < 3; ++i) {
         if (!params.output_connected[i]) continue;
         const tgt::ivec2 outSize = out[i]->getSize();
-        if (outSize == size) { writeOutport(*out[i], hostColor_[i], i == 0 ? &hostDepth_ : 0, size); continue; }
-        std::vector<uint16_t> up((size_t)outSize.x * outSize.y * 4);
-        std::vector<float> upDepth(i == 0 ? (size_t)outSize.x * outSize.y : 0);
-        failOn(b200rc_rescale(ctx_, &hostColor_[i][0], i == 0 ? &hostDepth_[0] : 0, size.x, size.y, B200RC_OUT_RGBA16,
-                              &up[0], i == 0 ? &upDepth[0] : 0, outSize.x, outSize.y, 0), "b200rc_rescale");
-        writeOutport(*out[i], up, i == 0 ? &upDepth : 0, outSize);
+        if (outSize == size) { writeOutport(*out[i], static_cast<const uint16_t*>(outColor[i]), i == 0 ? depth : 0, size); continue; }
+        const size_t opx = (size_t)outSize.x * outSize.y;
+        uint16_t* up = static_cast<uint16_t*>(pinScaled_.ensure(opx * 8));
+        float* upDepth = i == 0 ? static_cast<float*>(pinScaledDepth_.ensure(opx * 4)) : 0;
+        if (!up || (i == 0 && !upDepth)) throw VoreenException("b200raycast: out of page-locked host memory");
+        failOn(b200rc_rescale(ctx_, outColor[i], i == 0 ? depth : 0, size.x, size.y, B200RC_OUT_RGBA16,
+                              up, upDepth, outSize.x, outSize.y, 0), "b200rc_rescale");
+        writeOutport(*out[i], up, upDepth, outSize);
     }
     tgt::TextureUnit::setZeroUnit();
     LGL_ERROR;

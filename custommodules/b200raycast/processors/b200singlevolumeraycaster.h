@@ -52,9 +52,24 @@ private:
 
     void failOn(int status, const char* what);      ///< LERROR + VoreenException unless status == B200RC_OK
     void uploadVolume();                            ///< INVALID_PROGRAM on the volume port (volumeraycaster.cpp:44)
-    void uploadTransferFunctions(float stepSize);
-    void fillParams(b200rc_params& p, b200rc_camera& cam, const tgt::ivec2& size, float stepSize) const;
-    void writeOutport(RenderPort& port, const std::vector<uint16_t>& rgba16, const std::vector<float>* depth, const tgt::ivec2& size);
+    void uploadTransferFunctions(float stepSize);   ///< hands the TFs over; the library re-uploads / rebuilds only what changed
+    void fillParams(b200rc_params& p, b200rc_camera& cam, const tgt::ivec2& size, float stepSize);
+    void writeOutport(RenderPort& port, const uint16_t* rgba16, const float* depth, const tgt::ivec2& size);
+    void volumeInportOnChange();                    ///< singlevolumeraycaster.cpp:531-557
+    void adjustPropertyVisibilities();              ///< singlevolumeraycaster.cpp:474-529 (incl. the pre-integration rejection rules)
+
+    /// page-locked staging buffer (b200rc_host_alloc), grown on demand
+    struct Pinned {
+        void* ptr; size_t bytes;
+        Pinned() : ptr(0), bytes(0) {}
+        ~Pinned() { if (ptr) b200rc_host_free(ptr); }
+        void* ensure(size_t n) {
+            if (n > bytes) { if (ptr) b200rc_host_free(ptr); ptr = 0; bytes = 0; if (b200rc_host_alloc(n, &ptr) != B200RC_OK) return 0; bytes = n; }
+            return ptr;
+        }
+    private:
+        Pinned(const Pinned&); Pinned& operator=(const Pinned&);
+    };
 
     TransFuncTypeProperty transFuncTypeProp_;
     std::unique_ptr<TransFunc1DKeysProperty> tf1d_[kChannels];
@@ -66,9 +81,9 @@ private:
     CameraProperty camera_;
 
     b200rc_ctx* ctx_;
-    const VolumeBase* residentVolume_;              ///< volume currently held in HBM (re-upload on change)
-    std::vector<uint16_t> hostColor_[B200RC_MAX_OUTPUTS];
-    std::vector<float> hostDepth_;
+    const VolumeBase* residentVolume_;              ///< volume currently held in HBM (re-upload whenever the port changed)
+    const void* residentPreint_[kChannels];         ///< PreIntegrationTable handed over last (Voreen caches them per TF + step)
+    Pinned pinEntry_, pinExit_, pinEntryDepth_, pinExitDepth_, pinColor_[B200RC_MAX_OUTPUTS], pinDepth_, pinScaled_, pinScaledDepth_;
 
     static const std::string loggerCat_;
 };

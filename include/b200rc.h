@@ -31,7 +31,8 @@
 extern "C" {
 #endif
 
-#define B200RC_ABI_VERSION 3     /* 3: b200rc_params grew (raycaster, rgb_color_modulation); streaming upload, rescale, raw loader */
+#define B200RC_ABI_VERSION 4     /* 3: b200rc_params grew (raycaster, rgb_color_modulation); streaming upload, rescale, raw loader
+                                    4: b200rc_finalize takes ert_snap; pinned host buffers; post chain; octree; segmentation */
 #define B200RC_MAX_VOLUMES 4   /* MultiVolumeRaycaster: volume1..4 (multivolumeraycaster.cpp:41-65) */
 #define B200RC_MAX_CHANNELS 4  /* SingleVolumeRaycaster: NUM_CHANNELS 1..4 (singlevolumeraycaster.cpp:440-445) */
 #define B200RC_MAX_OUTPUTS 3   /* image.output, image.output1, image.output2 (volumeraycaster.cpp:44-49) */
@@ -233,6 +234,11 @@ const char* b200rc_last_error(const b200rc_ctx* ctx);
 int b200rc_set_stream(b200rc_ctx* ctx, void* cuda_stream);
 int b200rc_synchronize(b200rc_ctx* ctx);
 int b200rc_get_stats(b200rc_ctx* ctx, b200rc_stats* out);
+/* Page-locked host memory (cudaHostAlloc) for the buffers that cross PCIe every frame: the entry/exit images read back from the
+ * reference's RenderPorts (cpuraycaster.cpp:166-169 downloads them into heap memory) and the colour / depth images on their way
+ * to RenderPort::getColorTexture()->uploadTexture().  Pageable buffers work too, at roughly half the copy rate. */
+int b200rc_host_alloc(size_t bytes, void** out);
+int b200rc_host_free(void* p);
 
 /* ---- volume: replaces VolumeGL::generateTexture + GLSL::bindVolumeTexture
  *      (V/src/core/datastructures/volume/volumegl.cpp:106-139,336-381; V/src/core/utils/glsl.cpp:85-112).
@@ -347,8 +353,9 @@ int b200rc_composite_keyed(b200rc_ctx* ctx, const float* front_rgba, const float
                            const float* back_rgba, const float* back_key, const float* back_depth,
                            float* dst_rgba, float* dst_key, float* dst_depth, size_t n);
 
-/* ERT finalisation after merging (alpha >= 0.95 -> 1.0, mod_raysetup.frag:65-74) and conversion to out_format. */
-int b200rc_finalize(b200rc_ctx* ctx, const float* rgba_dev, const float* depth_dev, size_t n, int out_format,
+/* ERT finalisation after merging (ert_snap != 0: alpha >= 0.95 -> 1.0, mod_raysetup.frag:65-74 -- only when early ray
+ * termination is active for the output, i.e. not for mip / mop / mida, volumeraycaster.cpp:225-233) and conversion to out_format. */
+int b200rc_finalize(b200rc_ctx* ctx, const float* rgba_dev, const float* depth_dev, size_t n, int out_format, int ert_snap,
                     void* out_color_dev);
 
 #ifdef __cplusplus

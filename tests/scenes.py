@@ -116,3 +116,41 @@ def parity_report(a, b):
     per_px = d.reshape(d.shape[0], d.shape[1], -1).max(axis=2)
     finite = d[np.isfinite(d)]
     return float((per_px <= 1.0 / 255.0).mean()), float(finite.max() if finite.size else 0.0)
+
+
+# ---- the product's sort-last merge kernels on numpy images (upload -> b200rc_composite / b200rc_finalize -> download) ----------
+def product_composite(ctx, mode, front, back):
+    """front / back: (colour (n, 4) float32, depth (n,) float32).  Returns dst = front OVER back from b200rc_composite."""
+    import torch
+    dev = torch.device("cuda", 0)
+    fc, fd, bc, bd = (torch.from_numpy(np.ascontiguousarray(a, np.float32)).to(dev) for a in (front[0], front[1], back[0], back[1]))
+    dc, dd = torch.empty_like(fc), torch.empty_like(fd)
+    ctx.composite(mode, fc.data_ptr(), fd.data_ptr(), bc.data_ptr(), bd.data_ptr(), dc.data_ptr(), dd.data_ptr(), fd.shape[0])
+    ctx.synchronize()
+    return dc.cpu().numpy(), dd.cpu().numpy()
+
+
+def product_finalize(ctx, color, out_format, snap=True):
+    """(n, 4) float32 -> b200rc_finalize -> (n, 4) uint16 (RGBA16) or float32."""
+    import torch
+    from voreen_b200 import abi as _abi
+    dev = torch.device("cuda", 0)
+    c = torch.from_numpy(np.ascontiguousarray(color, np.float32)).to(dev)
+    n = c.shape[0]
+    out = torch.empty((n, 4), dtype=torch.int16 if out_format == _abi.OUT_RGBA16 else torch.float32, device=dev)
+    ctx.finalize(c.data_ptr(), 0, n, out_format, out.data_ptr(), snap=snap)
+    ctx.synchronize()
+    o = out.cpu().numpy()
+    return o.view(np.uint16) if out_format == _abi.OUT_RGBA16 else o
+
+
+def numpy_finalize(color, out_format, snap=True):
+    """mod_raysetup.frag:65-74 snap + GL_RGBA16 store (clamp, round half up) in numpy."""
+    from voreen_b200 import abi as _abi
+    c = np.array(color, np.float32, copy=True)
+    if snap:
+        c[:, 3] = np.where(c[:, 3] >= np.float32(0.95), np.float32(1.0), c[:, 3])
+    if out_format != _abi.OUT_RGBA16:
+        return c
+    v = np.where(c > 0, np.minimum(c, np.float32(1.0)), np.float32(0.0)).astype(np.float32)        # NaN -> 0 like to_unorm16
+    return np.floor(v * np.float32(65535.0) + np.float32(0.5)).astype(np.uint16)

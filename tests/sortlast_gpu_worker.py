@@ -9,7 +9,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))      # tests/ -> repo root
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402  (workload definition: TF keys, orbit)
 import voreen_b200 as vb  # noqa: E402

@@ -25,7 +25,7 @@ def test_libb200rc_exports_every_declared_symbol():
     assert set(declared) == set(abi.SYMBOLS), set(declared) ^ set(abi.SYMBOLS)
     for s in declared:
         assert hasattr(lib, s), s
-    assert lib.b200rc_abi_version() == abi.ABI_VERSION == 3
+    assert lib.b200rc_abi_version() == abi.ABI_VERSION == 4
 
 
 def test_libb200rc_host_exports_every_declared_symbol():

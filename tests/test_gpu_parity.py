@@ -270,13 +270,19 @@ def test_sharded_rendering_single_device(ctx, world, cls):
                     continue
                 a, b = imgs[r], imgs[r | (1 << rnd)]
                 front, back = (a, b) if sortlast.my_group_in_front(r, rnd, world, dims, cam_tex) else (b, a)
-                dc = np.empty_like(a[0]); dd = np.empty_like(a[1])
-                orc.lib().orc_composite(abi.COMP["dvr"] | abi.COMPOSITE_ERT, orc.fp(front[0]), orc.fp(front[1]), orc.fp(back[0]), orc.fp(back[1]), orc.fp(dc), orc.fp(dd), dc.shape[0])
+                # the PRODUCT's merge kernel (b200rc_composite) does the merge; the oracle's restatement checks it round by round
+                dc, dd = scenes.product_composite(ctx, abi.COMP["dvr"] | abi.COMPOSITE_ERT, front, back)
+                oc = np.empty_like(a[0]); od = np.empty_like(a[1])
+                orc.lib().orc_composite(abi.COMP["dvr"] | abi.COMPOSITE_ERT, orc.fp(front[0]), orc.fp(front[1]), orc.fp(back[0]), orc.fp(back[1]), orc.fp(oc), orc.fp(od), oc.shape[0])
+                assert float(np.abs(dc - oc).max()) <= 1e-6 and np.array_equal(dd, od)
                 nxt[r] = (dc, dd)
             imgs = nxt
         merged, mdepth = imgs[0]
-        merged = merged.reshape(s.H, s.W, 4).copy()
-        merged[..., 3] = np.where(merged[..., 3] >= 0.95, 1.0, merged[..., 3])       # ERT snap after the merge
+        fin = scenes.product_finalize(ctx, merged, abi.OUT_RGBA32F, snap=True)          # ERT snap after the merge: b200rc_finalize
+        assert np.array_equal(fin, scenes.numpy_finalize(merged, abi.OUT_RGBA32F, snap=True))
+        fin16 = scenes.product_finalize(ctx, merged, abi.OUT_RGBA16, snap=True)
+        assert np.array_equal(fin16, scenes.numpy_finalize(merged, abi.OUT_RGBA16, snap=True))
+        merged = fin.reshape(s.H, s.W, 4).copy()
         frac, mx = scenes.parity_report(ref_outs[0], merged)
         dfrac = float((np.abs(ref_depth.reshape(-1) - mdepth) <= 1e-4).mean())
         print(f"sharded x{world} {cls} keys={'translucent' if k is keys else 'ct'}: within 1/255 {frac:.5f} max {mx:.4f} depth {dfrac:.5f} re-marched pixels {remarched}")
@@ -918,11 +924,14 @@ def test_sharded_first_hit_modes_single_device(ctx, world, comp):
                 continue
             a, b = imgs[r], imgs[r | (1 << rnd)]
             front, back = (a, b) if sortlast.my_group_in_front(r, rnd, world, dims, cam_tex) else (b, a)
-            dc = np.empty_like(a[0]); dd = np.empty_like(a[1])
-            orc.lib().orc_composite(abi.COMP[comp], orc.fp(front[0]), orc.fp(front[1]), orc.fp(back[0]), orc.fp(back[1]), orc.fp(dc), orc.fp(dd), dc.shape[0])
+            dc, dd = scenes.product_composite(ctx, abi.COMP[comp], front, back)        # the product's merge kernel, checked by the oracle's
+            oc = np.empty_like(a[0]); od = np.empty_like(a[1])
+            orc.lib().orc_composite(abi.COMP[comp], orc.fp(front[0]), orc.fp(front[1]), orc.fp(back[0]), orc.fp(back[1]), orc.fp(oc), orc.fp(od), oc.shape[0])
+            assert np.array_equal(dc, oc) and np.array_equal(dd, od)
             nxt[r] = (dc, dd)
         imgs = nxt
     merged, mdepth = imgs[0]
+    merged = scenes.product_finalize(ctx, merged, abi.OUT_RGBA32F, snap=True)
     frac, mx = scenes.parity_report(ref_outs[0], merged.reshape(s.H, s.W, 4))
     dfrac = float((np.abs(ref_depth.reshape(-1) - mdepth) <= 1e-4).mean())
     hits = int((np.asarray(ref_outs[0])[..., 3] > 0).sum())

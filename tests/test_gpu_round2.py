@@ -1,0 +1,415 @@
+"""GPU parity tests added in round 2 (all through the C ABI):
+
+* the sort-last merge kernels themselves (b200rc_composite in every mode, b200rc_finalize with and without the ERT snap)
+  against the oracle's restatement / numpy on random and adversarial partial images;
+* BASELINE.json's configurations at FULL SIZE against the oracle: crops of the C2 / C3 / C4 frames are marched by the oracle
+  on a CPU-synthesized window of the same procedural volume (identical bytes) and must agree with the GPU frame to
+  <= 1/255 on >= 99.9 % of the pixels with equal ray, nominal-sample and shaded-sample counts;
+* the real multi-process sort-last / sort-first path (torchrun, one rank per GPU) when the box has >= 2 GPUs;
+* shards whose border voxels are opaque (the outer half voxel belongs to the border shard), sharded MIP end to end
+  (no alpha snap), and the rejection of key planes for multi-channel volumes.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import orc
+import scenes
+from voreen_b200 import abi
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# merge kernels
+# ---------------------------------------------------------------------------------------------------------------------
+def _partial_images(n, seed):
+    """Random premultiplied partial images + the adversarial values: alpha exactly at / around the 0.95 ERT threshold, empty
+    pixels, fully opaque pixels, equal keys, depth 1.0 (no hit), negative zero."""
+    rng = np.random.default_rng(seed)
+    def one():
+        a = rng.random(n, dtype=np.float32)
+        a[rng.random(n) < 0.2] = 0.0
+        c = rng.random((n, 3), dtype=np.float32) * a[:, None]
+        d = np.where(a > 0, rng.random(n, dtype=np.float32), np.float32(1.0)).astype(np.float32)
+        img = np.concatenate([c, a[:, None]], axis=1).astype(np.float32)
+        special = np.array([0.95, np.nextafter(np.float32(0.95), np.float32(0)), np.nextafter(np.float32(0.95), np.float32(1)), 1.0, 0.0, -0.0, 0.9499999, 0.5], np.float32)
+        k = min(n, 4096)
+        img[:k, 3] = special[rng.integers(0, len(special), k)]
+        return img, d
+    f, b = one(), one()
+    b[1][: n // 8] = f[1][: n // 8]         # equal keys / depths: the front image must win the tie
+    return f, b
+
+
+@pytest.mark.parametrize("mode", ["dvr+ert", "dvr", "iso", "fhp", "fhn", "mip", "mop"])
+def test_composite_kernel_against_the_oracle(ctx, mode):
+    m = (abi.COMP["dvr"] | abi.COMPOSITE_ERT) if mode == "dvr+ert" else abi.COMP[mode]
+    for n, seed in [(1, 1), (255, 2), (96 * 88, 3), (1 << 20, 4)]:
+        front, back = _partial_images(n, seed)
+        dc, dd = scenes.product_composite(ctx, m, front, back)
+        oc = np.empty_like(front[0]); od = np.empty_like(front[1])
+        orc.lib().orc_composite(m, orc.fp(front[0]), orc.fp(front[1]), orc.fp(back[0]), orc.fp(back[1]), orc.fp(oc), orc.fp(od), n)
+        if mode.startswith("dvr"):
+            # F + (1 - Fa) * B: the device contracts the multiply-add, the CPU may not -> one rounding apart at most
+            assert float(np.abs(dc - oc).max()) <= 2e-7, (mode, n)
+            if mode == "dvr+ert":       # a terminated front ray hides everything behind it, exactly
+                t = front[0][:, 3] >= np.float32(0.95)
+                assert np.array_equal(dc[t], front[0][t])
+        else:
+            assert np.array_equal(dc, oc), (mode, n)
+        assert np.array_equal(dd, od), (mode, n)
+        # in-place use (dst aliases front), as the binary swap does
+        import torch
+        dev = torch.device("cuda", 0)
+        fc, fd, bc, bd = (torch.from_numpy(a).to(dev) for a in (front[0], front[1], back[0], back[1]))
+        ctx.composite(m, fc.data_ptr(), fd.data_ptr(), bc.data_ptr(), bd.data_ptr(), fc.data_ptr(), fd.data_ptr(), n)
+        ctx.synchronize()
+        assert np.array_equal(fc.cpu().numpy(), dc) and np.array_equal(fd.cpu().numpy(), dd)
+
+
+@pytest.mark.parametrize("snap", [True, False])
+@pytest.mark.parametrize("fmt", ["rgba16", "rgba32f"])
+def test_finalize_kernel(ctx, snap, fmt):
+    f = abi.OUT_RGBA16 if fmt == "rgba16" else abi.OUT_RGBA32F
+    for n, seed in [(1, 5), (1000, 6), (1 << 18, 7)]:
+        img, _ = _partial_images(n, seed)[0]
+        img = img.copy()
+        img[: min(n, 64), 0] = np.linspace(-0.5, 1.5, min(n, 64), dtype=np.float32)       # clamps of the unorm16 store
+        if n > 100:
+            img[100, 1] = np.nan
+        got = scenes.product_finalize(ctx, img, f, snap=snap)
+        want = scenes.numpy_finalize(img, f, snap=snap)
+        if f == abi.OUT_RGBA32F:
+            assert np.array_equal(got, want, equal_nan=True)
+        else:
+            assert np.array_equal(got, want)
+        a = img[:, 3]
+        touched = (a >= np.float32(0.95)) & (a < 1)
+        if touched.any() and f == abi.OUT_RGBA32F:
+            assert np.all(got[touched, 3] == (1.0 if snap else a[touched]))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# full-size configurations against the oracle, crop by crop
+# ---------------------------------------------------------------------------------------------------------------------
+def _window_for(crops, dims):
+    lo = np.array([1e9] * 3); hi = np.array([-1e9] * 3)
+    for (e, ed, x, xd) in crops:
+        m = np.any(e[..., :3] != x[..., :3], axis=2)
+        if not m.any():
+            continue
+        pts = np.concatenate([e[m][:, :3], x[m][:, :3]])
+        lo = np.minimum(lo, pts.min(axis=0)); hi = np.maximum(hi, pts.max(axis=0))
+    if lo[0] > hi[0]:
+        return (0, 0, 0), (8, 8, 8)
+    d = np.array(dims, np.float64)
+    vlo = np.clip(np.floor(lo * d - 0.5).astype(int) - 4, 0, dims)
+    vhi = np.clip(np.ceil(hi * d - 0.5).astype(int) + 5, 0, dims)
+    return tuple(int(v) for v in vlo), tuple(int(v) for v in vhi)
+
+
+CROPS = [(0.5, 0.5), (0.31, 0.62), (0.2, 0.47)]     # centre, off-centre, across the silhouette (fractions of the image)
+
+
+@pytest.mark.parametrize("n,img,cls,comp", [(512, 1024, "tf", "dvr"), (2048, 2048, "preint", "dvr"), (2048, 2048, "tf", "mip"), (2048, 2048, "tf", "iso")])
+def test_full_size_crops_against_the_oracle(n, img, cls, comp):
+    """C2 / C3: the GPU renders the whole frame; 64x64 crops of it are (a) re-rendered on the GPU from the cropped entry/exit images
+    (b200rc_render) -- bit-identical to the frame -- and (b) marched by the oracle over a CPU-synthesized window of the volume."""
+    import voreen_b200 as vb
+    from voreen_b200 import host
+    from voreen_b200 import raycaster as rc
+    dims = (n, n, n)
+    step = float(np.float32(1.0) / (np.float32(n) * np.float32(2.0)))
+    edge = 64
+    c = vb.Context(0)
+    try:
+        c.synth_volume(0, vb.make_volume_desc(dims), 1234)
+        tf = orc.make_tf(scenes.CT_KEYS, domain=(0.0, 65535.0))
+        tf_tex = orc.tf1d_texture(tf, 4096)
+        preint = None
+        if cls == "preint":
+            c.set_tf1d(0, host.tf1d_texture(scenes.CT_KEYS, 1024), (0.0, 65535.0))
+            c.build_preint(0, 1024, step, abi.PI_CPU)
+            preint = orc.preint_cpu(tf, 1024, step)
+        c.set_tf1d(0, host.tf1d_texture(scenes.CT_KEYS, 4096), (0.0, 65535.0))
+        p = vb.default_params(step, classification=abi.CLASS_PREINT if cls == "preint" else abi.CLASS_TF, empty_space_skipping=2 if comp == "mip" else 1,
+                              out_format=abi.OUT_RGBA16, compositing=[abi.COMP[comp]] * 3, iso_value=0.5)
+        eep = vb.default_eep()
+        full_desc = rc.make_volume_desc(dims)
+        checked = 0
+        for k in (3, 20):
+            cam = host.make_camera(scenes.orbit_eye(k), W=img, H=img)
+            p.collect_stats = 0
+            outs, depth = c.render_camera(p, eep, cam, img, img)
+            frame = np.asarray(outs[0]).copy(); fdepth = depth.copy()
+            e, ed, x, xd = c.entry_exit(eep, cam, img, img)
+            crops = []
+            for fx, fy in CROPS:
+                x0, y0 = int(fx * img) - edge // 2, int(fy * img) - edge // 2
+                sl = (slice(y0, y0 + edge), slice(x0, x0 + edge))
+                crops.append((sl, tuple(np.ascontiguousarray(a[sl]) for a in (e, ed, x, xd))))
+            vlo, vhi = _window_for([cr[1] for cr in crops], dims)
+            rd = tuple(vhi[a] - vlo[a] for a in range(3))
+            data = orc.synth_volume(dims, 1234, vlo, rd)
+            wdesc = rc.make_volume_desc(dims, shard_lo=vlo, shard_hi=vhi, shard_apron=0)
+            ov = orc.make_volume(data, wdesc)
+            ocls = [orc.make_classifier(tf_tex, (0.0, 65535.0), preint=preint)]
+            for sl, (ce, ced, cx, cxd) in crops:
+                # (a) the same rays through b200rc_render with the cropped entry/exit images: the frame's pixels, bit for bit
+                p.collect_stats = 1
+                g_outs, g_depth = c.render(p, cam, edge, edge, ce, ced, cx, cxd)
+                st = c.stats()
+                assert np.array_equal(np.asarray(g_outs[0]), frame[sl]) and np.array_equal(g_depth, fdepth[sl])
+                # (b) the oracle (no empty-space skipping, float output)
+                po = rc.default_params(step, classification=p.vol[0].classification, empty_space_skipping=0, out_format=abi.OUT_RGBA32F,
+                                       compositing=[abi.COMP[comp]] * 3, iso_value=0.5)
+                po.collect_stats = 1
+                o_outs, o_depth, o_st = orc.raycast([ov], ocls, po, cam, edge, edge, ce, ced, cx, cxd)
+                # both sides as GL_RGBA16 (what the outport holds); 1/255 = 257 units
+                got = np.asarray(g_outs[0]).view(np.uint16).astype(np.int64)
+                want = scenes.numpy_finalize(np.asarray(o_outs[0], np.float32).reshape(-1, 4), abi.OUT_RGBA16, snap=False).reshape(got.shape).astype(np.int64)
+                d = np.abs(got - want).max(axis=2) / 65535.0
+                frac = float((d <= 1.0 / 255.0).mean())
+                dfrac = float((np.abs(o_depth - g_depth) <= 1e-4).mean())
+                print(f"C{'2' if n == 512 else '3'} {n}^3 @{img}^2 {cls} {comp} view {k} crop {sl[1].start},{sl[0].start}: within 1/255 {frac:.5f} max {d.max():.2e} depth {dfrac:.5f} "
+                      f"rays {st.rays_cast}/{o_st.rays_cast} nominal {st.samples_nominal}/{o_st.samples_nominal} shaded {st.samples_shaded}/{o_st.samples_shaded} "
+                      f"classified+skipped {st.samples_classified + st.samples_skipped}/{o_st.samples_classified}")
+                assert st.rays_cast == o_st.rays_cast and st.samples_nominal == o_st.samples_nominal
+                if comp != "mip":       # MIP culling (mode 2) classifies fewer samples by design; every other mode takes the oracle's decisions
+                    assert st.samples_shaded == o_st.samples_shaded
+                    assert st.samples_classified + st.samples_skipped == o_st.samples_classified
+                assert frac >= 0.999 and dfrac >= 0.999
+                checked += int(o_st.rays_cast)
+        assert checked > 5000
+    finally:
+        c.close()
+
+
+def test_c4_multivolume_crops_against_the_oracle():
+    """C4: MultiVolumeRaycaster, 4 x 1024^3 u16 with per-volume TFs, DVR at 2048^2 -- crops against the oracle as above."""
+    import voreen_b200 as vb
+    from voreen_b200 import host
+    from voreen_b200 import raycaster as rc
+    n, img, nvol, edge = 1024, 2048, 4, 48
+    dims = (n, n, n)
+    keys = [scenes.CT_KEYS, [(0.0, (0, 0, 0, 0)), (0.3, (0, 255, 0, 0)), (1.0, (0, 255, 0, 120))],
+            [(0.0, (0, 0, 0, 0)), (0.4, (0, 0, 255, 0)), (1.0, (0, 0, 255, 90))], [(0.0, (0, 0, 0, 0)), (0.5, (255, 0, 255, 0)), (1.0, (255, 0, 255, 60))]]
+    step_world = float(np.float32(2.0) / np.float32(n) / np.float32(2.0))      # multivolumeraycaster.cpp:326-344
+    step_tex = float(np.float32(1.0) / (np.float32(n) * np.float32(2.0)))
+    c = vb.Context(0)
+    try:
+        tex = []
+        for v in range(nvol):
+            c.synth_volume(v, vb.make_volume_desc(dims), 1234 + v)
+            tex.append(orc.tf1d_texture(orc.make_tf(keys[v], domain=(0.0, 65535.0)), 4096))
+            c.set_tf1d(v, host.tf1d_texture(keys[v], 4096), (0.0, 65535.0))
+        eep = vb.default_eep(world_coords=1)
+        checked = 0
+        for k in (3, 20):
+            cam = host.make_camera(scenes.orbit_eye(k), W=img, H=img)
+            e, ed, x, xd = c.entry_exit(eep, cam, img, img)
+            p = vb.default_params(step_world, empty_space_skipping=1, out_format=abi.OUT_RGBA16)
+            p.num_volumes = nvol; p.multi_volume = 1
+            p.mv_opacity_correction_factor = step_tex / step_world
+            outs, depth = c.render(p, cam, img, img, np.stack([e] * (nvol + 1)), ed, np.stack([x] * (nvol + 1)), xd)
+            frame = np.asarray(outs[0]).copy(); fdepth = depth.copy()
+            crops = []
+            for fx, fy in CROPS[:2]:
+                x0, y0 = int(fx * img) - edge // 2, int(fy * img) - edge // 2
+                sl = (slice(y0, y0 + edge), slice(x0, x0 + edge))
+                crops.append((sl, tuple(np.ascontiguousarray(a[sl]) for a in (e, ed, x, xd))))
+            # entry/exit are WORLD coordinates here: texture = (world + 1) / 2 for the [-1, 1]^3 cube of make_volume_desc
+            tex_crops = [((ce[..., :3] + 1.0) * 0.5, None, (cx[..., :3] + 1.0) * 0.5, None) for _, (ce, ced, cx, cxd) in crops]
+            vlo, vhi = _window_for([(np.concatenate([a, np.zeros(a.shape[:2] + (1,), a.dtype)], axis=2), None,
+                                     np.concatenate([b, np.zeros(b.shape[:2] + (1,), b.dtype)], axis=2), None) for a, _, b, _ in tex_crops], dims)
+            rd = tuple(vhi[a] - vlo[a] for a in range(3))
+            wdesc = rc.make_volume_desc(dims, shard_lo=vlo, shard_hi=vhi, shard_apron=0)
+            ovs = [orc.make_volume(orc.synth_volume(dims, 1234 + v, vlo, rd), wdesc) for v in range(nvol)]
+            ocls = [orc.make_classifier(tex[v], (0.0, 65535.0)) for v in range(nvol)]
+            for sl, (ce, ced, cx, cxd) in crops:
+                p.collect_stats = 1
+                g_outs, g_depth = c.render(p, cam, edge, edge, np.stack([ce] * (nvol + 1)), ced, np.stack([cx] * (nvol + 1)), cxd)
+                st = c.stats()
+                p.collect_stats = 0
+                assert np.array_equal(np.asarray(g_outs[0]), frame[sl]) and np.array_equal(g_depth, fdepth[sl])
+                po = rc.default_params(step_world, empty_space_skipping=0, out_format=abi.OUT_RGBA32F)
+                po.num_volumes = nvol; po.multi_volume = 1; po.collect_stats = 1
+                po.mv_opacity_correction_factor = step_tex / step_world
+                o_outs, o_depth, o_st = orc.raycast(ovs, ocls, po, cam, edge, edge, np.stack([ce] * (nvol + 1)), ced, np.stack([cx] * (nvol + 1)), cxd)
+                # both sides as GL_RGBA16 (what the outport holds); 1/255 = 257 units
+                got = np.asarray(g_outs[0]).view(np.uint16).astype(np.int64)
+                want = scenes.numpy_finalize(np.asarray(o_outs[0], np.float32).reshape(-1, 4), abi.OUT_RGBA16, snap=False).reshape(got.shape).astype(np.int64)
+                d = np.abs(got - want).max(axis=2) / 65535.0
+                frac = float((d <= 1.0 / 255.0).mean())
+                dfrac = float((np.abs(o_depth - g_depth) <= 1e-4).mean())
+                print(f"C4 4x{n}^3 @{img}^2 view {k} crop {sl[1].start},{sl[0].start}: within 1/255 {frac:.5f} max {d.max():.2e} depth {dfrac:.5f} "
+                      f"rays {st.rays_cast}/{o_st.rays_cast} shaded {st.samples_shaded}/{o_st.samples_shaded}")
+                assert st.rays_cast == o_st.rays_cast and st.samples_shaded == o_st.samples_shaded
+                assert frac >= 0.999 and dfrac >= 0.999
+                checked += int(o_st.rays_cast)
+        assert checked > 3000
+    finally:
+        c.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the real multi-process path (one rank per GPU)
+# ---------------------------------------------------------------------------------------------------------------------
+def _device_count():
+    import voreen_b200 as vb
+    return int(vb.abi.load_library().b200rc_device_count())
+
+
+@pytest.mark.parametrize("mode,transport,comp", [("sort-last", "p2p", "dvr"), ("sort-last", "nccl", "dvr"), ("sort-last", "p2p", "iso"),
+                                                 ("sort-last", "p2p", "mip"), ("sort-first", "p2p", "dvr")])
+def test_multi_gpu_partitions_match_the_single_gpu_image(mode, transport, comp):
+    """torchrun, one rank per GPU (2, 4 or 8): sharded march + exact-ERT second pass + binary swap (b200rc_composite reading the
+    partner's half over NVLink, b200rc_finalize storing into rank 0's image) against the single-GPU frame rendered on rank 0."""
+    ndev = _device_count()
+    if ndev < 2:
+        pytest.skip(f"needs >= 2 GPUs (this box has {ndev})")
+    world = 8 if ndev >= 8 else (4 if ndev >= 4 else 2)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", SL_TRANSPORT=transport, OMP_NUM_THREADS="1")
+    env.pop("SL_NOREF", None)
+    if comp != "dvr":
+        env["SL_COMP"] = comp
+    port = 29600 + (os.getpid() % 300)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(HERE, "sortlast_gpu_worker.py"), "256", "512", "tf" if comp == "mip" else "preint", mode]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+    print(r.stdout[-3000:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count(" OK") >= 6 and "FAIL" not in r.stdout
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# shards: opaque border voxels, MIP end to end, key-plane misuse
+# ---------------------------------------------------------------------------------------------------------------------
+def _shard_upload(ctx, vol, dims, r, world):
+    from voreen_b200 import raycaster as rc
+    from voreen_b200 import sortlast
+    lo, hi = sortlast.shard_range(dims, r, world)
+    rl = [max(0, lo[a] - sortlast.APRON) for a in range(3)]; rh = [min(dims[a], hi[a] + sortlast.APRON) for a in range(3)]
+    ctx.upload_volume(0, np.ascontiguousarray(vol[rl[2]:rh[2], rl[1]:rh[1], rl[0]:rh[0]]), desc=rc.make_volume_desc(dims, shard_lo=lo, shard_hi=hi, shard_apron=sortlast.APRON))
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_sharded_rendering_with_opaque_border_voxels(ctx, world):
+    """The samples of the outer half voxel (tap base index -1 on the low faces) belong to the border shards: a volume whose
+    border voxels are opaque must merge to the unsharded image (translucent TF: no early termination, the partition alone)."""
+    from voreen_b200 import sortlast
+    dims = (48, 40, 56)
+    rng = np.random.default_rng(9)
+    vol = (rng.random(dims[::-1]) * 20000 + 30000).astype(np.uint16)          # everything visible, border included
+    keys = [(0.0, (255, 140, 60, 3)), (1.00, (255, 255, 255, 5))]
+    for eye in [(1.4, 0.9, 2.9), (-2.2, -1.1, -1.9)]:
+        s = scenes.Scene(vol, keys=keys, W=96, H=88, eye=eye, out_format=abi.OUT_RGBA32F)
+        s.params.collect_stats = 1
+        ref_outs, ref_depth = s.cuda_render(ctx)
+        ref_st = ctx.stats()
+        cam_tex = sortlast.camera_texture_position(s.cam, s.desc)
+        s.params.partial_image = 1
+        parts, classified = {}, 0
+        for r in range(world):
+            _shard_upload(ctx, vol, dims, r, world)
+            outs, depth = ctx.render_camera(s.params, s.eep, s.cam, s.W, s.H)
+            classified += ctx.stats().samples_classified
+            parts[r] = (np.asarray(outs[0]).reshape(-1, 4).copy(), depth.reshape(-1).copy())
+        s.params.partial_image = 0
+        assert classified == ref_st.samples_classified, "the shards' sample sets must partition the single-GPU sample set"
+        imgs = parts
+        for rnd in range(world.bit_length() - 1):
+            nxt = {}
+            for r in sorted(imgs):
+                if (r >> rnd) & 1:
+                    continue
+                a, b = imgs[r], imgs[r | (1 << rnd)]
+                front, back = (a, b) if sortlast.my_group_in_front(r, rnd, world, dims, cam_tex) else (b, a)
+                nxt[r] = scenes.product_composite(ctx, abi.COMP["dvr"] | abi.COMPOSITE_ERT, front, back)
+            imgs = nxt
+        merged = scenes.product_finalize(ctx, imgs[0][0], abi.OUT_RGBA32F, snap=True).reshape(s.H, s.W, 4)
+        frac, mx = scenes.parity_report(ref_outs[0], merged)
+        print(f"opaque border x{world} eye {eye}: within 1/255 {frac:.5f} max {mx:.2e} classified {classified}")
+        assert frac >= 0.9999 and mx < 2e-3
+        assert float((np.abs(ref_depth.reshape(-1) - imgs[0][1]) <= 1e-4).mean()) >= 0.999
+        ctx.upload_volume(0, vol, desc=s.desc)
+
+
+def test_sharded_mip_end_to_end_keeps_unsnapped_alpha(ctx):
+    """MIP / MOP disable early ray termination (volumeraycaster.cpp:225-233): the sharded image must not snap alpha in [0.95, 1)."""
+    import torch
+    from voreen_b200 import sortlast
+    dims, world = (64, 56, 72), 2
+    vol = scenes.ct_like_volume(0, dims=dims)
+    keys = [(0.0, (0, 0, 0, 0)), (0.25, (0, 0, 0, 0)), (0.30, (255, 140, 60, 200)), (1.00, (255, 255, 255, 248))]       # alpha 0.97 at the top
+    s = scenes.Scene(vol, keys=keys, W=96, H=88, eye=(1.4, 0.9, 2.9), out_format=abi.OUT_RGBA32F, compositing=[abi.COMP["mip"]] * 3)
+    ref_outs, ref_depth = s.cuda_render(ctx)
+    ref = np.asarray(ref_outs[0]).reshape(-1, 4)
+    assert ((ref[:, 3] >= 0.95) & (ref[:, 3] < 1.0)).sum() > 20, "the scene must contain alphas the snap would change"
+    cam_tex = sortlast.camera_texture_position(s.cam, s.desc)
+    dev = torch.device("cuda", 0)
+    npix = s.W * s.H
+    s.params.partial_image = 1
+    col = [torch.empty((npix, 4), dtype=torch.float32, device=dev) for _ in range(world)]
+    key = [torch.empty((npix,), dtype=torch.float32, device=dev) for _ in range(world)]
+    dep = [torch.empty((npix,), dtype=torch.float32, device=dev) for _ in range(world)]
+    for r in range(world):
+        _shard_upload(ctx, vol, dims, r, world)
+        ctx.render_camera_ptrs(s.params, s.eep, s.cam, s.W, s.H, [col[r].data_ptr(), key[r].data_ptr(), 0], dep[r].data_ptr(), device=True)
+    s.params.partial_image = 0
+    f, b = (0, 1) if sortlast.my_group_in_front(0, 0, world, dims, cam_tex) else (1, 0)
+    ctx.composite_keyed(col[f].data_ptr(), key[f].data_ptr(), dep[f].data_ptr(), col[b].data_ptr(), key[b].data_ptr(), dep[b].data_ptr(),
+                        col[0].data_ptr(), key[0].data_ptr(), dep[0].data_ptr(), npix)
+    out = torch.empty((npix, 4), dtype=torch.float32, device=dev)
+    ctx.finalize(col[0].data_ptr(), 0, npix, abi.OUT_RGBA32F, out.data_ptr(), snap=False)        # what SortLast.render does for mip / mop
+    ctx.synchronize()
+    assert np.array_equal(out.cpu().numpy(), ref)
+    ctx.finalize(col[0].data_ptr(), 0, npix, abi.OUT_RGBA32F, out.data_ptr(), snap=True)
+    ctx.synchronize()
+    assert not np.array_equal(out.cpu().numpy(), ref)
+    ctx.upload_volume(0, vol, desc=s.desc)
+
+
+def test_key_plane_rejected_for_multichannel_and_extra_outputs(ctx):
+    import torch
+    vol = np.stack([scenes.ct_like_volume(24), scenes.ct_like_volume(24, seed=7)], axis=3)
+    s = scenes.Scene(vol, W=48, H=48, out_format=abi.OUT_RGBA32F, compositing=[abi.COMP["mip"]] * 3)
+    s.upload(ctx)
+    dev = torch.device("cuda", 0)
+    col = torch.empty((48 * 48, 4), dtype=torch.float32, device=dev); key = torch.empty((48 * 48,), dtype=torch.float32, device=dev)
+    dep = torch.empty((48 * 48,), dtype=torch.float32, device=dev)
+    s.params.partial_image = 1
+    with pytest.raises(abi.B200RCError):
+        ctx.render_camera_ptrs(s.params, s.eep, s.cam, 48, 48, [col.data_ptr(), key.data_ptr(), 0], dep.data_ptr(), device=True)
+    s1 = scenes.Scene(scenes.ct_like_volume(24), W=48, H=48, out_format=abi.OUT_RGBA32F, compositing=[abi.COMP["mip"]] * 3, output_connected=[1, 1, 0])
+    s1.upload(ctx)
+    s1.params.partial_image = 1
+    with pytest.raises(abi.B200RCError):       # a partial image renders image.output only: the slot of output 1 is the key plane
+        ctx.render_camera_ptrs(s1.params, s1.eep, s1.cam, 48, 48, [col.data_ptr(), key.data_ptr(), 0], dep.data_ptr(), device=True)
+
+
+def test_unchanged_transfer_functions_are_not_rebuilt(ctx):
+    """A drop-in processor hands its TFs over every frame: identical texels / tables must not bump the occupancy generation
+    (no rebuild, no allocation), a changed texel must."""
+    vol = scenes.ct_like_volume(32)
+    s = scenes.Scene(vol, W=64, H=64).use_preint("cpu")
+    a, ad = s.cuda_render(ctx)
+    launches0 = ctx.stats().kernel_launches
+    ctx.set_tf1d(0, scenes.host.tf1d_texture(s.keys_per_ch[0], s.tf_width), s.domain)
+    ctx.set_preint(0, s.preint[0])
+    assert ctx.stats().kernel_launches == launches0, "identical TF / table: nothing may be launched"
+    b, bd = s.cuda_render(ctx, upload=False)
+    assert np.array_equal(np.asarray(a[0]), np.asarray(b[0]))
+    t = scenes.host.tf1d_texture(s.keys_per_ch[0], s.tf_width).copy()
+    t[s.tf_width // 2, 3] ^= 0x40
+    ctx.set_tf1d(0, t, s.domain)
+    pre = s.preint[0].copy(); pre[250:900, 250:900, 3] = 0.9
+    ctx.set_preint(0, pre)
+    assert ctx.stats().kernel_launches > launches0
+    c, cd = s.cuda_render(ctx, upload=False)
+    assert not np.array_equal(np.asarray(a[0]), np.asarray(c[0]))

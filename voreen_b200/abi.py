@@ -24,7 +24,7 @@ CLAMP_TO_EDGE, CLAMP_TO_BORDER = 0, 1
 SAMPLER_EXACT, SAMPLER_TEX = 0, 1
 OUT_RGBA32F, OUT_RGBA16 = 0, 1
 INSIDE_NONE, INSIDE_GPU = 0, 1
-ABI_VERSION = 3          # include/b200rc.h B200RC_ABI_VERSION
+ABI_VERSION = 4          # include/b200rc.h B200RC_ABI_VERSION
 RAYCASTER_SINGLE, RAYCASTER_SIMPLE, RAYCASTER_RGB = 0, 1, 2
 PROXY_BBOX, PROXY_MINBBOX, PROXY_VISIBLE_BRICKS = 0, 1, 2
 COMPOSITE_ERT = 0x100
@@ -96,6 +96,7 @@ SYMBOLS = [
     "b200rc_build_preint", "b200rc_download_preint", "b200rc_set_tf2d", "b200rc_entry_exit", "b200rc_render",
     "b200rc_render_camera", "b200rc_render_camera_device", "b200rc_composite", "b200rc_finalize", "b200rc_ert_plan",
     "b200rc_remarch_device", "b200rc_upload_volume_begin", "b200rc_upload_volume_slab", "b200rc_upload_volume_end", "b200rc_load_raw_file", "b200rc_rescale", "b200rc_composite_keyed",
+    "b200rc_host_alloc", "b200rc_host_free",
 ]
 
 _lib = None
@@ -143,11 +144,13 @@ def load_library():
     lib.b200rc_render_camera.argtypes = [vp, C.POINTER(Params), C.POINTER(EepParams), C.POINTER(Camera), i32, i32, C.POINTER(vp * 3), pf]
     lib.b200rc_render_camera_device.argtypes = [vp, C.POINTER(Params), C.POINTER(EepParams), C.POINTER(Camera), i32, i32, C.POINTER(vp * 3), vp]
     lib.b200rc_composite.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, sz]
-    lib.b200rc_finalize.argtypes = [vp, vp, vp, sz, i32, vp]
+    lib.b200rc_finalize.argtypes = [vp, vp, vp, sz, i32, i32, vp]
     lib.b200rc_composite_keyed.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz]
     lib.b200rc_rescale.argtypes = [vp, vp, pf, i32, i32, i32, vp, pf, i32, i32, i32]
     lib.b200rc_ert_plan.argtypes = [vp, vp, i32, C.c_uint32, vp, vp, sz, vp, vp, C.POINTER(C.c_uint64)]
     lib.b200rc_remarch_device.argtypes = [vp, C.POINTER(Params), C.POINTER(Camera), i32, i32, vp, vp, C.POINTER(vp * 3), vp]
+    lib.b200rc_host_alloc.argtypes = [sz, C.POINTER(vp)]
+    lib.b200rc_host_free.argtypes = [vp]
     for s in SYMBOLS:
         fn = getattr(lib, s)
         if s not in ("b200rc_last_error",):

@@ -88,7 +88,7 @@ extern "C" int b200rc_create(int device, b200rc_ctx** out_ctx) {
     }
     ctx->stream = ctx->own_stream;
     for (int i = 0; i < 6; ++i) cudaEventCreate(&ctx->ev[i]);
-    cudaMalloc(&ctx->d_stats, 16 * sizeof(unsigned long long));     // [0..7] counters, [8..15] SLAB_PROFILE phase clocks
+    cudaMalloc(&ctx->d_stats, 24 * sizeof(unsigned long long));     // [0..7] counters, [8..17] SLAB_PROFILE phase clocks
     cudaMalloc(&ctx->d_tile_counter, 4 * sizeof(unsigned int));
     *out_ctx = ctx;
     return B200RC_OK;
@@ -126,6 +126,18 @@ extern "C" int b200rc_synchronize(b200rc_ctx* ctx) {
     if (!ctx) return B200RC_ERR_INVALID;
     cudaSetDevice(ctx->device);
     RC_CHECK(cudaStreamSynchronize(ctx->stream));
+    return B200RC_OK;
+}
+
+// page-locked host memory for the buffers that cross PCIe every frame (entry/exit images in, colour + depth out)
+extern "C" int b200rc_host_alloc(size_t bytes, void** out) {
+    if (!out) return B200RC_ERR_INVALID;
+    *out = nullptr;
+    if (cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); *out = nullptr; return B200RC_ERR_OOM; }
+    return B200RC_OK;
+}
+extern "C" int b200rc_host_free(void* p) {
+    if (p && cudaFreeHost(p) != cudaSuccess) { cudaGetLastError(); return B200RC_ERR_CUDA; }
     return B200RC_OK;
 }
 
@@ -263,7 +275,10 @@ static int build_params(b200rc_ctx* ctx, const b200rc_params* P, const b200rc_ca
         d.bricks = vs.bricks;
         for (int a = 0; a < 3; ++a) {
             d.dims[a] = vs.desc.dims[a]; d.res_lo[a] = vs.res_lo[a]; d.res_dims[a] = vs.res_dims[a];
-            d.own_lo[a] = vs.own_lo[a]; d.own_hi[a] = vs.own_hi[a];
+            // a shard that touches the volume border also owns the samples of the outer half voxel (tap base index -1, or
+            // dims when the exit point sits on the high face): they are composited with clamp-to-edge by the unsharded marcher
+            d.own_lo[a] = vs.own_lo[a] <= 0 ? -2 : vs.own_lo[a];
+            d.own_hi[a] = vs.own_hi[a] >= vs.desc.dims[a] ? vs.desc.dims[a] + 2 : vs.own_hi[a];
             d.clamp_lo[a] = vs.res_lo[a] > 0 ? vs.res_lo[a] : 0;
             const int hi = vs.res_lo[a] + vs.res_dims[a] - 1;
             d.clamp_hi[a] = hi < vs.desc.dims[a] - 1 ? hi : vs.desc.dims[a] - 1;
@@ -310,6 +325,7 @@ static int build_params(b200rc_ctx* ctx, const b200rc_params* P, const b200rc_ca
             d.tf = k.tf; d.tf_width = k.tf_width; d.corr_lut = k.corr_lut;
         } else if (mode == B200RC_CLASS_PREINT) {
             if (!k.preint) { ctx->set_error("render: no pre-integration table for channel/volume"); return B200RC_ERR_NOT_READY; }
+            if (P->sampler == B200RC_SAMPLER_TEX) { int rc = rc_tf_ensure_preint_texture(ctx, c); if (rc) return rc; }
             d.preint = k.preint; d.pres = k.pres; d.preint_tex = k.preint_tex;
         } else {
             if (!k.tf2d) { ctx->set_error("render: no 2D transfer function for channel/volume"); return B200RC_ERR_NOT_READY; }
@@ -381,7 +397,7 @@ int rc_march_launch(b200rc_ctx* ctx, const DevParams& p, int sampler, int nch, i
 }
 
 static int run_march(b200rc_ctx* ctx, const b200rc_params* P, DevParams& p, int nch, int dtype) {
-    if (P->collect_stats) RC_CHECK(cudaMemsetAsync(ctx->d_stats, 0, 16 * sizeof(unsigned long long), ctx->stream));
+    if (P->collect_stats) RC_CHECK(cudaMemsetAsync(ctx->d_stats, 0, 24 * sizeof(unsigned long long), ctx->stream));
     RC_CHECK(cudaEventRecord(ctx->ev[2], ctx->stream));
     int rc = rc_march_launch(ctx, p, P->sampler, nch, dtype);
     if (rc) return rc;
@@ -407,11 +423,11 @@ static int finish_frame(b200rc_ctx* ctx, const b200rc_params* P, bool had_eep) {
         ctx->stats.samples_nominal = h[3]; ctx->stats.samples_skipped = h[4]; ctx->stats.cells_touched = h[5];
         if (getenv("B200RC_DEBUG")) {
             fprintf(stderr, "[b200rc] slab ray-rounds with work %llu of %llu\n", h[6], h[7]);
-            unsigned long long ph[8];
+            unsigned long long ph[10];
             RC_CHECK(cudaMemcpy(ph, ctx->d_stats + 8, sizeof ph, cudaMemcpyDeviceToHost));
-            if (ph[7])      // only a -DSLAB_PROFILE build fills these: clock cycles of warp 0 of every CTA, summed
-                fprintf(stderr, "[b200rc] slab phases (cycles of thread 0, summed over CTAs): skip+zmin %llu wait1 %llu bbox %llu wait2 %llu leader+wait3 %llu stage %llu march %llu rounds %llu\n",
-                        ph[0], ph[1], ph[2], ph[3], ph[4], ph[5], ph[6], ph[7]);
+            if (ph[7])      // only a -DSLAB_PROFILE build fills these: clock cycles of lane 0 of every warp, summed
+                fprintf(stderr, "[b200rc] slab phases (cycles of lane 0 of every warp, summed): skip+zmin %llu wait1 %llu bbox %llu wait2 %llu leader+wait3 %llu stage %llu march %llu warp-rounds %llu | march-loop iterations %llu active lanes %.2f\n",
+                        ph[0], ph[1], ph[2], ph[3], ph[4], ph[5], ph[6], ph[7], ph[8], ph[8] ? (double)ph[9] / (double)ph[8] : 0.0);
         }
     }
     return B200RC_OK;
@@ -534,8 +550,12 @@ static int render_camera_impl(b200rc_ctx* ctx, const b200rc_params* P, const b20
     }
     p.out_depth = out_depth ? (device_out ? out_depth : ctx->d_out_depth) : nullptr;
     // sort-last partial MIP / MOP image: out_color[1] (unconnected) receives the merge key plane, one float per pixel
-    if (P->partial_image && device_out && !p.connected[1] && out_color && out_color[1] && (p.comp[0] == B200RC_COMP_MIP || p.comp[0] == B200RC_COMP_MOP))
+    if (P->partial_image && (p.connected[1] || p.connected[2])) { ctx->set_error("render_camera: a sort-last partial image renders image.output only (outputs 1 and 2 must be unconnected)"); return B200RC_ERR_INVALID; }
+    if (P->partial_image && device_out && out_color && out_color[1] && (p.comp[0] == B200RC_COMP_MIP || p.comp[0] == B200RC_COMP_MOP)) {
+        // multi-channel MIP composites per channel and adds the results (rc_singlevolume.frag:272-309): one key cannot merge that
+        if (nch != 1) { ctx->set_error("render_camera: the mip / mop merge key needs a single-channel volume"); return B200RC_ERR_INVALID; }
         p.out_key = (float*)out_color[1];
+    }
     rc = run_march(ctx, P, p, nch, dtype);
     if (rc) return rc;
     if (!device_out) {
@@ -597,10 +617,10 @@ extern "C" int b200rc_composite_keyed(b200rc_ctx* ctx, const float* front_rgba, 
     return rc_composite_keyed_launch(ctx, front_rgba, front_key, front_depth, back_rgba, back_key, back_depth, dst_rgba, dst_key, dst_depth, n);
 }
 
-extern "C" int b200rc_finalize(b200rc_ctx* ctx, const float* rgba_dev, const float* depth_dev, size_t n, int out_format, void* out_color_dev) {
+extern "C" int b200rc_finalize(b200rc_ctx* ctx, const float* rgba_dev, const float* depth_dev, size_t n, int out_format, int ert_snap, void* out_color_dev) {
     CTX_GUARD();
     if (!rgba_dev || !out_color_dev) { ctx->set_error("finalize: null image"); return B200RC_ERR_INVALID; }
-    return rc_finalize_launch(ctx, rgba_dev, depth_dev, n, out_format, out_color_dev);
+    return rc_finalize_launch(ctx, rgba_dev, depth_dev, n, out_format, ert_snap, out_color_dev);
 }
 
 extern "C" int b200rc_ert_plan(b200rc_ctx* ctx, const float* alphas_dev, int world, uint32_t front_mask, float* color_dev, float* depth_dev, size_t n,

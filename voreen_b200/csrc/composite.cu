@@ -111,10 +111,10 @@ int rc_composite_launch(b200rc_ctx* ctx, int mode, const float* fc, const float*
     return B200RC_OK;
 }
 
-int rc_finalize_launch(b200rc_ctx* ctx, const float* rgba, const float* depth, size_t n, int out_format, void* out) {
+int rc_finalize_launch(b200rc_ctx* ctx, const float* rgba, const float* depth, size_t n, int out_format, int snap, void* out) {
     (void)depth;
     if (!n) return B200RC_OK;
-    finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const float4*)rgba, n, out_format, 1, out);
+    finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const float4*)rgba, n, out_format, snap ? 1 : 0, out);
     ctx->launches++;
     RC_CHECK(cudaGetLastError());
     return B200RC_OK;

@@ -44,7 +44,13 @@ struct ClassifierSlot {
     uchar4* tf2d = nullptr; int tf2d_w = 0, tf2d_h = 0; float domy[2] = {0.f, 1.f};
     // "any alpha > 0" prefix sums along the intensity axis for the three lookup kinds (device, int[R+1])
     int* nz_tf = nullptr; int* nz_pi = nullptr; int* nz_2d = nullptr;
-    unsigned long long generation = 0;
+    unsigned long long generation = 0;  // bumped whenever anything the occupancy grids depend on changed
+    // change detection (a drop-in processor hands its TFs over every frame; nothing is re-uploaded or rebuilt unless it changed)
+    unsigned long long tf_gen = 0;      // bumped when the 1D TF texels / domain changed
+    unsigned long long pi_built_gen = 0; int pi_built_mode = -1; float pi_built_step = 0.f;     // table built from tf_gen with (mode, step)
+    unsigned long long pi_hash = 0; bool pi_uploaded = false;                                   // table uploaded from the host: its content hash
+    std::vector<uint8_t> tf2d_host;
+    int preint_array_res = 0; bool preint_tex_dirty = true; int nz_pi_res = 0;     // texture view of the table (B200RC_SAMPLER_TEX only), rebuilt lazily
 };
 
 struct b200rc_ctx {
@@ -91,6 +97,7 @@ int rc_tf_set_preint(b200rc_ctx* ctx, int chan, const float* rgba32f, int res);
 int rc_tf_build_preint(b200rc_ctx* ctx, int chan, int res, float step, int mode);
 int rc_tf_set_2d(b200rc_ctx* ctx, int chan, const uint8_t* rgba8, int w, int h, float lox, float hix, float loy, float hiy);
 int rc_tf_update_lut(b200rc_ctx* ctx, int chan, float step);
+int rc_tf_ensure_preint_texture(b200rc_ctx* ctx, int chan);
 // eep.cu
 int rc_eep_launch(b200rc_ctx* ctx, const b200rc_eep_params* eep, const b200rc_camera* cam, const float* boxes, int n_boxes,
                   const float model[16], int W, int H, float4* entry, float* entry_depth, float4* exitp, float* exit_depth);
@@ -106,7 +113,7 @@ int rc_composite_keyed_launch(b200rc_ctx* ctx, const float* fc, const float* fk,
                               float* dc, float* dk, float* dd, size_t n);
 int rc_rescale_launch(b200rc_ctx* ctx, const void* src, const float* sdepth, int sw, int sh, int format, void* dst, float* ddepth, int dw, int dh);
 int rc_composite_launch(b200rc_ctx* ctx, int mode, const float* fc, const float* fd, const float* bc, const float* bd, float* dc, float* dd, size_t n);
-int rc_finalize_launch(b200rc_ctx* ctx, const float* rgba, const float* depth, size_t n, int out_format, void* out);
+int rc_finalize_launch(b200rc_ctx* ctx, const float* rgba, const float* depth, size_t n, int out_format, int snap, void* out);
 int rc_ert_plan_launch(b200rc_ctx* ctx, const float* alphas, int world, unsigned front_mask, float* color, float* depth, size_t n,
                        float* prefix, unsigned char* flags, unsigned long long* counter);
 

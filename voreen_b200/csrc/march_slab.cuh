@@ -328,6 +328,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
     unsigned long long dbg_part = 0, dbg_rounds = 0;
 #ifdef SLAB_PROFILE
     long long pf_sched = 0, pf_stage = 0, pf_march = 0, pf_wait = 0, pf_setup = 0, pf_rounds = 0, pf_bbox = 0, pf_wait2 = 0, pf_leader = 0, pf_t = clock64();
+    long long pf_iters = 0, pf_lanes = 0;
 #define PF_MARK(acc) { const long long now_ = clock64(); acc += now_ - pf_t; pf_t = now_; }
 #else
 #define PF_MARK(acc)
@@ -526,6 +527,9 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
                 bool run = part;
                 if (p.collect_stats) { dbg_part += part ? 1u : 0u; dbg_rounds += 1u; }
                 while (__any_sync(0xffffffffu, run)) {
+#ifdef SLAB_PROFILE
+                    pf_iters++; pf_lanes += __popc(__ballot_sync(0xffffffffu, run));
+#endif
                     if (run) {
                         const float3 sp = f3(xadd(first.x, xmul(t, dir.x)), xadd(first.y, xmul(t, dir.y)), xadd(first.z, xmul(t, dir.z)));
                         const float sux = xsub(xmul(sp.x, V.dimf[0]), 0.5f), suy = xsub(xmul(sp.y, V.dimf[1]), 0.5f), suz = xsub(xmul(sp.z, V.dimf[2]), 0.5f);
@@ -680,10 +684,12 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
         }
     }
 #ifdef SLAB_PROFILE
-    if (p.collect_stats && p.stats && threadIdx.x == 0) {
+    // phase clocks of lane 0 of EVERY warp (summed): the barrier waits are what the warps that arrive early spend
+    if (p.collect_stats && p.stats && lane == 0) {
         atomicAdd(p.stats + 8, (unsigned long long)pf_sched); atomicAdd(p.stats + 9, (unsigned long long)pf_wait); atomicAdd(p.stats + 10, (unsigned long long)pf_bbox);
         atomicAdd(p.stats + 11, (unsigned long long)pf_wait2); atomicAdd(p.stats + 12, (unsigned long long)pf_leader); atomicAdd(p.stats + 13, (unsigned long long)pf_stage);
         atomicAdd(p.stats + 14, (unsigned long long)(pf_march + 0 * pf_setup)); atomicAdd(p.stats + 15, (unsigned long long)pf_rounds);
+        atomicAdd(p.stats + 16, (unsigned long long)pf_iters); atomicAdd(p.stats + 17, (unsigned long long)pf_lanes);
     }
 #endif
     if (p.collect_stats && p.stats) {

@@ -133,8 +133,12 @@ static int upload_prefix(b200rc_ctx* ctx, int** dst, const std::vector<int>& fla
 int rc_tf_set_1d(b200rc_ctx* ctx, int chan, const uint8_t* rgba8, int width, float lo, float hi) {
     if (chan < 0 || chan >= B200RC_MAX_CHANNELS || !rgba8 || width < 1 || width > 65536) { ctx->set_error("bad 1D transfer function"); return B200RC_ERR_INVALID; }
     ClassifierSlot& k = ctx->cls[chan];
+    // unchanged texels + domain: nothing to do (the occupancy grids, the opacity LUT and a table built from this TF stay valid)
+    if (k.tf && k.tf_width == width && k.dom[0] == lo && k.dom[1] == hi && k.tf_host.size() == (size_t)width * 4 &&
+        memcmp(k.tf_host.data(), rgba8, (size_t)width * 4) == 0) return B200RC_OK;
     if (k.tf_width != width) { cudaFree(k.tf); k.tf = nullptr; RC_CHECK(cudaMalloc(&k.tf, (size_t)width * 4)); }
     k.tf_width = width; k.dom[0] = lo; k.dom[1] = hi;
+    k.tf_gen++;
     k.tf_host.assign(rgba8, rgba8 + (size_t)width * 4);
     RC_CHECK(cudaMemcpyAsync(k.tf, k.tf_host.data(), (size_t)width * 4, cudaMemcpyHostToDevice, ctx->stream));
     std::vector<int> flags(width);
@@ -158,41 +162,71 @@ int rc_tf_update_lut(b200rc_ctx* ctx, int chan, float step) {
     return B200RC_OK;
 }
 
+// texture view of the table for B200RC_SAMPLER_TEX (hardware bilinear, clamp to edge, normalised coordinates): created on first
+// use, the array is kept while the resolution stays the same
+int rc_tf_ensure_preint_texture(b200rc_ctx* ctx, int chan) {
+    ClassifierSlot& k = ctx->cls[chan];
+    if (!k.preint) return B200RC_OK;
+    const int res = k.pres;
+    if (k.preint_tex && !k.preint_tex_dirty && k.preint_array_res == res) return B200RC_OK;
+    if (!k.preint_array || k.preint_array_res != res) {
+        if (k.preint_tex) { cudaDestroyTextureObject(k.preint_tex); k.preint_tex = 0; }
+        if (k.preint_array) { cudaFreeArray(k.preint_array); k.preint_array = nullptr; }
+        cudaChannelFormatDesc fd = cudaCreateChannelDesc<float4>();
+        RC_CHECK(cudaMallocArray(&k.preint_array, &fd, res, res));
+        k.preint_array_res = res;
+    }
+    RC_CHECK(cudaMemcpy2DToArrayAsync(k.preint_array, 0, 0, k.preint, (size_t)res * sizeof(float4), (size_t)res * sizeof(float4), res, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (!k.preint_tex) {
+        cudaResourceDesc rd; memset(&rd, 0, sizeof rd);
+        rd.resType = cudaResourceTypeArray; rd.res.array.array = k.preint_array;
+        cudaTextureDesc td; memset(&td, 0, sizeof td);
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModeLinear; td.readMode = cudaReadModeElementType; td.normalizedCoords = 1;
+        RC_CHECK(cudaCreateTextureObject(&k.preint_tex, &rd, &td, nullptr));
+    }
+    k.preint_tex_dirty = false;
+    return B200RC_OK;
+}
+
 static int preint_finish(b200rc_ctx* ctx, ClassifierSlot& k) {
     const int res = k.pres;
-    // texture view for the TEX sampler (hardware bilinear, clamp to edge, normalised coordinates)
-    if (k.preint_tex) { cudaDestroyTextureObject(k.preint_tex); k.preint_tex = 0; }
-    if (k.preint_array) { cudaFreeArray(k.preint_array); k.preint_array = nullptr; }
-    cudaChannelFormatDesc fd = cudaCreateChannelDesc<float4>();
-    RC_CHECK(cudaMallocArray(&k.preint_array, &fd, res, res));
-    RC_CHECK(cudaMemcpy2DToArrayAsync(k.preint_array, 0, 0, k.preint, (size_t)res * sizeof(float4), (size_t)res * sizeof(float4), res, cudaMemcpyDeviceToDevice, ctx->stream));
-    cudaResourceDesc rd; memset(&rd, 0, sizeof rd);
-    rd.resType = cudaResourceTypeArray; rd.res.array.array = k.preint_array;
-    cudaTextureDesc td; memset(&td, 0, sizeof td);
-    td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
-    td.filterMode = cudaFilterModeLinear; td.readMode = cudaReadModeElementType; td.normalizedCoords = 1;
-    RC_CHECK(cudaCreateTextureObject(&k.preint_tex, &rd, &td, nullptr));
-    // occupancy helper
-    int* d_flags = nullptr;
-    RC_CHECK(cudaMalloc(&d_flags, res * sizeof(int)));
-    cudaFree(k.nz_pi); k.nz_pi = nullptr;
-    RC_CHECK(cudaMalloc(&k.nz_pi, (res + 1) * sizeof(int)));
+    k.preint_tex_dirty = true;
+    // occupancy helper: "any alpha > 0" prefix sums over the table's diagonal band (scratch flags live behind the sums)
+    if (!k.nz_pi || k.nz_pi_res != res) {
+        cudaFree(k.nz_pi); k.nz_pi = nullptr;
+        RC_CHECK(cudaMalloc(&k.nz_pi, (2 * (size_t)res + 1) * sizeof(int)));
+        k.nz_pi_res = res;
+    }
+    int* d_flags = k.nz_pi + res + 1;
     preint_nz_kernel<<<(res + 127) / 128, 128, 0, ctx->stream>>>(k.preint, res, d_flags);
     exclusive_scan_small_kernel<<<1, 1, 0, ctx->stream>>>(d_flags, res, k.nz_pi);
     ctx->launches += 2;
     RC_CHECK(cudaGetLastError());
-    RC_CHECK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_flags);
     k.generation++;
     return B200RC_OK;
+}
+
+static unsigned long long hash_words(const void* data, size_t bytes) {      // 4 interleaved FNV-1a lanes over 64-bit words
+    const unsigned long long* w = (const unsigned long long*)data;
+    const size_t n = bytes / 8;
+    unsigned long long h[4] = {0xcbf29ce484222325ull, 0x84222325cbf29ce4ull, 0x9ce484222325cbf2ull, 0x2325cbf29ce48422ull};
+    size_t i = 0;
+    for (; i + 4 <= n; i += 4) for (int l = 0; l < 4; ++l) h[l] = (h[l] ^ w[i + l]) * 0x100000001b3ull;
+    for (; i < n; ++i) h[0] = (h[0] ^ w[i]) * 0x100000001b3ull;
+    return h[0] ^ (h[1] * 3) ^ (h[2] * 5) ^ (h[3] * 7) ^ (unsigned long long)bytes;
 }
 
 int rc_tf_set_preint(b200rc_ctx* ctx, int chan, const float* rgba32f, int res) {
     if (chan < 0 || chan >= B200RC_MAX_CHANNELS || !rgba32f || res < 2 || res > 4096) { ctx->set_error("bad pre-integration table"); return B200RC_ERR_INVALID; }
     ClassifierSlot& k = ctx->cls[chan];
+    const unsigned long long h = hash_words(rgba32f, (size_t)res * res * sizeof(float4));
+    if (k.preint && k.pres == res && k.pi_uploaded && k.pi_hash == h) return B200RC_OK;      // the table already resident
     if (k.pres != res) { cudaFree(k.preint); k.preint = nullptr; RC_CHECK(cudaMalloc(&k.preint, (size_t)res * res * sizeof(float4))); }
     k.pres = res;
     RC_CHECK(cudaMemcpyAsync(k.preint, rgba32f, (size_t)res * res * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    RC_CHECK(cudaStreamSynchronize(ctx->stream));       // the caller's buffer may be pageable / reused
+    k.pi_uploaded = true; k.pi_hash = h; k.pi_built_mode = -1;
     return preint_finish(ctx, k);
 }
 
@@ -204,18 +238,19 @@ int rc_tf_build_preint(b200rc_ctx* ctx, int chan, int res, float step, int mode)
     if (step <= 0.f) step = 1.f;
     if (res > 4096) { ctx->set_error("pre-integration resolution too large"); return B200RC_ERR_INVALID; }
     if (mode != B200RC_PI_GPU && k.tf_width != res) { ctx->set_error("PI_CPU/PI_APPROX need a TF texture of exactly `res` texels"); return B200RC_ERR_INVALID; }
+    if (k.preint && k.pres == res && !k.pi_uploaded && k.pi_built_mode == mode && k.pi_built_step == step && k.pi_built_gen == k.tf_gen) return B200RC_OK;
+    k.pi_uploaded = false; k.pi_built_mode = mode; k.pi_built_step = step; k.pi_built_gen = k.tf_gen;
     if (k.pres != res) { cudaFree(k.preint); k.preint = nullptr; RC_CHECK(cudaMalloc(&k.preint, (size_t)res * res * sizeof(float4))); }
     k.pres = res;
     dim3 block(16, 16), grid((res + 15) / 16, (res + 15) / 16);
     if (mode == B200RC_PI_APPROX) {
         float4* integ = nullptr;
-        RC_CHECK(cudaMalloc(&integ, res * sizeof(float4)));
+        RC_CHECK(cudaMallocAsync(&integ, res * sizeof(float4), ctx->stream));
         preint_integral_kernel<<<1, 32, 0, ctx->stream>>>(k.tf, res, integ);
         preint_approx_kernel<<<grid, block, 0, ctx->stream>>>(k.tf, integ, res, step, k.preint);
         ctx->launches += 2;
         RC_CHECK(cudaGetLastError());
-        RC_CHECK(cudaStreamSynchronize(ctx->stream));
-        cudaFree(integ);
+        RC_CHECK(cudaFreeAsync(integ, ctx->stream));
     } else {
         preint_build_kernel<<<grid, block, 0, ctx->stream>>>(k.tf, k.tf_width, res, step, mode, k.preint);
         ctx->launches++;
@@ -227,6 +262,9 @@ int rc_tf_build_preint(b200rc_ctx* ctx, int chan, int res, float step, int mode)
 int rc_tf_set_2d(b200rc_ctx* ctx, int chan, const uint8_t* rgba8, int w, int h, float lox, float hix, float loy, float hiy) {
     if (chan < 0 || chan >= B200RC_MAX_CHANNELS || !rgba8 || w < 1 || h < 1) { ctx->set_error("bad 2D transfer function"); return B200RC_ERR_INVALID; }
     ClassifierSlot& k = ctx->cls[chan];
+    if (k.tf2d && k.tf2d_w == w && k.tf2d_h == h && k.dom[0] == lox && k.dom[1] == hix && k.domy[0] == loy && k.domy[1] == hiy &&
+        k.tf2d_host.size() == (size_t)w * h * 4 && memcmp(k.tf2d_host.data(), rgba8, (size_t)w * h * 4) == 0) return B200RC_OK;
+    k.tf2d_host.assign(rgba8, rgba8 + (size_t)w * h * 4);
     cudaFree(k.tf2d); k.tf2d = nullptr;
     RC_CHECK(cudaMalloc(&k.tf2d, (size_t)w * h * 4));
     RC_CHECK(cudaMemcpyAsync(k.tf2d, rgba8, (size_t)w * h * 4, cudaMemcpyHostToDevice, ctx->stream));

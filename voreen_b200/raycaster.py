@@ -318,8 +318,9 @@ class Context:
     def composite_keyed(self, fc, fk, fd, bc, bk, bd, dc, dk, dd, n):
         self._check(self.lib.b200rc_composite_keyed(self.h, fc, fk, fd, bc, bk, bd, dc, dk, dd, n), "composite_keyed")
 
-    def finalize(self, rgba, depth, n, out_format, out):
-        self._check(self.lib.b200rc_finalize(self.h, rgba, depth, n, out_format, out), "finalize")
+    def finalize(self, rgba, depth, n, out_format, out, snap=True):
+        """snap: early ray termination was active for this output (alpha >= 0.95 -> 1.0); False for mip / mop / mida."""
+        self._check(self.lib.b200rc_finalize(self.h, rgba, depth, n, out_format, 1 if snap else 0, out), "finalize")
 
     def ert_plan(self, alphas, world, front_mask, color, depth, n, prefix, flags, count=False):
         c = C.c_uint64(0)

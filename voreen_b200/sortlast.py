@@ -67,6 +67,8 @@ def shard_range(dims, rank, world):
             lo.append(0); hi.append(dims[a])
         else:
             mid = (dims[a] // 2 + 7) // 8 * 8
+            if mid >= dims[a]:      # the upper half would be empty (and an all-zero shard range means "unsharded" to the library)
+                raise ValueError(f"axis {a} with {dims[a]} voxels is too small to split at a multiple of 8 voxels")
             lo.append(0 if c[a] == 0 else mid); hi.append(mid if c[a] == 0 else dims[a])
     return tuple(lo), tuple(hi)
 
@@ -320,8 +322,15 @@ class SortLast:
         else:
             raise abi.B200RCError("sort-last rendering supports dvr, iso, fhp, fhn (and mip, mop over peer memory); use the image partition (SortFirst) otherwise")
         keyed = comp in (abi.COMP["mip"], abi.COMP["mop"])
-        saved = (p.partial_image, p.out_format)
+        if keyed and self.desc.channels > 1:
+            # multi-channel MIP composites every channel on its own and adds the results (rc_singlevolume.frag:272-309): one key per
+            # pixel cannot pick the summed colour shard by shard
+            raise abi.B200RCError("sort-last mip / mop needs a single-channel volume; use the image partition (SortFirst) otherwise")
+        # only image.output is rendered: the partial image buffers hold one colour plane (+ the key plane in the slot of output 1)
+        saved = (p.partial_image, p.out_format, tuple(p.output_connected))
         p.partial_image, p.out_format = 1, abi.OUT_RGBA32F
+        p.output_connected[0], p.output_connected[1], p.output_connected[2] = 1, 0, 0
+        snap = comp not in (abi.COMP["mip"], abi.COMP["mop"], abi.COMP["mida"])     # USE_EARLY_TERMINATION (volumeraycaster.cpp:225-233)
         prof = self.profile
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if prof else None
         with torch.cuda.stream(self.stream):
@@ -350,7 +359,9 @@ class SortLast:
                     self.phases["remarch_ms"] = self.last_remarch_ms
             if prof:
                 ev[3].record(self.stream)
-            p.partial_image, p.out_format = saved
+            p.partial_image, p.out_format = saved[0], saved[1]
+            for o in range(3):
+                p.output_connected[o] = saved[2][o]
             flat16 = out_rgba16.view(-1, 4)
             flatd = out_depth.view(-1)
             if self.peer is not None:
@@ -362,7 +373,7 @@ class SortLast:
                 n = hi - lo
                 # finalise my 1/P (alpha snap + RGBA16) with the stores going to rank 0's image in peer memory
                 o16, od = self.npix * 20, self.npix * 28
-                self.ctx.finalize(self.color[lo:hi].data_ptr(), self.depth[lo:hi].data_ptr(), n, abi.OUT_RGBA16, self.peer.ptr(0, o16 + lo * 8))
+                self.ctx.finalize(self.color[lo:hi].data_ptr(), self.depth[lo:hi].data_ptr(), n, abi.OUT_RGBA16, self.peer.ptr(0, o16 + lo * 8), snap=snap)
                 self.peer.view(0, od, (self.npix,), torch.float32)[lo:hi].copy_(self.depth[lo:hi])
                 self.peer.barrier()         # every 1/P has landed; every read of this frame's partial images is done
                 if self.rank == 0:
@@ -374,7 +385,7 @@ class SortLast:
                 # finalise my 1/P of the image (alpha snap + RGBA16) and hand it to rank 0
                 n = hi - lo
                 if self.rank == 0:
-                    self.ctx.finalize(self.color[lo:hi].data_ptr(), self.depth[lo:hi].data_ptr(), n, abi.OUT_RGBA16, flat16[lo:hi].data_ptr())
+                    self.ctx.finalize(self.color[lo:hi].data_ptr(), self.depth[lo:hi].data_ptr(), n, abi.OUT_RGBA16, flat16[lo:hi].data_ptr(), snap=snap)
                     flatd[lo:hi].copy_(self.depth[lo:hi])
                     ops = []
                     for r in range(1, self.world):
@@ -385,7 +396,7 @@ class SortLast:
                         w.wait()
                 else:
                     part16 = torch.empty((n, 4), dtype=torch.int16, device=self.device)
-                    self.ctx.finalize(self.color[lo:hi].data_ptr(), self.depth[lo:hi].data_ptr(), n, abi.OUT_RGBA16, part16.data_ptr())
+                    self.ctx.finalize(self.color[lo:hi].data_ptr(), self.depth[lo:hi].data_ptr(), n, abi.OUT_RGBA16, part16.data_ptr(), snap=snap)
                     ops = [dist.P2POp(dist.isend, part16.view(torch.uint8), 0), dist.P2POp(dist.isend, self.depth[lo:hi], 0)]
                     for w in dist.batch_isend_irecv(ops):
                         w.wait()
