@@ -413,3 +413,30 @@ def test_unchanged_transfer_functions_are_not_rebuilt(ctx):
     assert ctx.stats().kernel_launches > launches0
     c, cd = s.cuda_render(ctx, upload=False)
     assert not np.array_equal(np.asarray(a[0]), np.asarray(c[0]))
+
+
+def test_device_preintegration_builders_against_the_reference_computeTable(ctx):
+    """b200rc_build_preint (PI_CPU / PI_APPROX, preint.cu) against tables printed by the REFERENCE'S OWN PreIntegrationTable::computeTable
+    (tests/golden/reference_pins.npz, generated from the reference's sources compiled where they lie)."""
+    import json
+    from voreen_b200 import host
+    z = np.load(os.path.join(HERE, "golden", "reference_pins.npz"))
+    meta = json.loads(bytes(z["meta"]).decode())
+    tfs = {c["name"]: c for c in meta["tf_cases"]}
+    done = 0
+    for pc in meta["pi_cases"]:
+        case = tfs[pc["tf"]]
+        if case["threshold"] != [0.0, 1.0] or case["alpha_mode"] != 1:
+            continue        # computeTable zeroes i >= back_start, the texture x > back_start: only the full threshold makes the TF texels the table's input
+        keys = [(k[0], tuple(k[1])) if k[2] is None else (k[0], tuple(k[1]), tuple(k[2])) for k in case["keys"]]
+        ctx.set_tf1d(0, host.tf1d_texture(keys, pc["res"], gamma=case["gamma"]), tuple(case["domain"]))
+        ctx.build_preint(0, pc["res"], pc["step"], abi.PI_APPROX if pc["integral"] else abi.PI_CPU)
+        got = ctx.download_preint(0, pc["res"])
+        want = z[f"pi_{pc['index']}_table"]
+        err = float(np.abs(got - want).max())
+        print(f"device pre-integration table vs reference computeTable: tf {pc['tf']} res {pc['res']} step {pc['step']:.5f} integral {pc['integral']}: max |d| {err:.2e}")
+        # powf / expf differ in the last bits between libm and the device; the integral variant divides by max(alpha, 0.001)
+        assert err <= (1e-4 if pc["integral"] else 2e-6)
+        assert np.array_equal(got[..., 3] > 0, want[..., 3] > 0), "alpha > 0 pattern (what empty-space skipping and the shaded-sample count depend on)"
+        done += 1
+    assert done >= 5

@@ -218,3 +218,151 @@ def test_host_mirror_tf_texture_equals_the_oracle():
                         assert np.array_equal(got, want), (keys, width, thr, gamma, amode)
                         checked += 1
     assert checked == len(key_sets) * 4 * 3 * 3 * 3
+
+
+# ---- the reference's own C++ (TransFunc1DKeys, TransFunc1D, PreIntegrationTable, VolumeRAM) compiled where it lies ----------------
+# tests/golden/reference_pins.npz holds what oracle/_ref/voreen_probe printed (tests/golden/make_reference_pins.py); the probe itself
+# is re-run live on further random inputs wherever the binary exists (this container, and the GPU box: it is a static binary).
+VOREEN_PROBE = os.path.join(os.path.dirname(orc.PROBE), "voreen_probe")
+
+
+def _pins():
+    z = np.load(os.path.join(GOLDEN, "reference_pins.npz"))
+    import json
+    return z, json.loads(bytes(z["meta"]).decode())
+
+
+def _keys_of(case):
+    return [(k[0], tuple(k[1])) if k[2] is None else (k[0], tuple(k[1]), tuple(k[2])) for k in case["keys"]]
+
+
+def _ulp_diff(a, b):
+    a = np.ascontiguousarray(a, np.float32).view(np.int32).astype(np.int64); b = np.ascontiguousarray(b, np.float32).view(np.int32).astype(np.int64)
+    a = np.where(a < 0, -(a & 0x7fffffff), a); b = np.where(b < 0, -(b & 0x7fffffff), b)
+    return np.abs(a - b)
+
+
+def test_tf_texture_matches_the_reference_transfunc1dkeys():
+    """TransFunc1D::createTextureData + TransFunc1DKeys::getMappingForValueUByte + TransFuncBase::applyAlpha, run from the reference's
+    sources: the oracle's texels AND the product host mirror's texels are the same bytes (split keys, thresholds, gamma, alpha modes)."""
+    z, meta = _pins()
+    for case in meta["tf_cases"]:
+        keys = _keys_of(case)
+        want = z[f"tf_{case['name']}_texture"]
+        tf = orc.make_tf(keys, domain=tuple(case["domain"]), threshold=tuple(case["threshold"]), gamma=case["gamma"], alpha_mode=case["alpha_mode"])
+        got = orc.tf1d_texture(tf, case["width"])
+        assert np.array_equal(got, want), case["name"]
+        got_h = host.tf1d_texture(keys, case["width"], threshold=tuple(case["threshold"]), gamma=case["gamma"], alpha_mode=case["alpha_mode"])
+        assert np.array_equal(got_h, want), ("host mirror", case["name"])
+        # getMappingForValueUByte at arbitrary positions: a texture of the right width samples exactly x = i / (w - 1); check the
+        # recorded mappings that fall on such positions of a 41-texel texture (gamma 1, full threshold)
+        if case["gamma"] == 1.0 and case["threshold"] == [0.0, 1.0] and case["alpha_mode"] == 1:
+            t41 = orc.tf1d_texture(tf, 41)
+            xs, rgba = z[f"tf_{case['name']}_map_x"][:41], z[f"tf_{case['name']}_map_rgba"][:41]
+            assert np.array_equal(xs, np.linspace(0, 1, 41, dtype=np.float32))
+            same = np.float32(np.arange(41, dtype=np.float32) / np.float32(40)) == xs         # i / (w - 1) in float == the linspace value
+            assert same.sum() >= 30 and np.array_equal(t41[same], rgba[same]), case["name"]
+
+
+def test_preintegration_table_matches_the_reference_computeTable():
+    """PreIntegrationTable::computeTable (both modes) and ::classify from the reference's sources vs orc_preint_cpu / orc_preint_classify."""
+    z, meta = _pins()
+    tfs = {c["name"]: c for c in meta["tf_cases"]}
+    worst = 0
+    for pc in meta["pi_cases"]:
+        case = tfs[pc["tf"]]
+        tf = orc.make_tf(_keys_of(case), domain=tuple(case["domain"]), threshold=tuple(case["threshold"]), gamma=case["gamma"], alpha_mode=case["alpha_mode"])
+        want = z[f"pi_{pc['index']}_table"]
+        got = orc.preint_cpu(tf, pc["res"], pc["step"], bool(pc["integral"]))
+        assert np.isfinite(want).all() and np.isfinite(got).all()
+        u = int(_ulp_diff(got, want).max())
+        worst = max(worst, u)
+        assert u <= 1, (pc, u, float(np.abs(got - want).max()))          # same libm, same operation order: bit-identical in practice
+        fs = z[f"pi_{pc['index']}_classify_in"]; out = z[f"pi_{pc['index']}_classify_out"]
+        for (a, b), w in zip(fs, out):
+            c = np.zeros(4, np.float32)
+            orc.lib().orc_preint_classify(orc.fp(np.ascontiguousarray(want)), pc["res"], float(a), float(b), orc.fp(c))
+            assert np.array_equal(c, w)
+    print(f"pre-integration tables vs the reference's computeTable: worst difference {worst} ulp over {len(meta['pi_cases'])} tables")
+
+
+def test_voxel_access_matches_the_reference_volumeram():
+    """VolumeAtomic<T>::getVoxelNormalized is the sampler's texel normalisation (bit-exact); VolumeRAM::getVoxelNormalizedLinear
+    (volumeram.cpp:78-97) is a software trilinear filter in voxel coordinates written as a sum of eight weighted taps -- the GL-spec
+    nested-lerp form the oracle uses differs from it by rounding only."""
+    z, meta = _pins()
+    for vc in meta["vol_cases"]:
+        i = vc["index"]
+        data = z[f"vol_{i}_data"]
+        dims = tuple(vc["dims"])
+        dt = {"uint8": abi.U8, "uint16": abi.U16, "float": abi.F32}[vc["format"]]
+        desc = rc.make_volume_desc(dims, dtype=dt)
+        ov = orc.make_volume(data, desc)
+        d = np.array(dims, np.float32)
+        for (x, y, zc), want in zip(z[f"vol_{i}_voxel_in"], z[f"vol_{i}_voxel_out"]):
+            p = ((np.array([x, y, zc], np.float32) + np.float32(0.5)) / d).astype(np.float32)      # texel centre -> the texel itself
+            out = np.zeros(4, np.float32)
+            orc.lib().orc_sample3d(C_byref(ov), abi.FILTER_NEAREST, abi.CLAMP_TO_EDGE, 0.0, orc.fp(p), orc.fp(out))
+            # VolumeAtomic<uint16_t>::getVoxelNormalized divides by 65535.f; the GL path the oracle restates multiplies by the float
+            # constant 1/65535 (llvmpipe lp_build_unsigned_norm_to_float; GL 4.x 2.3.5 allows either): at most one ulp apart
+            assert int(_ulp_diff(out[:1], np.array([want], np.float32)).max()) <= (0 if vc["format"] == "float" else 1), (vc, x, y, zc)
+        scale = 1.0 if vc["format"] == "float" else 1.0
+        errs = []
+        for pos, want in zip(z[f"vol_{i}_linear_in"], z[f"vol_{i}_linear_out"]):
+            p = ((pos + np.float32(0.5)) / d).astype(np.float32)
+            out = np.zeros(4, np.float32)
+            orc.lib().orc_sample3d(C_byref(ov), abi.FILTER_LINEAR, abi.CLAMP_TO_EDGE, 0.0, orc.fp(p), orc.fp(out))
+            errs.append(abs(float(out[0]) - float(want)))
+        # texture coordinate -> u = p * dim - 0.5 re-derives the voxel position with ~1e-6 relative error; the filter itself is linear
+        assert max(errs) <= 4e-6 * scale, (vc, max(errs))
+
+
+def C_byref(x):
+    import ctypes
+    return ctypes.byref(x)
+
+
+def test_reference_probe_live_random_transfer_functions():
+    """Where the probe binary exists: random key sets (incl. split keys, coinciding keys, thresholds, gamma) straight against the
+    reference's TransFunc1DKeys and PreIntegrationTable."""
+    if not os.path.exists(VOREEN_PROBE):
+        pytest.skip("oracle/_ref/voreen_probe not built (needs /root/reference at build time)")
+    import sys
+    sys.path.insert(0, GOLDEN)
+    import make_reference_pins as mk
+    rng = np.random.default_rng(99)
+    for trial in range(25):
+        n = int(rng.integers(1, 9))
+        xs = np.sort(rng.random(n).astype(np.float32))
+        if n > 2 and trial % 3 == 0:
+            xs[1] = xs[0]                                   # coinciding keys
+        keys = []
+        for x in xs:
+            l = tuple(int(v) for v in rng.integers(0, 256, 4))
+            r = tuple(int(v) for v in rng.integers(0, 256, 4)) if rng.random() < 0.3 else None
+            keys.append((float(x), l, r))
+        w = int(rng.choice([64, 256, 1024]))
+        thr = (float(np.float32(rng.random() * 0.3)), float(np.float32(0.7 + rng.random() * 0.3))) if trial % 2 else (0.0, 1.0)
+        gamma = float(np.float32(rng.choice([1.0, 0.5, 2.2])))
+        am = int(rng.choice([0, 1, 2]))
+        case = (f"r{trial}", w, keys, thr, gamma, am, (0.0, 1.0))
+        res_ = int(rng.choice([32, 64]))
+        step = float(np.float32(rng.choice([0.002, 0.01, 0.25, 1.0])))
+        integral = int(trial % 4 == 3)
+        res = mk.run(mk.tf_lines(case) + ["texture", f"preint {res_} {mk.f32(step)} {integral}"])
+        want_tex = np.array([int(t) for t in res[1].split()], np.uint8).reshape(-1, 4)
+        want_pi = mk.hexf(res[2]).reshape(res_, res_, 4)
+        # TransFunc1DKeys::addKey (transfunc1dkeys.cpp:197-210) inserts a key BEFORE the first key whose intensity is not smaller:
+        # coinciding keys end up in reverse order of insertion; the oracle takes the final key vector
+        ordered = []
+        for k in keys:
+            j = 0
+            while j < len(ordered) and k[0] > ordered[j][0]:
+                j += 1
+            ordered.insert(j, k)
+        okeys = [(k[0], k[1]) if k[2] is None else (k[0], k[1], k[2]) for k in ordered]
+        tf = orc.make_tf(okeys, domain=(0.0, 1.0), threshold=thr, gamma=gamma, alpha_mode=am)
+        assert np.array_equal(orc.tf1d_texture(tf, w), want_tex), case
+        assert np.array_equal(host.tf1d_texture(okeys, w, threshold=thr, gamma=gamma, alpha_mode=am), want_tex), ("host", case)
+        got_pi = orc.preint_cpu(tf, res_, step, bool(integral))
+        assert int(_ulp_diff(got_pi, want_pi).max()) <= 1, (case, res_, step, integral)
