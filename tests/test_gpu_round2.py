@@ -306,7 +306,7 @@ def test_sharded_rendering_with_opaque_border_voxels(ctx, world):
     dims = (48, 40, 56)
     rng = np.random.default_rng(9)
     vol = (rng.random(dims[::-1]) * 20000 + 30000).astype(np.uint16)          # everything visible, border included
-    keys = [(0.0, (255, 140, 60, 3)), (1.00, (255, 255, 255, 5))]
+    keys = [(0.0, (255, 140, 60, 1)), (1.00, (255, 255, 255, 1))]      # alpha 1/255 everywhere: the longest ray stays below the 0.95 ERT threshold
     for eye in [(1.4, 0.9, 2.9), (-2.2, -1.1, -1.9)]:
         s = scenes.Scene(vol, keys=keys, W=96, H=88, eye=eye, out_format=abi.OUT_RGBA32F)
         s.params.collect_stats = 1
@@ -346,7 +346,7 @@ def test_sharded_mip_end_to_end_keeps_unsnapped_alpha(ctx):
     from voreen_b200 import sortlast
     dims, world = (64, 56, 72), 2
     vol = scenes.ct_like_volume(0, dims=dims)
-    keys = [(0.0, (0, 0, 0, 0)), (0.25, (0, 0, 0, 0)), (0.30, (255, 140, 60, 200)), (1.00, (255, 255, 255, 248))]       # alpha 0.97 at the top
+    keys = [(0.0, (0, 0, 0, 0)), (0.25, (0, 0, 0, 0)), (0.30, (255, 140, 60, 200)), (0.60, (255, 240, 220, 246)), (1.00, (255, 255, 255, 250))]       # alpha 0.965 .. 0.98 above 0.6
     s = scenes.Scene(vol, keys=keys, W=96, H=88, eye=(1.4, 0.9, 2.9), out_format=abi.OUT_RGBA32F, compositing=[abi.COMP["mip"]] * 3)
     ref_outs, ref_depth = s.cuda_render(ctx)
     ref = np.asarray(ref_outs[0]).reshape(-1, 4)
@@ -436,7 +436,7 @@ def test_device_preintegration_builders_against_the_reference_computeTable(ctx):
         err = float(np.abs(got - want).max())
         print(f"device pre-integration table vs reference computeTable: tf {pc['tf']} res {pc['res']} step {pc['step']:.5f} integral {pc['integral']}: max |d| {err:.2e}")
         # powf / expf differ in the last bits between libm and the device; the integral variant divides by max(alpha, 0.001)
-        assert err <= (1e-4 if pc["integral"] else 2e-6)
+        assert err <= (1e-4 if pc["integral"] else 5e-6)
         assert np.array_equal(got[..., 3] > 0, want[..., 3] > 0), "alpha > 0 pattern (what empty-space skipping and the shaded-sample count depend on)"
         done += 1
     assert done >= 5

@@ -104,6 +104,11 @@ __device__ __forceinline__ float3 cross3(float3 a, float3 b) {
 }
 // GLSL normalize: a zero vector gives NaN (0 * rsq(0)); max()/min() below drop NaNs like FMNMX / maxps do.
 __device__ __forceinline__ float3 normalize3(float3 a) { float r = rsqrtf(dot3(a, a)); return f3(a.x * r, a.y * r, a.z * r); }
+// The same with rsqrt.approx.ftz: identical MUFU.RSQ result for normal operands, without the denormal pre-/post-scaling of rsqrtf
+// (a squared length below 1.2e-38 means a vector shorter than 1e-19: the differences of normalised voxel values that feed the
+// gradients are either exactly zero -- NaN normal either way -- or above 1e-12)
+__device__ __forceinline__ float rsqrt_ftz(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float3 normalize3_ftz(float3 a) { float r = rsqrt_ftz(dot3(a, a)); return f3(a.x * r, a.y * r, a.z * r); }
 __device__ __forceinline__ float length3(float3 a) { return sqrtf(dot3(a, a)); }
 __device__ __forceinline__ float3 ld3(const float* p) { return f3(p[0], p[1], p[2]); }
 __device__ __forceinline__ float3 mix3(float3 a, float3 b, float t) { return a * (1.f - t) + b * t; }

@@ -46,6 +46,8 @@ struct SlabShared {
     // j = (l + occ_off) >> 3 for the region-local voxel index l
     int occ_off[3], occ_ny;
     int cm_nx, cm_ok;           // MIP culling: cells per x-row of the staged cell maxima; 0 when the region has more cells than the table
+    float dom_rcp;              // refined reciprocal of the TF domain span (rw_to_tex_rcp), 0 = generic division
+    float step_rcp;             // ~1 / sampling step (first guess of the lattice index behind an empty cell; fixed up exactly)
     unsigned int occ[SLAB_OCC_WORDS];
 };
 
@@ -197,6 +199,46 @@ __device__ __forceinline__ bool slab_skip_empty(const DevParams& p, const VolDev
     return true;
 }
 
+// The same jump for a sample the STAGED occupancy bits already classified as lying in an empty level-0 cell (march loop): no grid
+// lookups, reciprocals instead of divisions.  (su*, f*) = the sample's continuous voxel coordinate u = p * dim - 0.5 and its floor.
+// The exit parameter is rounded DOWN (1e-6 relative + directed rounding), so it never lies behind the exit the divisions would
+// give: the jump may stop one lattice sample early -- that sample is still inside the empty cell, is tested against the staged bit
+// again and skipped by the next call -- but never late.  Pixels and the classified / skipped counters are unchanged.
+__device__ __forceinline__ void slab_skip_cell(const DevParams& p, const VolDev& V, float3 dir, float sux, float suy, float suz, float fx, float fy, float fz,
+                                               float tEnd, float step, float step_rcp, float& t, float& t_last, int& loop, bool& finished, RayStats& st) {
+    float dt = 3.0e38f;
+    {
+        const float su[3] = {sux, suy, suz}, ff[3] = {fx, fy, fz}, dd[3] = {dir.x, dir.y, dir.z};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const int ir = min(max((int)ff[a], 0), V.dims[a] - 1) - V.res_lo[a];       // resident voxel index, as ess_empty_cell_t
+            const int c = ir >> 3;
+            const float ur = su[a] - (float)V.res_lo[a];
+            const float v = dd[a] * V.dimf[a];
+            float r;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+            if (v > 0.f) { if (((c + 1) << 3) < V.res_dims[a]) dt = fminf(dt, ((float)((c + 1) << 3) - ur) * r); }
+            else if (v < 0.f) { if (c > 0) dt = fminf(dt, ((float)(c << 3) - ur) * r); }
+        }
+    }
+    const float t_exit = __fadd_rd(t, __fmul_rd(fmaxf(dt, 0.f), 0.999999f));
+    if (t_exit > tEnd) { st.skipped += (unsigned)floorf((tEnd - t) / step) + 1u; finished = true; return; }
+    int n = 1; float tn;
+    if (p.lattice_exact) {
+        int k1 = max(loop + 1, __float2int_ru(t_exit * step_rcp));
+        while ((float)k1 * step < t_exit) ++k1;
+        while (k1 - 1 > loop && (float)(k1 - 1) * step >= t_exit) --k1;
+        n = k1 - loop; tn = (float)k1 * step;
+        t_last = (float)(k1 - 1) * step;
+    } else {
+        t_last = t;
+        tn = xadd(t, step);
+        while (tn < t_exit && tn <= tEnd) { t_last = tn; tn = xadd(tn, step); ++n; }
+    }
+    st.skipped += n; loop += n; t = tn;
+    finished = (t > tEnd) || loop >= 256 * 256;
+}
+
 // ---- tile scheduling: longest-processing-time first ---------------------------------------------------------------------
 // The persistent CTAs pull 16x16 tiles from a counter.  A tile whose rays cross the whole volume costs ~1 ms; handed out
 // last it leaves the other CTAs idle for that long (the tail grows relative to the frame when the image is split across
@@ -313,7 +355,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
             for (int i = threadIdx.x; i < 256; i += blockDim.x) l[i] = cd.corr_lut[i];
             sm.tf[0] = dst; sm.lut[0] = l;
         }
-        if (threadIdx.x == 0) { sh.zmin = INT_MAX; sh.leader = INT_MAX; for (int a = 0; a < 3; ++a) { sh.lo[a] = INT_MAX; sh.hi[a] = INT_MIN; } }
+        if (threadIdx.x == 0) { sh.zmin = INT_MAX; sh.leader = INT_MAX; for (int a = 0; a < 3; ++a) { sh.lo[a] = INT_MAX; sh.hi[a] = INT_MIN; } sh.dom_rcp = domain_rcp(cd.dom_lo, cd.dom_hi); sh.step_rcp = 1.0f / p.step; }
         __syncthreads();
     }
     const VolDev& V = p.vol[0];
@@ -555,14 +597,10 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
                                 // pre-integration that also needs the PREVIOUS sample to lie in an empty cell: the value
                                 // ranges of the two (adjacent, overlapping) cells then form one interval on which the
                                 // transfer function is transparent, so the table entry (cur, prev) is transparent too.
-                                if (!slab_skip_empty<CULL>(p, V, first, dir, tStop, step, t, t_last, loop, finished, st, maxI)) {
-                                    // (cannot happen: the staged bit and the global grid agree) -- take the sample instead
-                                    empty = false;
-                                } else {
-                                    if (pi_mode) lastI_stale = true;
-                                    stale = true;
-                                    run = !finished;
-                                }
+                                slab_skip_cell(p, V, dir, sux, suy, suz, fx, fy, fz, tStop, step, sh.step_rcp, t, t_last, loop, finished, st);
+                                if (pi_mode) lastI_stale = true;
+                                stale = true;
+                                run = !finished;
                             }
                             if (!(empty && (!pi_mode || prev_empty))) {
                                 stale = true;
@@ -579,7 +617,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
                                     const float* c = S + (jz * ny + jy) * pitch + jx;
                                     const float d00 = xlerp(c[0], c[1], bx), d10 = xlerp(c[pitch], c[pitch + 1], bx);
                                     const float d01 = xlerp(c[slice], c[slice + 1], bx), d11 = xlerp(c[slice + pitch], c[slice + pitch + 1], bx);
-                                    lastI = rw_to_tex(p.cls[0].dom_lo, p.cls[0].dom_hi, xadd(xmul(xlerp(xlerp(d00, d10, by), xlerp(d01, d11, by), bz), V.rwm_scale), V.rwm_offset));
+                                    lastI = rw_to_tex_rcp(p.cls[0].dom_lo, p.cls[0].dom_hi, sh.dom_rcp, xadd(xmul(xlerp(xlerp(d00, d10, by), xlerp(d01, d11, by), bz), V.rwm_scale), V.rwm_offset));
                                     lastI_stale = false;
                                 }
                                 // ---- getVoxel: trilinear from the staged taps (GL float weights, identical to lerp_taps) ----
@@ -594,10 +632,16 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
                                 if (pi_mode) {
                                     // applyTFpi: texture(table, vec2(intensity, previous intensity)); the previous sample's texture
                                     // coordinate is carried along instead of being mapped a second time (same value)
-                                    const float s_cur = rw_to_tex(p.cls[0].dom_lo, p.cls[0].dom_hi, intensity);
-                                    color0 = preint_lookup<C>(p.cls[0], s_cur, lastI);
+                                    const float s_cur = rw_to_tex_rcp(p.cls[0].dom_lo, p.cls[0].dom_hi, sh.dom_rcp, intensity);
+                                    color0 = preint_lookup_unit(p.cls[0], s_cur, lastI);
                                     lastI = s_cur;
-                                } else color0 = classify<C>(cmode, p.cls[0], sm.tf[0], f3(0.f, 0.f, 0.f), intensity, lastI, a8);
+                                } else {        // applyTF (mod_transfunc.frag:71-78): sampler1D NEAREST = floor(s * w), clamp to edge
+                                    const float s_cur = rw_to_tex_rcp(p.cls[0].dom_lo, p.cls[0].dom_hi, sh.dom_rcp, intensity);
+                                    const int ti = min(max(__float2int_rd(xmul(s_cur, (float)p.cls[0].tf_width)), 0), p.cls[0].tf_width - 1);
+                                    const uchar4 q = sm.tf[0][ti];
+                                    a8 = q.w;
+                                    color0 = u8tof4(q);
+                                }
                                 if (color0.w > 0.f) st.shaded++;
                                 if (color0.w > 0.f && compositing_takes_sample(comp, result, intensity, color0.w, maxI, p.iso)) {
                                     float3 gradient;
