@@ -98,6 +98,18 @@ enum { B200RC_INSIDE_NONE = 0, B200RC_INSIDE_GPU = 1 };
 enum { B200RC_RAYCASTER_SINGLE = 0, B200RC_RAYCASTER_SIMPLE = 1, B200RC_RAYCASTER_RGB = 2 };
 enum { B200RC_PROXY_BBOX = 0, B200RC_PROXY_MINBBOX = 1, B200RC_PROXY_VISIBLE_BRICKS = 2 };
 
+/* voreen::Compositor "blendMode" options, in the order of V/modules/base/processors/image/compositor.cpp:47-60 */
+enum {
+    B200RC_COMPOSITOR_DEPTH_TEST = 0, B200RC_COMPOSITOR_ALPHA_COMPOSITING = 1, B200RC_COMPOSITOR_ALPHA_BLENDING = 2,
+    B200RC_COMPOSITOR_ALPHA_BLENDING_B_OVER_A = 3, B200RC_COMPOSITOR_WEIGHTED_AVERAGE = 4, B200RC_COMPOSITOR_TAKE_FIRST = 5,
+    B200RC_COMPOSITOR_TAKE_SECOND = 6, B200RC_COMPOSITOR_TAKE_SECOND_IF_READY = 7, B200RC_COMPOSITOR_FIRST_HAS_PRIORITY = 8,
+    B200RC_COMPOSITOR_SECOND_HAS_PRIORITY = 9, B200RC_COMPOSITOR_MAXIMUM_ALPHA = 10, B200RC_COMPOSITOR_DIFFERENCE = 11,
+    B200RC_COMPOSITOR_DIFFERENCE_ALPHA_MUL = 12, B200RC_COMPOSITOR_ADD = 13
+};
+/* voreen::Background "backgroundModeAsString" / "blendMode" (V/modules/base/processors/image/background.cpp:107-131) */
+enum { B200RC_BACKGROUND_MONOCHROME = 0, B200RC_BACKGROUND_GRADIENT = 1 };
+enum { B200RC_BACKGROUND_BLEND_ALPHA = 0, B200RC_BACKGROUND_BLEND_ADD = 1 };
+
 /* ---- PODs ------------------------------------------------------------------------------------ */
 
 /* What VolumeBase exposes to GLSL::setUniform (V/src/core/utils/glsl.cpp:38-83). */
@@ -208,6 +220,17 @@ typedef struct b200rc_eep_params {
     int32_t n_boxes;
 } b200rc_eep_params;
 
+/* voreen::Background properties (background.cpp:96-131): color1 / color2 / angle / backgroundModeAsString / blendMode.  The
+ * "radial", "texture" and "cloud" modes draw a texture loaded or generated on the host; hand such a background over as the first
+ * input of b200rc_image_compositor (mode ALPHA_BLENDING_B_OVER_A is the same blend as Background's alpha mode on straight alpha). */
+typedef struct b200rc_background_params {
+    int32_t mode;               /* B200RC_BACKGROUND_* */
+    int32_t blend_mode;         /* B200RC_BACKGROUND_BLEND_* */
+    float   color1[4];          /* "color1", default (1, 1, 1, 1) */
+    float   color2[4];          /* "color2", default (0.392, 0.392, 0.392, 1) */
+    int32_t angle_deg;          /* "angle", 0..359, default 60 */
+} b200rc_background_params;
+
 typedef struct b200rc_stats {
     double   last_render_ms;        /* device time of the last render call's kernels (CUDA events) */
     double   last_march_ms;         /* ... of the ray-marching kernel alone */
@@ -305,7 +328,12 @@ int b200rc_render(b200rc_ctx* ctx, const b200rc_params* params, const b200rc_cam
                   const float* entry_rgba, const float* entry_depth, const float* exit_rgba, const float* exit_depth,
                   void* out_color[B200RC_MAX_OUTPUTS], float* out_depth);
 
-/* Entry/exit generated on the device, then marched; nothing but parameters crosses PCIe on the way in. */
+/* Entry/exit generated on the device, then marched; nothing but parameters crosses PCIe on the way in.
+ * With params->multi_volume: all volumes must have identical geometry (dims, spacing, offset, transformation, shard range) -- the
+ * co-registered channels of config C4 -- and share one world-space entry/exit pair over their common proxy cube; volumes placed
+ * differently take per-volume entry/exit buffers through b200rc_render (MultiVolumeProxyGeometry, multivolumeraycaster.cpp:225-417).
+ * Sharded volumes (sort-last): a lattice sample -- with every volume's contribution at it, in the shader's order -- belongs to the
+ * rank that owns its tap base index, so the shards partition the single-GPU sample set for multi-volume rendering as well. */
 int b200rc_render_camera(b200rc_ctx* ctx, const b200rc_params* params, const b200rc_eep_params* eep,
                          const b200rc_camera* cam, int width, int height,
                          void* out_color[B200RC_MAX_OUTPUTS], float* out_depth);
@@ -345,6 +373,21 @@ int b200rc_remarch_device(b200rc_ctx* ctx, const b200rc_params* params, const b2
  * Host buffers unless on_device != 0; src_depth / dst_depth may both be NULL. */
 int b200rc_rescale(b200rc_ctx* ctx, const void* src_color, const float* src_depth, int src_w, int src_h, int format,
                    void* dst_color, float* dst_depth, int dst_w, int dst_h, int on_device);
+
+/* ---- image-space post chain: the two processors that follow the raycaster in the standard workspaces, so that a
+ *      frame can stay on the device up to the canvas.  Per-pixel maps over equal-sized images; `format` = B200RC_OUT_RGBA16 (what
+ *      RenderPorts hold) or B200RC_OUT_RGBA32F for all colour images; depth images are float and may be NULL (= 1.0 / not written).
+ *      Host pointers unless on_device != 0.
+ * voreen::Compositor (V/modules/base/glsl/image/compositor.frag:41-140): image 0 = "image.inport0", image 1 = "image.inport1";
+ * weighting_factor = "weightingFactor" (WEIGHTED_AVERAGE), weight_first / weight_second / add_depth = "weightFirst", "weightSecond",
+ * "addDepth" (ADD). */
+int b200rc_image_compositor(b200rc_ctx* ctx, int mode, float weighting_factor, float weight_first, float weight_second, int add_depth,
+                            const void* color0, const float* depth0, const void* color1, const float* depth1, int format,
+                            void* dst_color, float* dst_depth, int width, int height, int on_device);
+/* voreen::Background (background.cpp:161-230, background.frag:35-57): the generated background under `src` (src_color may be NULL:
+ * the background alone, as when "image.input" is unconnected).  Output depth = min(1, src depth). */
+int b200rc_image_background(b200rc_ctx* ctx, const b200rc_background_params* bg, const void* src_color, const float* src_depth, int format,
+                            void* dst_color, float* dst_depth, int width, int height, int on_device);
 
 /* Max-key merge for sharded MIP / MOP: dst = the image with the larger key (front on ties); colour, key and depth planes move together.
  * A partial MIP / MOP image is rendered with partial_image = 1 and out_color[1] (output 1 unconnected) pointing at a float-per-pixel

@@ -37,6 +37,20 @@ int b200host_camera(const float position[3], const float focus[3], const float u
  *      1dkeys/transfunc1dkeys.cpp:119-154, transfuncbase.cpp:177-210): keys -> RGBA8 texels.  alpha_mode: 0 zero, 1 use, 2 one. */
 int b200host_tf1d_keys_texture(const b200host_tf_key* keys, int n_keys, const float threshold[2], float gamma, int alpha_mode,
                                int width, uint8_t* out_rgba8);
+/* ---- TransFunc1DGaussian::getTexture ("1D Gaussian Color Map", transFuncGaussian1..4): the same texture generation with
+ *      TransFunc1DGaussian::getMappingForValueUByte (V/src/core/datastructures/transfunc/1d/1dgaussian/transfunc1dgaussian.cpp:122-178)
+ *      over TransFuncMappingCurve::getColorAt / getOpacityAt (.../1dgaussian/utils/transfuncmappingcurve.cpp:257-288): every active
+ *      curve contributes exp(-(x - intensity)^2 / (2 width)) between its base and peak colours; colours are mixed weighted by
+ *      opacity and normalised by min(sum of opacities, 1), the alpha is the maximum over the curves; every conversion truncates to
+ *      uint8 as the reference does. */
+typedef struct b200host_tf_curve {
+    float   intensity, width, base_value;   /* peak position [0,1], variance-like width, opacity far from the peak */
+    uint8_t color_l[4], color_r[4];         /* peak colour (+ peak alpha) left / right of the peak */
+    uint8_t base_color_l[4], base_color_r[4];   /* colour far from the peak (alpha ignored) */
+    int32_t active;
+} b200host_tf_curve;
+int b200host_tf1d_gaussian_texture(const b200host_tf_curve* curves, int n_curves, const float threshold[2], float gamma, int alpha_mode,
+                                   int width, uint8_t* out_rgba8);
 /* TransFuncPropertyBase texture width for a volume (transfuncpropertybase.cpp:155-165, transfunc1dkeysproperty.cpp:94-97) */
 int b200host_tf1d_width_for(int dtype, int* out_width);
 

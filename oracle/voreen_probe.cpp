@@ -18,12 +18,17 @@
 //   mapping x                   -> 4 integers:  TransFunc1DKeys::getMappingForValueUByte(x)
 //   preint res step integral    -> res*res*4 hex floats: PreIntegrationTable(tf, res, step, integral, false).getTable()
 //   classify fs fe              -> 4 hex floats: PreIntegrationTable::classify on the last table
+//   gauss W N thr_lo thr_hi gamma alpha_mode                followed by N lines: intensity width base lr lg lb la rr rg rb ra blr blg blb brr brg brb active
+//                               -> 4 W integers: the texture of a TransFunc1DGaussian (transfunc1dgaussian.cpp:122-178,
+//                                  transfuncmappingcurve.cpp:257-288) through TransFunc1D::createTextureData + applyAlpha
 //   vol fmt dx dy dz            followed by one line of dx*dy*dz values (fmt: uint8 uint16 float)
 //   voxel x y z                 -> hex float: getVoxelNormalized
 //   linear x y z                -> hex float: getVoxelNormalizedLinear (voxel coordinates)
 #include "voreen/core/datastructures/transfunc/1d/1dkeys/transfunc1dkeys.h"
 #include "voreen/core/datastructures/transfunc/1d/1dkeys/utils/transfuncmappingkey.h"
 #include "voreen/core/datastructures/transfunc/1d/preintegrationtable.h"
+#include "voreen/core/datastructures/transfunc/1d/1dgaussian/transfunc1dgaussian.h"
+#include "voreen/core/datastructures/transfunc/1d/1dgaussian/utils/transfuncmappingcurve.h"
 #include "voreen/core/datastructures/rendertarget/rendertarget.h"
 #include "voreen/core/datastructures/volume/volumeatomic.h"
 
@@ -69,6 +74,35 @@ int main() {
             tf->setAlphaMode((TransFuncBase::AlphaMode)alphaMode);
             tf->setDomain(dlo, dhi);
             std::printf("ok %d\n", tf->getNumKeys());
+        } else if (cmd == "gauss") {
+            int W, N, alphaMode; float tlo, thi, gamma;
+            is >> W >> N >> tlo >> thi >> gamma >> alphaMode;
+            TransFunc1DGaussian g(W);
+            g.clearCurves();
+            for (int i = 0; i < N; ++i) {
+                std::getline(std::cin, line);
+                std::istringstream ks(line);
+                float x, w, base; int c[14], active;
+                ks >> x >> w >> base;
+                for (int k = 0; k < 14; ++k) ks >> c[k];
+                ks >> active;
+                TransFuncMappingCurve* cv = new TransFuncMappingCurve(x, w, base, tgt::col4((uint8_t)c[0], (uint8_t)c[1], (uint8_t)c[2], (uint8_t)c[3]));
+                cv->colorL_ = tgt::col4((uint8_t)c[0], (uint8_t)c[1], (uint8_t)c[2], (uint8_t)c[3]);
+                cv->colorR_ = tgt::col4((uint8_t)c[4], (uint8_t)c[5], (uint8_t)c[6], (uint8_t)c[7]);
+                cv->baseColorL_ = tgt::col4((uint8_t)c[8], (uint8_t)c[9], (uint8_t)c[10], 0);
+                cv->baseColorR_ = tgt::col4((uint8_t)c[11], (uint8_t)c[12], (uint8_t)c[13], 0);
+                cv->active_ = active != 0;
+                g.addCurve(cv);
+            }
+            g.setThreshold(tlo, thi);
+            g.setGammaValue(gamma);
+            g.setAlphaMode((TransFuncBase::AlphaMode)alphaMode);
+            GLvoid* data = g.createTextureData();
+            g.applyAlpha(data);
+            const unsigned char* b = reinterpret_cast<const unsigned char*>(data);
+            const int n = g.getDimensions().x * 4;
+            for (int i = 0; i < n; ++i) std::printf("%d%c", (int)b[i], i == n - 1 ? '\n' : ' ');
+            delete[] reinterpret_cast<tgt::Vector4<GLubyte>*>(data);
         } else if (cmd == "texture" && tf) {
             GLvoid* data = tf->createTextureData();
             tf->applyAlpha(data);

@@ -1614,3 +1614,155 @@ void orc_rescale_rgba16(const uint16_t* src, const float* src_depth, int sw, int
             }
         }
 }
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* image-space post chain: Compositor (compositor.frag:41-140) and Background (background.frag:35-57 over the       */
+/* "monochrome" / "gradient" generators of background.cpp:262-300).  Per-pixel; RGBA16 unorm or RGBA32F images.     */
+/* ------------------------------------------------------------------------------------------------------------ */
+static inline void post_fetch(const void* img, int format, size_t i, float c[4]) {
+    if (format == B200RC_OUT_RGBA16) { const uint16_t* q = (const uint16_t*)img + 4 * i; for (int k = 0; k < 4; ++k) c[k] = (float)q[k] / 65535.f; }
+    else memcpy(c, (const float*)img + 4 * i, 4 * sizeof(float));
+}
+static inline uint16_t post_unorm16(float v) { if (!(v > 0.f)) return 0; if (v > 1.f) v = 1.f; return (uint16_t)floorf(v * 65535.f + 0.5f); }
+static inline void post_store(void* img, int format, size_t i, const float c[4]) {
+    if (format == B200RC_OUT_RGBA16) { uint16_t* q = (uint16_t*)img + 4 * i; for (int k = 0; k < 4; ++k) q[k] = post_unorm16(c[k]); }
+    else memcpy((float*)img + 4 * i, c, 4 * sizeof(float));
+}
+
+void orc_image_compositor(int mode, float wf, float w0, float w1, int add_depth, const void* c0p, const float* d0p, const void* c1p, const float* d1p,
+                          int format, void* dc, float* dd, size_t n) {
+    for (size_t i = 0; i < n; ++i) {
+        float a[4], b[4], f[4] = {0.f, 0.f, 0.f, 0.f}, fd = 1.0f;
+        post_fetch(c0p, format, i, a); post_fetch(c1p, format, i, b);
+        const float da = d0p ? d0p[i] : 1.0f, db = d1p ? d1p[i] : 1.0f;
+        switch (mode) {
+        case B200RC_COMPOSITOR_DEPTH_TEST:
+            if (da < db) { memcpy(f, a, sizeof f); fd = da; } else { memcpy(f, b, sizeof f); fd = db; }
+            break;
+        case B200RC_COMPOSITOR_ALPHA_COMPOSITING:
+            if (db <= da) { for (int k = 0; k < 3; ++k) f[k] = b[k] + a[k] * a[3] * (1.0f - b[3]); f[3] = b[3] + a[3] * (1.0f - b[3]); }
+            else { for (int k = 0; k < 3; ++k) f[k] = a[k] + b[k] * b[3] * (1.0f - a[3]); f[3] = a[3] + b[3] * (1.0f - a[3]); }
+            fd = da < db ? da : db;
+            break;
+        case B200RC_COMPOSITOR_ALPHA_BLENDING:
+            for (int k = 0; k < 3; ++k) f[k] = a[3] * a[k] + (1.0f - a[3]) * b[k];
+            f[3] = a[3] + b[3] * (1.0f - a[3]);
+            fd = a[3] > 0.f ? da : db;
+            break;
+        case B200RC_COMPOSITOR_ALPHA_BLENDING_B_OVER_A:
+            for (int k = 0; k < 3; ++k) f[k] = b[3] * b[k] + (1.0f - b[3]) * a[k];
+            f[3] = b[3] + a[3] * (1.0f - b[3]);
+            fd = b[3] > 0.f ? db : da;
+            break;
+        case B200RC_COMPOSITOR_WEIGHTED_AVERAGE:
+            fd = (wf == 0.0f) ? db : (wf == 1.0f ? da : (da < db ? da : db));
+            for (int k = 0; k < 4; ++k) f[k] = wf * a[k] + (1.0f - wf) * b[k];
+            break;
+        case B200RC_COMPOSITOR_TAKE_FIRST: case B200RC_COMPOSITOR_TAKE_SECOND_IF_READY: memcpy(f, a, sizeof f); fd = da; break;
+        case B200RC_COMPOSITOR_TAKE_SECOND: memcpy(f, b, sizeof f); fd = db; break;
+        case B200RC_COMPOSITOR_FIRST_HAS_PRIORITY: if (a[3] > 0.f) { memcpy(f, a, sizeof f); fd = da; } else { memcpy(f, b, sizeof f); fd = db; } break;
+        case B200RC_COMPOSITOR_SECOND_HAS_PRIORITY: if (b[3] > 0.f) { memcpy(f, b, sizeof f); fd = db; } else { memcpy(f, a, sizeof f); fd = da; } break;
+        case B200RC_COMPOSITOR_MAXIMUM_ALPHA:
+            fd = da < db ? da : db;
+            for (int k = 0; k < 3; ++k) f[k] = a[k] * a[3] + b[k] * b[3];
+            f[3] = a[3] > b[3] ? a[3] : b[3];
+            break;
+        case B200RC_COMPOSITOR_DIFFERENCE:
+            fd = fabsf(da - db);
+            for (int k = 0; k < 3; ++k) f[k] = 1.0f - fabsf(a[k] - b[k]);
+            f[3] = a[3] > b[3] ? a[3] : b[3];
+            break;
+        case B200RC_COMPOSITOR_DIFFERENCE_ALPHA_MUL:
+            fd = da < db ? da : db;
+            for (int k = 0; k < 3; ++k) f[k] = fabsf(a[k] * a[3] - b[k] * b[3]);
+            f[3] = 1.0f;
+            break;
+        case B200RC_COMPOSITOR_ADD:
+            for (int k = 0; k < 4; ++k) f[k] = w0 * a[k] + w1 * b[k];
+            fd = add_depth ? w0 * da + w1 * db : da;
+            break;
+        default: break;
+        }
+        post_store(dc, format, i, f);
+        if (dd) dd[i] = fd;
+    }
+}
+
+void orc_image_background(const b200rc_background_params* bp, const void* src, const float* sdepth, int format, void* dc, float* dd, int W, int H) {
+    const int ang = bp->angle_deg;
+    const float rad = (float)ang * 0.017453292519943295f;
+    const float s = 1.0f + (float)(45 - abs(ang % 90 - 45)) / 45.0f * 0.8284271247461900976033774484194f;
+    const float sin_a = sinf(rad), cos_a = cosf(rad), scale_rcp = 1.0f / s;
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            const size_t i = (size_t)y * W + x;
+            float bg[4];
+            memcpy(bg, bp->color1, sizeof bg);
+            if (bp->mode == B200RC_BACKGROUND_GRADIENT) {
+                const float X = ((float)x + 0.5f) * (2.0f / (float)W) - 1.0f, Y = ((float)y + 0.5f) * (2.0f / (float)H) - 1.0f;
+                const float ly = (-sin_a * X + cos_a * Y) * scale_rcp;
+                float w = 0.5f * ly + 0.5f;
+                w = w < 0.f ? 0.f : (w > 1.f ? 1.f : w);
+                for (int k = 0; k < 4; ++k) bg[k] = fmaf(w, bp->color2[k] - bp->color1[k], bp->color1[k]);
+            }
+            if (format == B200RC_OUT_RGBA16) for (int k = 0; k < 4; ++k) bg[k] = (float)post_unorm16(bg[k]) / 65535.f;
+            float f[4], fd = 1.0f;
+            memcpy(f, bg, sizeof f);
+            if (src) {
+                float c[4];
+                post_fetch(src, format, i, c);
+                const float d = sdepth ? sdepth[i] : 1.0f, om = 1.0f - c[3];
+                if (bp->blend_mode == B200RC_BACKGROUND_BLEND_ALPHA) {
+                    for (int k = 0; k < 3; ++k) f[k] = c[k] * c[3] + bg[k] * bg[3] * om;
+                    f[3] = c[3] + bg[3] * om;
+                } else
+                    for (int k = 0; k < 4; ++k) { f[k] = c[k] + bg[k] * om; if (f[k] > 1.0f) f[k] = 1.0f; }
+                fd = d < 1.0f ? d : 1.0f;
+            }
+            post_store(dc, format, i, f);
+            if (dd) dd[i] = fd;
+        }
+}
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* TransFunc1DGaussian texture (transfunc1dgaussian.cpp:122-178, transfuncmappingcurve.cpp:257-288,                 */
+/* transfunc1d.cpp:85-116)                                                                                          */
+/* ------------------------------------------------------------------------------------------------------------ */
+static float gcurve_opacity(const orc_tf_curve* c, float x) {
+    /* exp() is the double overload there: the product and the sum are evaluated in double, the result is returned as float */
+    double e = exp((double)(-(x - c->intensity) * (x - c->intensity) / (2 * c->width)));
+    float a = (float)(x < c->intensity ? c->color_l[3] : c->color_r[3]) / 255.f;
+    return (float)(e * (double)(a - c->base_value) + (double)c->base_value);
+}
+void orc_tf1d_gaussian_texture(const orc_tf_curve* curves, int n, const float thr[2], float gamma, int alpha_mode, int width, uint8_t* out) {
+    int front_end = iround_tgt(thr[0] * (float)width), back_start = iround_tgt(thr[1] * (float)width);
+    for (int x = 0; x < width; ++x) {
+        uint8_t* px = out + 4 * x;
+        px[0] = px[1] = px[2] = px[3] = 0;
+        if (!(x < front_end || x > back_start) && n > 0) {
+            float v = (float)x / (float)(width - 1);
+            if (gamma != 1.f) v = powf(v, gamma);
+            float col[4] = {0.f, 0.f, 0.f, 0.f}, alphaSum = 0.f;
+            for (int i = 0; i < n; ++i) {
+                const orc_tf_curve* c = curves + i;
+                if (!c->active) continue;
+                float yRatio = (float)exp((double)(-(v - c->intensity) * (v - c->intensity) / (2 * c->width)));
+                const uint8_t* peak = v < c->intensity ? c->color_l : c->color_r;
+                const uint8_t* base = v < c->intensity ? c->base_color_l : c->base_color_r;
+                uint8_t cc[4];
+                for (int k = 0; k < 3; ++k) cc[k] = (uint8_t)((float)peak[k] * yRatio + (float)base[k] * (1.f - yRatio));
+                cc[3] = (uint8_t)(gcurve_opacity(c, v) * 255);
+                float alpha = gcurve_opacity(c, v);
+                if (alpha < FLT_MIN) alpha = FLT_MIN;
+                alphaSum += alpha;
+                for (int k = 0; k < 3; ++k) col[k] += ((float)cc[k] * alpha);
+                col[3] = ((float)cc[3] > col[3] ? (float)cc[3] : col[3]);
+            }
+            if (alphaSum > 1.f) alphaSum = 1.f;
+            for (int k = 0; k < 3; ++k) col[k] = col[k] / alphaSum;
+            for (int k = 0; k < 4; ++k) { float t = col[k]; t = t < 0.f ? 0.f : (t > 255.f ? 255.f : t); px[k] = (uint8_t)t; }
+        }
+        if (alpha_mode == 2) { if (px[3]) px[3] = 255; }
+        else if (alpha_mode == 0) px[3] = 0;
+    }
+}

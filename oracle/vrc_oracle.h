@@ -137,6 +137,19 @@ void orc_synth_volume(const int32_t dims[3], const int32_t lo[3], const int32_t 
  * RGBA16-unorm colour image (as uint16) + DEPTH24 depth to another size. */
 void orc_rescale_rgba16(const uint16_t* src, const float* src_depth, int sw, int sh, uint16_t* dst, float* dst_depth, int dw, int dh);
 
+/* image-space post chain (compositor.frag:41-140; background.frag:35-57 + background.cpp:262-300) */
+void orc_image_compositor(int mode, float weighting_factor, float weight_first, float weight_second, int add_depth, const void* color0, const float* depth0,
+                          const void* color1, const float* depth1, int format, void* dst_color, float* dst_depth, size_t n);
+void orc_image_background(const b200rc_background_params* bg, const void* src_color, const float* src_depth, int format, void* dst_color, float* dst_depth, int W, int H);
+
+/* TransFuncMappingCurve + TransFunc1DGaussian::getTexture (transfunc1dgaussian.cpp:122-178, transfuncmappingcurve.cpp:257-288) */
+typedef struct orc_tf_curve {
+    float intensity, width, base_value;
+    uint8_t color_l[4], color_r[4], base_color_l[4], base_color_r[4];
+    int32_t active;
+} orc_tf_curve;
+void orc_tf1d_gaussian_texture(const orc_tf_curve* curves, int n, const float threshold[2], float gamma, int alpha_mode, int width, uint8_t* out_rgba8);
+
 #ifdef __cplusplus
 }
 #endif

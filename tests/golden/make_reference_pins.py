@@ -42,6 +42,30 @@ PI_CASES = [("ct1024", 256, 1.0 / 4096.0, 0), ("ct1024", 128, 1.0 / 1024.0, 1), 
             ("opaque", 128, 1.0 / 96.0, 1), ("nucleon", 256, 1.0, 0)]
 
 
+# Gaussian transfer functions: (name, width, curves, threshold, gamma, alpha_mode)
+def _curve(x, w, base, cl, cr=None, bl=None, br=None, active=True):
+    return {"intensity": float(np.float32(x)), "width": float(np.float32(w)), "base_value": float(np.float32(base)), "color_l": list(cl), "color_r": list(cr or cl),
+            "base_color_l": list(bl or cl)[:3] + [0], "base_color_r": list(br or cr or cl)[:3] + [0], "active": bool(active)}
+
+
+GAUSS_CASES = [
+    ("g_single", 256, [_curve(0.5, 0.01, 0.0, (255, 128, 0, 200))], (0.0, 1.0), 1.0, 1),
+    ("g_two", 1024, [_curve(0.3, 0.004, 0.0, (255, 0, 0, 255), (200, 40, 0, 120), (20, 20, 90), (0, 0, 0)), _curve(0.7, 0.02, 0.1, (0, 255, 30, 100), None, (9, 9, 9))], (0.0, 1.0), 1.0, 1),
+    ("g_inactive", 128, [_curve(0.2, 0.01, 0.05, (10, 200, 250, 180)), _curve(0.6, 0.05, 0.0, (250, 250, 250, 250), active=False), _curve(0.8, 0.001, 0.0, (90, 60, 30, 255))], (0.1, 0.9), 2.0, 1),
+    ("g_one_alpha", 64, [_curve(0.5, 0.03, 0.0, (255, 255, 255, 128))], (0.0, 1.0), 1.0, 2),
+    ("g_empty", 32, [], (0.0, 1.0), 1.0, 1),
+]
+
+
+def gauss_lines(case):
+    name, w, curves, thr, gamma, am = case
+    out = [f"gauss {w} {len(curves)} {thr[0]!r} {thr[1]!r} {gamma!r} {am}"]
+    for c in curves:
+        v = c["color_l"] + c["color_r"] + c["base_color_l"][:3] + c["base_color_r"][:3]
+        out.append(f"{c['intensity']!r} {c['width']!r} {c['base_value']!r} " + " ".join(str(int(t)) for t in v) + f" {1 if c['active'] else 0}")
+    return out
+
+
 def tf_lines(case):
     name, w, keys, thr, gamma, am, dom = case
     out = [f"tf {w} {len(keys)} {thr[0]!r} {thr[1]!r} {gamma!r} {am} {dom[0]!r} {dom[1]!r}"]
@@ -113,6 +137,11 @@ def main():
         out[f"vol_{i}_linear_in"] = pos
         out[f"vol_{i}_linear_out"] = np.array([float.fromhex(t) for t in res[1 + len(vox):]], np.float32)
         meta["vol_cases"].append({"index": i, "format": fmt, "dims": list(dims)})
+    meta["gauss_cases"] = []
+    for case in GAUSS_CASES:
+        res = run(gauss_lines(case))
+        out[f"gauss_{case[0]}_texture"] = np.array([int(t) for t in res[0].split()], np.uint8).reshape(-1, 4)
+        meta["gauss_cases"].append({"name": case[0], "width": case[1], "curves": case[2], "threshold": list(case[3]), "gamma": case[4], "alpha_mode": case[5]})
     out["meta"] = np.frombuffer(json.dumps(meta).encode(), np.uint8)
     path = os.path.join(HERE, "reference_pins.npz")
     np.savez_compressed(path, **out)

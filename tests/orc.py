@@ -77,6 +77,10 @@ def lib():
         _lib.orc_image_diff_count.argtypes = [pf, pf, C.c_int, C.c_int, C.c_float, C.c_int]
         _lib.orc_image_diff_count.restype = C.c_int64
         _lib.orc_set_threads.argtypes = [C.c_int]
+        _lib.orc_image_compositor.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
+        _lib.orc_image_compositor.restype = None
+        _lib.orc_image_background.argtypes = [C.POINTER(abi.BackgroundParams), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        _lib.orc_image_background.restype = None
         _lib.orc_synth_volume.argtypes = [C.POINTER(C.c_int32 * 3), C.POINTER(C.c_int32 * 3), C.POINTER(C.c_int32 * 3), C.c_uint64, C.c_void_p]
     return _lib
 
@@ -234,4 +238,32 @@ def rescale_rgba16(color, depth, dw, dh):
     sh, sw = color.shape[:2]
     out = np.empty((dh, dw, 4), np.uint16); od = np.empty((dh, dw), np.float32)
     lib().orc_rescale_rgba16(color.ctypes.data, fp(depth), sw, sh, out.ctypes.data, fp(od), dw, dh)
+    return out, od
+
+
+def image_compositor(mode, color0, depth0, color1, depth1, weighting_factor=0.5, weight_first=1.0, weight_second=1.0, add_depth=False):
+    """voreen::Compositor (compositor.frag) on (H, W, 4) uint16 / float32 images + (H, W) depths (or None)."""
+    color0 = np.ascontiguousarray(color0); color1 = np.ascontiguousarray(color1, color0.dtype)
+    fmt = abi.OUT_RGBA16 if color0.dtype == np.uint16 else abi.OUT_RGBA32F
+    H, W = color0.shape[:2]
+    out = np.empty_like(color0); od = np.empty((H, W), np.float32)
+    d0 = np.ascontiguousarray(depth0, np.float32) if depth0 is not None else None
+    d1 = np.ascontiguousarray(depth1, np.float32) if depth1 is not None else None
+    lib().orc_image_compositor(abi.COMPOSITOR[mode], weighting_factor, weight_first, weight_second, 1 if add_depth else 0, color0.ctypes.data,
+                               d0.ctypes.data if d0 is not None else None, color1.ctypes.data, d1.ctypes.data if d1 is not None else None, fmt,
+                               out.ctypes.data, od.ctypes.data, W * H)
+    return out, od
+
+
+def image_background(W, H, color=None, depth=None, mode="monochrome", blend="alpha-blending", color1=(1, 1, 1, 1), color2=(0.392, 0.392, 0.392, 1), angle=60, dtype=np.uint16):
+    bp = abi.BackgroundParams()
+    bp.mode, bp.blend_mode, bp.angle_deg = abi.BACKGROUND[mode], abi.BACKGROUND_BLEND[blend], int(angle)
+    bp.color1[:] = [float(v) for v in color1]; bp.color2[:] = [float(v) for v in color2]
+    if color is not None:
+        color = np.ascontiguousarray(color); dtype = color.dtype
+    fmt = abi.OUT_RGBA16 if dtype == np.uint16 else abi.OUT_RGBA32F
+    out = np.empty((H, W, 4), dtype); od = np.empty((H, W), np.float32)
+    d = np.ascontiguousarray(depth, np.float32) if depth is not None else None
+    lib().orc_image_background(C.byref(bp), color.ctypes.data if color is not None else None, d.ctypes.data if d is not None else None, fmt,
+                               out.ctypes.data, od.ctypes.data, W, H)
     return out, od

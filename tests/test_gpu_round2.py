@@ -440,3 +440,174 @@ def test_device_preintegration_builders_against_the_reference_computeTable(ctx):
         assert np.array_equal(got[..., 3] > 0, want[..., 3] > 0), "alpha > 0 pattern (what empty-space skipping and the shaded-sample count depend on)"
         done += 1
     assert done >= 5
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# config 4: MultiVolumeRaycaster, sharded (sort-last), on one device shard by shard
+# ---------------------------------------------------------------------------------------------------------------------
+MV_KEYS = [scenes.CT_KEYS, [(0.0, (0, 0, 0, 0)), (0.3, (0, 255, 0, 0)), (1.0, (0, 255, 0, 120))],
+           [(0.0, (0, 0, 0, 0)), (0.4, (0, 0, 255, 0)), (1.0, (0, 0, 255, 90))], [(0.0, (0, 0, 0, 0)), (0.5, (255, 0, 255, 0)), (1.0, (255, 0, 255, 60))]]
+
+
+@pytest.mark.parametrize("world", [2, 8])
+@pytest.mark.parametrize("cls", ["tf", "preint"])
+def test_sharded_multivolume_single_device(ctx, world, cls):
+    """Four co-registered volumes bricked identically (config C4): every shard marches the lattice samples it owns -- all volumes'
+    contributions at them, in the shader's order -- into a partial image; exact-ERT second pass; merge with the product's kernels.
+    Against (a) the unsharded b200rc_render_camera_device frame, (b) that frame against the oracle's MultiVolumeRaycaster."""
+    import torch
+    from voreen_b200 import host, sortlast
+    from voreen_b200 import raycaster as rc
+    nvol, dims = 4, (48, 40, 56)
+    vols = [scenes.ct_like_volume(0, dims=dims, seed=300 + v) for v in range(nvol)]
+    desc = rc.make_volume_desc(dims)
+    W, H = 96, 88
+    cam = orc.make_camera((1.4, 0.9, 2.9), W=W, H=H)
+    eep = rc.default_eep(world_coords=1)
+    step_world = float(np.float32(2.0) * np.float32(max(d / max(dims) for d in dims)) / np.float32(max(dims)) / np.float32(2.0))
+    step_tex = float(np.float32(1.0) / (np.float32(max(dims)) * np.float32(2.0)))
+    tfs = [orc.make_tf(MV_KEYS[v], domain=(0.0, 65535.0)) for v in range(nvol)]
+    tex = [orc.tf1d_texture(t, 4096) for t in tfs]
+    pre = [orc.preint_cpu(t, 1024, step_tex) for t in tfs] if cls == "preint" else None
+    p = rc.default_params(step_world, out_format=abi.OUT_RGBA32F)
+    p.num_volumes = nvol; p.multi_volume = 1
+    p.mv_opacity_correction_factor = step_tex / step_world
+    if pre:
+        for v in range(nvol):
+            p.vol[v].classification = abi.CLASS_PREINT
+    dev = torch.device("cuda", 0)
+    npix = W * H
+
+    def load(shard):
+        for v in range(nvol):
+            if shard is None:
+                ctx.upload_volume(v, vols[v], desc=desc)
+            else:
+                lo, hi = sortlast.shard_range(dims, shard, world)
+                rl = [max(0, lo[a] - sortlast.APRON) for a in range(3)]; rh = [min(dims[a], hi[a] + sortlast.APRON) for a in range(3)]
+                ctx.upload_volume(v, np.ascontiguousarray(vols[v][rl[2]:rh[2], rl[1]:rh[1], rl[0]:rh[0]]),
+                                  desc=rc.make_volume_desc(dims, shard_lo=lo, shard_hi=hi, shard_apron=sortlast.APRON))
+            ctx.set_tf1d(v, tex[v], (0.0, 65535.0))
+            if pre:
+                ctx.set_preint(v, pre[v])
+
+    def render_dev(col, dep):
+        ctx.render_camera_ptrs(p, eep, cam, W, H, [col.data_ptr(), 0, 0], dep.data_ptr(), device=True)
+
+    # unsharded frame (in-kernel world-space entry/exit shared by the four volumes)
+    load(None)
+    col0 = torch.empty((npix, 4), dtype=torch.float32, device=dev); dep0 = torch.empty((npix,), dtype=torch.float32, device=dev)
+    p.collect_stats = 1
+    render_dev(col0, dep0)
+    ctx.synchronize()
+    ref_st = ctx.stats()
+    ref, ref_d = col0.cpu().numpy().reshape(H, W, 4), dep0.cpu().numpy().reshape(H, W)
+    # ... which is the oracle's frame for the same entry/exit images
+    e, ed, x, xd = ctx.entry_exit(eep, cam, W, H)
+    ovs = [orc.make_volume(vols[v], desc) for v in range(nvol)]
+    ocls = [orc.make_classifier(tex[v], (0.0, 65535.0), preint=pre[v] if pre else None) for v in range(nvol)]
+    o_outs, o_depth, o_st = orc.raycast(ovs, ocls, p, cam, W, H, np.stack([e] * (nvol + 1)), ed, np.stack([x] * (nvol + 1)), xd)
+    frac_o, mx_o = scenes.parity_report(o_outs[0], ref)
+    assert frac_o >= 0.999 and ref_st.rays_cast == o_st.rays_cast and ref_st.samples_shaded == o_st.samples_shaded, (frac_o, mx_o)
+
+    cam_tex = sortlast.camera_texture_position(cam, desc)
+    p.partial_image = 1
+    col = [torch.empty((npix, 4), dtype=torch.float32, device=dev) for _ in range(world)]
+    dep = [torch.empty((npix,), dtype=torch.float32, device=dev) for _ in range(world)]
+    shaded = 0
+    for r in range(world):
+        load(r)
+        render_dev(col[r], dep[r])
+        shaded += ctx.stats().samples_shaded
+    alphas = torch.cat([c[:, 3].contiguous() for c in col]).contiguous()
+    prefix = torch.empty((npix,), dtype=torch.float32, device=dev); flags = torch.empty((npix,), dtype=torch.uint8, device=dev)
+    remarched = 0
+    for r in range(world):
+        load(r)
+        render_dev(col[r], dep[r])      # restores the entry/exit images + first-pass result of this shard
+        remarched += ctx.ert_plan(alphas.data_ptr(), world, sortlast.front_mask(r, world, dims, cam_tex), col[r].data_ptr(), dep[r].data_ptr(), npix,
+                                  prefix.data_ptr(), flags.data_ptr(), count=True)
+        ctx.remarch_device(p, cam, W, H, prefix.data_ptr(), flags.data_ptr(), [col[r].data_ptr(), 0, 0], dep[r].data_ptr())
+    ctx.synchronize()
+    p.partial_image = 0
+    imgs = {r: (col[r].cpu().numpy().copy(), dep[r].cpu().numpy().copy()) for r in range(world)}
+    for rnd in range(world.bit_length() - 1):
+        nxt = {}
+        for r in sorted(imgs):
+            if (r >> rnd) & 1:
+                continue
+            a, b = imgs[r], imgs[r | (1 << rnd)]
+            front, back = (a, b) if sortlast.my_group_in_front(r, rnd, world, dims, cam_tex) else (b, a)
+            nxt[r] = scenes.product_composite(ctx, abi.COMP["dvr"] | abi.COMPOSITE_ERT, front, back)
+        imgs = nxt
+    merged = scenes.product_finalize(ctx, imgs[0][0], abi.OUT_RGBA32F, snap=True).reshape(H, W, 4)
+    frac, mx = scenes.parity_report(ref, merged)
+    dfrac = float((np.abs(ref_d.reshape(-1) - imgs[0][1]) <= 1e-4).mean())
+    print(f"sharded multi-volume x{world} {cls}: within 1/255 {frac:.5f} max {mx:.4f} depth {dfrac:.5f} re-marched {remarched} shaded (first pass) {shaded}/{ref_st.samples_shaded}; "
+          f"unsharded vs oracle {frac_o:.5f}")
+    assert frac >= 0.999 and dfrac >= 0.999, (frac, mx)
+    assert shaded >= ref_st.samples_shaded          # local early termination can only march further than the global one
+    for v in range(1, nvol):
+        ctx.lib.b200rc_release_volume(ctx.h, v)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# image-space post chain (SURVEY 8f rank 3): Compositor and Background against the oracle's restatement of the shaders
+# ---------------------------------------------------------------------------------------------------------------------
+def _render_pair(ctx, dtype):
+    """Two real renderings (DVR and first-hit normals of the same scene) + random-alpha noise rows, as RGBA16 or RGBA32F."""
+    vol = scenes.ct_like_volume(32)
+    fmt = abi.OUT_RGBA16 if dtype == np.uint16 else abi.OUT_RGBA32F
+    a = scenes.Scene(vol, W=72, H=56, out_format=fmt)
+    b = scenes.Scene(vol, W=72, H=56, out_format=fmt, compositing=[abi.COMP["fhn"]] * 3, eye=(1.0, 1.3, 3.0))
+    (ao, ad), (bo, bd) = a.cuda_render(ctx), b.cuda_render(ctx)
+    c0, c1 = np.asarray(ao[0]).copy(), np.asarray(bo[0]).copy()
+    rng = np.random.default_rng(3)
+    if dtype == np.uint16:
+        c0 = c0.view(np.uint16); c1 = c1.view(np.uint16)
+        c0[:6] = rng.integers(0, 65536, c0[:6].shape); c1[:6] = rng.integers(0, 65536, c1[:6].shape)
+        c0[6, :, 3] = 0; c1[7, :, 3] = 65535
+    else:
+        c0[:6] = rng.random(c0[:6].shape); c1[:6] = rng.random(c1[:6].shape)
+        c0[6, :, 3] = 0; c1[7, :, 3] = 1
+    ad = ad.copy(); bd = bd.copy()
+    ad[:6] = rng.random(ad[:6].shape); bd[:6] = rng.random(bd[:6].shape); bd[3] = ad[3]
+    return c0, ad, c1, bd
+
+
+@pytest.mark.parametrize("dtype", [np.uint16, np.float32])
+def test_compositor_all_modes_against_the_oracle(ctx, dtype):
+    c0, d0, c1, d1 = _render_pair(ctx, dtype)
+    for mode in abi.COMPOSITOR:
+        for kw in ([dict(weighting_factor=w) for w in (0.0, 0.3, 1.0)] if mode == "weighted-average" else
+                   [dict(weight_first=0.7, weight_second=0.6, add_depth=ad_) for ad_ in (False, True)] if mode == "add" else [{}]):
+            got, gd = ctx.image_compositor(mode, c0, d0, c1, d1, **kw)
+            want, wd = orc.image_compositor(mode, c0, d0, c1, d1, **kw)
+            assert np.array_equal(got, want, equal_nan=True) and np.array_equal(gd, wd), (mode, kw)
+    # spot checks of the semantics themselves (compositor.frag:56-69): depth test picks the nearer fragment, alpha compositing is the over operator
+    got, gd = ctx.image_compositor("depth-test", c0, d0, c1, d1)
+    near0 = d0 < d1
+    assert np.array_equal(got[near0], c0[near0]) and np.array_equal(got[~near0], c1[~near0]) and np.array_equal(gd, np.minimum(d0, d1))
+
+
+@pytest.mark.parametrize("dtype", [np.uint16, np.float32])
+def test_background_against_the_oracle(ctx, dtype):
+    c0, d0, _, _ = _render_pair(ctx, dtype)
+    H, W = d0.shape
+    for mode in ("monochrome", "gradient"):
+        for blend in ("alpha-blending", "add"):
+            for angle in (0, 60, 135, 359):
+                kw = dict(mode=mode, blend=blend, color1=(1.0, 0.9, 0.2, 1.0), color2=(0.1, 0.392, 0.7, 0.8), angle=angle)
+                got, gd = ctx.image_background(W, H, c0, d0, **kw)
+                want, wd = orc.image_background(W, H, c0, d0, **kw)
+                assert np.array_equal(got, want, equal_nan=True) and np.array_equal(gd, wd), kw
+            got, gd = ctx.image_background(W, H, None, None, mode=mode, blend=blend, dtype=dtype)      # "image.input" unconnected: the background alone
+            want, wd = orc.image_background(W, H, None, None, mode=mode, blend=blend, dtype=dtype)
+            assert np.array_equal(got, want) and np.all(gd == 1.0)
+    # semantics: an opaque pixel hides the background, an empty one shows it (background.frag:43-46)
+    got, _ = ctx.image_background(W, H, c0, d0, mode="monochrome", color1=(0.25, 0.5, 0.75, 1.0))
+    a = c0[..., 3].astype(np.float64) / (65535.0 if dtype == np.uint16 else 1.0)
+    empty = a == 0
+    bgc = np.array([0.25, 0.5, 0.75, 1.0])
+    ref = (np.floor(bgc * 65535 + 0.5).astype(np.uint16) if dtype == np.uint16 else bgc.astype(np.float32))
+    assert empty.any() and np.all(got[empty] == ref)

@@ -366,3 +366,49 @@ def test_reference_probe_live_random_transfer_functions():
         assert np.array_equal(host.tf1d_texture(okeys, w, threshold=thr, gamma=gamma, alpha_mode=am), want_tex), ("host", case)
         got_pi = orc.preint_cpu(tf, res_, step, bool(integral))
         assert int(_ulp_diff(got_pi, want_pi).max()) <= 1, (case, res_, step, integral)
+
+
+def _orc_gaussian_texture(curves, width, threshold, gamma, alpha_mode):
+    import ctypes as C
+
+    class Curve(C.Structure):
+        _fields_ = [("intensity", C.c_float), ("width", C.c_float), ("base_value", C.c_float), ("color_l", C.c_uint8 * 4), ("color_r", C.c_uint8 * 4),
+                    ("base_color_l", C.c_uint8 * 4), ("base_color_r", C.c_uint8 * 4), ("active", C.c_int32)]
+    arr = (Curve * max(1, len(curves)))()
+    for i, c in enumerate(curves):
+        arr[i].intensity, arr[i].width, arr[i].base_value, arr[i].active = c["intensity"], c["width"], c["base_value"], 1 if c["active"] else 0
+        arr[i].color_l[:] = c["color_l"]; arr[i].color_r[:] = c["color_r"]; arr[i].base_color_l[:] = c["base_color_l"]; arr[i].base_color_r[:] = c["base_color_r"]
+    out = np.zeros((width, 4), np.uint8)
+    thr = (C.c_float * 2)(*threshold)
+    fn = orc.lib().orc_tf1d_gaussian_texture
+    fn.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.c_float, C.c_int, C.c_int, C.c_void_p]
+    fn.restype = None
+    fn(C.cast(arr, C.c_void_p), len(curves), thr, gamma, alpha_mode, width, out.ctypes.data)
+    return out
+
+
+def test_gaussian_tf_texture_matches_the_reference_transfunc1dgaussian():
+    """TransFunc1DGaussian::getMappingForValueUByte over TransFuncMappingCurve::getColorAt / getOpacityAt, run from the reference's sources:
+    the oracle's and the product host mirror's texels are the same bytes; live random curve sets where the probe binary exists."""
+    z, meta = _pins()
+    cases = [(c["curves"], c["width"], tuple(c["threshold"]), c["gamma"], c["alpha_mode"], z[f"gauss_{c['name']}_texture"], c["name"]) for c in meta["gauss_cases"]]
+    if os.path.exists(VOREEN_PROBE):
+        import sys
+        sys.path.insert(0, GOLDEN)
+        import make_reference_pins as mk
+        rng = np.random.default_rng(5)
+        for trial in range(20):
+            curves = [mk._curve(rng.random(), float(rng.choice([0.0005, 0.005, 0.02, 0.2])), float(rng.choice([0.0, 0.0, 0.1, 0.3])), tuple(int(v) for v in rng.integers(0, 256, 4)),
+                                tuple(int(v) for v in rng.integers(0, 256, 4)) if rng.random() < 0.4 else None, tuple(int(v) for v in rng.integers(0, 256, 3)),
+                                tuple(int(v) for v in rng.integers(0, 256, 3)), active=rng.random() < 0.85) for _ in range(int(rng.integers(1, 5)))]
+            w = int(rng.choice([64, 256, 1024]))
+            thr = (0.0, 1.0) if trial % 2 else (float(np.float32(0.1)), float(np.float32(0.95)))
+            gamma = float(np.float32(rng.choice([1.0, 0.5, 2.0])))
+            am = int(rng.choice([0, 1, 2]))
+            res = mk.run(mk.gauss_lines((f"r{trial}", w, curves, thr, gamma, am)))
+            cases.append((curves, w, thr, gamma, am, np.array([int(t) for t in res[0].split()], np.uint8).reshape(-1, 4), f"live{trial}"))
+    for curves, w, thr, gamma, am, want, name in cases:
+        got = _orc_gaussian_texture(curves, w, thr, gamma, am)
+        assert np.array_equal(got, want), (name, np.argwhere(got != want)[:5], got[got != want][:5], want[got != want][:5])
+        got_h = host.tf1d_gaussian_texture(curves, w, threshold=thr, gamma=gamma, alpha_mode=am)
+        assert np.array_equal(got_h, want), ("host mirror", name)

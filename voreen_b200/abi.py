@@ -74,6 +74,17 @@ class EepParams(C.Structure):
                 ("boxes", C.POINTER(C.c_float)), ("n_boxes", C.c_int32)]
 
 
+class BackgroundParams(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("blend_mode", C.c_int32), ("color1", C.c_float * 4), ("color2", C.c_float * 4), ("angle_deg", C.c_int32)]
+
+
+COMPOSITOR = {"depth-test": 0, "alpha-compositing": 1, "alpha-blending": 2, "alpha-blending-b-over-a": 3, "weighted-average": 4, "take-first": 5,
+              "take-second": 6, "take-second-if-ready": 7, "first-has-priority": 8, "second-has-priority": 9, "maximum-alpha": 10, "difference": 11,
+              "difference-alpha-mul": 12, "add": 13}       # compositor.cpp:47-60 option keys
+BACKGROUND = {"monochrome": 0, "gradient": 1}
+BACKGROUND_BLEND = {"alpha-blending": 0, "add": 1}
+
+
 class Stats(C.Structure):
     _fields_ = [("last_render_ms", C.c_double), ("last_march_ms", C.c_double), ("last_eep_ms", C.c_double),
                 ("rays_cast", C.c_uint64), ("samples_classified", C.c_uint64), ("samples_shaded", C.c_uint64),
@@ -96,7 +107,7 @@ SYMBOLS = [
     "b200rc_build_preint", "b200rc_download_preint", "b200rc_set_tf2d", "b200rc_entry_exit", "b200rc_render",
     "b200rc_render_camera", "b200rc_render_camera_device", "b200rc_composite", "b200rc_finalize", "b200rc_ert_plan",
     "b200rc_remarch_device", "b200rc_upload_volume_begin", "b200rc_upload_volume_slab", "b200rc_upload_volume_end", "b200rc_load_raw_file", "b200rc_rescale", "b200rc_composite_keyed",
-    "b200rc_host_alloc", "b200rc_host_free",
+    "b200rc_host_alloc", "b200rc_host_free", "b200rc_image_compositor", "b200rc_image_background",
 ]
 
 _lib = None
@@ -149,6 +160,8 @@ def load_library():
     lib.b200rc_rescale.argtypes = [vp, vp, pf, i32, i32, i32, vp, pf, i32, i32, i32]
     lib.b200rc_ert_plan.argtypes = [vp, vp, i32, C.c_uint32, vp, vp, sz, vp, vp, C.POINTER(C.c_uint64)]
     lib.b200rc_remarch_device.argtypes = [vp, C.POINTER(Params), C.POINTER(Camera), i32, i32, vp, vp, C.POINTER(vp * 3), vp]
+    lib.b200rc_image_compositor.argtypes = [vp, i32, f32, f32, f32, i32, vp, vp, vp, vp, i32, vp, vp, i32, i32, i32]
+    lib.b200rc_image_background.argtypes = [vp, C.POINTER(BackgroundParams), vp, vp, i32, vp, vp, i32, i32, i32]
     lib.b200rc_host_alloc.argtypes = [sz, C.POINTER(vp)]
     lib.b200rc_host_free.argtypes = [vp]
     for s in SYMBOLS:

@@ -350,7 +350,7 @@ static int build_params(b200rc_ctx* ctx, const b200rc_params* P, const b200rc_ca
     // volume, i.e. the last channel; multi-channel volumes keep marching every sample)
     if (P->empty_space_skipping && P->multi_volume) {
         for (int v = 0; v < nv; ++v) {
-            if (ctx->vol[v].desc.channels != 1 || ctx->vol[v].sharded) continue;
+            if (ctx->vol[v].desc.channels != 1) continue;
             int mode = P->vol[v].classification;
             int rc = rc_volume_build_occupancy(ctx, v, &mode, 1, true, P->vol[v].clamp, P->vol[v].border_intensity);
             if (rc) return rc;
@@ -498,6 +498,7 @@ extern "C" int b200rc_render(b200rc_ctx* ctx, const b200rc_params* P, const b200
     DevParams p; int nch = 1, dtype = 0;
     int rc = build_params(ctx, P, cam, W, H, p, &nch, &dtype);
     if (rc) return rc;
+    if (P->multi_volume && ctx->vol[0].sharded) { ctx->set_error("render: sharded multi-volume rendering goes through b200rc_render_camera_device (identical geometry, in-kernel entry/exit)"); return B200RC_ERR_INVALID; }
     const size_t px = (size_t)W * H;
     const int images = P->multi_volume ? 1 + P->num_volumes : 1;
     rc = ensure_frame_buffers(ctx, px, images);
@@ -519,10 +520,25 @@ extern "C" int b200rc_render(b200rc_ctx* ctx, const b200rc_params* P, const b200
 static int render_camera_impl(b200rc_ctx* ctx, const b200rc_params* P, const b200rc_eep_params* eep, const b200rc_camera* cam, int W, int H,
                               void* out_color[3], float* out_depth, bool device_out, const float* prefix = nullptr, const unsigned char* flags = nullptr) {
     if (!eep && !flags) { ctx->set_error("render_camera: eep params missing"); return B200RC_ERR_INVALID; }
-    if (P && P->multi_volume) { ctx->set_error("render_camera: multi-volume rendering takes explicit entry/exit buffers (b200rc_render)"); return B200RC_ERR_INVALID; }
+    // MultiVolumeRaycaster with in-kernel entry/exit: one proxy cube for all volumes, i.e. volumes of identical geometry (config C4:
+    // four co-registered channels); world-space entry/exit points (multivolumeraycaster.cpp:326-344), every volume reads plane 0.
+    // Volumes placed differently take explicit per-volume entry/exit buffers (b200rc_render), as MultiVolumeProxyGeometry provides.
+    b200rc_eep_params eep_world;
+    if (P && P->multi_volume) {
+        for (int v = 1; v < P->num_volumes && v < B200RC_MAX_VOLUMES; ++v) {
+            const b200rc_volume_desc &a = ctx->vol[0].desc, &b = ctx->vol[v].desc;
+            if (!ctx->vol[v].valid || memcmp(a.dims, b.dims, sizeof a.dims) || memcmp(a.spacing, b.spacing, sizeof a.spacing) || memcmp(a.offset, b.offset, sizeof a.offset) ||
+                memcmp(a.phys_to_world, b.phys_to_world, sizeof a.phys_to_world) || memcmp(a.shard_lo, b.shard_lo, sizeof a.shard_lo) || memcmp(a.shard_hi, b.shard_hi, sizeof a.shard_hi)) {
+                ctx->set_error("render_camera: multi-volume rendering with in-kernel entry/exit needs volumes of identical geometry (and identical shards); use b200rc_render with per-volume entry/exit buffers otherwise");
+                return B200RC_ERR_INVALID;
+            }
+        }
+        if (eep) { eep_world = *eep; eep_world.world_coords = 1; eep = &eep_world; }
+    }
     DevParams p; int nch = 1, dtype = 0;
     int rc = build_params(ctx, P, cam, W, H, p, &nch, &dtype);
     if (rc) return rc;
+    if (P->multi_volume) p.eep_shared = 1;
     const size_t px = (size_t)W * H;
     rc = ensure_frame_buffers(ctx, px, 1);
     if (rc) return rc;
@@ -646,4 +662,53 @@ extern "C" int b200rc_remarch_device(b200rc_ctx* ctx, const b200rc_params* P, co
     if (!prefix_dev || !flags_dev) { ctx->set_error("remarch: prefix / flags missing"); return B200RC_ERR_INVALID; }
     if (!P || !P->partial_image) { ctx->set_error("remarch: needs partial_image rendering"); return B200RC_ERR_INVALID; }
     return render_camera_impl(ctx, P, nullptr, cam, W, H, out_color_dev, out_depth_dev, true, prefix_dev, flags_dev);
+}
+
+// ---- image-space post chain -----------------------------------------------------------------------------------------------------
+// host <-> device staging for the per-pixel image maps (stream-ordered allocations; nothing persists)
+struct PostBuf {
+    b200rc_ctx* ctx; void* d = nullptr; size_t bytes = 0; bool ok = true;
+    PostBuf(b200rc_ctx* c, const void* host, size_t n, bool upload) : ctx(c), bytes(n) {
+        if (!n) return;
+        if (cudaMallocAsync(&d, n, ctx->stream) != cudaSuccess) { cudaGetLastError(); d = nullptr; ok = false; return; }
+        if (upload && host && cudaMemcpyAsync(d, host, n, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { cudaGetLastError(); ok = false; }
+    }
+    ~PostBuf() { if (d) cudaFreeAsync(d, ctx->stream); }
+};
+
+extern "C" int b200rc_image_compositor(b200rc_ctx* ctx, int mode, float wf, float w0, float w1, int add_depth, const void* color0, const float* depth0,
+                                       const void* color1, const float* depth1, int format, void* dst_color, float* dst_depth, int W, int H, int on_device) {
+    CTX_GUARD();
+    if (!color0 || !color1 || !dst_color || W < 1 || H < 1 || mode < B200RC_COMPOSITOR_DEPTH_TEST || mode > B200RC_COMPOSITOR_ADD ||
+        (format != B200RC_OUT_RGBA16 && format != B200RC_OUT_RGBA32F)) { ctx->set_error("image_compositor: bad arguments"); return B200RC_ERR_INVALID; }
+    const size_t n = (size_t)W * H, cb = n * out_pixel_bytes(format), db = n * sizeof(float);
+    if (on_device) return rc_compositor_launch(ctx, mode, wf, w0, w1, add_depth, color0, depth0, color1, depth1, format, dst_color, dst_depth, n);
+    PostBuf c0(ctx, color0, cb, true), c1(ctx, color1, cb, true), d0(ctx, depth0, depth0 ? db : 0, true), d1(ctx, depth1, depth1 ? db : 0, true);
+    PostBuf oc(ctx, nullptr, cb, false), od(ctx, nullptr, dst_depth ? db : 0, false);
+    if (!c0.ok || !c1.ok || !d0.ok || !d1.ok || !oc.ok || !od.ok) { ctx->set_error("image_compositor: out of device memory"); return B200RC_ERR_OOM; }
+    int rc = rc_compositor_launch(ctx, mode, wf, w0, w1, add_depth, c0.d, (const float*)d0.d, c1.d, (const float*)d1.d, format, oc.d, (float*)od.d, n);
+    if (rc) return rc;
+    RC_CHECK(cudaMemcpyAsync(dst_color, oc.d, cb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (dst_depth) RC_CHECK(cudaMemcpyAsync(dst_depth, od.d, db, cudaMemcpyDeviceToHost, ctx->stream));
+    RC_CHECK(cudaStreamSynchronize(ctx->stream));
+    return B200RC_OK;
+}
+
+extern "C" int b200rc_image_background(b200rc_ctx* ctx, const b200rc_background_params* bg, const void* src_color, const float* src_depth, int format,
+                                       void* dst_color, float* dst_depth, int W, int H, int on_device) {
+    CTX_GUARD();
+    if (!bg || !dst_color || W < 1 || H < 1 || (format != B200RC_OUT_RGBA16 && format != B200RC_OUT_RGBA32F) || bg->mode < B200RC_BACKGROUND_MONOCHROME ||
+        bg->mode > B200RC_BACKGROUND_GRADIENT || bg->blend_mode < B200RC_BACKGROUND_BLEND_ALPHA || bg->blend_mode > B200RC_BACKGROUND_BLEND_ADD || bg->angle_deg < 0 || bg->angle_deg > 359) {
+        ctx->set_error("image_background: bad arguments"); return B200RC_ERR_INVALID;
+    }
+    const size_t n = (size_t)W * H, cb = n * out_pixel_bytes(format), db = n * sizeof(float);
+    if (on_device) return rc_background_launch(ctx, bg, src_color, src_depth, format, dst_color, dst_depth, W, H);
+    PostBuf sc(ctx, src_color, src_color ? cb : 0, true), sd(ctx, src_depth, (src_color && src_depth) ? db : 0, true), oc(ctx, nullptr, cb, false), od(ctx, nullptr, dst_depth ? db : 0, false);
+    if (!sc.ok || !sd.ok || !oc.ok || !od.ok) { ctx->set_error("image_background: out of device memory"); return B200RC_ERR_OOM; }
+    int rc = rc_background_launch(ctx, bg, sc.d, (const float*)sd.d, format, oc.d, (float*)od.d, W, H);
+    if (rc) return rc;
+    RC_CHECK(cudaMemcpyAsync(dst_color, oc.d, cb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (dst_depth) RC_CHECK(cudaMemcpyAsync(dst_depth, od.d, db, cudaMemcpyDeviceToHost, ctx->stream));
+    RC_CHECK(cudaStreamSynchronize(ctx->stream));
+    return B200RC_OK;
 }

@@ -59,6 +59,7 @@ struct DevParams {
     float* out_key;                 // sort-last partial MIP / MOP image: the merge key (max intensity / max alpha) per pixel, or null
     int out_format, quantize_depth24;
     int nvol, multi;
+    int eep_shared;                 // multi-volume: every volume uses entry/exit plane 0 (identical proxy geometry, in-kernel entry/exit)
     VolDev vol[B200RC_MAX_VOLUMES];
     ClsDev cls[B200RC_MAX_CHANNELS];
     int classification[B200RC_MAX_VOLUMES], shading[B200RC_MAX_VOLUMES];

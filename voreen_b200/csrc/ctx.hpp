@@ -117,6 +117,11 @@ int rc_finalize_launch(b200rc_ctx* ctx, const float* rgba, const float* depth, s
 int rc_ert_plan_launch(b200rc_ctx* ctx, const float* alphas, int world, unsigned front_mask, float* color, float* depth, size_t n,
                        float* prefix, unsigned char* flags, unsigned long long* counter);
 
+// post.cu
+int rc_compositor_launch(b200rc_ctx* ctx, int mode, float wf, float w0, float w1, int add_depth, const void* c0, const float* d0, const void* c1, const float* d1,
+                         int format, void* dc, float* dd, size_t n);
+int rc_background_launch(b200rc_ctx* ctx, const b200rc_background_params* bp, const void* src, const float* sdepth, int format, void* dc, float* dd, int W, int H);
+
 // host matrix helpers (api.cu), tgt semantics (V/ext/tgt/matrix.h)
 void rc_mat4_mul(const float a[16], const float b[16], float out[16]);
 bool rc_mat4_invert(const float m[16], float out[16]);

@@ -17,7 +17,35 @@ SYMBOLS = [
     "b200host_svrc_get_sampling_step", "b200host_svrc_set_volume", "b200host_svrc_set_synthetic_volume",
     "b200host_svrc_set_transfer_function", "b200host_svrc_set_camera", "b200host_svrc_connect_output",
     "b200host_svrc_set_entry_exit", "b200host_svrc_is_ready", "b200host_svrc_process", "b200host_vvd_parse", "b200host_vvd_count", "b200host_optimized_proxy_geometry",
+    "b200host_tf1d_gaussian_texture",
 ]
+
+
+class TFCurve(C.Structure):
+    _fields_ = [("intensity", C.c_float), ("width", C.c_float), ("base_value", C.c_float), ("color_l", C.c_uint8 * 4), ("color_r", C.c_uint8 * 4),
+                ("base_color_l", C.c_uint8 * 4), ("base_color_r", C.c_uint8 * 4), ("active", C.c_int32)]
+
+
+def make_curves(curves):
+    """[dict(intensity, width, base_value, color_l, color_r, base_color_l, base_color_r, active)] -> TFCurve array (TransFuncMappingCurve)."""
+    arr = (TFCurve * max(1, len(curves)))()
+    for i, c in enumerate(curves):
+        arr[i].intensity, arr[i].width, arr[i].base_value = c["intensity"], c["width"], c.get("base_value", 0.0)
+        arr[i].color_l[:] = list(c["color_l"]); arr[i].color_r[:] = list(c.get("color_r", c["color_l"]))
+        arr[i].base_color_l[:] = list(c.get("base_color_l", c["color_l"])); arr[i].base_color_r[:] = list(c.get("base_color_r", c.get("color_r", c["color_l"])))
+        arr[i].active = 1 if c.get("active", True) else 0
+    return arr
+
+
+def tf1d_gaussian_texture(curves, width, threshold=(0.0, 1.0), gamma=1.0, alpha_mode=1):
+    """TransFunc1DGaussian::getTexture: RGBA8 texels of a Gaussian-curve 1D transfer function."""
+    arr = make_curves(curves)
+    out = np.zeros((width, 4), np.uint8)
+    thr = (C.c_float * 2)(*threshold)
+    rc = load_library().b200host_tf1d_gaussian_texture(arr, len(curves), thr, gamma, alpha_mode, width, out.ctypes.data_as(C.c_void_p))
+    if rc:
+        raise abi.B200RCError(f"b200host_tf1d_gaussian_texture: status {rc}")
+    return out
 
 
 class TFKey(C.Structure):
@@ -43,6 +71,7 @@ def load_library():
     pf, vp, i32, f32 = C.POINTER(C.c_float), C.c_void_p, C.c_int, C.c_float
     lib.b200host_camera.argtypes = [pf, pf, pf, f32, f32, f32, f32, i32, i32, C.POINTER(abi.Camera)]
     lib.b200host_tf1d_keys_texture.argtypes = [C.POINTER(TFKey), i32, pf, f32, i32, i32, vp]
+    lib.b200host_tf1d_gaussian_texture.argtypes = [C.POINTER(TFCurve), i32, pf, f32, i32, i32, vp]
     lib.b200host_tf1d_width_for.argtypes = [i32, C.POINTER(i32)]
     lib.b200host_volume_desc.argtypes = [C.POINTER(C.c_int32 * 3), i32, C.c_char_p, pf, pf, pf, C.POINTER(abi.VolumeDesc)]
     lib.b200host_svrc_create.argtypes = [i32, C.POINTER(vp)]

@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -119,6 +120,57 @@ extern "C" int b200host_tf1d_keys_texture(const b200host_tf_key* keys, int n_key
         }
         if (alpha_mode == 2) { if (px[3]) px[3] = 255; }        // TF_ONE_ALPHA (transfuncbase.cpp:177-210)
         else if (alpha_mode == 0) px[3] = 0;                    // TF_ZERO_ALPHA
+    }
+    return B200RC_OK;
+}
+
+// TransFuncMappingCurve::getOpacityAt / getColorAt (transfuncmappingcurve.cpp:257-288) and
+// TransFunc1DGaussian::getMappingForValueUByte (transfunc1dgaussian.cpp:122-178)
+static float curve_opacity(const b200host_tf_curve& c, float x) {
+    // ::exp(double) is what the reference's unqualified exp() resolves to: product and sum in double, returned as float
+    const double e = ::exp(static_cast<double>(-(x - c.intensity) * (x - c.intensity) / (2 * c.width)));
+    const float a = (x < c.intensity ? c.color_l[3] : c.color_r[3]) / 255.f;
+    return static_cast<float>(e * (a - c.base_value) + c.base_value);
+}
+static void gaussian_mapping(const b200host_tf_curve* curves, int n, float x, uint8_t out[4]) {
+    out[0] = out[1] = out[2] = out[3] = 0;
+    if (n <= 0) return;
+    float col[4] = {0.f, 0.f, 0.f, 0.f}, alphaSum = 0.f;
+    for (int i = 0; i < n; ++i) {
+        const b200host_tf_curve& c = curves[i];
+        if (!c.active) continue;
+        const float yRatio = static_cast<float>(::exp(static_cast<double>(-(x - c.intensity) * (x - c.intensity) / (2 * c.width))));
+        const uint8_t* peak = x < c.intensity ? c.color_l : c.color_r;
+        const uint8_t* base = x < c.intensity ? c.base_color_l : c.base_color_r;
+        uint8_t cc[4];
+        for (int k = 0; k < 3; ++k) cc[k] = static_cast<uint8_t>((peak[k] * yRatio + base[k] * (1.f - yRatio)));
+        cc[3] = static_cast<uint8_t>(curve_opacity(c, x) * 255);
+        float alpha = curve_opacity(c, x);
+        if (alpha < std::numeric_limits<float>::min()) alpha = std::numeric_limits<float>::min();
+        alphaSum += alpha;
+        col[0] += (cc[0] * alpha); col[1] += (cc[1] * alpha); col[2] += (cc[2] * alpha);
+        col[3] = (cc[3] > col[3] ? cc[3] : col[3]);
+    }
+    if (alphaSum > 1.f) alphaSum = 1.f;
+    for (int k = 0; k < 3; ++k) col[k] = col[k] / alphaSum;
+    for (int k = 0; k < 4; ++k) { float v = col[k]; v = v < 0.f ? 0.f : (v > 255.f ? 255.f : v); out[k] = static_cast<uint8_t>(v); }     // tgt::clamp; NaN (0/0) -> 0 as min/max do
+}
+
+extern "C" int b200host_tf1d_gaussian_texture(const b200host_tf_curve* curves, int n_curves, const float threshold[2], float gamma, int alpha_mode,
+                                              int width, uint8_t* out) {
+    if ((!curves && n_curves > 0) || n_curves < 0 || width < 2 || !out) return B200RC_ERR_INVALID;
+    const float thr0 = threshold ? threshold[0] : 0.f, thr1 = threshold ? threshold[1] : 1.f;
+    const int front_end = iround(thr0 * (float)width), back_start = iround(thr1 * (float)width);      // TransFunc1D::createTextureData (transfunc1d.cpp:85-116)
+    for (int x = 0; x < width; ++x) {
+        uint8_t* px = out + 4 * x;
+        if (x < front_end || x > back_start) px[0] = px[1] = px[2] = px[3] = 0;
+        else {
+            float v = (float)x / (float)(width - 1);
+            if (gamma != 1.f) v = std::pow(v, gamma);
+            gaussian_mapping(curves, n_curves, v, px);
+        }
+        if (alpha_mode == 2) { if (px[3]) px[3] = 255; }
+        else if (alpha_mode == 0) px[3] = 0;
     }
     return B200RC_OK;
 }

@@ -315,6 +315,35 @@ class Context:
                                             out.ctypes.data_as(C.c_void_p), _fp(od) if od is not None else None, dw, dh, 0), "rescale")
         return out, od
 
+    # -- image-space post chain (host numpy images) -------------------------------------------------------------------
+    def image_compositor(self, mode, color0, depth0, color1, depth1, weighting_factor=0.5, weight_first=1.0, weight_second=1.0, add_depth=False):
+        """voreen::Compositor on two (H, W, 4) uint16 / float32 images (+ (H, W) float32 depths or None)."""
+        color0 = np.ascontiguousarray(color0); color1 = np.ascontiguousarray(color1, color0.dtype)
+        fmt = abi.OUT_RGBA16 if color0.dtype == np.uint16 else abi.OUT_RGBA32F
+        H, W = color0.shape[:2]
+        out = np.empty_like(color0); od = np.empty((H, W), np.float32)
+        d0 = np.ascontiguousarray(depth0, np.float32) if depth0 is not None else None
+        d1 = np.ascontiguousarray(depth1, np.float32) if depth1 is not None else None
+        self._check(self.lib.b200rc_image_compositor(self.h, abi.COMPOSITOR[mode] if isinstance(mode, str) else mode, weighting_factor, weight_first, weight_second,
+                                                     1 if add_depth else 0, color0.ctypes.data, d0.ctypes.data if d0 is not None else None, color1.ctypes.data,
+                                                     d1.ctypes.data if d1 is not None else None, fmt, out.ctypes.data, od.ctypes.data, W, H, 0), "image_compositor")
+        return out, od
+
+    def image_background(self, W, H, color=None, depth=None, mode="monochrome", blend="alpha-blending", color1=(1, 1, 1, 1), color2=(0.392, 0.392, 0.392, 1), angle=60,
+                         dtype=np.uint16):
+        """voreen::Background under an (H, W, 4) image (or alone when color is None)."""
+        bp = abi.BackgroundParams()
+        bp.mode, bp.blend_mode, bp.angle_deg = abi.BACKGROUND[mode], abi.BACKGROUND_BLEND[blend], int(angle)
+        bp.color1[:] = [float(v) for v in color1]; bp.color2[:] = [float(v) for v in color2]
+        if color is not None:
+            color = np.ascontiguousarray(color); dtype = color.dtype
+        fmt = abi.OUT_RGBA16 if dtype == np.uint16 else abi.OUT_RGBA32F
+        out = np.empty((H, W, 4), dtype); od = np.empty((H, W), np.float32)
+        d = np.ascontiguousarray(depth, np.float32) if depth is not None else None
+        self._check(self.lib.b200rc_image_background(self.h, C.byref(bp), color.ctypes.data if color is not None else None, d.ctypes.data if d is not None else None, fmt,
+                                                     out.ctypes.data, od.ctypes.data, W, H, 0), "image_background")
+        return out, od
+
     def composite_keyed(self, fc, fk, fd, bc, bk, bd, dc, dk, dd, n):
         self._check(self.lib.b200rc_composite_keyed(self.h, fc, fk, fd, bc, bk, bd, dc, dk, dd, n), "composite_keyed")
 
