@@ -95,8 +95,12 @@ enum { B200RC_INSIDE_NONE = 0, B200RC_INSIDE_GPU = 1 };
 /* OptimizedProxyGeometry "modeString" (optimizedproxygeometry.cpp:107-114).  The library itself builds the
  * bounding-box cube (processCube :420-448); for the TF-dependent modes the host mirror classifies the min/max
  * regions (b200rc_region_minmax) with the TF keys and hands the resulting cubes over as explicit boxes. */
-enum { B200RC_RAYCASTER_SINGLE = 0, B200RC_RAYCASTER_SIMPLE = 1, B200RC_RAYCASTER_RGB = 2 };
-enum { B200RC_PROXY_BBOX = 0, B200RC_PROXY_MINBBOX = 1, B200RC_PROXY_VISIBLE_BRICKS = 2 };
+enum { B200RC_RAYCASTER_SINGLE = 0, B200RC_RAYCASTER_SIMPLE = 1, B200RC_RAYCASTER_RGB = 2, B200RC_RAYCASTER_SEGMENTATION = 3 };
+/* OUTER_FACES ("outerfaces", optimizedproxygeometry.cpp:1392-1604) emits only the cell faces between a non-empty and an empty cell:
+ * the boundary of the union of the non-empty cells.  Rendered by MeshEntryExitPoints (nearest front face / farthest back face) that
+ * boundary gives the same entry/exit images as the cubes of VISIBLE_BRICKS, whose interior faces are never nearest or farthest;
+ * the cell classification (min/max over [llf-1, urb+1], 256^2 pre-integration table, threshold) is the same code (:1436-1455). */
+enum { B200RC_PROXY_BBOX = 0, B200RC_PROXY_MINBBOX = 1, B200RC_PROXY_VISIBLE_BRICKS = 2, B200RC_PROXY_OUTER_FACES = 3 };
 
 /* voreen::Compositor "blendMode" options, in the order of V/modules/base/processors/image/compositor.cpp:47-60 */
 enum {
@@ -201,6 +205,14 @@ typedef struct b200rc_params {
      * the "applyColorModulation" property (colour *= TF colour).  Otherwise like SIMPLE.  No empty-space skipping (the alpha
      * of a cell is not a function of a scalar range). */
     int32_t rgb_color_modulation;
+    /* B200RC_RAYCASTER_SEGMENTATION = voreen::SegmentationRaycaster (V/modules/base/glsl/rc_segmentation.frag:104-160): one-channel
+     * intensity volume in slot 0; the loop of SingleVolumeRaycaster with ka = kd = ks = the classified colour (:137) and early ray
+     * termination on image.output's alpha alone (:145).  apply_segmentation ("applySegmentation"): the segmentation volume in slot 1
+     * (uint8 / uint16, NEAREST, clamp to edge) selects per sample one of 256 transfer functions (b200rc_set_segmentation_tf): segment =
+     * min(value * (2^bits - 1), 255); the intensity is mapped through that segment's domain and looked up with LINEAR filtering in row
+     * (3 * segment + 1.5) / height of the segmentation TF texture (:67-98).  segmentation_bit_depth = 8, 12 or 16 (bitDepth_). */
+    int32_t apply_segmentation;
+    int32_t segmentation_bit_depth;
 } b200rc_params;
 
 /* MeshEntryExitPoints + proxy geometry settings for b200rc_render_camera / b200rc_entry_exit. */
@@ -305,6 +317,10 @@ int b200rc_set_preint(b200rc_ctx* ctx, int chan, const float* rgba32f, int res);
  * PreIntegrationTable::computeTable (the TF texture must then have exactly `res` texels). */
 int b200rc_build_preint(b200rc_ctx* ctx, int chan, int res, float sampling_step, int mode);
 int b200rc_download_preint(b200rc_ctx* ctx, int chan, float* rgba32f, int res);
+/* SegmentationRaycaster: the segmentation transfer-function texture (segmentationraycaster.cpp:175-178,381-415): rgba8, `width` x
+ * `height` (= 3 rows per segment, 256 segments: 768), LINEAR + CLAMP, every segment's 1D TF resampled into the three rows
+ * 3 i .. 3 i + 2; domains = 256 x {lower, upper} real-world domain per segment (segmentationTransferFuncDomains_). */
+int b200rc_set_segmentation_tf(b200rc_ctx* ctx, const uint8_t* rgba8, int width, int height, const float* domains);
 /* 2D TF (intensity x gradient magnitude), rgba8, LINEAR filtered (transfunc2dprimitives). */
 int b200rc_set_tf2d(b200rc_ctx* ctx, int chan, const uint8_t* rgba8, int width, int height,
                     float domain_lo_x, float domain_hi_x, float domain_lo_y, float domain_hi_y);

@@ -910,6 +910,10 @@ static void raycast_single(const orc_volume* vol, const orc_classifier* cls, con
     const int preint = (cmode == B200RC_CLASS_PREINT);
     const int requires_gradient = (cmode == B200RC_CLASS_TF2D);   /* CLASSIFICATION_REQUIRES_GRADIENT */
     const float step = P->sampling_step;
+    /* SegmentationRaycaster (rc_segmentation.frag:104-160): the same loop with ka = kd = ks = colour (:137), early ray termination on
+     * result.a alone (:145) and, with applySegmentation, the per-segment classification of :67-98 */
+    const int seg = (P->raycaster == B200RC_RAYCASTER_SEGMENTATION), seg_apply = seg && P->apply_segmentation;
+    const float seg_scale = P->segmentation_bit_depth == 12 ? 4095.0f : (P->segmentation_bit_depth == 16 ? 65535.0f : 255.0f);
     /* USE_EARLY_TERMINATION (volumeraycaster.cpp:225-233, usePortgroup_ = true) */
     int ert = 1;
     for (int o = 0; o < 3; ++o) {
@@ -964,6 +968,17 @@ static void raycast_single(const orc_volume* vol, const orc_classifier* cls, con
                     s_class++;
                     v4 color[4];
                     int hasOpacity = 0;
+                    if (seg_apply) {
+                        float segValue = tex3d(&vol[1], B200RC_FILTER_NEAREST, B200RC_CLAMP_TO_EDGE, 0.f, samplePos).w;
+                        float segment = gl_min(segValue * seg_scale, 255.0f);
+                        int index = (int)segment;
+                        float lo = cls[1].seg_domains[2 * index], hi = cls[1].seg_domains[2 * index + 1], dv;
+                        if (voxel.w <= lo) dv = 0.0f;
+                        else if (voxel.w >= hi) dv = 1.0f;
+                        else dv = (voxel.w - lo) / (hi - lo);
+                        color[0] = tex2d_linear_u8(cls[1].tf2d_rgba8, cls[1].tf2d_w, cls[1].tf2d_h, dv, (segment * 3.0f + 1.5f) / (float)cls[1].tf2d_h);
+                        hasOpacity = color[0].w > 0.f;
+                    } else
                     for (int c = 0; c < nch; ++c) {
                         color[c] = classify(cmode, &cls[c], V4(gradient.x, gradient.y, gradient.z, comp4(voxel, c)), comp4(lastIntensity, c));
                         hasOpacity = hasOpacity || (color[c].w > 0.f);
@@ -976,7 +991,7 @@ static void raycast_single(const orc_volume* vol, const orc_classifier* cls, con
                         for (int c = 0; c < nch; ++c) {
                             /* quirk (:245,251): channels 3 and 4 write the shaded colour into color2 -> composited unshaded */
                             v3 rgb = V3(color[c].x, color[c].y, color[c].z);
-                            v3 shaded = apply_shading(P->vol[0].shading, &P->light, gradient, posPhys, lightPhys, camPhys, rgb, rgb, V3(1, 1, 1));
+                            v3 shaded = apply_shading(P->vol[0].shading, &P->light, gradient, posPhys, lightPhys, camPhys, rgb, rgb, seg ? rgb : V3(1, 1, 1));
                             if (c < 2) { color[c].x = shaded.x; color[c].y = shaded.y; color[c].z = shaded.z; }
                             else { color[1].x = shaded.x; color[1].y = shaded.y; color[1].z = shaded.z; }
                             for (int o = 0; o < 3; ++o) {
@@ -989,7 +1004,9 @@ static void raycast_single(const orc_volume* vol, const orc_classifier* cls, con
                     lastIntensity = voxel;
                     if (ert) {      /* earlyRayTermination (mod_raysetup.frag:65-74) on RESULTn_1.a */
                         float a1 = result[0][0].w, a2 = result[1][0].w, a3 = result[2][0].w;
-                        if (gl_min(a1, gl_min(a2, a3)) >= ERT_OPACITY) {
+                        if (seg) {      /* the two-argument overload (mod_raysetup.frag:56-63) */
+                            if (a1 >= ERT_OPACITY) { result[0][0].w = 1.0f; finished = 1; }
+                        } else if (gl_min(a1, gl_min(a2, a3)) >= ERT_OPACITY) {
                             result[0][0].w = 1.0f; result[1][0].w = 1.0f; result[2][0].w = 1.0f;
                             finished = 1;
                         }

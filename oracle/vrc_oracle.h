@@ -65,6 +65,7 @@ typedef struct orc_classifier {
     const uint8_t* tf2d_rgba8;  /* 2D TF, LINEAR */
     int32_t tf2d_w, tf2d_h;
     float   domain_y[2];
+    const float* seg_domains;   /* SegmentationRaycaster (classifier 1): 256 x {lower, upper} per-segment domains; tf2d_* = the segmentation TF texture */
 } orc_classifier;
 
 int  orc_abi_version(void);

@@ -32,7 +32,8 @@ class Volume(C.Structure):
 class Classifier(C.Structure):
     _fields_ = [("tf_rgba8", C.c_void_p), ("tf_width", C.c_int32), ("domain", C.c_float * 2),
                 ("preint", C.POINTER(C.c_float)), ("preint_res", C.c_int32),
-                ("tf2d_rgba8", C.c_void_p), ("tf2d_w", C.c_int32), ("tf2d_h", C.c_int32), ("domain_y", C.c_float * 2)]
+                ("tf2d_rgba8", C.c_void_p), ("tf2d_w", C.c_int32), ("tf2d_h", C.c_int32), ("domain_y", C.c_float * 2),
+                ("seg_domains", C.POINTER(C.c_float))]
 
 
 _lib = None
@@ -187,7 +188,7 @@ def entry_exit(boxes, model, eep, cam, W, H):
     return e, ed, x, xd
 
 
-def make_classifier(tf_tex=None, domain=(0.0, 1.0), preint=None, tf2d=None, domain_y=(0.0, 1.0)):
+def make_classifier(tf_tex=None, domain=(0.0, 1.0), preint=None, tf2d=None, domain_y=(0.0, 1.0), seg_domains=None):
     c = Classifier()
     c._keep = []
     if tf_tex is not None:
@@ -199,6 +200,9 @@ def make_classifier(tf_tex=None, domain=(0.0, 1.0), preint=None, tf2d=None, doma
     if tf2d is not None:
         t = np.ascontiguousarray(tf2d, np.uint8); c._keep.append(t)
         c.tf2d_rgba8 = t.ctypes.data; c.tf2d_h, c.tf2d_w = t.shape[0], t.shape[1]
+    if seg_domains is not None:
+        t = np.ascontiguousarray(seg_domains, np.float32); c._keep.append(t)
+        c.seg_domains = fp(t)
     c.domain[:] = list(domain)
     c.domain_y[:] = list(domain_y)
     return c

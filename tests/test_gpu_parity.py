@@ -603,7 +603,7 @@ def test_full_size_properties(n, img, cls, comp):
 
 # ---- OptimizedProxyGeometry, TF-dependent modes: the product's cubes (host mirror over the device region structure)
 #      against the oracle's restatement -- same cubes, hence bit-identical entry/exit images ------------------------------------------
-@pytest.mark.parametrize("mode", ["minboundingbox", "visiblebricks"])
+@pytest.mark.parametrize("mode", ["minboundingbox", "visiblebricks", "outerfaces"])
 @pytest.mark.parametrize("clip", [False, True])
 @pytest.mark.parametrize("cell,threshold", [(4, 1.0), (7, 40.0)])
 def test_optimized_proxy_geometry_modes(ctx, mode, clip, cell, threshold):
@@ -614,7 +614,7 @@ def test_optimized_proxy_geometry_modes(ctx, mode, clip, cell, threshold):
     desc = rc.make_volume_desc((40, 40, 40))
     keys = [(0.0, (0, 0, 0, 0)), (0.3, (0, 0, 0, 0)), (0.35, (255, 120, 40, 3)), (0.7, (255, 255, 255, 120)), (1.0, (255, 255, 255, 255))]
     dom, thr, gamma, amode = (0.0, 65535.0), (0.05, 0.95), 1.0, 1
-    eep = rc.default_eep(proxy_mode={"minboundingbox": abi.PROXY_MINBBOX, "visiblebricks": abi.PROXY_VISIBLE_BRICKS}[mode],
+    eep = rc.default_eep(proxy_mode={"minboundingbox": abi.PROXY_MINBBOX, "visiblebricks": abi.PROXY_VISIBLE_BRICKS, "outerfaces": abi.PROXY_OUTER_FACES}[mode],
                          proxy_cell_size=cell, proxy_threshold=threshold)
     if clip:
         eep.enable_clipping = 1

@@ -611,3 +611,72 @@ def test_background_against_the_oracle(ctx, dtype):
     bgc = np.array([0.25, 0.5, 0.75, 1.0])
     ref = (np.floor(bgc * 65535 + 0.5).astype(np.uint16) if dtype == np.uint16 else bgc.astype(np.float32))
     assert empty.any() and np.all(got[empty] == ref)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# SegmentationRaycaster: rc_segmentation.frag
+# ---------------------------------------------------------------------------------------------------------------------
+def _segmentation_tf(segment_keys, width=256):
+    """segmentationraycaster.cpp:381-415: every segment's 1D TF (width 256 here) resampled into rows 3 i .. 3 i + 2 of a 768-row texture;
+    unset segments use the default TF."""
+    tex = np.zeros((768, width, 4), np.uint8)
+    dom = np.zeros((256, 2), np.float32)
+    default = segment_keys[None]
+    for i in range(256):
+        keys, d = segment_keys.get(i, default)
+        src = orc.tf1d_texture(orc.make_tf(keys, domain=d), 256)
+        fac = np.float32(1.0) * np.float32(256) / np.float32(width)
+        idx = np.minimum((fac * np.arange(width, dtype=np.float32)).astype(np.int32), 255)        # resampleTexture1D
+        tex[3 * i: 3 * i + 3] = src[idx]
+        dom[i] = d
+    return tex, dom
+
+
+@pytest.mark.parametrize("apply_seg", [0, 1])
+@pytest.mark.parametrize("seg_dtype", [np.uint8, np.uint16])
+def test_segmentation_raycaster(ctx, apply_seg, seg_dtype):
+    from voreen_b200 import raycaster as rc
+    n = 40
+    vol = scenes.ct_like_volume(n)
+    # segmentation: ids by octant-ish regions + a sphere, incl. id 0 and ids whose normalisation lands just below an integer
+    z, y, x = np.meshgrid(*(np.arange(n),) * 3, indexing="ij")
+    seg = ((x > n // 2).astype(np.int32) + 2 * (y > n // 3) + 4 * (z > n // 2)) % 5
+    seg[(x - 20) ** 2 + (y - 18) ** 2 + (z - 22) ** 2 < 64] = 7
+    seg = seg.astype(seg_dtype)
+    s = scenes.Scene(vol, W=96, H=88, compositing=[abi.COMP["dvr"], abi.COMP["mip"], abi.COMP["fhn"]], output_connected=[1, 1, 1])
+    s.params.raycaster = abi.RAYCASTER_SEGMENTATION
+    s.params.apply_segmentation = apply_seg
+    s.params.segmentation_bit_depth = 8 if seg_dtype == np.uint8 else 16
+    s.params.empty_space_skipping = 1
+    seg_keys = {None: (scenes.CT_KEYS, (0.0, 65535.0)),
+                1: ([(0.0, (0, 0, 0, 0)), (0.3, (0, 255, 0, 0)), (1.0, (0, 255, 0, 160))], (0.0, 40000.0)),
+                3: ([(0.0, (0, 0, 0, 0)), (0.2, (0, 0, 255, 30)), (1.0, (90, 0, 255, 255))], (10000.0, 65535.0)),
+                7: ([(0.0, (255, 0, 0, 0)), (0.1, (255, 0, 0, 120)), (1.0, (255, 255, 0, 255))], (0.0, 65535.0))}
+    tex, dom = _segmentation_tf(seg_keys)
+    # 16-bit ids 1..7 normalise to ~1e-4: scale 65535 brings them back (rc_segmentation.frag:72-76)
+    seg_desc = rc.make_volume_desc((n, n, n), dtype=abi.U8 if seg_dtype == np.uint8 else abi.U16)
+    ctx.upload_volume(1, seg, desc=seg_desc)
+    ctx.set_segmentation_tf(tex, dom)
+    s.upload(ctx)
+    s.params.collect_stats = 1
+    c_outs, c_depth = ctx.render_camera(s.params, s.eep, s.cam, s.W, s.H)
+    st = ctx.stats()
+    # oracle
+    ov = orc.make_volume(s.vol, s.desc); osg = orc.make_volume(seg, seg_desc)
+    e, ed, x_, xd = s.oracle_eep()
+    cls = [orc.make_classifier(s.tf_tex[0], s.domain), orc.make_classifier(tf2d=tex, seg_domains=dom)]
+    po = s.params
+    ess = po.empty_space_skipping; po.empty_space_skipping = 0
+    o_outs, o_depth, o_st = orc.raycast([ov, osg], cls, po, s.cam, s.W, s.H, e, ed, x_, xd)
+    po.empty_space_skipping = ess
+    for o in range(3):
+        frac, mx = scenes.parity_report(o_outs[o], c_outs[o])
+        print(f"segmentation raycaster apply={apply_seg} {np.dtype(seg_dtype).name} out{o}: within 1/255 {frac:.5f} max {mx:.2e} shaded {st.samples_shaded}/{o_st.samples_shaded}")
+        assert frac >= 0.999, (o, frac, mx)
+    assert st.rays_cast == o_st.rays_cast and st.samples_shaded == o_st.samples_shaded and o_st.samples_shaded > 1000
+    assert float((np.abs(o_depth - c_depth) <= 1e-4).mean()) >= 0.999
+    if apply_seg:       # the per-segment TFs must actually differ from the plain classification
+        s.params.apply_segmentation = 0
+        plain, _ = ctx.render_camera(s.params, s.eep, s.cam, s.W, s.H)
+        assert float(np.abs(np.asarray(plain[0]) - np.asarray(c_outs[0])).max()) > 0.05
+    ctx.lib.b200rc_release_volume(ctx.h, 1)

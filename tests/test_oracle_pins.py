@@ -412,3 +412,50 @@ def test_gaussian_tf_texture_matches_the_reference_transfunc1dgaussian():
         assert np.array_equal(got, want), (name, np.argwhere(got != want)[:5], got[got != want][:5], want[got != want][:5])
         got_h = host.tf1d_gaussian_texture(curves, w, threshold=thr, gamma=gamma, alpha_mode=am)
         assert np.array_equal(got_h, want), ("host mirror", name)
+
+
+def test_outer_faces_mesh_gives_the_entry_exit_of_the_brick_cubes():
+    """OptimizedProxyGeometry "outerfaces" (optimizedproxygeometry.cpp:1392-1604) emits the cell faces between a non-empty and an empty
+    cell (or the volume border).  MeshEntryExitPoints takes the nearest front face and the farthest back face per ray, so that mesh
+    yields the same entry/exit points as the non-empty cells rendered as cubes ("visiblebricks", what B200RC_PROXY_OUTER_FACES emits):
+    checked here on random occupancy grids with rays in float64 -- faces as rectangles against cubes as slabs."""
+    rng = np.random.default_rng(12)
+    for trial in range(6):
+        n = (6, 5, 7)
+        occ = rng.random(n) < (0.25 + 0.1 * trial)
+        occ[2:4, 1:3, 2:5] = True
+        faces = []          # (axis, plane coordinate, lo (2), hi (2), outward sign)
+        for idx in np.argwhere(occ):
+            for a in range(3):
+                for sgn in (-1, 1):
+                    nb = idx.copy(); nb[a] += sgn
+                    if nb[a] < 0 or nb[a] >= n[a] or not occ[tuple(nb)]:
+                        o = [b for b in range(3) if b != a]
+                        faces.append((a, idx[a] + (1 if sgn > 0 else 0), (idx[o[0]], idx[o[1]]), (idx[o[0]] + 1, idx[o[1]] + 1), sgn))
+        cubes = [(idx.astype(float), idx.astype(float) + 1.0) for idx in np.argwhere(occ)]
+        for _ in range(300):
+            org = rng.normal(size=3); org = org / np.linalg.norm(org) * 12.0 + np.array(n) / 2
+            tgt_ = rng.random(3) * np.array(n)
+            d = tgt_ - org; d /= np.linalg.norm(d)
+            t_in, t_out = np.inf, -np.inf
+            for lo, hi in cubes:
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    t0 = (lo - org) / d; t1 = (hi - org) / d
+                tn = np.max(np.minimum(t0, t1)); tf = np.min(np.maximum(t0, t1))
+                if tn <= tf and tf > 0:
+                    t_in = min(t_in, tn); t_out = max(t_out, tf)
+            f_in, f_out = np.inf, -np.inf
+            for a, plane, lo, hi, sgn in faces:
+                if d[a] == 0:
+                    continue
+                t = (plane - org[a]) / d[a]
+                p = org + t * d
+                o = [b for b in range(3) if b != a]
+                if t > 0 and lo[0] <= p[o[0]] <= hi[0] and lo[1] <= p[o[1]] <= hi[1]:
+                    if d[a] * sgn < 0:
+                        f_in = min(f_in, t)         # front face: outward normal against the ray
+                    else:
+                        f_out = max(f_out, t)
+            assert np.isinf(t_in) == np.isinf(f_in)
+            if np.isfinite(t_in):
+                assert abs(t_in - f_in) < 1e-9 and abs(t_out - f_out) < 1e-9

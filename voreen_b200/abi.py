@@ -25,8 +25,8 @@ SAMPLER_EXACT, SAMPLER_TEX = 0, 1
 OUT_RGBA32F, OUT_RGBA16 = 0, 1
 INSIDE_NONE, INSIDE_GPU = 0, 1
 ABI_VERSION = 4          # include/b200rc.h B200RC_ABI_VERSION
-RAYCASTER_SINGLE, RAYCASTER_SIMPLE, RAYCASTER_RGB = 0, 1, 2
-PROXY_BBOX, PROXY_MINBBOX, PROXY_VISIBLE_BRICKS = 0, 1, 2
+RAYCASTER_SINGLE, RAYCASTER_SIMPLE, RAYCASTER_RGB, RAYCASTER_SEGMENTATION = 0, 1, 2, 3
+PROXY_BBOX, PROXY_MINBBOX, PROXY_VISIBLE_BRICKS, PROXY_OUTER_FACES = 0, 1, 2, 3
 COMPOSITE_ERT = 0x100
 
 
@@ -63,7 +63,8 @@ class Params(C.Structure):
                 ("light", Light),
                 ("sampler", C.c_int32), ("empty_space_skipping", C.c_int32), ("out_format", C.c_int32),
                 ("quantize_depth24", C.c_int32), ("collect_stats", C.c_int32), ("partial_image", C.c_int32),
-                ("image_band_modulus", C.c_int32), ("image_band_remainder", C.c_int32), ("raycaster", C.c_int32), ("rgb_color_modulation", C.c_int32)]
+                ("image_band_modulus", C.c_int32), ("image_band_remainder", C.c_int32), ("raycaster", C.c_int32), ("rgb_color_modulation", C.c_int32),
+                ("apply_segmentation", C.c_int32), ("segmentation_bit_depth", C.c_int32)]
 
 
 class EepParams(C.Structure):
@@ -107,7 +108,7 @@ SYMBOLS = [
     "b200rc_build_preint", "b200rc_download_preint", "b200rc_set_tf2d", "b200rc_entry_exit", "b200rc_render",
     "b200rc_render_camera", "b200rc_render_camera_device", "b200rc_composite", "b200rc_finalize", "b200rc_ert_plan",
     "b200rc_remarch_device", "b200rc_upload_volume_begin", "b200rc_upload_volume_slab", "b200rc_upload_volume_end", "b200rc_load_raw_file", "b200rc_rescale", "b200rc_composite_keyed",
-    "b200rc_host_alloc", "b200rc_host_free", "b200rc_image_compositor", "b200rc_image_background",
+    "b200rc_host_alloc", "b200rc_host_free", "b200rc_image_compositor", "b200rc_image_background", "b200rc_set_segmentation_tf",
 ]
 
 _lib = None
@@ -150,6 +151,7 @@ def load_library():
     lib.b200rc_build_preint.argtypes = [vp, i32, i32, f32, i32]
     lib.b200rc_download_preint.argtypes = [vp, i32, pf, i32]
     lib.b200rc_set_tf2d.argtypes = [vp, i32, vp, i32, i32, f32, f32, f32, f32]
+    lib.b200rc_set_segmentation_tf.argtypes = [vp, vp, i32, i32, pf]
     lib.b200rc_entry_exit.argtypes = [vp, C.POINTER(EepParams), C.POINTER(Camera), i32, i32, pf, pf, pf, pf]
     lib.b200rc_render.argtypes = [vp, C.POINTER(Params), C.POINTER(Camera), i32, i32, pf, pf, pf, pf, C.POINTER(vp * 3), pf]
     lib.b200rc_render_camera.argtypes = [vp, C.POINTER(Params), C.POINTER(EepParams), C.POINTER(Camera), i32, i32, C.POINTER(vp * 3), pf]

@@ -107,6 +107,7 @@ extern "C" int b200rc_destroy(b200rc_ctx* ctx) {
     }
     cudaFree(ctx->d_entry); cudaFree(ctx->d_exit); cudaFree(ctx->d_entry_depth); cudaFree(ctx->d_exit_depth);
     for (int o = 0; o < 3; ++o) cudaFree(ctx->d_out[o]);
+    cudaFree(ctx->d_seg_domains);
     cudaFree(ctx->d_out_depth); cudaFree(ctx->d_stats); cudaFree(ctx->d_tile_counter); cudaFree(ctx->d_remarch_list); cudaFree(ctx->d_tile_cost); cudaFree(ctx->d_tile_order); cudaFree(ctx->d_boxes);
     for (int i = 0; i < 6; ++i) cudaEventDestroy(ctx->ev[i]);
     cudaStreamDestroy(ctx->own_stream);
@@ -191,6 +192,16 @@ extern "C" int b200rc_download_preint(b200rc_ctx* ctx, int chan, float* rgba32f,
     RC_CHECK(cudaStreamSynchronize(ctx->stream));
     return B200RC_OK;
 }
+extern "C" int b200rc_set_segmentation_tf(b200rc_ctx* ctx, const uint8_t* rgba8, int width, int height, const float* domains) {
+    CTX_GUARD();
+    if (!rgba8 || !domains || width < 2 || height < 3) { ctx->set_error("set_segmentation_tf: bad arguments"); return B200RC_ERR_INVALID; }
+    int rc = rc_tf_set_2d(ctx, 1, rgba8, width, height, 0.f, 1.f, 0.f, 1.f);        // LINEAR-filtered rgba8 image: the 2D-TF storage of classifier slot 1
+    if (rc) return rc;
+    if (!ctx->d_seg_domains) RC_CHECK(cudaMalloc(&ctx->d_seg_domains, 256 * sizeof(float2)));
+    RC_CHECK(cudaMemcpyAsync(ctx->d_seg_domains, domains, 256 * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    RC_CHECK(cudaStreamSynchronize(ctx->stream));
+    return B200RC_OK;
+}
 extern "C" int b200rc_set_tf2d(b200rc_ctx* ctx, int chan, const uint8_t* rgba8, int w, int h, float lox, float hix, float loy, float hiy) {
     CTX_GUARD(); return rc_tf_set_2d(ctx, chan, rgba8, w, h, lox, hix, loy, hiy);
 }
@@ -240,7 +251,19 @@ static int build_params(b200rc_ctx* ctx, const b200rc_params* P, const b200rc_ca
     p.simple = P->multi_volume ? 0 : (P->raycaster == B200RC_RAYCASTER_SIMPLE ? 1 : (P->raycaster == B200RC_RAYCASTER_RGB ? 2 : 0));
     p.rgb_modulate = P->rgb_color_modulation ? 1 : 0;
     if (p.simple == 2 && ctx->vol[0].valid && ctx->vol[0].desc.channels < 3) { ctx->set_error("render: RGBRaycaster needs a 3- or 4-channel volume"); return B200RC_ERR_INVALID; }
-    if (P->raycaster < B200RC_RAYCASTER_SINGLE || P->raycaster > B200RC_RAYCASTER_RGB) { ctx->set_error("render: unknown raycaster kind"); return B200RC_ERR_INVALID; }
+    if (P->raycaster < B200RC_RAYCASTER_SINGLE || P->raycaster > B200RC_RAYCASTER_SEGMENTATION) { ctx->set_error("render: unknown raycaster kind"); return B200RC_ERR_INVALID; }
+    if (!P->multi_volume && P->raycaster == B200RC_RAYCASTER_SEGMENTATION) {
+        if (ctx->vol[0].valid && ctx->vol[0].desc.channels != 1) { ctx->set_error("render: SegmentationRaycaster needs a one-channel intensity volume"); return B200RC_ERR_INVALID; }
+        p.seg = 1; p.seg_apply = P->apply_segmentation ? 1 : 0;
+        if (p.seg_apply) {
+            const VolumeSlot& sv = ctx->vol[1];
+            if (!sv.valid || sv.desc.channels != 1 || sv.desc.dtype == B200RC_F32 || sv.sharded) { ctx->set_error("render: applySegmentation needs a one-channel uint8 / uint16 segmentation volume in slot 1"); return B200RC_ERR_NOT_READY; }
+            if (!ctx->cls[1].tf2d || !ctx->d_seg_domains) { ctx->set_error("render: no segmentation transfer functions (b200rc_set_segmentation_tf)"); return B200RC_ERR_NOT_READY; }
+            const int bits = P->segmentation_bit_depth;
+            p.seg_scale = bits == 12 ? 4095.0f : (bits == 16 ? 65535.0f : 255.0f);      // rc_segmentation.frag:72-76
+            p.seg_dom = ctx->d_seg_domains;
+        }
+    }
     p.iso = P->iso_value;
     p.light = P->light;
     p.near_d = cam->near_dist; p.far_d = cam->far_dist;
@@ -267,10 +290,12 @@ static int build_params(b200rc_ctx* ctx, const b200rc_params* P, const b200rc_ca
     p.channel_shift = (!P->multi_volume && P->enable_channel_shift) ? 1 : 0;
     memcpy(p.shift, P->channel_shift, sizeof p.shift);
     float w2p[16];
-    for (int v = 0; v < nv; ++v) {
+    const int nv_fill = p.seg_apply ? 2 : nv;      // SegmentationRaycaster: slot 1 = the segmentation volume (NEAREST, clamp to edge)
+    for (int v = 0; v < nv_fill; ++v) {
         VolumeSlot& vs = ctx->vol[v];
         if (!vs.valid) { ctx->set_error("render: volume slot is empty"); return B200RC_ERR_NOT_READY; }
-        const b200rc_volume_params& vp = P->vol[v];
+        b200rc_volume_params vp = P->vol[v];
+        if (p.seg_apply && v == 1) { vp.filter = B200RC_FILTER_NEAREST; vp.clamp = B200RC_CLAMP_TO_EDGE; vp.border_intensity = 0.f; vp.classification = B200RC_CLASS_TF; vp.shading = B200RC_SHADE_NONE; }
         VolDev& d = p.vol[v];
         d.bricks = vs.bricks;
         for (int a = 0; a < 3; ++a) {
@@ -318,6 +343,7 @@ static int build_params(b200rc_ctx* ctx, const b200rc_params* P, const b200rc_ca
         const int mode = p.simple ? B200RC_CLASS_TF : (P->multi_volume ? P->vol[c].classification : P->vol[0].classification);
         ClsDev& d = p.cls[c];
         d.dom_lo = k.dom[0]; d.dom_hi = k.dom[1]; d.domy_lo = k.domy[0]; d.domy_hi = k.domy[1];
+        if (p.seg_apply) continue;      // classified through the segmentation TF texture
         if (mode == B200RC_CLASS_TF) {
             if (!k.tf) { ctx->set_error("render: no 1D transfer function for channel/volume"); return B200RC_ERR_NOT_READY; }
             int rc = rc_tf_update_lut(ctx, c, P->sampling_step);
@@ -332,9 +358,13 @@ static int build_params(b200rc_ctx* ctx, const b200rc_params* P, const b200rc_ca
             d.tf2d = k.tf2d; d.tf2d_w = k.tf2d_w; d.tf2d_h = k.tf2d_h;
         }
     }
+    if (p.seg_apply) {      // the segmentation TF texture: LINEAR-filtered rgba8 image in the 2D-TF storage of classifier slot 1
+        p.cls[1].tf2d = ctx->cls[1].tf2d; p.cls[1].tf2d_w = ctx->cls[1].tf2d_w; p.cls[1].tf2d_h = ctx->cls[1].tf2d_h;
+    }
     // empty-space skipping (no channel shift): occupancy for the current TFs
     if (p.simple) { p.classification[0] = B200RC_CLASS_TF; p.channel_shift = 0; p.preint_comp = 0; }
-    if (P->empty_space_skipping && !P->multi_volume && !p.channel_shift && !(p.simple && (p.simple == 2 || ctx->vol[0].desc.channels != 1))) {
+    if (p.seg) p.channel_shift = 0;
+    if (P->empty_space_skipping && !P->multi_volume && !p.channel_shift && !p.seg_apply && !(p.simple && (p.simple == 2 || ctx->vol[0].desc.channels != 1))) {
         int modes[4];
         for (int c = 0; c < ncls; ++c) modes[c] = p.simple ? B200RC_CLASS_TF : P->vol[0].classification;
         int rc = rc_volume_build_occupancy(ctx, 0, modes, ncls, false, P->vol[0].clamp, P->vol[0].border_intensity);
@@ -388,7 +418,7 @@ int rc_march_launch(b200rc_ctx* ctx, const DevParams& p, int sampler, int nch, i
     // marcher 2.4 ms, per-ray kernel 3.4 ms -> the slab marcher stays; B200RC_REMARCH=ray selects the per-ray kernel (A/B)
     static const bool remarch_ray = getenv("B200RC_REMARCH") && !strcmp(getenv("B200RC_REMARCH"), "ray");
     const bool slab_ok = ctx->use_slab && !(p.flags && (remarch_ray || p.pixel_list));
-    if (p.simple) return rc_march_generic(ctx, p, sampler, nch);      // SimpleRaycaster: the run-time-switched per-ray kernel
+    if (p.simple || p.seg) return rc_march_generic(ctx, p, sampler, nch);      // Simple / RGB / SegmentationRaycaster: the run-time-switched per-ray kernel
     if (slab_ok && rc_march_slab(ctx, p, sampler, nch, dtype, &rc)) return rc;
     if (rc_march_fast(ctx, p, sampler, nch, dtype, &rc)) return rc;
     if (rc_march_fast_multi(ctx, p, sampler, &rc)) return rc;

@@ -83,6 +83,7 @@ struct DevParams {
     const float* prefix; const unsigned char* flags;
     // ... compacted by ert_plan_kernel: the per-ray kernel marches pixel_list[0 .. *pixel_count) instead of image tiles
     const unsigned int* pixel_list; const unsigned int* pixel_count;
+    int seg, seg_apply; float seg_scale; const float2* seg_dom;      // SegmentationRaycaster (rc_segmentation.frag); the segmentation TF sits in cls[1].tf2d, the segmentation volume in vol[1]
     int simple;                     // 1: SimpleRaycaster (rc_simple.frag), 2: RGBRaycaster (rc_rgb.frag); per-ray generic kernel
     int rgb_modulate;               // RGBRaycaster applyColorModulation
     int band_mod, band_rem;         // sort-first: render only the pixel-row bands with band % band_mod == band_rem (band_mod <= 1: all)

@@ -72,6 +72,7 @@ struct b200rc_ctx {
     const void* plan_flags = nullptr; size_t plan_n = 0;                   // ... and the flags buffer / pixel count that call was made for
     float* d_tile_cost = nullptr; unsigned int* d_tile_order = nullptr; size_t tile_capacity = 0;
     float* d_boxes = nullptr; int boxes_capacity = 0;
+    float2* d_seg_domains = nullptr;    // SegmentationRaycaster: 256 per-segment TF domains
     b200rc_stats stats{};
     unsigned long long launches = 0;
     bool use_slab = true;               // B200RC_MARCHER=ray (environment) selects the per-ray kernels for A/B measurements

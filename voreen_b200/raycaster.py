@@ -255,6 +255,12 @@ class Context:
         h, w = rgba8.shape[:2]
         self._check(self.lib.b200rc_set_tf2d(self.h, chan, rgba8.ctypes.data_as(C.c_void_p), w, h, domain_x[0], domain_x[1], domain_y[0], domain_y[1]), "set_tf2d")
 
+    def set_segmentation_tf(self, rgba8, domains):
+        """SegmentationRaycaster: (3 * 256, width, 4) uint8 texture (three rows per segment) + (256, 2) float32 per-segment domains."""
+        rgba8 = np.ascontiguousarray(rgba8, np.uint8); domains = np.ascontiguousarray(domains, np.float32)
+        h, w = rgba8.shape[:2]
+        self._check(self.lib.b200rc_set_segmentation_tf(self.h, rgba8.ctypes.data_as(C.c_void_p), w, h, domains.ctypes.data_as(C.POINTER(C.c_float))), "set_segmentation_tf")
+
     # -- entry / exit ---------------------------------------------------------------------------------------------
     def entry_exit(self, eep, cam, W, H):
         e = np.empty((H, W, 4), np.float32); x = np.empty((H, W, 4), np.float32)
