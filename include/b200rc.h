@@ -243,6 +243,26 @@ typedef struct b200rc_background_params {
     int32_t angle_deg;          /* "angle", 0..359, default 60 */
 } b200rc_background_params;
 
+/* VolumeOctree facts (V/include/voreen/core/datastructures/octree/volumeoctreebase.h): getOctreeDim, getBrickDim, getNumLevels,
+ * getActualTreeDepth, getNumNodes, getNumBricks. */
+typedef struct b200rc_octree_info {
+    int32_t octree_dim;         /* next power of two >= the largest volume dimension (cubic octree) */
+    int32_t brick_dim;
+    int32_t num_levels;         /* log2(octree_dim / brick_dim) + 1 */
+    int32_t actual_depth;       /* levels that hold at least one node after the homogeneity optimisation */
+    uint64_t num_nodes;         /* nodes of the (optimised) tree, dummy nodes outside the volume included, as VolumeOctreeNode::getNodeCount */
+    uint64_t num_bricks;
+    double   build_ms;          /* device time of the construction kernels */
+} b200rc_octree_info;
+
+/* SingleOctreeRaycasterCL render parameters (singleoctreeraycastercl.cpp:731-749): samplingStepSize = 1 / (avgDim * samplingRate),
+ * node_level = level of detail counted from the root (num_levels - 1 = full resolution, "Full" quality; < 0 = full resolution). */
+typedef struct b200rc_octree_render_params {
+    float   sampling_step;
+    int32_t node_level;
+    int32_t filter;             /* B200RC_FILTER_* inside a brick (TEXTURE_FILTER_LINEAR define) */
+} b200rc_octree_render_params;
+
 typedef struct b200rc_stats {
     double   last_render_ms;        /* device time of the last render call's kernels (CUDA events) */
     double   last_march_ms;         /* ... of the ray-marching kernel alone */
@@ -389,6 +409,23 @@ int b200rc_remarch_device(b200rc_ctx* ctx, const b200rc_params* params, const b2
  * Host buffers unless on_device != 0; src_depth / dst_depth may both be NULL. */
 int b200rc_rescale(b200rc_ctx* ctx, const void* src_color, const float* src_depth, int src_w, int src_h, int format,
                    void* dst_color, float* dst_depth, int dst_w, int dst_h, int on_device);
+
+/* ---- octree / multi-resolution brick pool: replaces VolumeOctree construction
+ *      (V/src/core/datastructures/octree/volumeoctree.cpp:637-961,1186-1536) and the DVR traversal of SingleOctreeRaycasterCL
+ *      (V/modules/opencl/cl/singleoctreeraycaster.cl:190-300, octree_config.cl, octree_dvr.cl) for one-channel uint8 / uint16 volumes.
+ * build: from the resident volume of `slot`; brick_dim a power of two; homogeneity_threshold relative to the value range
+ *        (< 0: complete tree, no optimisation; >= 0: nodes with max - min <= threshold * 65535 keep no brick and no subtree);
+ *        half_sample: 0 mean, 1 max, 2 min (VolumeOctree::HalfSampleAggregateFunction).
+ * download: node values of `level` (0 = root; (2^level)^3 nodes, x fastest) and, optionally, their bricks (brick_dim^3 uint16 each,
+ *        node order); flags bit 0 = node exists, 1 = inside the volume, 2 = has a brick, 3 = has children.  Any pointer may be NULL.
+ * render: DVR through the octree at `node_level` with the 1D TF of classifier slot 0 (LINEAR-filtered, as read_imagef does) --
+ *        no shading, early termination at 0.95, out_rgba32f W x H x 4 floats, out_firsthit (may be NULL) the first-hit ray
+ *        parameter / ray length.  Entry/exit points are generated on the device (eep, texture coordinates). */
+int b200rc_octree_build(b200rc_ctx* ctx, int slot, int brick_dim, float homogeneity_threshold, int half_sample);
+int b200rc_octree_get_info(b200rc_ctx* ctx, int slot, b200rc_octree_info* out);
+int b200rc_octree_download(b200rc_ctx* ctx, int slot, int level, uint16_t* avg, uint16_t* min_values, uint16_t* max_values, uint8_t* flags, uint16_t* bricks);
+int b200rc_octree_render(b200rc_ctx* ctx, int slot, const b200rc_octree_render_params* params, const b200rc_eep_params* eep, const b200rc_camera* cam,
+                         int width, int height, float* out_rgba32f, float* out_firsthit);
 
 /* ---- image-space post chain: the two processors that follow the raycaster in the standard workspaces, so that a
  *      frame can stay on the device up to the canvas.  Per-pixel maps over equal-sized images; `format` = B200RC_OUT_RGBA16 (what

@@ -1783,3 +1783,110 @@ void orc_tf1d_gaussian_texture(const orc_tf_curve* curves, int n, const float th
         else if (alpha_mode == 0) px[3] = 0;
     }
 }
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* SingleOctreeRaycasterCL, DVR (singleoctreeraycaster.cl:190-300; octree_config.cl:150-155,313-368,402-413,         */
+/* 437-506,590-646; octree_dvr.cl:52-80), one channel, over the dense per-level node arrays of oracle/octree_ref.py   */
+/* (all levels concatenated at (8^k - 1) / 7; flags bit 2 = has brick, bit 3 = has children)                          */
+/* ------------------------------------------------------------------------------------------------------------ */
+static inline size_t oct_off(int k) { return (((size_t)1 << (3 * k)) - 1) / 7; }
+static v4 oct_tf_linear(const uint8_t* tf, int w, float s) {      /* read_imagef, CLK_FILTER_LINEAR, CLK_ADDRESS_CLAMP_TO_EDGE, UNORM_INT8 */
+    float u = s * (float)w - 0.5f, fu = floorf(u), a = u - fu;
+    int x0 = (int)fu, x1 = x0 + 1;
+    if (x0 < 0) x0 = 0; if (x0 > w - 1) x0 = w - 1; if (x1 < 0) x1 = 0; if (x1 > w - 1) x1 = w - 1;
+    v4 c0 = V4(tf[4 * x0] / 255.f, tf[4 * x0 + 1] / 255.f, tf[4 * x0 + 2] / 255.f, tf[4 * x0 + 3] / 255.f);
+    v4 c1 = V4(tf[4 * x1] / 255.f, tf[4 * x1 + 1] / 255.f, tf[4 * x1 + 2] / 255.f, tf[4 * x1 + 3] / 255.f);
+    return lerp4(c0, c1, a);
+}
+void orc_octree_raycast(const uint16_t* avg, const uint8_t* flags, const uint16_t* bricks, int levels, int B, const int32_t dims[3], int octree_dim,
+                        const uint8_t* tf, int tf_width, float dom_lo, float dom_hi, float rwm_scale, float rwm_offset,
+                        float step, int lod, int filter_linear, const float* entry, const float* exitp, int W, int H, float* out, float* out_firsthit) {
+    (void)levels;
+    const float sc[3] = {(float)dims[0] / (float)octree_dim, (float)dims[1] / (float)octree_dim, (float)dims[2] / (float)octree_dim};
+#pragma omp parallel for schedule(dynamic, 2)
+    for (int py = 0; py < H; ++py)
+        for (int px = 0; px < W; ++px) {
+            size_t pix = (size_t)py * W + px;
+            v3 en = V3(entry[4 * pix] * sc[0], entry[4 * pix + 1] * sc[1], entry[4 * pix + 2] * sc[2]);
+            v3 ex = V3(exitp[4 * pix] * sc[0], exitp[4 * pix + 1] * sc[1], exitp[4 * pix + 2] * sc[2]);
+            v4 color = V4(0, 0, 0, 0); float firsthit = 1.0f;
+            v3 dir = sub3(ex, en);
+            float tEnd = sqrtf((dir.x * dir.x + dir.y * dir.y) + dir.z * dir.z);
+            int moving = tEnd > 0.f;
+            if (moving) dir = V3(dir.x / tEnd, dir.y / tEnd, dir.z / tEnd);
+            if (entry[4 * pix + 3] > 0.f || exitp[4 * pix + 3] > 0.f) {
+                float param = 0.f, tEndNode = -1.f;
+                v3 nllf = V3(0, 0, 0), nrcp = V3(1, 1, 1); size_t node = 0; int has_brick = 0;
+                while (param <= tEnd) {
+                    v3 s = V3(en.x + param * dir.x, en.y + param * dir.y, en.z + param * dir.z);
+                    if (param > (tEndNode + 1.e-6f)) {
+                        int k = 0, ix = 0, iy = 0, iz = 0; v3 llf = V3(0, 0, 0); float half = 1.0f;
+                        node = 0;
+                        while (k < lod && (flags[node] & 8)) {          /* getNodeAtSamplePos */
+                            half = half * 0.5f;
+                            int cx = s.x >= llf.x + half, cy = s.y >= llf.y + half, cz = s.z >= llf.z + half;
+                            ix = ix * 2 + cx; iy = iy * 2 + cy; iz = iz * 2 + cz;
+                            llf = V3(llf.x + half * (float)cx, llf.y + half * (float)cy, llf.z + half * (float)cz);
+                            ++k;
+                            int G = 1 << k;
+                            node = oct_off(k) + ((size_t)iz * G + iy) * G + ix;
+                        }
+                        nllf = llf;
+                        v3 urb = V3(llf.x + half, llf.y + half, llf.z + half);
+                        has_brick = (flags[node] & 4) != 0;
+                        nrcp = V3(1.f / (urb.x - llf.x), 1.f / (urb.y - llf.y), 1.f / (urb.z - llf.z));
+                        if (moving) {       /* fetchNextRayNode over computeNodeExitPoint */
+                            float ex_ = dir.x >= 0.f ? urb.x : llf.x, ey_ = dir.y >= 0.f ? urb.y : llf.y, ez_ = dir.z >= 0.f ? urb.z : llf.z;
+                            float tx = dir.x != 0.f ? (ex_ - s.x) / dir.x : 1e6f, ty = dir.y != 0.f ? (ey_ - s.y) / dir.y : 1e6f, tz = dir.z != 0.f ? (ez_ - s.z) / dir.z : 1e6f;
+                            float tmin = gl_min(tx, gl_min(ty, tz)) - 1e-6f;
+                            v3 nexit = V3(s.x + tmin * dir.x, s.y + tmin * dir.y, s.z + tmin * dir.z);
+                            float toff = gl_min((nexit.x - s.x) / dir.x, gl_min((nexit.y - s.y) / dir.y, (nexit.z - s.z) / dir.z));
+                            toff = floorf(toff / step) * step;
+                            tEndNode = param + toff;
+                        } else tEndNode = param;
+                    }
+                    float intensity;
+                    if (s.x < 0.f || s.x > 1.f || s.y < 0.f || s.y > 1.f || s.z < 0.f || s.z > 1.f) intensity = 0.f;
+                    else if (has_brick) {
+                        const uint16_t* brick = bricks + node * (size_t)B * B * B;
+                        v3 q = V3((s.x - nllf.x) * nrcp.x, (s.y - nllf.y) * nrcp.y, (s.z - nllf.z) * nrcp.z);
+                        if (filter_linear) {
+                            float cxf = q.x * (float)(B - 1), cyf = q.y * (float)(B - 1), czf = q.z * (float)(B - 1);
+                            int fx = (int)floorf(cxf), fy = (int)floorf(cyf), fz = (int)floorf(czf);
+                            int lx = fx < 0 ? 0 : (fx > B - 1 ? B - 1 : fx), ly = fy < 0 ? 0 : (fy > B - 1 ? B - 1 : fy), lz = fz < 0 ? 0 : (fz > B - 1 ? B - 1 : fz);
+                            int hx = fx + 1 > B - 1 ? B - 1 : fx + 1, hy = fy + 1 > B - 1 ? B - 1 : fy + 1, hz = fz + 1 > B - 1 ? B - 1 : fz + 1;
+                            float pxw = cxf - (float)lx, pyw = cyf - (float)ly, pzw = czf - (float)lz;
+#define OV(x, y, z) ((float)brick[((size_t)(z) * B + (y)) * B + (x)])
+                            float acc = OV(lx, ly, lz) * (1.f - pxw) * (1.f - pyw) * (1.f - pzw);
+                            acc = acc + OV(lx, ly, hz) * (1.f - pxw) * (1.f - pyw) * pzw;
+                            acc = acc + OV(lx, hy, lz) * (1.f - pxw) * pyw * (1.f - pzw);
+                            acc = acc + OV(lx, hy, hz) * (1.f - pxw) * pyw * pzw;
+                            acc = acc + OV(hx, ly, lz) * pxw * (1.f - pyw) * (1.f - pzw);
+                            acc = acc + OV(hx, ly, hz) * pxw * (1.f - pyw) * pzw;
+                            acc = acc + OV(hx, hy, lz) * pxw * pyw * (1.f - pzw);
+                            acc = acc + OV(hx, hy, hz) * pxw * pyw * pzw;
+#undef OV
+                            intensity = acc * (1.f / 65536.f);
+                        } else {
+                            int cx = (int)rintf(q.x * (float)B - 0.5f), cy = (int)rintf(q.y * (float)B - 0.5f), cz = (int)rintf(q.z * (float)B - 0.5f);
+                            cx = cx < 0 ? 0 : (cx > B - 1 ? B - 1 : cx); cy = cy < 0 ? 0 : (cy > B - 1 ? B - 1 : cy); cz = cz < 0 ? 0 : (cz > B - 1 ? B - 1 : cz);
+                            intensity = (float)brick[((size_t)cz * B + cy) * B + cx] * (1.f / 65536.f);
+                        }
+                    } else intensity = clampf((float)avg[node] * 1.f / 65535.f, 0.f, 1.f);
+                    float rw = intensity * rwm_scale + rwm_offset;
+                    v4 c = oct_tf_linear(tf, tf_width, (rw - dom_lo) / (dom_hi - dom_lo));
+                    if (c.w > 0.f) {
+                        v3 rgb = V3(gl_min(c.x, 1.f), gl_min(c.y, 1.f), gl_min(c.z, 1.f));
+                        float a = 1.f - powf(1.f - c.w, step * 200.f);
+                        float k = (1.f - color.w) * a;
+                        color.x += k * rgb.x; color.y += k * rgb.y; color.z += k * rgb.z; color.w += k;
+                        firsthit = gl_min(param / tEnd, firsthit);
+                    }
+                    if (color.w >= 0.95f) { color.w = 1.f; param = tEnd + step; }
+                    param += step;
+                }
+            }
+            out[4 * pix] = color.x; out[4 * pix + 1] = color.y; out[4 * pix + 2] = color.z; out[4 * pix + 3] = color.w;
+            if (out_firsthit) out_firsthit[pix] = firsthit;
+        }
+}

@@ -151,6 +151,11 @@ typedef struct orc_tf_curve {
 } orc_tf_curve;
 void orc_tf1d_gaussian_texture(const orc_tf_curve* curves, int n, const float threshold[2], float gamma, int alpha_mode, int width, uint8_t* out_rgba8);
 
+/* SingleOctreeRaycasterCL DVR traversal over dense per-level node arrays (oracle/octree_ref.py builds them) */
+void orc_octree_raycast(const uint16_t* avg, const uint8_t* flags, const uint16_t* bricks, int levels, int brick_dim, const int32_t dims[3], int octree_dim,
+                        const uint8_t* tf_rgba8, int tf_width, float dom_lo, float dom_hi, float rwm_scale, float rwm_offset,
+                        float step, int node_level, int filter_linear, const float* entry_rgba, const float* exit_rgba, int W, int H, float* out_rgba, float* out_firsthit);
+
 #ifdef __cplusplus
 }
 #endif

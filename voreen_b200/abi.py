@@ -75,6 +75,15 @@ class EepParams(C.Structure):
                 ("boxes", C.POINTER(C.c_float)), ("n_boxes", C.c_int32)]
 
 
+class OctreeInfo(C.Structure):
+    _fields_ = [("octree_dim", C.c_int32), ("brick_dim", C.c_int32), ("num_levels", C.c_int32), ("actual_depth", C.c_int32),
+                ("num_nodes", C.c_uint64), ("num_bricks", C.c_uint64), ("build_ms", C.c_double)]
+
+
+class OctreeRenderParams(C.Structure):
+    _fields_ = [("sampling_step", C.c_float), ("node_level", C.c_int32), ("filter", C.c_int32)]
+
+
 class BackgroundParams(C.Structure):
     _fields_ = [("mode", C.c_int32), ("blend_mode", C.c_int32), ("color1", C.c_float * 4), ("color2", C.c_float * 4), ("angle_deg", C.c_int32)]
 
@@ -109,6 +118,7 @@ SYMBOLS = [
     "b200rc_render_camera", "b200rc_render_camera_device", "b200rc_composite", "b200rc_finalize", "b200rc_ert_plan",
     "b200rc_remarch_device", "b200rc_upload_volume_begin", "b200rc_upload_volume_slab", "b200rc_upload_volume_end", "b200rc_load_raw_file", "b200rc_rescale", "b200rc_composite_keyed",
     "b200rc_host_alloc", "b200rc_host_free", "b200rc_image_compositor", "b200rc_image_background", "b200rc_set_segmentation_tf",
+    "b200rc_octree_build", "b200rc_octree_get_info", "b200rc_octree_download", "b200rc_octree_render",
 ]
 
 _lib = None
@@ -164,6 +174,10 @@ def load_library():
     lib.b200rc_remarch_device.argtypes = [vp, C.POINTER(Params), C.POINTER(Camera), i32, i32, vp, vp, C.POINTER(vp * 3), vp]
     lib.b200rc_image_compositor.argtypes = [vp, i32, f32, f32, f32, i32, vp, vp, vp, vp, i32, vp, vp, i32, i32, i32]
     lib.b200rc_image_background.argtypes = [vp, C.POINTER(BackgroundParams), vp, vp, i32, vp, vp, i32, i32, i32]
+    lib.b200rc_octree_build.argtypes = [vp, i32, i32, f32, i32]
+    lib.b200rc_octree_get_info.argtypes = [vp, i32, C.POINTER(OctreeInfo)]
+    lib.b200rc_octree_download.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
+    lib.b200rc_octree_render.argtypes = [vp, i32, C.POINTER(OctreeRenderParams), C.POINTER(EepParams), C.POINTER(Camera), i32, i32, pf, pf]
     lib.b200rc_host_alloc.argtypes = [sz, C.POINTER(vp)]
     lib.b200rc_host_free.argtypes = [vp]
     for s in SYMBOLS:

@@ -98,6 +98,7 @@ extern "C" int b200rc_destroy(b200rc_ctx* ctx) {
     if (!ctx) return B200RC_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    rc_octree_destroy_all(ctx);
     for (int s = 0; s < B200RC_MAX_VOLUMES; ++s) rc_volume_release(ctx, s);
     for (int c = 0; c < B200RC_MAX_CHANNELS; ++c) {
         ClassifierSlot& k = ctx->cls[c];
@@ -740,5 +741,44 @@ extern "C" int b200rc_image_background(b200rc_ctx* ctx, const b200rc_background_
     RC_CHECK(cudaMemcpyAsync(dst_color, oc.d, cb, cudaMemcpyDeviceToHost, ctx->stream));
     if (dst_depth) RC_CHECK(cudaMemcpyAsync(dst_depth, od.d, db, cudaMemcpyDeviceToHost, ctx->stream));
     RC_CHECK(cudaStreamSynchronize(ctx->stream));
+    return B200RC_OK;
+}
+
+// ---- octree / multi-resolution brick pool -------------------------------------------------------------------------------------------
+extern "C" int b200rc_octree_build(b200rc_ctx* ctx, int slot, int brick_dim, float homogeneity_threshold, int half_sample) {
+    CTX_GUARD();
+    if (slot < 0 || slot >= B200RC_MAX_VOLUMES || !ctx->vol[slot].valid) { ctx->set_error("octree_build: volume slot is empty"); return B200RC_ERR_NOT_READY; }
+    const VolumeSlot& vs = ctx->vol[slot];
+    VolDev v; memset(&v, 0, sizeof v);
+    v.bricks = vs.bricks; v.nbx = vs.nbx; v.nby = vs.nby;
+    return rc_octree_build(ctx, slot, brick_dim, homogeneity_threshold, half_sample, v, vs);
+}
+extern "C" int b200rc_octree_get_info(b200rc_ctx* ctx, int slot, b200rc_octree_info* out) {
+    CTX_GUARD();
+    if (!out) return B200RC_ERR_INVALID;
+    return rc_octree_info(ctx, slot, out);
+}
+extern "C" int b200rc_octree_download(b200rc_ctx* ctx, int slot, int level, uint16_t* avg, uint16_t* mn, uint16_t* mx, uint8_t* flags, uint16_t* bricks) {
+    CTX_GUARD();
+    return rc_octree_download(ctx, slot, level, avg, mn, mx, flags, bricks);
+}
+extern "C" int b200rc_octree_render(b200rc_ctx* ctx, int slot, const b200rc_octree_render_params* rp, const b200rc_eep_params* eep, const b200rc_camera* cam,
+                                    int W, int H, float* out_rgba32f, float* out_firsthit) {
+    CTX_GUARD();
+    if (!rp || !eep || !cam || !out_rgba32f || W < 1 || H < 1 || slot != 0) { ctx->set_error("octree_render: bad arguments (the octree of slot 0 is rendered)"); return B200RC_ERR_INVALID; }
+    const size_t px = (size_t)W * H;
+    int rc = ensure_frame_buffers(ctx, px, 1);
+    if (rc) return rc;
+    b200rc_eep_params e = *eep; e.world_coords = 0;
+    rc = run_eep(ctx, &e, cam, W, H);
+    if (rc) return rc;
+    RC_CHECK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    rc = rc_octree_render(ctx, slot, rp, ctx->d_entry, ctx->d_exit, W, H, (float4*)ctx->d_out[0], out_firsthit ? ctx->d_out_depth : nullptr);
+    if (rc) return rc;
+    RC_CHECK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    RC_CHECK(cudaMemcpyAsync(out_rgba32f, ctx->d_out[0], px * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_firsthit) RC_CHECK(cudaMemcpyAsync(out_firsthit, ctx->d_out_depth, px * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    RC_CHECK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f; cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->stats.last_march_ms = ms;
     return B200RC_OK;
 }

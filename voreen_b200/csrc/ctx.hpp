@@ -53,6 +53,8 @@ struct ClassifierSlot {
     int preint_array_res = 0; bool preint_tex_dirty = true; int nz_pi_res = 0;     // texture view of the table (B200RC_SAMPLER_TEX only), rebuilt lazily
 };
 
+struct OctreeSlot;
+
 struct b200rc_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -72,6 +74,7 @@ struct b200rc_ctx {
     const void* plan_flags = nullptr; size_t plan_n = 0;                   // ... and the flags buffer / pixel count that call was made for
     float* d_tile_cost = nullptr; unsigned int* d_tile_order = nullptr; size_t tile_capacity = 0;
     float* d_boxes = nullptr; int boxes_capacity = 0;
+    OctreeSlot* octree[B200RC_MAX_VOLUMES] = {nullptr, nullptr, nullptr, nullptr};    // multi-resolution brick pools (octree.cu)
     float2* d_seg_domains = nullptr;    // SegmentationRaycaster: 256 per-segment TF domains
     b200rc_stats stats{};
     unsigned long long launches = 0;
@@ -122,6 +125,14 @@ int rc_ert_plan_launch(b200rc_ctx* ctx, const float* alphas, int world, unsigned
 int rc_compositor_launch(b200rc_ctx* ctx, int mode, float wf, float w0, float w1, int add_depth, const void* c0, const float* d0, const void* c1, const float* d1,
                          int format, void* dc, float* dd, size_t n);
 int rc_background_launch(b200rc_ctx* ctx, const b200rc_background_params* bp, const void* src, const float* sdepth, int format, void* dc, float* dd, int W, int H);
+
+// octree.cu
+int rc_octree_build(b200rc_ctx* ctx, int slot, int brick_dim, float homogeneity_threshold, int halfsample_fn, const VolDev& v, const VolumeSlot& vs);
+int rc_octree_release(b200rc_ctx* ctx, int slot);
+void rc_octree_destroy_all(b200rc_ctx* ctx);
+int rc_octree_info(b200rc_ctx* ctx, int slot, b200rc_octree_info* out);
+int rc_octree_download(b200rc_ctx* ctx, int slot, int level, uint16_t* avg, uint16_t* mn, uint16_t* mx, uint8_t* flags, uint16_t* bricks);
+int rc_octree_render(b200rc_ctx* ctx, int slot, const b200rc_octree_render_params* rp, const float4* entry, const float4* exitp, int W, int H, float4* out, float* out_firsthit);
 
 // host matrix helpers (api.cu), tgt semantics (V/ext/tgt/matrix.h)
 void rc_mat4_mul(const float a[16], const float b[16], float out[16]);

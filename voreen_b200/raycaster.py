@@ -321,6 +321,29 @@ class Context:
                                             out.ctypes.data_as(C.c_void_p), _fp(od) if od is not None else None, dw, dh, 0), "rescale")
         return out, od
 
+    # -- octree / multi-resolution brick pool ---------------------------------------------------------------------------
+    def octree_build(self, slot, brick_dim, homogeneity_threshold=-1.0, half_sample="mean"):
+        fn = {"mean": 0, "max": 1, "min": 2}[half_sample]
+        self._check(self.lib.b200rc_octree_build(self.h, slot, brick_dim, homogeneity_threshold, fn), "octree_build")
+        info = abi.OctreeInfo()
+        self._check(self.lib.b200rc_octree_get_info(self.h, slot, C.byref(info)), "octree_get_info")
+        return info
+
+    def octree_level(self, slot, level, brick_dim, bricks=True):
+        """(avg, mn, mx, flags) as (G, G, G) arrays of level `level` (0 = root) and, optionally, the bricks (G^3, B, B, B)."""
+        G = 1 << level
+        avg = np.empty((G, G, G), np.uint16); mn = np.empty((G, G, G), np.uint16); mx = np.empty((G, G, G), np.uint16); fl = np.empty((G, G, G), np.uint8)
+        br = np.empty((G ** 3, brick_dim, brick_dim, brick_dim), np.uint16) if bricks else None
+        self._check(self.lib.b200rc_octree_download(self.h, slot, level, avg.ctypes.data, mn.ctypes.data, mx.ctypes.data, fl.ctypes.data,
+                                                    br.ctypes.data if br is not None else None), "octree_download")
+        return avg, mn, mx, fl, br
+
+    def octree_render(self, slot, step, node_level, eep, cam, W, H, linear=True):
+        rp = abi.OctreeRenderParams(); rp.sampling_step = step; rp.node_level = node_level; rp.filter = abi.FILTER_LINEAR if linear else abi.FILTER_NEAREST
+        out = np.empty((H, W, 4), np.float32); fh = np.empty((H, W), np.float32)
+        self._check(self.lib.b200rc_octree_render(self.h, slot, C.byref(rp), C.byref(eep), C.byref(cam), W, H, _fp(out), _fp(fh)), "octree_render")
+        return out, fh
+
     # -- image-space post chain (host numpy images) -------------------------------------------------------------------
     def image_compositor(self, mode, color0, depth0, color1, depth1, weighting_factor=0.5, weight_first=1.0, weight_second=1.0, add_depth=False):
         """voreen::Compositor on two (H, W, 4) uint16 / float32 images (+ (H, W) float32 depths or None)."""
