@@ -234,10 +234,10 @@ def run_reference(args, rank, world):
 # GPU leg
 # ---------------------------------------------------------------------------------------------------------------------
 def run_b200(args, rank, world, local_rank):
+    import copy
     import torch
     import torch.distributed as dist
     import voreen_b200 as vb
-    from voreen_b200 import abi, host
 
     # NCCL and friends print to stdout ("NCCL version ..."): keep fd 1 for the one JSON line, send everything else to stderr
     sys.stdout.flush()
@@ -250,6 +250,43 @@ def run_b200(args, rank, world, local_rank):
     ctx = vb.Context(local_rank)
     stream = torch.cuda.Stream(device=dev)
     ctx.set_stream(stream.cuda_stream)
+
+    line = measure(args, rank, world, local_rank, ctx, dev, stream, args.parallelism, light=False)
+    # N > 1: the partition the north star names -- the SHARDED volume, sort-last with binary-swap compositing and the exact-ERT second
+    # pass -- measured in the same run, next to the headline (which, for a volume that fits one GPU, is the image partition)
+    if world > 1 and not args.no_sortlast_record:
+        def summary(l):
+            return None if l is None else {"ms_per_frame": l["ms_per_frame"], "value": l["value"], "unit": l["unit"], "gsamples_classified_per_s": l["gsamples_classified_per_s"],
+                                           "workload": l["config"]["workload"], "parallelism": l["config"]["parallelism"], "transport": l["config"]["transport"],
+                                           "exact_ert": True, "phases": l["sortlast_phases"], "steps": l["steps"]}
+        headline_is_sortlast = line is not None and line["config"]["parallelism"].startswith("sort-last")
+        flag = torch.tensor([1 if headline_is_sortlast else 0], device=dev)
+        dist.broadcast(flag, 0)
+        if int(flag.item()) == 0:
+            a2 = copy.copy(args); a2.steps = min(args.steps, 12); a2.warmup = 3
+            l2 = measure(a2, rank, world, local_rank, ctx, dev, stream, "sort-last", light=True)
+            if line is not None:
+                line["sortlast"] = summary(l2)
+        if world == 8 and not args.no_c5 and args.size == 2048:
+            # config C5: 4096^3 u16 (128 GiB, 16 GiB + apron per GPU) at 3840 x 2160, sort-last across the 8 GPUs
+            a5 = copy.copy(args); a5.size = 4096; a5.image = 3840; a5.image_h = 2160; a5.steps = min(args.steps, 8); a5.warmup = 3
+            l5 = measure(a5, rank, world, local_rank, ctx, dev, stream, "sort-last", light=True)
+            if line is not None:
+                line["sortlast_c5"] = summary(l5)
+    if rank == 0:
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+def measure(args, rank, world, local_rank, ctx, dev, stream, parallelism, light):
+    """One measurement of the workload `args` describes; returns the bench line (rank 0) or None.  light: no e2e / CPU baseline / clocks."""
+    import torch
+    import torch.distributed as dist
+    import voreen_b200 as vb
+    from voreen_b200 import abi, host
 
     dims = (args.size,) * 3
     W, H = args.image, (args.image_h or args.image)
@@ -266,7 +303,7 @@ def run_b200(args, rank, world, local_rank):
     fits = need < 0.6 * torch.cuda.get_device_properties(dev).total_memory and not args.treat_as_sharded_only
     if world > 1:
         from voreen_b200 import sortlast
-        mode = args.parallelism
+        mode = parallelism
         if mode == "auto":
             mode = "sort-first" if fits else "sort-last"
         if mode == "sort-last":
@@ -299,7 +336,7 @@ def run_b200(args, rank, world, local_rank):
     if first_desc is not None:
         ctx.synth_volume(0, first_desc, args.seed)
         ctx.synchronize()
-        # the empty-space-skipping min/max build (brick_partials_u16_kernel + cell_fold_u16_kernel): HBM streaming, one read of
+        # the empty-space-skipping min/max build (brick_partials_u16_async_kernel + cell_fold_u16_kernel): HBM streaming, one read of
         # the volume; timed by the library with CUDA events on its stream during the upload above
         _, mm_ms = ctx.download_minmax(0)
         mm_vox = int(np.prod(stats_dims if sl is not None else dims))
@@ -376,7 +413,7 @@ def run_b200(args, rank, world, local_rank):
     for k in range(args.warmup):
         frame(k)
     barrier()
-    clocks = ClockSampler(local_rank) if rank == 0 else None
+    clocks = ClockSampler(local_rank) if (rank == 0 and not light) else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = ctx.stats().kernel_launches
     march_ms = []
@@ -441,42 +478,55 @@ def run_b200(args, rank, world, local_rank):
         except Exception:
             pass
 
-    # ---- e2e: the drop-in call with host buffers ------------------------------------------------------------------------
+    # ---- e2e: what the drop-in PROCESSOR does per frame, through the host mirror of SingleVolumeRaycaster (b200host_svrc_process):
+    #      property translation, transfer-function hand-over (texture regenerated from the keys and handed to the library, which
+    #      recognises unchanged texels / tables), entry/exit images from HOST memory in, RGBA16 + depth to HOST memory out --------
     e2e = None
-    if world == 1 and not args.no_e2e:
+    if world == 1 and not args.no_e2e and not light:
+        import ctypes as C
         n_e2e_views = 6
         ev = [k * (N_VIEWS // n_e2e_views) for k in range(n_e2e_views)]
-        host = []
+        hostbuf = []
         for v in ev:
             e, ed, x, xd = ctx.entry_exit(eep, cams[v], W, H)          # what MeshEntryExitPoints hands to the raycaster
-            host.append(tuple(torch.from_numpy(a).pin_memory() for a in (e, ed, x, xd)))
+            hostbuf.append(tuple(torch.from_numpy(a).pin_memory() for a in (e, ed, x, xd)))
         h_rgba = torch.empty((H, W, 4), dtype=torch.int16).pin_memory()
         h_depth = torch.empty((H, W), dtype=torch.float32).pin_memory()
-        import ctypes as C
         pf = C.POINTER(C.c_float)
+        sv = host.SingleVolumeRaycaster(local_rank)
+        try:
+            sv.set_synthetic_volume(desc, args.seed)
+            for pid, val in [("samplingRate", args.rate), ("classification", "pre-integrated-cpu" if use_pi else "transfer-function"), ("gradient", "central-differences"),
+                             ("shading", "phong"), ("compositing", "dvr"), ("emptySpaceSkipping", True), ("outputFormat", "rgba16")]:
+                sv.set_property(pid, val)
+            keys = host.make_keys(CT_KEYS)
+            thr = (C.c_float * 2)(0.0, 1.0)
 
-        def e2e_frame(i):
-            e, ed, x, xd = host[i % n_e2e_views]
-            ptrs = (C.c_void_p * 3)(h_rgba.data_ptr(), None, None)
-            rc = ctx.lib.b200rc_render(ctx.h, C.byref(params), C.byref(cams[ev[i % n_e2e_views]]), W, H,
-                                       C.cast(e.data_ptr(), pf), C.cast(ed.data_ptr(), pf), C.cast(x.data_ptr(), pf), C.cast(xd.data_ptr(), pf),
-                                       C.byref(ptrs), C.cast(h_depth.data_ptr(), pf))
-            ctx._check(rc, "render")
-        for i in range(max(3, args.warmup)):
-            e2e_frame(i)
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
-        for i in range(args.steps):
-            e2e_frame(i)
-        torch.cuda.synchronize(dev)
-        dt = time.perf_counter() - t0
+            def e2e_frame(i):
+                e, ed, x, xd = hostbuf[i % n_e2e_views]
+                sv.set_camera(orbit_eye(ev[i % n_e2e_views]))
+                sv._check(sv.lib.b200host_svrc_set_transfer_function(sv.h, 0, keys, len(CT_KEYS), 0.0, 65535.0, thr, 1.0), "setTransferFunction")
+                sv._check(sv.lib.b200host_svrc_set_entry_exit(sv.h, W, H, C.cast(e.data_ptr(), pf), C.cast(ed.data_ptr(), pf), C.cast(x.data_ptr(), pf), C.cast(xd.data_ptr(), pf)), "setEntryExit")
+                ptrs = (C.c_void_p * 3)(h_rgba.data_ptr(), None, None)
+                sv._check(sv.lib.b200host_svrc_process(sv.h, W, H, C.byref(ptrs), C.cast(h_depth.data_ptr(), pf)), "process")
+            for i in range(max(3, args.warmup)):
+                e2e_frame(i)
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            for i in range(args.steps):
+                e2e_frame(i)
+            torch.cuda.synchronize(dev)
+            dt = time.perf_counter() - t0
+        finally:
+            sv.close()
         S2 = sum(ref_samples[ev[i % n_e2e_views]] for i in range(args.steps))
         e2e = {"value": S2 / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": px * (16 + 16 + 4 + 4), "d2h_bytes_per_step": px * (8 + 4),
-               "ms_per_step": 1e3 * dt / args.steps, "call": "b200rc_render (host entry/exit in, host RGBA16 + depth out, pinned)"}
+               "ms_per_step": 1e3 * dt / args.steps,
+               "call": "b200host_svrc_process: the SingleVolumeRaycaster mirror (property translation, TF hand-over, host entry/exit in, host RGBA16 + depth out, pinned)"}
 
     # ---- CPU baseline: the oracle on a bounded sample of the same frames --------------------------------------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not light:
         cs = CpuSample(args, dims)
         edge = cs.calibrate(target_s=4.0)
         t, ns = 0.0, 0
@@ -497,6 +547,8 @@ def run_b200(args, rank, world, local_rank):
             "config": {"workload": workload_name(args), "sampler": args.sampler, "parallelism": f"{mode} x{world}" if world > 1 else "single GPU",
                        "transport": (sl or sf).transport if world > 1 else None,
                        "l2": f"volume {int(np.prod(dims)) * 2 / 2**30:.1f} GiB >> 126 MB L2, a different view every step",
+                       "value_is": "reference-equivalent samples/s: the samples the reference's shader executes for these frames (classified + skipped by ESS); "
+                                   "the samples this kernel actually classifies are in gsamples_classified_per_s (SURVEY 8d's Gsamples/s)",
                        "samples": "exact (unsharded rendering of the same frames)" if fits else
                                   f"nominal exact; reference-equivalent = nominal x ratio measured on the {stats_dims[0]}^3 rendering of the same procedural volume"},
             "ms_per_frame": ms_total / args.steps,
@@ -504,15 +556,12 @@ def run_b200(args, rank, world, local_rank):
             "gsamples_nominal_per_s": sum(nominal[v] for v in steps_views) / (ms_total * 1e-3) / 1e9,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
             "synth_s": t_synth, "sortlast_phases": sl_phases,
-            "minmax_build": {"kernel": "brick_partials_u16_kernel + cell_fold_u16_kernel", "ms": mm_ms, "alg_bytes": mm_bytes,
+            "minmax_build": {"kernel": "brick_partials_u16_async_kernel + cell_fold_u16_kernel", "ms": mm_ms, "alg_bytes": mm_bytes,
                              "achieved": mm_bytes / (mm_ms * 1e-3) / 1e9 if mm_ms > 0 else None, "peak": peak, "unit": "GB/s",
                              "frac": (mm_bytes / (mm_ms * 1e-3) / 1e9 / peak) if mm_ms > 0 else None, "bound": "hbm"},
         }
-        os.write(json_fd, (json.dumps(line) + "\n").encode())
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    ctx.close()
+        return line
+    return None
 
 
 def main():
@@ -534,6 +583,8 @@ def main():
     ap.add_argument("--treat-as-sharded-only", action="store_true", help="testing: take the C5 code path (volume never rendered unsharded)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sortlast-record", action="store_true", help="N > 1: skip the additional sort-last (sharded volume) measurement")
+    ap.add_argument("--no-c5", action="store_true", help="N = 8: skip the 4096^3 @3840x2160 sort-last measurement")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -263,11 +263,151 @@ __global__ void __launch_bounds__(256) brick_partials_u16_kernel(const uint4* __
     }
 }
 
+// ---- pass A, asynchronous variant (the default) ---------------------------------------------------------------------------------
+// ncu on the kernel above (profiles/r1_pass35_minmax_ncu_summary.txt): l1tex throughput 99 %, DRAM 46 % -- every LDG.128 of a warp
+// touches 32 different 128-byte lines (one per thread), so the L1 tag stage, not HBM, sets the pace.  Here a warp copies its 4 KiB
+// (32 slabs = 4 bricks) with COALESCED 16-byte cp.async (LDGSTS, L2 -> shared memory, no registers, 4 lines per instruction) into a
+// slab-padded buffer (144-byte slab pitch: the later LDS.128 of 8 consecutive threads hit 8 different bank groups), two sub-chunks in
+// flight per warp, and then runs the same register arithmetic on LDS.128 rows.  Everything is warp-local: no CTA barrier.  The 27
+// partial words of 32 consecutive bricks are collected in shared memory and leave as 27 full 128-byte lines instead of 16-byte pieces.
+#define MMA_SUB_SLABS 32                            // slabs (128 B each) per sub-chunk = one warp pass
+#define MMA_SUBS 8                                  // sub-chunks per super-chunk: 32 bricks
+#define MMA_STAGE_BYTES (MMA_SUB_SLABS * 144)
+#ifndef MMA_STAGES
+#define MMA_STAGES 2                                // stage buffers per warp: MMA_STAGES sub-chunks in flight while one is reduced from registers
+#endif
+#ifndef MMA_WARPS
+#define MMA_WARPS 16
+#endif
+#define MMA_PW_CLASS (9 * 32 + 4)                   // words per z class in the partial staging (+4: the three storing lanes of a brick hit different banks)
+#define MMA_WARP_BYTES (MMA_STAGES * MMA_STAGE_BYTES + 3 * MMA_PW_CLASS * 4)
+
+__device__ __forceinline__ void mm_cp_async16(unsigned smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
+// same word as mm_pack with fewer instructions: the fold of the two halves stays in the SIMD unit, 65535 - x == ~x on 16 bits
+__device__ __forceinline__ unsigned mm_pack2(unsigned mn2, unsigned mx2) {
+    const unsigned mn = __vminu2(mn2, mn2 >> 16), mx = __vmaxu2(mx2, mx2 >> 16);      // low halves: min / max of both voxels
+    return __byte_perm(mn, ~mx, 0x5410);
+}
+
+__global__ void __launch_bounds__(MMA_WARPS * 32) brick_partials_u16_async_kernel(const uint4* __restrict__ bricks, unsigned* __restrict__ part, long long nbricks) {
+    extern __shared__ __align__(16) unsigned char mm_smem[];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    unsigned char* wbase = mm_smem + (size_t)warp * MMA_WARP_BYTES;
+    unsigned* pw = (unsigned*)(wbase + MMA_STAGES * MMA_STAGE_BYTES);
+    const long long nslabs = nbricks * 8;
+    const long long nsuper = (nbricks + 31) / 32;
+    const long long gw = (long long)blockIdx.x * MMA_WARPS + warp, tw = (long long)gridDim.x * MMA_WARPS;
+    if (gw >= nsuper) return;
+    // The warp's work is ONE stream of sub-chunks g = 0 .. G-1 (super-chunk gw + (g >> 3) tw, sub-chunk g & 7 of it), so the copy
+    // pipeline never drains at a super-chunk boundary: the partial lines of a finished super-chunk leave while the next one's
+    // first sub-chunks are already in flight.
+    const int G = (int)((nsuper - gw + tw - 1) / tw) * MMA_SUBS;
+    // sub-chunk g -> stage g % MMA_STAGES: lane i copies uint4 (i + 32 j), j = 0..7, of the sub-chunk's 256 uint4 (coalesced: 512 B per
+    // instruction); uint4 e = i + 32 j is row e & 7 of slab e >> 3, so j only adds constants to both addresses
+    const unsigned sm_lane = (unsigned)__cvta_generic_to_shared(wbase) + (lane >> 3) * 144u + (lane & 7u) * 16u;
+    auto prefetch = [&](int g) {
+        if (g < G) {
+            const long long sslab = ((gw + (long long)(g >> 3) * tw) * MMA_SUBS + (g & 7)) * MMA_SUB_SLABS;
+            const uint4* src = bricks + sslab * 8 + lane;
+            const unsigned dst = sm_lane + (unsigned)(g % MMA_STAGES) * MMA_STAGE_BYTES;
+            if (sslab + MMA_SUB_SLABS <= nslabs) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) mm_cp_async16(dst + j * (4 * 144), src + j * 32);
+            } else {                                                // the volume's last, partial sub-chunk (whole bricks: nslabs = 8 nbricks)
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (sslab + (lane >> 3) + 4 * j < nslabs) mm_cp_async16(dst + j * (4 * 144), src + j * 32);
+            }
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");     // one group per call (empty past the end): group g is sub-chunk g
+    };
+    // z classes over the brick's 8 lanes (lane & 7 = z) without indexed shuffles: after the first butterfly step lane 0 holds
+    // min(z0, z1) = class L, after all three every lane holds class A, and lane 7's own word is class H -- lanes 7 / 2 / 0 store.
+    const unsigned z = lane & 7u;
+    const bool z_h = z == 7u, z_l = z == 0u, stores = z_h || z_l || z == 2u;
+    unsigned* pws = pw + (z_h ? 0 : (z_l ? 2 : 1)) * MMA_PW_CLASS + (lane >> 3);
+#pragma unroll
+    for (int g = 0; g < MMA_STAGES; ++g) prefetch(g);
+#pragma unroll 1
+    for (int g = 0; g < G; ++g) {
+        const int s = g & 7;
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(MMA_STAGES - 1) : "memory");
+        __syncwarp();
+        // a dead slab (past the volume's end) reads stale shared memory: whole bricks are dead together and their words are never written out
+        const uint4* src = (const uint4*)(wbase + (g % MMA_STAGES) * MMA_STAGE_BYTES + lane * 144);
+        uint4 r[8];
+#pragma unroll
+        for (int y = 0; y < 8; ++y) r[y] = src[y];
+        __syncwarp();                                               // every lane has its rows in registers: the stage is free again
+        prefetch(g + MMA_STAGES);
+        unsigned An = 0xffffffffu, Ax = 0u, Ln = 0xffffffffu, Lx = 0u, Hn = 0xffffffffu, Hx = 0u;
+        unsigned yl[6] = {0, 0, 0, 0, 0, 0};
+        unsigned rn = 0, rx = 0, r0 = 0, r3 = 0;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) {
+            rn = __vminu2(__vminu2(r[y].x, r[y].y), __vminu2(r[y].z, r[y].w));
+            rx = __vmaxu2(__vmaxu2(r[y].x, r[y].y), __vmaxu2(r[y].z, r[y].w));
+            r0 = r[y].x; r3 = r[y].w;
+            An = __vminu2(An, rn); Ax = __vmaxu2(Ax, rx);
+            Ln = __vminu2(Ln, r0); Lx = __vmaxu2(Lx, r0);
+            Hn = __vminu2(Hn, r3); Hx = __vmaxu2(Hx, r3);
+            if (y == 1) { yl[0] = An; yl[1] = Ax; yl[2] = Ln; yl[3] = Lx; yl[4] = Hn; yl[5] = Hx; }
+        }
+        // x = 7 is the high half of word 3: duplicate it into both halves (PRMT) so the generic fold applies
+        unsigned v[9];
+        {
+            const unsigned t3 = __byte_perm(r3, 0, 0x3232);
+            v[0] = mm_pack2(t3, t3); v[1] = mm_pack2(rn, rx); v[2] = mm_pack2(r0, r0);
+        }
+        v[3] = mm_pack2(__byte_perm(Hn, 0, 0x3232), __byte_perm(Hx, 0, 0x3232)); v[4] = mm_pack2(An, Ax); v[5] = mm_pack2(Ln, Lx);
+        v[6] = mm_pack2(__byte_perm(yl[4], 0, 0x3232), __byte_perm(yl[5], 0, 0x3232)); v[7] = mm_pack2(yl[0], yl[1]); v[8] = mm_pack2(yl[2], yl[3]);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const unsigned s1 = __vminu2(v[k], __shfl_xor_sync(0xffffffffu, v[k], 1));
+            unsigned za = __vminu2(s1, __shfl_xor_sync(0xffffffffu, s1, 2));
+            za = __vminu2(za, __shfl_xor_sync(0xffffffffu, za, 4));
+            v[k] = z_h ? v[k] : (z_l ? s1 : za);
+        }
+        if (stores) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) pws[k * 32 + s * 4] = v[k];
+        }
+        if (s == MMA_SUBS - 1) {
+            __syncwarp();
+            const long long brick0 = (gw + (long long)(g >> 3) * tw) * 32;
+            const int nb = (int)min((long long)32, nbricks - brick0);
+            if ((int)lane < nb) {
+#pragma unroll
+                for (int zc = 0; zc < 3; ++zc)
+#pragma unroll
+                    for (int k = 0; k < 9; ++k)                     // one full 128-byte line per stream
+                        part[(size_t)(zc * 9 + k) * nbricks + brick0 + lane] = pw[zc * MMA_PW_CLASS + k * 32 + lane];
+            }
+            __syncwarp();
+        }
+    }
+}
+
 __global__ void cell_fold_u16_kernel(const unsigned* __restrict__ part, float2* __restrict__ out, int ncx, int ncy, int ncz, float norm) {
     const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long ncell = (long long)ncx * ncy * ncz;
     if (cell >= ncell) return;
     const int cx = (int)(cell % ncx), cy = (int)((cell / ncx) % ncy), cz = (int)(cell / ((long long)ncx * ncy));
+    // 27 independent loads (addresses clamped into the grid, out-of-grid neighbours replaced by the neutral word afterwards), so they
+    // are all in flight before the first fold
+    unsigned w[27];
+#pragma unroll
+    for (int dz = -1; dz <= 1; ++dz)
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int x = min(max(cx + dx, 0), ncx - 1), y = min(max(cy + dy, 0), ncy - 1), z = min(max(cz + dz, 0), ncz - 1);
+                const int k = (dz + 1) * 9 + (dy + 1) * 3 + (dx + 1);
+                w[k] = __ldg(part + (size_t)k * ncell + ((long long)z * ncy + y) * ncx + x);
+            }
     unsigned acc = 0xffffffffu;
 #pragma unroll
     for (int dz = -1; dz <= 1; ++dz)
@@ -275,11 +415,8 @@ __global__ void cell_fold_u16_kernel(const unsigned* __restrict__ part, float2* 
         for (int dy = -1; dy <= 1; ++dy)
 #pragma unroll
             for (int dx = -1; dx <= 1; ++dx) {
-                const int x = cx + dx, y = cy + dy, z = cz + dz;
-                if ((unsigned)x < (unsigned)ncx && (unsigned)y < (unsigned)ncy && (unsigned)z < (unsigned)ncz) {
-                    const int k = (dz + 1) * 9 + (dy + 1) * 3 + (dx + 1);
-                    acc = __vminu2(acc, __ldg(part + (size_t)k * ncell + ((long long)z * ncy + y) * ncx + x));
-                }
+                const bool in = (unsigned)(cx + dx) < (unsigned)ncx && (unsigned)(cy + dy) < (unsigned)ncy && (unsigned)(cz + dz) < (unsigned)ncz;
+                acc = __vminu2(acc, in ? w[(dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)] : 0xffffffffu);
             }
     // same normalisation as the sampler: raw * (1/65535) -- monotone, so min/max commute with it
     out[cell] = make_float2(__fmul_rn((float)(acc & 0xffffu), norm), __fmul_rn((float)(65535u - (acc >> 16)), norm));
@@ -459,7 +596,16 @@ static int volume_build_minmax(b200rc_ctx* ctx, int slot) {
         unsigned* part = nullptr;
         if (cudaMalloc(&part, sizeof(unsigned) * 27 * (size_t)ncell) != cudaSuccess) { cudaGetLastError(); ctx->set_error("out of device memory for min/max partials"); return B200RC_ERR_OOM; }
         const long long slabs = ncell * 8;
-        brick_partials_u16_kernel<<<(unsigned)((slabs + 255) / 256), 256, 0, ctx->stream>>>((const uint4*)v.bricks, part, ncell);
+        static const bool sync_partials = getenv("B200RC_MINMAX_SYNC") != nullptr;    // A/B: the register-staged kernel of round 1
+        if (sync_partials) brick_partials_u16_kernel<<<(unsigned)((slabs + 255) / 256), 256, 0, ctx->stream>>>((const uint4*)v.bricks, part, ncell);
+        else {
+            const size_t smem = (size_t)MMA_WARPS * MMA_WARP_BYTES;
+            RC_CHECK(cudaFuncSetAttribute(brick_partials_u16_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const long long nsuper = (ncell + 31) / 32;
+            long long grid = (nsuper + MMA_WARPS - 1) / MMA_WARPS;
+            if (grid > ctx->num_sms) grid = ctx->num_sms;       // persistent: one CTA of 16 warps per SM
+            brick_partials_u16_async_kernel<<<(unsigned)grid, MMA_WARPS * 32, smem, ctx->stream>>>((const uint4*)v.bricks, part, ncell);
+        }
         cell_fold_u16_kernel<<<(unsigned)((ncell + 255) / 256), 256, 0, ctx->stream>>>(part, v.minmax, v.cells[0], v.cells[1], v.cells[2], 1.0f / 65535.0f);
         ctx->launches++;
         RC_CHECK(cudaGetLastError());

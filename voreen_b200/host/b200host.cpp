@@ -560,9 +560,14 @@ extern "C" int b200host_svrc_set_transfer_function(b200host_svrc* p, int channel
                                                    float domain_lo, float domain_hi, const float threshold[2], float gamma) {
     if (!p || channel < 0 || channel >= B200RC_MAX_CHANNELS || (!keys && n_keys > 0) || n_keys < 0) return B200RC_ERR_INVALID;
     TransFunc& t = p->tf[channel];
+    const float thr0 = threshold ? threshold[0] : 0.f, thr1 = threshold ? threshold[1] : 1.f;
+    // a property set to the value it already has invalidates nothing (Property::set compares first): the per-frame hand-over of an
+    // unchanged transfer function costs this comparison, not a texture / pre-integration table rebuild
+    if (t.set && (int)t.keys.size() == n_keys && (n_keys == 0 || std::memcmp(t.keys.data(), keys, (size_t)n_keys * sizeof(b200host_tf_key)) == 0) &&
+        t.domain[0] == domain_lo && t.domain[1] == domain_hi && t.threshold[0] == thr0 && t.threshold[1] == thr1 && t.gamma == gamma) return B200RC_OK;
     t.keys.assign(keys, keys + n_keys);
     t.domain[0] = domain_lo; t.domain[1] = domain_hi;
-    t.threshold[0] = threshold ? threshold[0] : 0.f; t.threshold[1] = threshold ? threshold[1] : 1.f;
+    t.threshold[0] = thr0; t.threshold[1] = thr1;
     t.gamma = gamma; t.set = true; t.dirty = true;
     return B200RC_OK;
 }
