@@ -99,8 +99,10 @@ enum { B200RC_RAYCASTER_SINGLE = 0, B200RC_RAYCASTER_SIMPLE = 1, B200RC_RAYCASTE
 /* OUTER_FACES ("outerfaces", optimizedproxygeometry.cpp:1392-1604) emits only the cell faces between a non-empty and an empty cell:
  * the boundary of the union of the non-empty cells.  Rendered by MeshEntryExitPoints (nearest front face / farthest back face) that
  * boundary gives the same entry/exit images as the cubes of VISIBLE_BRICKS, whose interior faces are never nearest or farthest;
- * the cell classification (min/max over [llf-1, urb+1], 256^2 pre-integration table, threshold) is the same code (:1436-1455). */
-enum { B200RC_PROXY_BBOX = 0, B200RC_PROXY_MINBBOX = 1, B200RC_PROXY_VISIBLE_BRICKS = 2, B200RC_PROXY_OUTER_FACES = 3 };
+ * the cell classification (min/max over [llf-1, urb+1], 256^2 pre-integration table, threshold) is the same code (:1436-1455).
+ * VOLUME_OCTREE ("volumeoctree", optimizedproxygeometry.cpp:1620-1737): one cube per non-transparent LEAF of the volume's octree
+ * (b200rc_octree_build must have run on the slot), classified by the leaf's min / max values, stretched by one voxel (:1689-1694). */
+enum { B200RC_PROXY_BBOX = 0, B200RC_PROXY_MINBBOX = 1, B200RC_PROXY_VISIBLE_BRICKS = 2, B200RC_PROXY_OUTER_FACES = 3, B200RC_PROXY_VOLUME_OCTREE = 4 };
 
 /* voreen::Compositor "blendMode" options, in the order of V/modules/base/processors/image/compositor.cpp:47-60 */
 enum {

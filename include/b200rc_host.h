@@ -51,6 +51,27 @@ typedef struct b200host_tf_curve {
 } b200host_tf_curve;
 int b200host_tf1d_gaussian_texture(const b200host_tf_curve* curves, int n_curves, const float threshold[2], float gamma, int alpha_mode,
                                    int width, uint8_t* out_rgba8);
+/* ---- TransFunc2DPrimitives (V/src/core/datastructures/transfunc/2d/2dprimitives/transfunc2dprimitives.cpp:150-250,313-333,
+ *      utils/transfuncprimitive.cpp:98-189 triangle, :240-352 quad, :405-490 banana; TransFunc2D::createTextureData
+ *      transfunc2d.cpp:75-124; TransFuncBase::applyAlpha transfuncbase.cpp:177-210).  The reference paints the primitives with
+ *      OpenGL into a float RGBA help texture (orthographic [0,1]^2, per-vertex colours, glBlendEquation(GL_MAX), clear colour 0)
+ *      and resamples that into the transfer-function texture (thresholds, gamma, alpha mode).  Here the same triangle lists are
+ *      rasterised in software: a texel receives a fragment when its centre ((x + 0.5) / W, (y + 0.5) / H) lies inside or on the
+ *      edge of a non-degenerate triangle, colours are interpolated barycentrically (double precision), fragments combine with max.
+ *      OpenGL leaves the sub-pixel snapping and the tie-breaking rule to the implementation, so this is the GL result up to what
+ *      implementations differ in among themselves.  type: 0 triangle (3 points), 1 quad (4 points: the reference's corner order),
+ *      2 banana (4 points: left end, upper middle, lower middle, right end; 20 steps).
+ *      out_rgba32f (W x H x 4, may be NULL) is the texture the reference uploads (TF_FLOAT); out_rgba8 (may be NULL) its
+ *      round-to-nearest uint8 quantisation for b200rc_set_tf2d. */
+typedef struct b200host_tf2d_primitive {
+    int32_t type;
+    float   fuzziness;              /* TransFuncPrimitive::fuzziness_ (1 = no fade-out border) */
+    float   position[4][2];         /* control points, [0,1]^2: x = intensity, y = gradient magnitude */
+    uint8_t color[4][4];
+} b200host_tf2d_primitive;
+int b200host_tf2d_primitives_texture(const b200host_tf2d_primitive* prims, int n_prims, int width, int height,
+                                     const float threshold_x[2], const float threshold_y[2], const float gamma[2], int alpha_mode,
+                                     float* out_rgba32f, uint8_t* out_rgba8);
 /* TransFuncPropertyBase texture width for a volume (transfuncpropertybase.cpp:155-165, transfunc1dkeysproperty.cpp:94-97) */
 int b200host_tf1d_width_for(int dtype, int* out_width);
 

@@ -272,3 +272,39 @@ def pool_arrays(tree):
         for (x, y, z), b in lv["bricks"].items():
             pool[off + (z * G + y) * G + x] = b
     return avg, mn, mx, flags, pool
+
+
+# ---- OptimizedProxyGeometry "volumeoctree" mode -----------------------------------------------------------------------------------------
+def proxy_boxes(tree, region_empty, clip=None):
+    """VolumeOctreeBackgroundThread::traverseOctreeAndCreateGeometry (V/modules/base/processors/proxygeometry/
+    optimizedproxygeometry.cpp:1657-1737) over the pointer tree: one cube (llf, urb in TEXTURE space, as addCubeMesh :480-491 emits
+    them) per leaf whose [min, max] (uint16) `region_empty(mn, mx)` does not call transparent.  clip = (llf, urb) voxel clip bounds or None."""
+    dims = np.array(tree.dims, np.float32)
+    out = []
+    f32 = np.float32
+
+    def visit(node, llf, urb):
+        if not node.children:
+            if region_empty(node.mn, node.mx):
+                return
+            if np.any(llf >= dims):                                                   # :1684-1685
+                return
+            u = np.minimum(urb, dims - f32(1))
+            lo = np.maximum(llf - f32(1), f32(-0.5))                                  # :1693-1694
+            hi = np.minimum(u + f32(1), dims - f32(0.5))
+            if clip is not None:
+                c_lo, c_hi = np.array(clip[0], np.float32) - f32(0.5), np.array(clip[1], np.float32) + f32(0.5)
+                if not (np.all(lo >= c_lo) and np.all(hi <= c_hi)):                   # not containsVolume
+                    if np.any(lo > c_hi) or np.any(hi < c_lo):                        # not intersects either (touching counts, bounds.h:162-170)
+                        return
+                    lo, hi = np.maximum(lo, c_lo), np.minimum(hi, c_hi)               # addCubeMeshClip (:493-512)
+            out.append(np.concatenate([(lo + f32(0.5)) / dims, (hi + f32(0.5)) / dims]).astype(np.float32))
+            return
+        half = (urb - llf + f32(1)) / f32(2)
+        for i, c in enumerate(node.children):
+            if c is None:
+                continue
+            cl = llf + np.array([i & 1, (i >> 1) & 1, i >> 2], np.float32) * half
+            visit(c, cl, cl + half - f32(1))
+    visit(tree.root, np.zeros(3, np.float32), np.full(3, tree.octree_dim - 1, np.float32))
+    return np.array(out, np.float32).reshape(-1, 6)

@@ -1890,3 +1890,166 @@ void orc_octree_raycast(const uint16_t* avg, const uint8_t* flags, const uint16_
             if (out_firsthit) out_firsthit[pix] = firsthit;
         }
 }
+
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* TransFunc2DPrimitives                                                                                         */
+/* ------------------------------------------------------------------------------------------------------------ */
+typedef struct { float p[2]; float c[4]; } tfp_vertex;
+typedef struct { tfp_vertex* v; int n, cap; } tfp_list;
+
+static void tfp_push(tfp_list* l, const float p[2], const float c[4], int zero_alpha) {
+    if (l->n == l->cap) { l->cap = l->cap ? l->cap * 2 : 256; l->v = (tfp_vertex*)realloc(l->v, sizeof(tfp_vertex) * (size_t)l->cap); }
+    tfp_vertex* v = &l->v[l->n++];
+    v->p[0] = p[0]; v->p[1] = p[1];
+    v->c[0] = c[0]; v->c[1] = c[1]; v->c[2] = c[2]; v->c[3] = zero_alpha ? 0.f : c[3];
+}
+/* primitives of an IMode.begin(TRIANGLE_STRIP / TRIANGLE_FAN / TRIANGLES) ... end() block -> independent triangles */
+static void tfp_emit(tfp_list* tris, const tfp_list* blk, int mode /* 0 strip, 1 fan, 2 triangles */) {
+    for (int i = 0; i + 2 < blk->n; i += (mode == 2 ? 3 : 1)) {
+        const tfp_vertex* a = mode == 1 ? &blk->v[0] : &blk->v[i];
+        const tfp_vertex *b = &blk->v[i + 1], *c = &blk->v[i + 2];
+        tfp_push(tris, a->p, a->c, 0); tfp_push(tris, b->p, b->c, 0); tfp_push(tris, c->p, c->c, 0);
+    }
+}
+
+/* TransFuncTriangle::paint (:98-189) / TransFuncQuad::paint (:240-352) */
+static void tfp_polygon(tfp_list* tris, const orc_tf2d_primitive* P, int n) {
+    float col[4][4], center[2] = {0.f, 0.f}, ccol[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = 0; i < n; ++i) {
+        for (int k = 0; k < 4; ++k) col[i][k] = (float)P->color[i][k] / 255.f;
+        center[0] += P->position[i][0]; center[1] += P->position[i][1];
+        for (int k = 0; k < 4; ++k) ccol[k] += col[i][k];
+    }
+    center[0] /= (float)n; center[1] /= (float)n;
+    for (int k = 0; k < 4; ++k) ccol[k] /= (float)n;
+    float mid[4][2], midc[4][4], in[4][2];
+    for (int i = 0; i < n; ++i) {
+        const int j = (i + 1) % n;
+        for (int k = 0; k < 2; ++k) mid[i][k] = 0.5f * P->position[i][k] + 0.5f * P->position[j][k];
+        for (int k = 0; k < 3; ++k) midc[i][k] = 0.5f * col[i][k] + 0.5f * col[j][k];
+        midc[i][3] = 0.f;
+        for (int k = 0; k < 2; ++k) in[i][k] = P->fuzziness * P->position[i][k] + (1.f - P->fuzziness) * center[k];
+    }
+    /* the strips, as sequences of (kind, index): O outer corner (alpha 0), I inner corner, M edge middle */
+    static const char* tri_blocks[] = {"O0I0M2I2O2M1", "I2I1M1O1", "O1I1M0I0O0", 0};
+    static const char* quad_blocks[] = {"O0I0M3I3O3M2", "I3I2M2O2", "O2I2M1I1O1M0", "I1I0M0O0", 0};
+    const char** blocks = n == 3 ? tri_blocks : quad_blocks;
+    for (int b = 0; blocks[b]; ++b) {
+        tfp_list blk = {0, 0, 0};
+        for (const char* s = blocks[b]; *s; s += 2) {
+            const int i = s[1] - '0';
+            if (s[0] == 'O') tfp_push(&blk, P->position[i], col[i], 1);
+            else if (s[0] == 'I') tfp_push(&blk, in[i], col[i], 0);
+            else tfp_push(&blk, mid[i], midc[i], 0);
+        }
+        tfp_emit(tris, &blk, 0);
+        free(blk.v);
+    }
+    tfp_list blk = {0, 0, 0};
+    if (n == 3) {
+        for (int i = 0; i < 3; ++i) tfp_push(&blk, in[i], col[i], 0);
+        tfp_emit(tris, &blk, 2);
+    } else {
+        tfp_push(&blk, center, ccol, 0);
+        for (int i = 0; i < 4; ++i) tfp_push(&blk, in[i], col[i], 0);
+        tfp_push(&blk, in[0], col[0], 0);
+        tfp_emit(tris, &blk, 1);
+    }
+    free(blk.v);
+}
+
+/* TransFuncBanana::paintInner (:405-490) */
+static void tfp_banana(tfp_list* tris, const orc_tf2d_primitive* P) {
+    const int steps = 20;
+    float c[4][4];
+    for (int i = 0; i < 4; ++i) for (int k = 0; k < 4; ++k) c[i][k] = (float)P->color[i][k] / 255.f;
+    float t1[2], t2[2], tc[2], t3[2], t4[2], t1c[4], t2c[4], tcc[4], t3c[4], t4c[4];
+    for (int k = 0; k < 2; ++k) {
+        t1[k] = (2.f * P->position[1][k]) - (0.5f * P->position[0][k]) - (0.5f * P->position[3][k]);
+        t2[k] = (2.f * P->position[2][k]) - (0.5f * P->position[0][k]) - (0.5f * P->position[3][k]);
+        tc[k] = (t1[k] + t2[k]) / 2.f;
+        t3[k] = P->fuzziness * t1[k] + (1.f - P->fuzziness) * tc[k];
+        t4[k] = P->fuzziness * t2[k] + (1.f - P->fuzziness) * tc[k];
+    }
+    for (int k = 0; k < 4; ++k) {
+        t1c[k] = (2.f * c[1][k]) - (0.5f * c[0][k]) - (0.5f * c[3][k]);
+        t2c[k] = (2.f * c[2][k]) - (0.5f * c[0][k]) - (0.5f * c[3][k]);
+        tcc[k] = (t1c[k] + t2c[k]) / 2.f;
+        t3c[k] = P->fuzziness * t1c[k] + (1.f - P->fuzziness) * tcc[k];
+        t4c[k] = P->fuzziness * t2c[k] + (1.f - P->fuzziness) * tcc[k];
+    }
+    const float* upper[3] = {t1, t3, t4}; const float* lower[3] = {t3, t4, t2};
+    const float* upper_c[3] = {t1c, t3c, t4c}; const float* lower_c[3] = {t3c, t4c, t2c};
+    tfp_list blk = {0, 0, 0};
+    for (int band = 0; band < 3; ++band) {
+        tfp_push(&blk, P->position[0], c[0], 0);
+        for (int i = 0; i < steps; ++i) {
+            const float t = (float)i / (float)(steps - 1);
+            float v1[2], v2[2], v1c[4], v2c[4];
+            for (int k = 0; k < 2; ++k) {
+                v1[k] = (((1 - t) * (1 - t)) * P->position[0][k]) + ((2 * (1 - t) * t) * upper[band][k]) + ((t * t) * P->position[3][k]);
+                v2[k] = (((1 - t) * (1 - t)) * P->position[0][k]) + ((2 * (1 - t) * t) * lower[band][k]) + ((t * t) * P->position[3][k]);
+            }
+            for (int k = 0; k < 4; ++k) {
+                v1c[k] = (((1 - t) * (1 - t)) * c[0][k]) + ((2 * (1 - t) * t) * upper_c[band][k]) + ((t * t) * c[3][k]);
+                v2c[k] = (((1 - t) * (1 - t)) * c[0][k]) + ((2 * (1 - t) * t) * lower_c[band][k]) + ((t * t) * c[3][k]);
+            }
+            tfp_push(&blk, v1, v1c, band == 0);
+            tfp_push(&blk, v2, v2c, band == 2);
+        }
+        tfp_push(&blk, P->position[3], c[3], 0);
+    }
+    tfp_emit(tris, &blk, 0);
+    free(blk.v);
+}
+
+void orc_tf2d_primitives_texture(const orc_tf2d_primitive* prims, int n, int width, int height, const float thr_x[2], const float thr_y[2],
+                                 const float gamma[2], int alpha_mode, float* out) {
+    tfp_list tris = {0, 0, 0};
+    for (int i = 0; i < n; ++i) {
+        if (prims[i].type == 0) tfp_polygon(&tris, &prims[i], 3);
+        else if (prims[i].type == 1) tfp_polygon(&tris, &prims[i], 4);
+        else tfp_banana(&tris, &prims[i]);
+    }
+    const size_t npix = (size_t)width * height;
+    float* help = (float*)calloc(npix * 4, sizeof(float));      /* glClear: (0, 0, 0, 0) */
+    /* every texel centre against every triangle, in paint order (GL_MAX is order independent) */
+    for (int y = 0; y < height; ++y)
+        for (int x = 0; x < width; ++x) {
+            const double px = ((double)x + 0.5) / (double)width, py = ((double)y + 0.5) / (double)height;
+            float* d = help + ((size_t)y * width + x) * 4;
+            for (int k = 0; k + 2 < tris.n; k += 3) {
+                const tfp_vertex *A = &tris.v[k], *B = &tris.v[k + 1], *Cv = &tris.v[k + 2];
+                const double area = ((double)B->p[0] - A->p[0]) * ((double)Cv->p[1] - A->p[1]) - ((double)B->p[1] - A->p[1]) * ((double)Cv->p[0] - A->p[0]);
+                if (area == 0.0) continue;
+                const double w0 = (((double)B->p[0] - px) * ((double)Cv->p[1] - py) - ((double)B->p[1] - py) * ((double)Cv->p[0] - px)) / area;
+                const double w1 = (((double)Cv->p[0] - px) * ((double)A->p[1] - py) - ((double)Cv->p[1] - py) * ((double)A->p[0] - px)) / area;
+                const double w2 = (((double)A->p[0] - px) * ((double)B->p[1] - py) - ((double)A->p[1] - py) * ((double)B->p[0] - px)) / area;
+                if (w0 < 0.0 || w1 < 0.0 || w2 < 0.0) continue;
+                for (int ch = 0; ch < 4; ++ch) {
+                    const float f = (float)(w0 * A->c[ch] + w1 * B->c[ch] + w2 * Cv->c[ch]);
+                    if (f > d[ch]) d[ch] = f;
+                }
+            }
+        }
+    free(tris.v);
+    const int xf = iround_tgt(thr_x[0] * (float)width), xb = iround_tgt(thr_x[1] * (float)width);
+    const int yf = iround_tgt(thr_y[0] * (float)height), yb = iround_tgt(thr_y[1] * (float)height);
+    for (int y = 0; y < height; ++y)
+        for (int x = 0; x < width; ++x) {
+            float* o = out + ((size_t)y * width + x) * 4;
+            o[0] = o[1] = o[2] = o[3] = 0.f;
+            if (y < yf || y > yb || x < xf || x > xb) continue;
+            float vx = (float)x / (float)(width - 1), vy = (float)y / (float)(height - 1);        /* applyGammaToValues (:140-149) */
+            if (gamma[0] != 1.f) vx = powf(vx, gamma[0]);
+            if (gamma[1] != 1.f) vy = powf(vy, gamma[1]);
+            int tx = (int)(vx * (float)width), ty = (int)(vy * (float)height);                      /* getMappingForValueFloat (:150-160) */
+            tx = tx < 0 ? 0 : (tx > width - 1 ? width - 1 : tx); ty = ty < 0 ? 0 : (ty > height - 1 ? height - 1 : ty);
+            const float* h = help + ((size_t)ty * width + tx) * 4;
+            o[0] = h[0]; o[1] = h[1]; o[2] = h[2]; o[3] = h[3];
+            if (alpha_mode == 2) { if (o[3]) o[3] = 1.f; }
+            else if (alpha_mode == 0) o[3] = 0.f;
+        }
+    free(help);
+}

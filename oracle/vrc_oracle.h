@@ -151,6 +151,20 @@ typedef struct orc_tf_curve {
 } orc_tf_curve;
 void orc_tf1d_gaussian_texture(const orc_tf_curve* curves, int n, const float threshold[2], float gamma, int alpha_mode, int width, uint8_t* out_rgba8);
 
+/* TransFunc2DPrimitives: triangle lists of the primitives (transfuncprimitive.cpp:98-189,240-352,405-490), the help texture a GL_MAX
+ * rasterisation of them gives (transfunc2dprimitives.cpp:165-250,313-333: ortho [0,1]^2, texel centres, inclusive edges, barycentric
+ * colours in double precision -- OpenGL itself leaves sub-pixel snapping to the implementation, so there is no reference bit pattern
+ * to pin this against: PARITY UNPINNED for the rasteriser), then TransFunc2D::createTextureData (transfunc2d.cpp:75-124, TF_FLOAT) and
+ * TransFuncBase::applyAlpha (transfuncbase.cpp:177-210). */
+typedef struct orc_tf2d_primitive {
+    int32_t type;               /* 0 triangle, 1 quad, 2 banana */
+    float fuzziness;
+    float position[4][2];
+    uint8_t color[4][4];
+} orc_tf2d_primitive;
+void orc_tf2d_primitives_texture(const orc_tf2d_primitive* prims, int n, int width, int height, const float thr_x[2], const float thr_y[2],
+                                 const float gamma[2], int alpha_mode, float* out_rgba32f);
+
 /* SingleOctreeRaycasterCL DVR traversal over dense per-level node arrays (oracle/octree_ref.py builds them) */
 void orc_octree_raycast(const uint16_t* avg, const uint8_t* flags, const uint16_t* bricks, int levels, int brick_dim, const int32_t dims[3], int octree_dim,
                         const uint8_t* tf_rgba8, int tf_width, float dom_lo, float dom_hi, float rwm_scale, float rwm_offset,

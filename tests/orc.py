@@ -86,6 +86,8 @@ def lib():
                                             C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, pf, pf, C.c_int, C.c_int, pf, pf]
         _lib.orc_octree_raycast.restype = None
         _lib.orc_synth_volume.argtypes = [C.POINTER(C.c_int32 * 3), C.POINTER(C.c_int32 * 3), C.POINTER(C.c_int32 * 3), C.c_uint64, C.c_void_p]
+        _lib.orc_tf2d_primitives_texture.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, pf, pf, pf, C.c_int, pf]
+        _lib.orc_tf2d_primitives_texture.restype = None
     return _lib
 
 
@@ -286,3 +288,16 @@ def octree_raycast(avg, flags, pool, levels, brick_dim, dims, octree_dim, tf_tex
     lib().orc_octree_raycast(avg.ctypes.data, flags.ctypes.data, pool.ctypes.data, levels, brick_dim, C.byref(d), octree_dim, tf_tex.ctypes.data, tf_tex.shape[0],
                              domain[0], domain[1], rwm[0], rwm[1], step, node_level, 1 if linear else 0, fp(entry), fp(exitp), W, H, fp(out), fp(fh))
     return out, fh
+
+
+def tf2d_primitives_texture(prims, width=256, height=256, threshold_x=(0.0, 1.0), threshold_y=(0.0, 1.0), gamma=(1.0, 1.0), alpha_mode=1):
+    """TransFunc2DPrimitives texture (float32 (H, W, 4)); prims as voreen_b200.host.make_primitives takes them."""
+    from voreen_b200 import host
+
+    class Prim(C.Structure):        # orc_tf2d_primitive (same layout as the product's POD, declared independently in vrc_oracle.h)
+        _fields_ = [("type", C.c_int32), ("fuzziness", C.c_float), ("position", (C.c_float * 2) * 4), ("color", (C.c_uint8 * 4) * 4)]
+    arr = host.make_primitives(prims, cls=Prim)
+    out = np.zeros((height, width, 4), np.float32)
+    tx, ty, g = (C.c_float * 2)(*threshold_x), (C.c_float * 2)(*threshold_y), (C.c_float * 2)(*gamma)
+    lib().orc_tf2d_primitives_texture(C.cast(arr, C.c_void_p), len(prims), width, height, tx, ty, g, alpha_mode, fp(out))
+    return out

@@ -31,23 +31,41 @@ def main():
     dims = (size,) * 3
     step = float(np.float32(1.0) / (np.float32(size) * np.float32(2.0)))
     params = vb.default_params(step, classification=abi.CLASS_PREINT if cls == "preint" else abi.CLASS_TF, out_format=abi.OUT_RGBA16)
+    # SL_MULTI=n: MultiVolumeRaycaster over n co-registered volumes bricked identically (config C4): world-space entry/exit shared by
+    # the volumes, world-space sampling step, per-volume transfer functions, mvOpacityCorrection
+    nvol = int(os.environ.get("SL_MULTI", "1"))
+    if nvol > 1:
+        step_world = float(np.float32(2.0) / np.float32(size) / np.float32(2.0))
+        params = vb.default_params(step_world, classification=abi.CLASS_PREINT if cls == "preint" else abi.CLASS_TF, out_format=abi.OUT_RGBA16)
+        params.num_volumes = nvol; params.multi_volume = 1
+        params.mv_opacity_correction_factor = step / step_world
+        for v in range(nvol):
+            params.vol[v].classification = abi.CLASS_PREINT if cls == "preint" else abi.CLASS_TF
     if os.environ.get("SL_COMP"):         # e.g. iso / fhn / fhp: merged by "front-most hit wins"
         params.compositing[:] = [abi.COMP[os.environ["SL_COMP"]]] * 3
-    eep = vb.default_eep()
+    eep = vb.default_eep(world_coords=1) if nvol > 1 else vb.default_eep()
     views = [0, 5, 9, 14, 22, 31]
     cams = {k: host.make_camera(bench.orbit_eye(k), W=img, H=img) for k in views}
 
+    mv_keys = [bench.CT_KEYS, [(0.0, (0, 0, 0, 0)), (0.3, (0, 255, 0, 0)), (1.0, (0, 255, 0, 120))],
+               [(0.0, (0, 0, 0, 0)), (0.4, (0, 0, 255, 0)), (1.0, (0, 0, 255, 90))], [(0.0, (0, 0, 0, 0)), (0.5, (255, 0, 255, 0)), (1.0, (255, 0, 255, 60))]]
+
     def load_tf():
-        if cls == "preint":
-            ctx.set_tf1d(0, host.tf1d_texture(bench.CT_KEYS, 1024), (0.0, 65535.0))
-            ctx.build_preint(0, 1024, step, abi.PI_CPU)
-        ctx.set_tf1d(0, host.tf1d_texture(bench.CT_KEYS, 4096), (0.0, 65535.0))
+        for v in range(nvol):
+            if cls == "preint":
+                ctx.set_tf1d(v, host.tf1d_texture(mv_keys[v], 1024), (0.0, 65535.0))
+                ctx.build_preint(v, 1024, step, abi.PI_CPU)
+            ctx.set_tf1d(v, host.tf1d_texture(mv_keys[v], 4096), (0.0, 65535.0))
+
+    def synth(desc):
+        for v in range(nvol):
+            ctx.synth_volume(v, desc, 1234 + 77 * v)
 
     out = torch.empty((img, img, 4), dtype=torch.int16, device=dev)
     depth = torch.empty((img, img), dtype=torch.float32, device=dev)
     ref = {}
     if rank == 0 and not os.environ.get("SL_NOREF"):
-        ctx.synth_volume(0, vb.make_volume_desc(dims), 1234)
+        synth(vb.make_volume_desc(dims))
         load_tf()
         for k in views:
             ctx.render_camera_ptrs(params, eep, cams[k], img, img, [out.data_ptr(), 0, 0], depth.data_ptr(), device=True)
@@ -58,11 +76,11 @@ def main():
         sl = sortlast.SortFirst(ctx, rank, world, img, img, device=dev, stream=stream, transport=os.environ.get("SL_TRANSPORT", "auto"))
         sl.phases = {}
         if rank != 0 or os.environ.get("SL_NOREF"):
-            ctx.synth_volume(0, vb.make_volume_desc(dims), 1234)
+            synth(vb.make_volume_desc(dims))
             load_tf()
     else:
         sl = sortlast.SortLast(ctx, dims, rank, world, img, img, device=dev, stream=stream, transport=os.environ.get("SL_TRANSPORT", "auto"))
-        ctx.synth_volume(0, sl.shard_desc(), 1234)
+        synth(sl.shard_desc())
         load_tf()
         sl.profile = True
     ok = True
@@ -98,7 +116,7 @@ def main():
             dfrac = float((np.abs(depth.cpu().numpy() - ref[k][1]) <= 1e-4).mean())
             good = frac >= 0.999 and dfrac >= 0.999
             ok = ok and good
-            print(f"{mode} x{world} {size}^3 @{img}^2 {cls} view {k}: within-1/255 {frac:.6f} max|d| {d.max():.4f} depth-ok {dfrac:.6f} "
+            print(f"{mode} x{world} {nvol} x {size}^3 @{img}^2 {cls} view {k}: within-1/255 {frac:.6f} max|d| {d.max():.4f} depth-ok {dfrac:.6f} "
                   f"rank0 march {ms:.2f} ms frame {frame_ms:.2f} ms transport {sl.transport} {'OK' if good else 'FAIL'}", flush=True)
     dist.barrier()
     dist.destroy_process_group()

@@ -266,7 +266,8 @@ def _device_count():
 
 
 @pytest.mark.parametrize("mode,transport,comp", [("sort-last", "p2p", "dvr"), ("sort-last", "nccl", "dvr"), ("sort-last", "p2p", "iso"),
-                                                 ("sort-last", "p2p", "mip"), ("sort-first", "p2p", "dvr")])
+                                                 ("sort-last", "p2p", "mip"), ("sort-first", "p2p", "dvr"), ("sort-last", "p2p", "multi4"),
+                                                 ("sort-first", "p2p", "multi4")])
 def test_multi_gpu_partitions_match_the_single_gpu_image(mode, transport, comp):
     """torchrun, one rank per GPU (2, 4 or 8): sharded march + exact-ERT second pass + binary swap (b200rc_composite reading the
     partner's half over NVLink, b200rc_finalize storing into rank 0's image) against the single-GPU frame rendered on rank 0."""
@@ -276,7 +277,10 @@ def test_multi_gpu_partitions_match_the_single_gpu_image(mode, transport, comp):
     world = 8 if ndev >= 8 else (4 if ndev >= 4 else 2)
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", SL_TRANSPORT=transport, OMP_NUM_THREADS="1")
     env.pop("SL_NOREF", None)
-    if comp != "dvr":
+    env.pop("SL_MULTI", None)
+    if comp.startswith("multi"):        # config C4: MultiVolumeRaycaster, every volume sharded the same way
+        env["SL_MULTI"] = comp[5:]
+    elif comp != "dvr":
         env["SL_COMP"] = comp
     port = 29600 + (os.getpid() % 300)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1", "--master-port", str(port),
@@ -680,3 +684,35 @@ def test_segmentation_raycaster(ctx, apply_seg, seg_dtype):
         plain, _ = ctx.render_camera(s.params, s.eep, s.cam, s.W, s.H)
         assert float(np.abs(np.asarray(plain[0]) - np.asarray(c_outs[0])).max()) > 0.05
     ctx.lib.b200rc_release_volume(ctx.h, 1)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# TransFunc2DPrimitives end to end: primitives -> texture (host mirror) -> TFT_2DPRIMITIVES classification in the marcher
+# ---------------------------------------------------------------------------------------------------------------------
+def test_tf2d_primitives_end_to_end(ctx):
+    """A 2D transfer function painted from a quad, a triangle and a banana (b200host_tf2d_primitives_texture), rendered with
+    applyTF(tf, tex2D, intensity, |gradient|) (mod_transfunc.frag:80-95), against the oracle marching the oracle's own texture."""
+    from voreen_b200 import host
+    vol = scenes.ct_like_volume(48)
+    s = scenes.Scene(vol, W=96, H=96, gradient=abi.GRAD["central-differences"], classification=abi.CLASS_TF2D)
+    prims = [{"type": "quad", "points": [(0.30, 0.0), (0.62, 0.0), (0.62, 0.5), (0.30, 0.5)], "colors": (255, 160, 60, 40), "fuzziness": 0.6},
+             {"type": "banana", "points": [(0.35, 0.30), (0.65, 0.95), (0.65, 0.55), (0.98, 0.30)], "colors": (80, 200, 255, 230), "fuzziness": 0.7},
+             {"type": "triangle", "points": [(0.60, 0.0), (1.0, 0.0), (0.85, 0.35)], "colors": [(255, 255, 255, 255), (255, 255, 200, 255), (255, 200, 200, 120)], "fuzziness": 0.8}]
+    f32, u8 = host.tf2d_primitives_texture(prims, 128, 64)
+    want = orc.tf2d_primitives_texture(prims, 128, 64)
+    assert np.array_equal(f32, want)
+    o_u8 = np.clip(np.floor(want * np.float32(255.0) + np.float32(0.5)), 0, 255).astype(np.uint8)
+    assert np.array_equal(u8, o_u8) and int((u8[..., 3] > 0).sum()) > 1000
+    dom_x, dom_y = (0.0, s.desc.rwm_scale), (0.0, 0.6 * s.desc.rwm_scale)
+    ov = orc.make_volume(s.vol, s.desc)
+    e, ed, x, xd = s.oracle_eep()
+    s.params.collect_stats = 1
+    o_outs, o_depth, o_st = orc.raycast([ov], [orc.make_classifier(tf2d=o_u8, domain=dom_x, domain_y=dom_y)], s.params, s.cam, s.W, s.H, e, ed, x, xd)
+    ctx.upload_volume(0, s.vol, desc=s.desc)
+    ctx.set_tf2d(0, u8, dom_x, dom_y)
+    c_outs, c_depth = ctx.render_camera(s.params, s.eep, s.cam, s.W, s.H)
+    st = ctx.stats()
+    frac, mx = scenes.parity_report(o_outs[0], c_outs[0])
+    print(f"tf2d primitives: within-1/255 {frac:.5f} max|d| {mx:.2e} shaded {st.samples_shaded}/{o_st.samples_shaded}")
+    assert o_st.samples_shaded > 1000 and st.rays_cast == o_st.rays_cast and frac >= 0.999
+    assert abs(int(st.samples_shaded) - int(o_st.samples_shaded)) <= 0.002 * o_st.samples_shaded

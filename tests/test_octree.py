@@ -184,3 +184,53 @@ def test_octree_dvr_traversal_against_the_oracle(ctx, thr, linear):
     a, _ = ctx.octree_render(0, step, info.num_levels - 1, eep, cam, W, H, linear=linear)
     b, _ = ctx.octree_render(0, step, 0, eep, cam, W, H, linear=linear)
     assert float(np.abs(a - b).max()) > 0.05
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("clip", [False, True])
+@pytest.mark.parametrize("dims,brick,thr", [((64, 64, 64), 8, 0.0), ((61, 48, 57), 8, 0.002), ((40, 40, 40), 4, -1.0)])
+def test_volumeoctree_proxy_geometry(ctx, dims, brick, thr, clip):
+    """OptimizedProxyGeometry "volumeoctree" (optimizedproxygeometry.cpp:1620-1737): the host mirror over the library's octree against
+    the restatement over the pointer tree -- same cubes, in the reference's traversal order; then the entry/exit images they give."""
+    import ctypes as C
+    from voreen_b200 import host
+    from voreen_b200 import raycaster as rc
+    vol = scenes.ct_like_volume(0, dims=dims)
+    vol[:, :, : dims[0] // 4] = 0                     # a transparent slab: homogeneous, pruned by the optimisation when thr >= 0
+    desc = rc.make_volume_desc(dims)
+    keys = [(0.0, (0, 0, 0, 0)), (0.3, (0, 0, 0, 0)), (0.35, (255, 120, 40, 3)), (0.7, (255, 255, 255, 120)), (1.0, (255, 255, 255, 255))]
+    dom, thr_tf, gamma, amode = (0.0, 65535.0), (0.0, 1.0), 1.0, 1
+    eep = rc.default_eep(proxy_mode=abi.PROXY_VOLUME_OCTREE, proxy_threshold=1.0)
+    if clip:
+        eep.enable_clipping = 1
+        eep.clip_llf[:] = [3.0, 0.0, 5.0]; eep.clip_urb[:] = [30.0, 39.0, 33.0]
+    ctx.upload_volume(0, vol, desc=desc)
+    with pytest.raises(abi.B200RCError):              # no octree yet (a new volume drops the octree of the previous one)
+        host.optimized_proxy_geometry(ctx, 0, desc, eep, [(keys, dom, thr_tf, gamma, amode)])
+    info = ctx.octree_build(0, brick, thr, "mean")
+    got = host.optimized_proxy_geometry(ctx, 0, desc, eep, [(keys, dom, thr_tf, gamma, amode)])
+    tree = oref.Octree(vol, brick, thr, "mean")
+    tf = orc.make_tf(keys, domain=dom, threshold=thr_tf, gamma=gamma, alpha_mode=amode)
+    table = orc.preint_cpu(tf, 256, 1.0)              # getPreIntegrationTable(1.f, 256) (:1637)
+    cl = np.zeros(4, np.float32)
+
+    def region_empty(mn, mx):                           # :1668-1676 + isRegionEmptyPi (:878-880)
+        f = []
+        for v in (mn, mx):
+            rw = np.float32(np.float32(v) / np.float32(65535.0)) * np.float32(desc.rwm_scale) + np.float32(desc.rwm_offset)
+            f.append(0.0 if rw < dom[0] else (1.0 if rw > dom[1] else float(np.float32(rw - np.float32(dom[0])) / np.float32(dom[1] - dom[0]))))
+        orc.lib().orc_preint_classify(orc.fp(table), 256, f[0], f[1], orc.fp(cl))
+        return bool(cl[3] <= np.float32(0.0001) * np.float32(eep.proxy_threshold))
+    want = oref.proxy_boxes(tree, region_empty, clip=(list(eep.clip_llf), list(eep.clip_urb)) if clip else None)
+    print(f"volumeoctree proxy geometry {dims} brick {brick} thr {thr} clip={clip}: {len(got)} cubes (restatement {len(want)}), tree nodes {info.num_nodes}")
+    assert len(got) == len(want) and len(got) >= 2
+    assert np.array_equal(got, want)
+    if thr >= 0:                                        # leaves of different sizes: the pruned slab is one big (transparent) leaf, opaque leaves differ in extent
+        ext = np.round((got[:, 3] - got[:, 0]) * dims[0])
+        assert len(np.unique(ext)) >= 1
+    cam = orc.make_camera((1.4, 0.8, 2.9), W=96, H=96)
+    eep2 = rc.default_eep(proxy_mode=eep.proxy_mode, enable_clipping=eep.enable_clipping, clip_llf=list(eep.clip_llf), clip_urb=list(eep.clip_urb), boxes=got)
+    e, ed, x, xd = ctx.entry_exit(eep2, cam, 96, 96)
+    oe, oed, ox, oxd = orc.entry_exit(want, orc.texture_to_world(desc), eep, cam, 96, 96)
+    assert np.array_equal(e, oe) and np.array_equal(x, ox) and np.array_equal(ed, oed) and np.array_equal(xd, oxd)
+    assert int((e[..., 3] > 0).sum()) > 500

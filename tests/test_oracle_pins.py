@@ -459,3 +459,67 @@ def test_outer_faces_mesh_gives_the_entry_exit_of_the_brick_cubes():
             assert np.isinf(t_in) == np.isinf(f_in)
             if np.isfinite(t_in):
                 assert abs(t_in - f_in) < 1e-9 and abs(t_out - f_out) < 1e-9
+
+
+# ---- TransFunc2DPrimitives: host mirror against the oracle's restatement, plus what the reference's paint code
+#      implies for specific texels.  The rasteriser itself is OpenGL in the reference: PARITY UNPINNED (no reference bit pattern exists) ---
+TF2D_PRIMS = [
+    {"type": "quad", "points": [(0.30, 0.10), (0.70, 0.10), (0.70, 0.60), (0.30, 0.60)], "colors": (255, 128, 0, 200), "fuzziness": 0.5},
+    {"type": "triangle", "points": [(0.05, 0.55), (0.45, 0.95), (0.10, 0.98)], "colors": [(0, 255, 0, 255), (0, 0, 255, 128), (255, 0, 255, 64)], "fuzziness": 0.7},
+    {"type": "banana", "points": [(0.55, 0.65), (0.75, 0.97), (0.75, 0.80), (0.97, 0.66)], "colors": (20, 200, 250, 180), "fuzziness": 0.6},
+    {"type": "quad", "points": [(0.0, 0.0), (0.2, 0.0), (0.2, 0.2), (0.0, 0.2)], "colors": (255, 255, 255, 255), "fuzziness": 1.0},
+]
+
+
+@pytest.mark.parametrize("size", [(256, 256), (128, 96), (33, 57)])
+@pytest.mark.parametrize("variant", ["plain", "thresholds+gamma", "one-alpha", "zero-alpha"])
+def test_tf2d_primitives_texture(size, variant):
+    W, H = size
+    kw = {"plain": {}, "thresholds+gamma": {"threshold_x": (0.1, 0.8), "threshold_y": (0.05, 0.9), "gamma": (1.5, 0.7)}, "one-alpha": {"alpha_mode": 2},
+          "zero-alpha": {"alpha_mode": 0}}[variant]
+    f, u = host.tf2d_primitives_texture(TF2D_PRIMS, W, H, **kw)
+    want = orc.tf2d_primitives_texture(TF2D_PRIMS, W, H, **kw)
+    assert np.array_equal(f, want)
+    assert np.array_equal(u, np.clip(np.floor(want * np.float32(255.0) + np.float32(0.5)), 0, 255).astype(np.uint8))
+    if variant == "zero-alpha":
+        assert not want[..., 3].any() and want[..., :3].any()
+        return
+    if variant == "one-alpha":
+        assert set(np.unique(want[..., 3])) <= {0.0, 1.0}
+        return
+    if variant == "plain":
+        def texel(x, y):
+            return want[min(int(y * H), H - 1), min(int(x * W), W - 1)]
+        # the core of the first quad (inside its inner quad: fuzziness 0.5 -> [0.4, 0.6] x [0.225, 0.475]) carries the full colour
+        assert np.allclose(texel(0.5, 0.35), np.array([255, 128, 0, 200]) / 255.0, atol=1e-6)
+        # its faded border: full rgb, alpha strictly between 0 and the full value, growing towards the core
+        a_out, a_in = texel(0.33, 0.35)[3], texel(0.38, 0.35)[3]
+        assert 0.0 < a_out < a_in < 200 / 255.0 and np.allclose(texel(0.33, 0.35)[:3], np.array([255, 128, 0]) / 255.0, atol=1e-6)
+        # nothing painted between the primitives
+        assert not texel(0.85, 0.3).any()
+        # fuzziness 1: no border, the whole quad is opaque white
+        assert np.allclose(texel(0.1, 0.1), 1.0, atol=1e-6) and np.allclose(texel(0.01, 0.19), 1.0, atol=1e-6)
+        # the triangle interpolates its vertex colours: green dominates near the first vertex, blue near the second
+        g, b = texel(0.12, 0.66), texel(0.36, 0.9)
+        assert g[1] > g[2] and b[2] > b[1]
+        # the banana: opaque along its centre line between the two middle control points, transparent above the upper curve
+        assert texel(0.75, 0.86)[3] > 0.5 and texel(0.75, 0.99)[3] == 0.0
+    if variant == "thresholds+gamma":
+        xf, xb = int(math.floor(0.1 * W + 0.5)), int(math.floor(0.8 * W + 0.5))
+        yf, yb = int(math.floor(0.05 * H + 0.5)), int(math.floor(0.9 * H + 0.5))
+        assert not want[:, :xf].any() and not want[:, xb + 1:].any() and not want[:yf].any() and not want[yb + 1:].any()
+        assert want[yf:yb + 1, xf:xb + 1, 3].any()
+
+
+def test_tf2d_primitives_invalid_input():
+    with pytest.raises(abi.B200RCError):
+        host.tf2d_primitives_texture(TF2D_PRIMS, 1, 64)
+    lib = host.load_library()
+    arr = host.make_primitives(TF2D_PRIMS[:1])
+    arr[0].type = 7
+    import ctypes as C
+    thr, g = (C.c_float * 2)(0.0, 1.0), (C.c_float * 2)(1.0, 1.0)
+    out = np.zeros((8, 8, 4), np.float32)
+    assert lib.b200host_tf2d_primitives_texture(arr, 1, 8, 8, thr, thr, g, 1, out.ctypes.data_as(C.POINTER(C.c_float)), None) != 0
+    f, u = host.tf2d_primitives_texture([], 16, 16)       # no primitives: a transparent texture
+    assert not f.any() and not u.any()

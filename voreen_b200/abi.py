@@ -26,7 +26,7 @@ OUT_RGBA32F, OUT_RGBA16 = 0, 1
 INSIDE_NONE, INSIDE_GPU = 0, 1
 ABI_VERSION = 4          # include/b200rc.h B200RC_ABI_VERSION
 RAYCASTER_SINGLE, RAYCASTER_SIMPLE, RAYCASTER_RGB, RAYCASTER_SEGMENTATION = 0, 1, 2, 3
-PROXY_BBOX, PROXY_MINBBOX, PROXY_VISIBLE_BRICKS, PROXY_OUTER_FACES = 0, 1, 2, 3
+PROXY_BBOX, PROXY_MINBBOX, PROXY_VISIBLE_BRICKS, PROXY_OUTER_FACES, PROXY_VOLUME_OCTREE = 0, 1, 2, 3, 4
 COMPOSITE_ERT = 0x100
 
 

@@ -549,6 +549,7 @@ int rc_volume_release(b200rc_ctx* ctx, int slot) {
     if (v.array) cudaFreeArray(v.array);
     cudaFree(v.bricks); cudaFree(v.minmax); cudaFree(v.max1); cudaFree(v.occ0); cudaFree(v.occ1); cudaFree(v.touched);
     v = VolumeSlot();
+    rc_octree_release(ctx, slot);           // an octree describes the volume it was built from
     return B200RC_OK;
 }
 

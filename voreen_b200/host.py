@@ -17,7 +17,7 @@ SYMBOLS = [
     "b200host_svrc_get_sampling_step", "b200host_svrc_set_volume", "b200host_svrc_set_synthetic_volume",
     "b200host_svrc_set_transfer_function", "b200host_svrc_set_camera", "b200host_svrc_connect_output",
     "b200host_svrc_set_entry_exit", "b200host_svrc_is_ready", "b200host_svrc_process", "b200host_vvd_parse", "b200host_vvd_count", "b200host_optimized_proxy_geometry",
-    "b200host_tf1d_gaussian_texture",
+    "b200host_tf1d_gaussian_texture", "b200host_tf2d_primitives_texture",
 ]
 
 
@@ -48,6 +48,43 @@ def tf1d_gaussian_texture(curves, width, threshold=(0.0, 1.0), gamma=1.0, alpha_
     return out
 
 
+class TF2DPrimitive(C.Structure):
+    _fields_ = [("type", C.c_int32), ("fuzziness", C.c_float), ("position", (C.c_float * 2) * 4), ("color", (C.c_uint8 * 4) * 4)]
+
+
+PRIMITIVE = {"triangle": 0, "quad": 1, "banana": 2}
+
+
+def make_primitives(prims, cls=None):
+    """[dict(type="triangle" | "quad" | "banana", points=[(x, y)] (3 or 4), colors=[rgba8] (one per point, or a single one), fuzziness=1.0)]
+    -> TF2DPrimitive array (TransFuncTriangle / TransFuncQuad / TransFuncBanana)."""
+    cls = cls or TF2DPrimitive
+    arr = (cls * max(1, len(prims)))()
+    for i, p in enumerate(prims):
+        arr[i].type = PRIMITIVE[p["type"]]
+        arr[i].fuzziness = p.get("fuzziness", 1.0)
+        n = 3 if p["type"] == "triangle" else 4
+        cols = p["colors"] if isinstance(p["colors"][0], (list, tuple)) else [p["colors"]] * n
+        for k in range(n):
+            arr[i].position[k][0], arr[i].position[k][1] = p["points"][k]
+            for c in range(4):
+                arr[i].color[k][c] = int(cols[k][c])
+    return arr
+
+
+def tf2d_primitives_texture(prims, width=256, height=256, threshold_x=(0.0, 1.0), threshold_y=(0.0, 1.0), gamma=(1.0, 1.0), alpha_mode=1):
+    """TransFunc2DPrimitives::getTexture: (float32 (H, W, 4) texture the reference uploads, its uint8 quantisation for Context.set_tf2d)."""
+    arr = make_primitives(prims)
+    f = np.zeros((height, width, 4), np.float32)
+    u = np.zeros((height, width, 4), np.uint8)
+    tx, ty, g = (C.c_float * 2)(*threshold_x), (C.c_float * 2)(*threshold_y), (C.c_float * 2)(*gamma)
+    rc = load_library().b200host_tf2d_primitives_texture(arr, len(prims), width, height, tx, ty, g, alpha_mode, f.ctypes.data_as(C.POINTER(C.c_float)),
+                                                         u.ctypes.data_as(C.c_void_p))
+    if rc:
+        raise abi.B200RCError(f"b200host_tf2d_primitives_texture: status {rc}")
+    return f, u
+
+
 class TFKey(C.Structure):
     _fields_ = [("intensity", C.c_float), ("color_l", C.c_uint8 * 4), ("color_r", C.c_uint8 * 4), ("split", C.c_int32)]
 
@@ -72,6 +109,7 @@ def load_library():
     lib.b200host_camera.argtypes = [pf, pf, pf, f32, f32, f32, f32, i32, i32, C.POINTER(abi.Camera)]
     lib.b200host_tf1d_keys_texture.argtypes = [C.POINTER(TFKey), i32, pf, f32, i32, i32, vp]
     lib.b200host_tf1d_gaussian_texture.argtypes = [C.POINTER(TFCurve), i32, pf, f32, i32, i32, vp]
+    lib.b200host_tf2d_primitives_texture.argtypes = [C.POINTER(TF2DPrimitive), i32, i32, i32, pf, pf, pf, i32, pf, vp]
     lib.b200host_tf1d_width_for.argtypes = [i32, C.POINTER(i32)]
     lib.b200host_volume_desc.argtypes = [C.POINTER(C.c_int32 * 3), i32, C.c_char_p, pf, pf, pf, C.POINTER(abi.VolumeDesc)]
     lib.b200host_svrc_create.argtypes = [i32, C.POINTER(vp)]

@@ -250,7 +250,221 @@ float rw_to_normalized(float rw, const float dom[2]) {
     if (dom[0] == dom[1]) return 0.f;
     return (rw - dom[0]) / (dom[1] - dom[0]);
 }
+
+// ---- TransFunc2DPrimitives -----------------------------------------------------------------------------------------------------
+struct PVert { float x, y, r, g, b, a; };
+struct PCol { float r, g, b, a; };
+inline PCol pcol(const uint8_t c[4]) { return {(float)c[0] / 255.f, (float)c[1] / 255.f, (float)c[2] / 255.f, (float)c[3] / 255.f}; }     // getColorNormalized
+inline PVert pv(float x, float y, const PCol& c) { return {x, y, c.r, c.g, c.b, c.a}; }
+inline PVert pv0(float x, float y, const PCol& c) { return {x, y, c.r, c.g, c.b, 0.f}; }                                                   // vec4(colour.xyz, 0)
+// GL_TRIANGLE_STRIP / GL_TRIANGLE_FAN -> triangles
+void strip(std::vector<PVert>& tris, const std::vector<PVert>& v) {
+    for (size_t i = 0; i + 2 < v.size(); ++i) { tris.push_back(v[i]); tris.push_back(v[i + 1]); tris.push_back(v[i + 2]); }
+}
+void fan(std::vector<PVert>& tris, const std::vector<PVert>& v) {
+    for (size_t i = 1; i + 1 < v.size(); ++i) { tris.push_back(v[0]); tris.push_back(v[i]); tris.push_back(v[i + 1]); }
+}
+// TransFuncTriangle::paint (:98-189) and TransFuncQuad::paint (:240-352): n corner points, faded border + full-colour core
+void polygon_primitive(std::vector<PVert>& tris, const b200host_tf2d_primitive& p, int n) {
+    float cx = 0.f, cy = 0.f;
+    PCol cc = {0.f, 0.f, 0.f, 0.f}, col[4];
+    for (int i = 0; i < n; ++i) {
+        col[i] = pcol(p.color[i]);
+        cx += p.position[i][0]; cy += p.position[i][1];
+        cc.r += col[i].r; cc.g += col[i].g; cc.b += col[i].b; cc.a += col[i].a;
+    }
+    cx /= (float)n; cy /= (float)n; cc.r /= (float)n; cc.g /= (float)n; cc.b /= (float)n; cc.a /= (float)n;
+    float mx[4], my[4], ix[4], iy[4];
+    PCol mc[4];
+    const float f = p.fuzziness;
+    for (int i = 0; i < n; ++i) {
+        const int j = (i + 1) % n;
+        mx[i] = 0.5f * p.position[i][0] + 0.5f * p.position[j][0]; my[i] = 0.5f * p.position[i][1] + 0.5f * p.position[j][1];
+        mc[i] = {0.5f * col[i].r + 0.5f * col[j].r, 0.5f * col[i].g + 0.5f * col[j].g, 0.5f * col[i].b + 0.5f * col[j].b, 0.f};
+        ix[i] = f * p.position[i][0] + (1.f - f) * cx; iy[i] = f * p.position[i][1] + (1.f - f) * cy;
+    }
+    auto outer = [&](int i) { return pv0(p.position[i][0], p.position[i][1], col[i]); };
+    auto inner = [&](int i) { return pv(ix[i], iy[i], col[i]); };
+    auto mid = [&](int i) { return pv(mx[i], my[i], mc[i]); };
+    if (n == 3) {
+        strip(tris, {outer(0), inner(0), mid(2), inner(2), outer(2), mid(1)});
+        strip(tris, {inner(2), inner(1), mid(1), outer(1)});
+        strip(tris, {outer(1), inner(1), mid(0), inner(0), outer(0)});
+        tris.push_back(inner(0)); tris.push_back(inner(1)); tris.push_back(inner(2));
+    } else {
+        strip(tris, {outer(0), inner(0), mid(3), inner(3), outer(3), mid(2)});
+        strip(tris, {inner(3), inner(2), mid(2), outer(2)});
+        strip(tris, {outer(2), inner(2), mid(1), inner(1), outer(1), mid(0)});
+        strip(tris, {inner(1), inner(0), mid(0), outer(0)});
+        fan(tris, {pv(cx, cy, cc), inner(0), inner(1), inner(2), inner(3), inner(0)});
+    }
+}
+// TransFuncBanana::paintInner (:405-490): three bands between four quadratic Bezier curves, one triangle strip
+void banana_primitive(std::vector<PVert>& tris, const b200host_tf2d_primitive& p) {
+    const int steps = 20;
+    PCol c[4];
+    for (int i = 0; i < 4; ++i) c[i] = pcol(p.color[i]);
+    const float* P0 = p.position[0]; const float* P1 = p.position[1]; const float* P2 = p.position[2]; const float* P3 = p.position[3];
+    auto mid2 = [](float b, float a, float d) { return (2.f * b) - (0.5f * a) - (0.5f * d); };
+    const float t1[2] = {mid2(P1[0], P0[0], P3[0]), mid2(P1[1], P0[1], P3[1])}, t2[2] = {mid2(P2[0], P0[0], P3[0]), mid2(P2[1], P0[1], P3[1])};
+    const PCol t1c = {mid2(c[1].r, c[0].r, c[3].r), mid2(c[1].g, c[0].g, c[3].g), mid2(c[1].b, c[0].b, c[3].b), mid2(c[1].a, c[0].a, c[3].a)};
+    const PCol t2c = {mid2(c[2].r, c[0].r, c[3].r), mid2(c[2].g, c[0].g, c[3].g), mid2(c[2].b, c[0].b, c[3].b), mid2(c[2].a, c[0].a, c[3].a)};
+    const float tc[2] = {(t1[0] + t2[0]) / 2.f, (t1[1] + t2[1]) / 2.f};
+    const PCol tcc = {(t1c.r + t2c.r) / 2.f, (t1c.g + t2c.g) / 2.f, (t1c.b + t2c.b) / 2.f, (t1c.a + t2c.a) / 2.f};
+    const float f = p.fuzziness;
+    auto mix = [&](float a, float b) { return f * a + (1.f - f) * b; };
+    const float t3[2] = {mix(t1[0], tc[0]), mix(t1[1], tc[1])}, t4[2] = {mix(t2[0], tc[0]), mix(t2[1], tc[1])};
+    const PCol t3c = {mix(t1c.r, tcc.r), mix(t1c.g, tcc.g), mix(t1c.b, tcc.b), mix(t1c.a, tcc.a)}, t4c = {mix(t2c.r, tcc.r), mix(t2c.g, tcc.g), mix(t2c.b, tcc.b), mix(t2c.a, tcc.a)};
+    auto bez = [](float t, float a, float m, float d) { return (((1 - t) * (1 - t)) * a) + ((2 * (1 - t) * t) * m) + ((t * t) * d); };
+    auto bez_v = [&](float t, const float m[2], const PCol& mc, bool zero_alpha) {
+        PVert v = {bez(t, P0[0], m[0], P3[0]), bez(t, P0[1], m[1], P3[1]), bez(t, c[0].r, mc.r, c[3].r), bez(t, c[0].g, mc.g, c[3].g), bez(t, c[0].b, mc.b, c[3].b),
+                   bez(t, c[0].a, mc.a, c[3].a)};
+        if (zero_alpha) v.a = 0.f;
+        return v;
+    };
+    std::vector<PVert> s;
+    const float* ma[3] = {t1, t3, t4}; const float* mb[3] = {t3, t4, t2};
+    const PCol* ca[3] = {&t1c, &t3c, &t4c}; const PCol* cb[3] = {&t3c, &t4c, &t2c};
+    for (int band = 0; band < 3; ++band) {
+        s.push_back(pv(P0[0], P0[1], c[0]));
+        for (int i = 0; i < steps; ++i) {
+            const float t = (float)i / (float)(steps - 1);
+            s.push_back(bez_v(t, ma[band], *ca[band], band == 0));      // the outermost curves carry alpha 0
+            s.push_back(bez_v(t, mb[band], *cb[band], band == 2));
+        }
+        s.push_back(pv(P3[0], P3[1], c[3]));
+    }
+    strip(tris, s);
+}
+
+// "volumeoctree" mode: VolumeOctreeBackgroundThread::traverseOctreeAndCreateGeometry (optimizedproxygeometry.cpp:1657-1737) over the
+// dense per-level node arrays of the library's octree (level k: (2^k)^3 nodes, x fastest; flags bit 0 exists, bit 3 has children).
+// One channel (the library's octree holds one).  llf / urb = the clipped volume cube of processCube (clip bounds -+ 0.5).
+int octree_proxy_geometry(b200rc_ctx* ctx, int slot, const b200rc_volume_desc* desc, const b200rc_eep_params* eep, const b200host_tf1d* tfs, int n_tfs,
+                          const float llf[3], const float urb[3], float* out, int max_boxes, int* n_boxes) {
+    b200rc_octree_info info;
+    int rc = b200rc_octree_get_info(ctx, slot, &info);
+    if (rc) return rc;
+    (void)n_tfs;
+    const int* dim = desc->dims;
+    const int L = info.num_levels;
+    std::vector<std::vector<uint16_t>> mn((size_t)L), mx((size_t)L);
+    std::vector<std::vector<uint8_t>> fl((size_t)L);
+    for (int k = 0; k < L; ++k) {
+        const size_t n = (size_t)1 << (3 * k);
+        mn[k].resize(n); mx[k].resize(n); fl[k].resize(n);
+        rc = b200rc_octree_download(ctx, slot, k, nullptr, mn[k].data(), mx[k].data(), fl[k].data(), nullptr);
+        if (rc) return rc;
+    }
+    std::vector<float> pi;
+    preint_alpha_table(tfs[0], 256, 1.f, pi);                                                   // getPreIntegrationTable(1.f, 256) (:1637)
+    const double limit = 0.0001 * (double)eep->proxy_threshold;                                 // isRegionEmptyPi (:878-880)
+    int n = 0;
+    struct Item { int k, x, y, z; };
+    std::vector<Item> stack;
+    stack.push_back({0, 0, 0, 0});
+    while (!stack.empty()) {
+        const Item it = stack.back();
+        stack.pop_back();
+        const int G = 1 << it.k;
+        const size_t idx = ((size_t)it.z * G + it.y) * G + it.x;
+        if (!(fl[it.k][idx] & 1)) continue;
+        const int span = info.octree_dim >> it.k;                                                // voxels per node edge at this level
+        if ((fl[it.k][idx] & 8) && it.k + 1 < L) {
+            // children in the reference's order (childID = x + 2 y + 4 z, :1722-1733); the stack reverses it, so push backwards
+            for (int c = 7; c >= 0; --c) stack.push_back({it.k + 1, it.x * 2 + (c & 1), it.y * 2 + ((c >> 1) & 1), it.z * 2 + (c >> 2)});
+            continue;
+        }
+        // leaf: normalised min / max -> real world -> TF domain (:1668-1676)
+        const float mn_rw = ((float)mn[it.k][idx] / 65535.f) * desc->rwm_scale + desc->rwm_offset;
+        const float mx_rw = ((float)mx[it.k][idx] / 65535.f) * desc->rwm_scale + desc->rwm_offset;
+        const float fs = rw_to_normalized(mn_rw, tfs[0].domain), fe = rw_to_normalized(mx_rw, tfs[0].domain);
+        const int i1 = std::min(std::max(iround(fs * 255.f), 0), 255), i2 = std::min(std::max(iround(fe * 255.f), 0), 255);
+        if ((double)pi[(size_t)i2 * 256 + i1] <= limit) continue;
+        const int pos[3] = {it.x, it.y, it.z};
+        float lo[3], hi[3];
+        bool outside_volume = false;
+        for (int a = 0; a < 3; ++a) {
+            const float node_llf = (float)(pos[a] * span), node_urb = (float)(pos[a] * span + span - 1);
+            if (node_llf >= (float)dim[a]) outside_volume = true;                               // :1684-1685
+            const float u = std::min(node_urb, (float)(dim[a] - 1));
+            lo[a] = std::max(node_llf - 1.f, -0.5f);                                             // one voxel further for the trilinear footprint (:1693-1694)
+            hi[a] = std::min(u + 1.f, (float)dim[a] - 0.5f);
+        }
+        if (outside_volume) continue;
+        if (eep->enable_clipping) {             // containsVolume -> whole cube; intersects -> addCubeMeshClip; else nothing (:1700-1706)
+            bool separated = false;
+            for (int a = 0; a < 3; ++a) { lo[a] = std::max(lo[a], llf[a]); hi[a] = std::min(hi[a], urb[a]); separated = separated || lo[a] > hi[a]; }
+            if (separated) continue;
+        }
+        if (n < max_boxes)
+            for (int a = 0; a < 3; ++a) { out[6 * n + a] = (lo[a] + 0.5f) / (float)dim[a]; out[6 * n + 3 + a] = (hi[a] + 0.5f) / (float)dim[a]; }
+        ++n;
+    }
+    *n_boxes = n;
+    return B200RC_OK;
+}
 }  // namespace
+
+extern "C" int b200host_tf2d_primitives_texture(const b200host_tf2d_primitive* prims, int n_prims, int width, int height,
+                                                const float threshold_x[2], const float threshold_y[2], const float gamma[2], int alpha_mode,
+                                                float* out_rgba32f, uint8_t* out_rgba8) {
+    if (n_prims < 0 || (n_prims > 0 && !prims) || width < 2 || height < 2 || width > 4096 || height > 4096 || !threshold_x || !threshold_y || !gamma) return B200RC_ERR_INVALID;
+    std::vector<PVert> tris;
+    for (int i = 0; i < n_prims; ++i) {
+        if (prims[i].type == 0) polygon_primitive(tris, prims[i], 3);
+        else if (prims[i].type == 1) polygon_primitive(tris, prims[i], 4);
+        else if (prims[i].type == 2) banana_primitive(tris, prims[i]);
+        else return B200RC_ERR_INVALID;
+    }
+    // the help texture: updateHelpTexture + paint (:165-250,313-333)
+    std::vector<float> help((size_t)width * height * 4, 0.f);
+    for (size_t k = 0; k + 2 < tris.size(); k += 3) {
+        const PVert &A = tris[k], &B = tris[k + 1], &Cc = tris[k + 2];
+        const double area = ((double)B.x - A.x) * ((double)Cc.y - A.y) - ((double)B.y - A.y) * ((double)Cc.x - A.x);
+        if (area == 0.0) continue;
+        const float xmin = std::min(A.x, std::min(B.x, Cc.x)), xmax = std::max(A.x, std::max(B.x, Cc.x));
+        const float ymin = std::min(A.y, std::min(B.y, Cc.y)), ymax = std::max(A.y, std::max(B.y, Cc.y));
+        const int x0 = std::max(0, (int)std::floor(xmin * (float)width - 0.5f)), x1 = std::min(width - 1, (int)std::ceil(xmax * (float)width - 0.5f));
+        const int y0 = std::max(0, (int)std::floor(ymin * (float)height - 0.5f)), y1 = std::min(height - 1, (int)std::ceil(ymax * (float)height - 0.5f));
+        for (int y = y0; y <= y1; ++y)
+            for (int x = x0; x <= x1; ++x) {
+                const double px = ((double)x + 0.5) / (double)width, py = ((double)y + 0.5) / (double)height;
+                const double w0 = (((double)B.x - px) * ((double)Cc.y - py) - ((double)B.y - py) * ((double)Cc.x - px)) / area;
+                const double w1 = (((double)Cc.x - px) * ((double)A.y - py) - ((double)Cc.y - py) * ((double)A.x - px)) / area;
+                const double w2 = (((double)A.x - px) * ((double)B.y - py) - ((double)A.y - py) * ((double)B.x - px)) / area;
+                if (w0 < 0.0 || w1 < 0.0 || w2 < 0.0) continue;
+                float* d = &help[((size_t)y * width + x) * 4];
+                const float frag[4] = {(float)(w0 * A.r + w1 * B.r + w2 * Cc.r), (float)(w0 * A.g + w1 * B.g + w2 * Cc.g), (float)(w0 * A.b + w1 * B.b + w2 * Cc.b),
+                                       (float)(w0 * A.a + w1 * B.a + w2 * Cc.a)};
+                for (int ch = 0; ch < 4; ++ch) d[ch] = std::max(d[ch], frag[ch]);       // glBlendEquation(GL_MAX)
+            }
+    }
+    // TransFunc2D::createTextureData (TF_FLOAT branch, :103-121) + getMappingForValueFloat (:150-160) + applyAlpha
+    const int xf = iround(threshold_x[0] * (float)width), xb = iround(threshold_x[1] * (float)width);
+    const int yf = iround(threshold_y[0] * (float)height), yb = iround(threshold_y[1] * (float)height);
+    std::vector<float> tex((size_t)width * height * 4, 0.f);
+    for (int y = 0; y < height; ++y) {
+        if (y < yf || y > yb) continue;
+        for (int x = 0; x < width; ++x) {
+            if (x < xf || x > xb) continue;
+            float vx = (float)x / (float)(width - 1), vy = (float)y / (float)(height - 1);
+            if (gamma[0] != 1.f) vx = powf(vx, gamma[0]);
+            if (gamma[1] != 1.f) vy = powf(vy, gamma[1]);
+            const int tx = std::min(std::max((int)(vx * (float)width), 0), width - 1), ty = std::min(std::max((int)(vy * (float)height), 0), height - 1);
+            for (int ch = 0; ch < 4; ++ch) tex[((size_t)y * width + x) * 4 + ch] = help[((size_t)ty * width + tx) * 4 + ch];
+        }
+    }
+    if (alpha_mode != 1)
+        for (size_t i = 0; i < (size_t)width * height; ++i) {
+            if (alpha_mode == 2) { if (tex[i * 4 + 3] != 0.f) tex[i * 4 + 3] = 1.f; }
+            else tex[i * 4 + 3] = 0.f;
+        }
+    if (out_rgba32f) std::memcpy(out_rgba32f, tex.data(), tex.size() * sizeof(float));
+    if (out_rgba8)
+        for (size_t i = 0; i < tex.size(); ++i) out_rgba8[i] = (uint8_t)std::min(std::max(iround(tex[i] * 255.f), 0), 255);
+    return B200RC_OK;
+}
 
 extern "C" int b200host_optimized_proxy_geometry(b200rc_ctx* ctx, int slot, const b200rc_volume_desc* desc, const b200rc_eep_params* eep,
                                                  const b200host_tf1d* tfs, int n_tfs, float* out, int max_boxes, int* n_boxes) {
@@ -265,6 +479,8 @@ extern "C" int b200host_optimized_proxy_geometry(b200rc_ctx* ctx, int slot, cons
         for (int a = 0; a < 3; ++a) { out[6 * k + a] = (lo[a] + 0.5f) / (float)dim[a]; out[6 * k + 3 + a] = (hi[a] + 0.5f) / (float)dim[a]; }
     };
     if (eep->proxy_mode == B200RC_PROXY_BBOX || n_tfs <= 0) { emit(0, llf, urb); *n_boxes = 1; return B200RC_OK; }
+
+    if (eep->proxy_mode == B200RC_PROXY_VOLUME_OCTREE) return octree_proxy_geometry(ctx, slot, desc, eep, tfs, n_tfs, llf, urb, out, max_boxes, n_boxes);
 
     const int step = eep->proxy_cell_size < 1 ? 1 : eep->proxy_cell_size;
     int32_t cells[3] = {0, 0, 0};
