@@ -716,3 +716,84 @@ def test_tf2d_primitives_end_to_end(ctx):
     print(f"tf2d primitives: within-1/255 {frac:.5f} max|d| {mx:.2e} shaded {st.samples_shaded}/{o_st.samples_shaded}")
     assert o_st.samples_shaded > 1000 and st.rays_cast == o_st.rays_cast and frac >= 0.999
     assert abs(int(st.samples_shaded) - int(o_st.samples_shaded)) <= 0.002 * o_st.samples_shaded
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# config 4 on the staging marcher (march_mslab.cuh): against the per-ray multi-volume kernel and the oracle
+# ---------------------------------------------------------------------------------------------------------------------
+def _ctx_with_marcher(marcher):
+    import voreen_b200 as vb
+    old = os.environ.get("B200RC_MARCHER")
+    if marcher == "ray":
+        os.environ["B200RC_MARCHER"] = "ray"        # read once, when the context is created
+    try:
+        return vb.Context(0)
+    finally:
+        if old is None:
+            os.environ.pop("B200RC_MARCHER", None)
+        else:
+            os.environ["B200RC_MARCHER"] = old
+
+
+@pytest.mark.parametrize("cls", ["tf", "preint"])
+@pytest.mark.parametrize("nvol,dims,img,comp", [(4, (48, 40, 56), (96, 88), "dvr"), (2, (33, 47, 29), (70, 61), "dvr"), (3, (64, 64, 64), (128, 128), "mip"),
+                                                (4, (40, 40, 40), (64, 64), "fhn")])
+def test_multivolume_staging_marcher(cls, nvol, dims, img, comp):
+    """Co-registered volumes through b200rc_render_camera: the staging marcher (one shared-memory region per volume) against the
+    per-ray kernel of the same library (B200RC_MARCHER=ray) -- identical sample decisions (rays, classified, shaded), images within
+    the gradient's rounding -- against the oracle's MultiVolumeRaycaster, and with empty-space skipping off (bit-identical)."""
+    import torch
+    from voreen_b200 import raycaster as rc
+    W, H = img
+    vols = [scenes.ct_like_volume(0, dims=dims, seed=500 + v) for v in range(nvol)]
+    desc = rc.make_volume_desc(dims)
+    cam = orc.make_camera((1.3, 1.0, 2.8), W=W, H=H)
+    eep = rc.default_eep(world_coords=1)
+    step_world = float(np.float32(2.0) * np.float32(max(d / max(dims) for d in dims)) / np.float32(max(dims)) / np.float32(2.0))
+    step_tex = float(np.float32(1.0) / (np.float32(max(dims)) * np.float32(2.0)))
+    tfs = [orc.make_tf(MV_KEYS[v], domain=(0.0, 65535.0)) for v in range(nvol)]
+    tex = [orc.tf1d_texture(t, 4096) for t in tfs]
+    pre = [orc.preint_cpu(t, 1024, step_tex) for t in tfs] if cls == "preint" else None
+
+    def params(ess):
+        p = rc.default_params(step_world, out_format=abi.OUT_RGBA32F, empty_space_skipping=ess, compositing=[abi.COMP[comp]] * 3)
+        p.num_volumes = nvol; p.multi_volume = 1
+        p.mv_opacity_correction_factor = step_tex / step_world
+        p.collect_stats = 1
+        if pre:
+            for v in range(nvol):
+                p.vol[v].classification = abi.CLASS_PREINT
+        return p
+
+    def render(c, ess):
+        for v in range(nvol):
+            c.upload_volume(v, vols[v], desc=desc)
+            c.set_tf1d(v, tex[v], (0.0, 65535.0))
+            if pre:
+                c.set_preint(v, pre[v])
+        outs, depth = c.render_camera(params(ess), eep, cam, W, H)
+        return np.asarray(outs[0]).copy(), np.asarray(depth).copy(), c.stats()
+
+    slab, ray = _ctx_with_marcher("slab"), _ctx_with_marcher("ray")
+    try:
+        a, ad, sa_ = render(slab, 1)
+        a0, ad0, sa0 = render(slab, 0)
+        b, bd, sb = render(ray, 1)
+        launches = slab.stats().kernel_launches
+        assert np.array_equal(a, a0) and np.array_equal(ad, ad0), "empty-space skipping must not change a pixel"
+        assert (sa_.rays_cast, sa_.samples_classified, sa_.samples_shaded, sa_.samples_nominal) == (sb.rays_cast, sb.samples_classified, sb.samples_shaded, sb.samples_nominal)
+        assert sa0.samples_shaded == sa_.samples_shaded and sa0.samples_classified > sa_.samples_classified and sa_.samples_skipped > 0
+        frac, mx = scenes.parity_report(b, a)
+        dfrac = float((np.abs(ad - bd) <= 1e-6).mean())
+        print(f"multi-volume staging marcher x{nvol} {dims} {cls} {comp}: vs per-ray within 1/255 {frac:.5f} max {mx:.2e} depth-equal {dfrac:.5f}; "
+              f"classified {sa_.samples_classified} shaded {sa_.samples_shaded} skipped {sa_.samples_skipped} (per-ray {sb.samples_skipped}) launches {launches}")
+        assert frac >= (0.999 if comp == "fhn" else 0.9999) and (comp != "dvr" or mx < 2e-2) and dfrac >= 0.9999
+        # the oracle's MultiVolumeRaycaster on the same entry/exit images
+        e, ed, x, xd = slab.entry_exit(eep, cam, W, H)
+        ovs = [orc.make_volume(vols[v], desc) for v in range(nvol)]
+        ocls = [orc.make_classifier(tex[v], (0.0, 65535.0), preint=pre[v] if pre else None) for v in range(nvol)]
+        o_outs, o_depth, o_st = orc.raycast(ovs, ocls, params(0), cam, W, H, np.stack([e] * (nvol + 1)), ed, np.stack([x] * (nvol + 1)), xd)
+        frac_o, mx_o = scenes.parity_report(o_outs[0], a.reshape(H, W, 4))
+        assert frac_o >= 0.999 and o_st.samples_shaded == sa_.samples_shaded and o_st.rays_cast == sa_.rays_cast, (frac_o, mx_o)
+    finally:
+        slab.close(); ray.close()

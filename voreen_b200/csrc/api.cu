@@ -422,7 +422,7 @@ int rc_march_launch(b200rc_ctx* ctx, const DevParams& p, int sampler, int nch, i
     if (p.simple || p.seg) return rc_march_generic(ctx, p, sampler, nch);      // Simple / RGB / SegmentationRaycaster: the run-time-switched per-ray kernel
     if (slab_ok && rc_march_slab(ctx, p, sampler, nch, dtype, &rc)) return rc;
     if (rc_march_fast(ctx, p, sampler, nch, dtype, &rc)) return rc;
-    if (rc_march_fast_multi(ctx, p, sampler, &rc)) return rc;
+    if (slab_ok && rc_march_mslab(ctx, p, sampler, &rc)) return rc;      // co-registered multi-volume: one staged region per volume
     if (rc_march_fast_multi(ctx, p, sampler, &rc)) return rc;
     return rc_march_generic(ctx, p, sampler, nch);
 }

@@ -110,6 +110,7 @@ int rc_proxy_boxes(b200rc_ctx* ctx, int slot, const b200rc_eep_params* eep, floa
 int rc_march_generic(b200rc_ctx* ctx, const DevParams& p, int sampler, int nch);
 bool rc_march_fast(b200rc_ctx* ctx, const DevParams& p, int sampler, int nch, int dtype, int* rc_out);
 bool rc_march_fast_multi(b200rc_ctx* ctx, const DevParams& p, int sampler, int* rc_out);
+bool rc_march_mslab(b200rc_ctx* ctx, const DevParams& p, int sampler, int* rc_out);
 bool rc_march_slab(b200rc_ctx* ctx, const DevParams& p, int sampler, int nch, int dtype, int* rc_out);
 int rc_march_launch(b200rc_ctx* ctx, const DevParams& p, int sampler, int nch, int dtype);
 // composite.cu

@@ -51,7 +51,7 @@ struct SlabShared {
     unsigned int occ[SLAB_OCC_WORDS];
 };
 
-struct SlabArgs { int depth; int cap_floats; const unsigned int* order; };   // order: tile ids, most expensive first; p.tile_counter[1] of them
+struct SlabArgs { int depth; int cap_floats; const unsigned int* order; int exact_lattice; };   // exact_lattice (march_mslab): t_k = fl(t_{k-1} + step) == k * step for every k   // order: tile ids, most expensive first; p.tile_counter[1] of them
 
 __device__ __forceinline__ int pick3(int a, int b, int c, int axis) { return axis == 0 ? a : (axis == 1 ? b : c); }
 __device__ __forceinline__ float pick3f(float a, float b, float c, int axis) { return axis == 0 ? a : (axis == 1 ? b : c); }
@@ -140,7 +140,7 @@ __device__ __forceinline__ void slab_stage(const VolDev& v, const SlabShared& sh
 
 // occupancy bits of the region's level-0 cells -> shared memory (one word per (jy, jz) row of cells)
 template <bool CULL>
-__device__ __forceinline__ void slab_stage_occ(const VolDev& v, SlabShared& sh, float* __restrict__ cmax) {
+__device__ __forceinline__ void slab_stage_occ(const VolDev& v, SlabShared& sh, float* __restrict__ cmax, unsigned int* __restrict__ occ_dst) {
     int off[3], n[3], c0[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
@@ -160,7 +160,7 @@ __device__ __forceinline__ void slab_stage_occ(const VolDev& v, SlabShared& sh, 
             const int cx = min(max(c0[0] + jx, 0), v.occ0_dims[0] - 1);
             bits |= ((__ldg(rowp + (cx >> 5)) >> (cx & 31)) & 1u) << jx;
         }
-        sh.occ[w] = bits;
+        occ_dst[w] = bits;
     }
     if (CULL && v.mip_cull) {       // level-0 cell maxima of the same cells (normalised texture values)
         const int tot = n[0] * n[1] * n[2];
@@ -245,7 +245,7 @@ __device__ __forceinline__ void slab_skip_cell(const DevParams& p, const VolDev&
 // GPUs).  slab_tile_cost_kernel estimates every tile's work as the summed ray length (inside this rank's shard, of the
 // pixels this launch renders), slab_tile_order_kernel sorts the tiles by that estimate, most expensive first, and drops
 // the tiles that own no pixel of this launch (another rank's band, no flagged pixel in the second sort-last pass).  Tile ids keep the Z-order numbering of the marcher (8x8 super-tiles).
-__global__ void __launch_bounds__(SLAB_THREADS) slab_tile_cost_kernel(const __grid_constant__ DevParams p, float* __restrict__ cost) {
+static __global__ void __launch_bounds__(SLAB_THREADS) slab_tile_cost_kernel(const __grid_constant__ DevParams p, float* __restrict__ cost) {
     __shared__ float part[SLAB_THREADS / 32];
     const unsigned tile = blockIdx.x;
     const unsigned super_x = (unsigned)p.tiles_x >> 3;
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(SLAB_THREADS) slab_tile_cost_kernel(const __gr
 }
 
 // A/B switch (B200RC_TILE_ORDER=0): Z-order numbering as is; only the tiles that own no pixel are dropped
-__global__ void slab_tile_order_plain_kernel(const float* __restrict__ cost, unsigned ntiles, unsigned int* __restrict__ order, unsigned int* __restrict__ counter) {
+static __global__ void slab_tile_order_plain_kernel(const float* __restrict__ cost, unsigned ntiles, unsigned int* __restrict__ order, unsigned int* __restrict__ counter) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         unsigned n = 0;
         for (unsigned i = 0; i < ntiles; ++i) if (cost[i] > 0.f) order[n++] = i;
@@ -292,7 +292,7 @@ __global__ void slab_tile_order_plain_kernel(const float* __restrict__ cost, uns
 }
 
 #define SLAB_ORDER_BINS 1024
-__global__ void __launch_bounds__(1024) slab_tile_order_kernel(const float* __restrict__ cost, unsigned ntiles, unsigned int* __restrict__ order,
+static __global__ void __launch_bounds__(1024) slab_tile_order_kernel(const float* __restrict__ cost, unsigned ntiles, unsigned int* __restrict__ order,
                                                                unsigned int* __restrict__ counter) {
     __shared__ unsigned hist[SLAB_ORDER_BINS];
     __shared__ float wmax[32];
@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
             PF_MARK(pf_leader)
             // (4) stage voxels + occupancy bits
             slab_stage<C>(V, sh, S);
-            if (V.ess) slab_stage_occ<CULL>(V, sh, sh_cmax);
+            if (V.ess) slab_stage_occ<CULL>(V, sh, sh_cmax, sh.occ);
             __syncthreads();
             PF_MARK(pf_stage)
             // (5) march while the footprint of the next sample lies inside the region.  The loop is warp-synchronous
