@@ -261,6 +261,12 @@ def run_b200(args, rank, world, local_rank):
     ctx.set_stream(stream.cuda_stream)
 
     line = measure(args, rank, world, local_rank, ctx, dev, stream, args.parallelism, light=False)
+    # config C4 (MultiVolumeRaycaster: 4 co-registered 1024^3 u16 volumes, per-volume transfer functions, DVR at 2048^2), one GPU
+    if world == 1 and line is not None and not args.no_c4 and args.size == 2048:
+        try:
+            line["c4_multivolume"] = measure_c4(ctx, dev, steps=min(args.steps, 8))
+        except Exception as e:      # the headline line must not depend on it
+            line["c4_multivolume"] = {"error": f"{type(e).__name__}: {e}"}
     # N > 1: the partition the north star names -- the SHARDED volume, sort-last with binary-swap compositing and the exact-ERT second
     # pass -- measured in the same run, next to the headline (which, for a volume that fits one GPU, is the image partition)
     if world > 1 and not args.no_sortlast_record:
@@ -288,6 +294,51 @@ def run_b200(args, rank, world, local_rank):
         dist.barrier()
         dist.destroy_process_group()
     ctx.close()
+
+
+C4_KEYS = [CT_KEYS, [(0.0, (0, 0, 0, 0)), (0.3, (0, 255, 0, 0)), (1.0, (0, 255, 0, 120))],
+           [(0.0, (0, 0, 0, 0)), (0.4, (0, 0, 255, 0)), (1.0, (0, 0, 255, 90))], [(0.0, (0, 0, 0, 0)), (0.5, (255, 0, 255, 0)), (1.0, (255, 0, 255, 60))]]
+
+
+def measure_c4(ctx, dev, steps=8, n=1024, img=2048, nvol=4):
+    """BASELINE config 4 through b200rc_render_camera_device: device time per frame (CUDA events of the library around its kernels),
+    TF classification and pre-integration; multi-volume staging marcher (march_mslab.cuh)."""
+    import torch
+    import voreen_b200 as vb
+    from voreen_b200 import abi, host
+    desc = vb.make_volume_desc((n, n, n))
+    step_world = float(np.float32(2.0) / np.float32(n) / np.float32(2.0))          # multivolumeraycaster.cpp:326-344, sampling rate 2
+    step_tex = float(np.float32(1.0) / (np.float32(n) * np.float32(2.0)))
+    for v in range(nvol):
+        ctx.synth_volume(v, desc, 1234 + v)
+    out_rgba = torch.empty((img, img, 4), dtype=torch.int16, device=dev)
+    out_depth = torch.empty((img, img), dtype=torch.float32, device=dev)
+    eep = vb.default_eep(world_coords=1)
+    res = {"workload": f"{nvol} x synthetic CT-like {n}^3 u16, per-volume transfer functions, ESS, central-diff + Phong, DVR, rate 2, {img}^2, orbit views",
+           "kernel": "march_mslab_kernel"}
+    try:
+        for cls in ("tf", "preint"):
+            for v in range(nvol):
+                if cls == "preint":
+                    ctx.set_tf1d(v, host.tf1d_texture(C4_KEYS[v], 1024), (0.0, 65535.0))
+                    ctx.build_preint(v, 1024, step_tex, abi.PI_CPU)
+                ctx.set_tf1d(v, host.tf1d_texture(C4_KEYS[v], 4096), (0.0, 65535.0))
+            p = vb.default_params(step_world, empty_space_skipping=1, out_format=abi.OUT_RGBA16)
+            p.num_volumes = nvol; p.multi_volume = 1
+            p.mv_opacity_correction_factor = step_tex / step_world
+            for v in range(nvol):
+                p.vol[v].classification = abi.CLASS_PREINT if cls == "preint" else abi.CLASS_TF
+            ms = []
+            for k in range(3 + steps):
+                cam = host.make_camera(orbit_eye((k * 5) % N_VIEWS), W=img, H=img)
+                ctx.render_camera_ptrs(p, eep, cam, img, img, [out_rgba.data_ptr(), 0, 0], out_depth.data_ptr(), device=True)
+                if k >= 3:
+                    ms.append(ctx.stats().last_render_ms)
+            res[f"ms_per_frame_{cls}"] = sum(ms) / len(ms)
+    finally:
+        for v in range(1, nvol):
+            ctx.lib.b200rc_release_volume(ctx.h, v)
+    return res
 
 
 def measure(args, rank, world, local_rank, ctx, dev, stream, parallelism, light):
@@ -638,6 +689,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-sortlast-record", action="store_true", help="N > 1: skip the additional sort-last (sharded volume) measurement")
     ap.add_argument("--no-c5", action="store_true", help="N = 8: skip the 4096^3 @3840x2160 sort-last measurement")
+    ap.add_argument("--no-c4", action="store_true", help="N = 1: skip the config-4 (multi-volume) record")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

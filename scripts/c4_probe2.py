@@ -36,7 +36,7 @@ for cls in modes:
         p.vol[v].classification = abi.CLASS_PREINT if cls == "preint" else abi.CLASS_TF
     eep = vb.default_eep(world_coords=1)
     tot = []
-    for k in (0, 9, 18, 27):
+    for k in ([int(a) for a in os.environ["C4_VIEWS"].split(",")] if os.environ.get("C4_VIEWS") else (0, 9, 18, 27)):
         cam = host.make_camera(scenes.orbit_eye(k), W=img, H=img)
         p.collect_stats = 0
         ctx.render_camera(p, eep, cam, img, img)

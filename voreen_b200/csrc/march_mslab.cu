@@ -40,15 +40,15 @@ static int launch_mslab(b200rc_ctx* ctx, const DevParams& p0) {
     if (env_cap >= 8 && env_cap < cap_kb) cap_kb = env_cap;
     if (cap_kb < 8) return -1;
     SlabArgs sa; sa.cap_floats = cap_kb * 256; sa.order = nullptr; sa.exact_lattice = mslab_lattice_exact(p.step, 65537) ? 1 : 0;
-    // slab depth: as deep as the region capacity allows for the lateral extent a tile's rays are expected to have (pixel footprint in
-    // voxels x tile edge + the gradient apron), between 4 and 12 planes; B200RC_MSLAB_DEPTH overrides
+    // slab depth: chosen per tile in the kernel -- the deepest slab (4..12 planes) whose region fits the capacity, given the lateral drift
+    // of the tile's rays per plane and `ext`, the lateral extent a tile's region has at depth 0: 16 pixels' footprint in voxels (+ 20 %
+    // perspective spread) + the gradient apron and slack (calibrated on config C4: profiles/r2_c4_mslab_depth_sweep.txt);
+    // B200RC_MSLAB_DEPTH fixes the depth for A/B runs
     {
         const float dmax = fmaxf(p.vol[0].dimf[0], fmaxf(p.vol[0].dimf[1], p.vol[0].dimf[2]));
         const float vpp = 1.2f * dmax / (float)(p.W > p.H ? p.W : p.H);
-        const int l1 = (int)(vpp * SLAB_TILE) + 6, l2 = (int)(vpp * SLAB_TILE_H) + 6;
-        int d = sa.cap_floats / (l1 * (l2 | 1)) - 3;
-        d = d < 4 ? 4 : (d > 12 ? 12 : d);
-        sa.depth = env_depth > 0 ? env_depth : d;
+        sa.ext = (int)(vpp * SLAB_TILE) + 12;
+        sa.depth = env_depth;
     }
     const size_t smem = (size_t)p.nvol * sa.cap_floats * sizeof(float);
     RC_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

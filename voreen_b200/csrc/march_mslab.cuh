@@ -95,11 +95,11 @@ __global__ void __launch_bounds__(SLAB_THREADS, MSLAB_MIN_CTAS) march_mslab_kern
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ SlabShared sh;
     __shared__ MSlabShared msh;
+    __shared__ float2 vote_slope[SLAB_THREADS / 32];
     float* S = (float*)smem_raw;                    // region of volume v: S + v * sa.cap_floats
     const VolDev& V = p.vol[0];                     // geometry (identical for all volumes: checked by the launcher)
     const int nv = p.nvol;
     const float step = p.step;
-    const int DEPTH = sa.depth;
     const bool exact = sa.exact_lattice != 0;
     const float step_rcp = 1.0f / step;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -167,21 +167,34 @@ __global__ void __launch_bounds__(SLAB_THREADS, MSLAB_MIN_CTAS) march_mslab_kern
         const float rcpT = 1.0f / tEnd;
         // slab orientation: major axis + travel direction of the tile's first casting ray (voxels per unit t, up to the common 1 / tEnd)
         const float vx = vdir.x * V.dimf[0] * rcpT, vy = vdir.y * V.dimf[1] * rcpT, vz = vdir.z * V.dimf[2] * rcpT;
-        int axis; float sgn;
+        int axis, DEPTH; float sgn;
         {
             const float ax_ = fabsf(vx), ay_ = fabsf(vy), az_ = fabsf(vz);
             const int my_axis = (ax_ >= ay_ && ax_ >= az_) ? 0 : (ay_ >= az_ ? 1 : 2);
             const unsigned m = __ballot_sync(0xffffffffu, cast);
             const int mine = my_axis | (pick3f(vx, vy, vz, my_axis) < 0.f ? 4 : 0);
             const int wa = m ? __shfl_sync(0xffffffffu, mine, __ffs(m) - 1) : 8;
-            if (lane == 0) sh.axis_vote[warp] = wa;
+            // lateral slopes of that ray (voxels per major-axis plane): they decide how deep a slab fits the region capacity
+            const float vm = fmaxf(fabsf(pick3f(vx, vy, vz, my_axis)), 1e-20f);
+            const float my_s1 = fabsf(pick3f(vx, vy, vz, (my_axis + 1) % 3)) / vm, my_s2 = fabsf(pick3f(vx, vy, vz, (my_axis + 2) % 3)) / vm;
+            const float ws1 = m ? __shfl_sync(0xffffffffu, my_s1, __ffs(m) - 1) : 0.f, ws2 = m ? __shfl_sync(0xffffffffu, my_s2, __ffs(m) - 1) : 0.f;
+            if (lane == 0) { sh.axis_vote[warp] = wa; vote_slope[warp] = make_float2(ws1, ws2); }
             __syncthreads();
             int a = 8;
+            float2 sl = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int w = 0; w < SLAB_THREADS / 32; ++w) if (a == 8 && sh.axis_vote[w] != 8) a = sh.axis_vote[w];
+            for (int w = 0; w < SLAB_THREADS / 32; ++w) if (a == 8 && sh.axis_vote[w] != 8) { a = sh.axis_vote[w]; sl = vote_slope[w]; }
             if (a == 8) a = 2;
             axis = a & 3;
             sgn = (a & 4) ? -1.f : 1.f;
+            DEPTH = sa.depth;
+            if (DEPTH <= 0) {       // deepest slab (4..12 planes) whose region -- tile extent + drift of the rays + apron -- fits the capacity
+                DEPTH = 4;
+                for (int d = 12; d > 4; --d) {
+                    const int n1 = sa.ext + (int)ceilf((float)d * sl.x), n2 = sa.ext + (int)ceilf((float)d * sl.y);
+                    if ((long long)(n1 | 1) * (n2 | 1) * (d + 3) <= sa.cap_floats) { DEPTH = d; break; }
+                }
+            }
         }
         const float vmaj = fabsf(pick3f(vx, vy, vz, axis));
         bool plan_stale = true;

@@ -32,7 +32,7 @@ static int launch_slab(b200rc_ctx* ctx, const DevParams& p0) {
     RC_CHECK(cudaFuncGetAttributes(&fa, kern));
     const int share_kb = (int)((227 * 1024 / SLAB_MIN_CTAS - 1024 - (long long)fa.sharedSizeBytes) / 1024);
     if (cap_kb + (int)((tf_bytes + 1023) / 1024) > share_kb) cap_kb = share_kb - (int)((tf_bytes + 1023) / 1024);
-    SlabArgs sa; sa.depth = p0.flags ? env_depth_remarch : env_depth; sa.cap_floats = cap_kb * 256; sa.exact_lattice = 0;
+    SlabArgs sa; sa.depth = p0.flags ? env_depth_remarch : env_depth; sa.cap_floats = cap_kb * 256; sa.exact_lattice = 0; sa.ext = 0;
     // pre-integration + empty-space skipping restores lastIntensity from the staged footprint: needs <= 1 voxel per step
     if (C::CLS == B200RC_CLASS_PREINT && p.vol[0].ess) {
         const float m = fmaxf(p.vol[0].dimf[0], fmaxf(p.vol[0].dimf[1], p.vol[0].dimf[2]));

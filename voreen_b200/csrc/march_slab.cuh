@@ -51,7 +51,7 @@ struct SlabShared {
     unsigned int occ[SLAB_OCC_WORDS];
 };
 
-struct SlabArgs { int depth; int cap_floats; const unsigned int* order; int exact_lattice; };   // exact_lattice (march_mslab): t_k = fl(t_{k-1} + step) == k * step for every k   // order: tile ids, most expensive first; p.tile_counter[1] of them
+struct SlabArgs { int depth; int cap_floats; const unsigned int* order; int exact_lattice; int ext; };   // march_mslab: exact_lattice = (t_k = fl(t_{k-1} + step) == k * step for every k); ext = expected lateral extent of a tile's region at depth 0 (depth <= 0: per-tile depth)   // order: tile ids, most expensive first; p.tile_counter[1] of them
 
 __device__ __forceinline__ int pick3(int a, int b, int c, int axis) { return axis == 0 ? a : (axis == 1 ? b : c); }
 __device__ __forceinline__ float pick3f(float a, float b, float c, int axis) { return axis == 0 ? a : (axis == 1 ? b : c); }
