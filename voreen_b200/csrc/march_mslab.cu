@@ -48,7 +48,7 @@ static int launch_mslab(b200rc_ctx* ctx, const DevParams& p0) {
         const float dmax = fmaxf(p.vol[0].dimf[0], fmaxf(p.vol[0].dimf[1], p.vol[0].dimf[2]));
         const float vpp = 1.2f * dmax / (float)(p.W > p.H ? p.W : p.H);
         sa.ext = (int)(vpp * SLAB_TILE) + 12;
-        sa.depth = env_depth;
+        sa.depth = env_depth; sa.dmin = 4; sa.dmax = 12;
     }
     const size_t smem = (size_t)p.nvol * sa.cap_floats * sizeof(float);
     RC_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

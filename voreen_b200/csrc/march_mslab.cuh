@@ -189,8 +189,8 @@ __global__ void __launch_bounds__(SLAB_THREADS, MSLAB_MIN_CTAS) march_mslab_kern
             sgn = (a & 4) ? -1.f : 1.f;
             DEPTH = sa.depth;
             if (DEPTH <= 0) {       // deepest slab (4..12 planes) whose region -- tile extent + drift of the rays + apron -- fits the capacity
-                DEPTH = 4;
-                for (int d = 12; d > 4; --d) {
+                DEPTH = sa.dmin;
+                for (int d = sa.dmax; d > sa.dmin; --d) {
                     const int n1 = sa.ext + (int)ceilf((float)d * sl.x), n2 = sa.ext + (int)ceilf((float)d * sl.y);
                     if ((long long)(n1 | 1) * (n2 | 1) * (d + 3) <= sa.cap_floats) { DEPTH = d; break; }
                 }

@@ -51,7 +51,7 @@ struct SlabShared {
     unsigned int occ[SLAB_OCC_WORDS];
 };
 
-struct SlabArgs { int depth; int cap_floats; const unsigned int* order; int exact_lattice; int ext; };   // march_mslab: exact_lattice = (t_k = fl(t_{k-1} + step) == k * step for every k); ext = expected lateral extent of a tile's region at depth 0 (depth <= 0: per-tile depth)   // order: tile ids, most expensive first; p.tile_counter[1] of them
+struct SlabArgs { int depth; int cap_floats; const unsigned int* order; int exact_lattice; int ext; int dmin, dmax; };   // march_mslab: exact_lattice = (t_k = fl(t_{k-1} + step) == k * step for every k); ext = expected lateral extent of a tile's region at depth 0 (depth <= 0: per-tile depth)   // order: tile ids, most expensive first; p.tile_counter[1] of them
 
 __device__ __forceinline__ int pick3(int a, int b, int c, int axis) { return axis == 0 ? a : (axis == 1 ? b : c); }
 __device__ __forceinline__ float pick3f(float a, float b, float c, int axis) { return axis == 0 ? a : (axis == 1 ? b : c); }
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
     constexpr bool pi_mode = (cmode == B200RC_CLASS_PREINT);
     const int smode = C::SHADE >= 0 ? C::SHADE : p.shading[0];
     const float step = p.step;
-    const int DEPTH = sa.depth;
+    __shared__ float2 vote_slope[SLAB_THREADS / 32];
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     RayStats st = {0u, 0u, 0u, 0u, 0ull};
     unsigned long long dbg_part = 0, dbg_rounds = 0;
@@ -435,21 +435,34 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
         }
         const float vx = dir.x * V.dimf[0], vy = dir.y * V.dimf[1], vz = dir.z * V.dimf[2];
         // slab orientation: major axis + travel direction of the tile's first casting ray, uniform over the CTA
-        int axis; float sgn;
+        int axis, DEPTH; float sgn;
         {
             const float ax_ = fabsf(vx), ay_ = fabsf(vy), az_ = fabsf(vz);
             const int my_axis = (ax_ >= ay_ && ax_ >= az_) ? 0 : (ay_ >= az_ ? 1 : 2);
             const unsigned m = __ballot_sync(0xffffffffu, cast);
             const int mine = my_axis | (pick3f(vx, vy, vz, my_axis) < 0.f ? 4 : 0);
             const int wa = m ? __shfl_sync(0xffffffffu, mine, __ffs(m) - 1) : 8;
-            if (lane == 0) sh.axis_vote[warp] = wa;
+            // lateral slopes of that ray (voxels per major-axis plane): they decide how deep a slab fits the region capacity
+            const float vm = fmaxf(fabsf(pick3f(vx, vy, vz, my_axis)), 1e-20f);
+            const float my_s1 = fabsf(pick3f(vx, vy, vz, (my_axis + 1) % 3)) / vm, my_s2 = fabsf(pick3f(vx, vy, vz, (my_axis + 2) % 3)) / vm;
+            const float ws1 = m ? __shfl_sync(0xffffffffu, my_s1, __ffs(m) - 1) : 0.f, ws2 = m ? __shfl_sync(0xffffffffu, my_s2, __ffs(m) - 1) : 0.f;
+            if (lane == 0) { sh.axis_vote[warp] = wa; vote_slope[warp] = make_float2(ws1, ws2); }
             __syncthreads();
             int a = 8;
+            float2 sl = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int w = 0; w < SLAB_THREADS / 32; ++w) if (a == 8 && sh.axis_vote[w] != 8) a = sh.axis_vote[w];
+            for (int w = 0; w < SLAB_THREADS / 32; ++w) if (a == 8 && sh.axis_vote[w] != 8) { a = sh.axis_vote[w]; sl = vote_slope[w]; }
             if (a == 8) a = 2;
             axis = a & 3;
             sgn = (a & 4) ? -1.f : 1.f;
+            DEPTH = sa.depth;
+            if (DEPTH <= 0) {       // per tile: the deepest slab (4..12 planes) whose region -- tile extent + drift of the rays + apron -- fits the capacity
+                DEPTH = sa.dmin;
+                for (int d = sa.dmax; d > sa.dmin; --d) {
+                    const int n1 = sa.ext + (int)ceilf((float)d * sl.x), n2 = sa.ext + (int)ceilf((float)d * sl.y);
+                    if ((long long)(n1 | 1) * (n2 | 1) * (d + 3) <= sa.cap_floats) { DEPTH = d; break; }
+                }
+            }
         }
         const float vmaj = fabsf(pick3f(vx, vy, vz, axis));
         // cached plan of the next sample (recomputed only after the ray moved)
