@@ -401,6 +401,11 @@ int b200rc_composite(b200rc_ctx* ctx, int mode, const float* front_rgba, const f
  * preceding b200rc_render_camera_device call, and overwrites those pixels of the partial image. */
 int b200rc_ert_plan(b200rc_ctx* ctx, const float* alphas_dev, int world, uint32_t front_mask, float* color_dev, float* depth_dev, size_t n,
                     float* prefix_dev, uint8_t* flags_dev, uint64_t* remarch_count);
+/* The same plan without the all-gather: alpha_planes_dev is a HOST array of `world` device pointers, entry r = rank r's alpha plane
+ * (n floats; peer-mapped memory of another GPU is fine, the kernel reads it over NVLink; entries of ranks outside front_mask may be NULL).
+ * A DVR partial image rendered by b200rc_render_camera_device with an unconnected out_color_dev[1] writes its alpha plane there. */
+int b200rc_ert_plan_planes(b200rc_ctx* ctx, const float* const* alpha_planes_dev, int world, uint32_t front_mask, float* color_dev, float* depth_dev,
+                           size_t n, float* prefix_dev, uint8_t* flags_dev, uint64_t* remarch_count);
 int b200rc_remarch_device(b200rc_ctx* ctx, const b200rc_params* params, const b200rc_camera* cam, int width, int height,
                           const float* prefix_dev, const uint8_t* flags_dev, void* out_color_dev[B200RC_MAX_OUTPUTS], float* out_depth_dev);
 

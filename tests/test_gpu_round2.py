@@ -797,3 +797,71 @@ def test_multivolume_staging_marcher(cls, nvol, dims, img, comp):
         assert frac_o >= 0.999 and o_st.samples_shaded == sa_.samples_shaded and o_st.rays_cast == sa_.rays_cast, (frac_o, mx_o)
     finally:
         slab.close(); ray.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# exact-ERT plan without the all-gather: alpha planes by pointer; DVR partial images export their alpha plane
+# ---------------------------------------------------------------------------------------------------------------------
+def test_ert_plan_over_plane_pointers_equals_the_gathered_plan(ctx):
+    import torch
+    dev = torch.device("cuda", 0)
+    world, n = 4, 70001
+    g = torch.Generator(device="cpu").manual_seed(5)
+    alphas = torch.rand((world, n), generator=g)
+    alphas[:, ::7] = 0.0; alphas[1, ::5] = 0.97; alphas[2, 1::11] = 1.0
+    alphas = alphas.to(dev).contiguous()
+    color = torch.rand((n, 4), generator=g).to(dev); color[::3] = 0.0
+    depth = torch.rand((n,), generator=g).to(dev)
+    for me, mask in ((0, 0b1110), (3, 0b0011), (2, 0b0000)):
+        color[:, 3] = alphas[me]
+        outs = []
+        for planes in (False, True):
+            c, d = color.clone(), depth.clone()
+            prefix = torch.empty((n,), dtype=torch.float32, device=dev); flags = torch.empty((n,), dtype=torch.uint8, device=dev)
+            if planes:
+                ptrs = [alphas[r].data_ptr() if (mask >> r) & 1 else 0 for r in range(world)]
+                cnt = ctx.ert_plan_planes(ptrs, mask, c.data_ptr(), d.data_ptr(), n, prefix.data_ptr(), flags.data_ptr(), count=True)
+            else:
+                cnt = ctx.ert_plan(alphas.data_ptr(), world, mask, c.data_ptr(), d.data_ptr(), n, prefix.data_ptr(), flags.data_ptr(), count=True)
+            ctx.synchronize()
+            outs.append((cnt, c.cpu().numpy(), d.cpu().numpy(), prefix.cpu().numpy(), flags.cpu().numpy()))
+        assert outs[0][0] == outs[1][0]
+        for a, b in zip(outs[0][1:], outs[1][1:]):
+            assert np.array_equal(a, b)
+        if mask:
+            assert outs[0][0] > 0 and int((outs[0][4] == 1).sum()) > 0
+    with pytest.raises(abi.B200RCError):        # a rank in front without a plane
+        ctx.ert_plan_planes([0, 0, 0, 0], 0b0010, color.data_ptr(), depth.data_ptr(), n, prefix.data_ptr(), flags.data_ptr())
+
+
+@pytest.mark.parametrize("kind", ["slab", "ray", "multi"])
+def test_dvr_partial_image_exports_its_alpha_plane(kind):
+    import torch
+    from voreen_b200 import raycaster as rc
+    from voreen_b200 import sortlast
+    dev = torch.device("cuda", 0)
+    c = _ctx_with_marcher("ray" if kind == "ray" else "slab")
+    try:
+        dims, W, H = (48, 40, 56), 96, 88
+        nvol = 2 if kind == "multi" else 1
+        lo, hi = sortlast.shard_range(dims, 1, 2)
+        rl = [max(0, lo[a] - sortlast.APRON) for a in range(3)]; rh = [min(dims[a], hi[a] + sortlast.APRON) for a in range(3)]
+        step = float(np.float32(1.0) / (np.float32(max(dims)) * np.float32(2.0)))
+        for v in range(nvol):
+            vol = scenes.ct_like_volume(0, dims=dims, seed=900 + v)
+            c.upload_volume(v, np.ascontiguousarray(vol[rl[2]:rh[2], rl[1]:rh[1], rl[0]:rh[0]]), desc=rc.make_volume_desc(dims, shard_lo=lo, shard_hi=hi, shard_apron=sortlast.APRON))
+            c.set_tf1d(v, orc.tf1d_texture(orc.make_tf(MV_KEYS[v], domain=(0.0, 65535.0)), 4096), (0.0, 65535.0))
+        p = rc.default_params(step if nvol == 1 else float(np.float32(2.0) * np.float32(max(d / max(dims) for d in dims)) / np.float32(max(dims)) / np.float32(2.0)), out_format=abi.OUT_RGBA32F)
+        p.partial_image = 1
+        if nvol > 1:
+            p.num_volumes = nvol; p.multi_volume = 1; p.mv_opacity_correction_factor = 0.5
+        eep = rc.default_eep(world_coords=1) if nvol > 1 else rc.default_eep()
+        cam = orc.make_camera((1.4, 0.9, 2.9), W=W, H=H)
+        col = torch.zeros((W * H, 4), dtype=torch.float32, device=dev); dep = torch.zeros((W * H,), dtype=torch.float32, device=dev)
+        key = torch.full((W * H,), -1.0, dtype=torch.float32, device=dev)
+        c.render_camera_ptrs(p, eep, cam, W, H, [col.data_ptr(), key.data_ptr(), 0], dep.data_ptr(), device=True)
+        c.synchronize()
+        a = col[:, 3].cpu().numpy(); k = key.cpu().numpy()
+        assert np.array_equal(a, k) and float(a.max()) > 0.3
+    finally:
+        c.close()

@@ -115,7 +115,7 @@ SYMBOLS = [
     "b200rc_set_stream", "b200rc_synchronize", "b200rc_get_stats", "b200rc_upload_volume", "b200rc_release_volume",
     "b200rc_synth_volume", "b200rc_download_volume", "b200rc_region_minmax", "b200rc_download_minmax", "b200rc_set_tf1d", "b200rc_set_preint",
     "b200rc_build_preint", "b200rc_download_preint", "b200rc_set_tf2d", "b200rc_entry_exit", "b200rc_render",
-    "b200rc_render_camera", "b200rc_render_camera_device", "b200rc_composite", "b200rc_finalize", "b200rc_ert_plan",
+    "b200rc_render_camera", "b200rc_render_camera_device", "b200rc_composite", "b200rc_finalize", "b200rc_ert_plan", "b200rc_ert_plan_planes",
     "b200rc_remarch_device", "b200rc_upload_volume_begin", "b200rc_upload_volume_slab", "b200rc_upload_volume_end", "b200rc_load_raw_file", "b200rc_rescale", "b200rc_composite_keyed",
     "b200rc_host_alloc", "b200rc_host_free", "b200rc_image_compositor", "b200rc_image_background", "b200rc_set_segmentation_tf",
     "b200rc_octree_build", "b200rc_octree_get_info", "b200rc_octree_download", "b200rc_octree_render",
@@ -171,6 +171,7 @@ def load_library():
     lib.b200rc_composite_keyed.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz]
     lib.b200rc_rescale.argtypes = [vp, vp, pf, i32, i32, i32, vp, pf, i32, i32, i32]
     lib.b200rc_ert_plan.argtypes = [vp, vp, i32, C.c_uint32, vp, vp, sz, vp, vp, C.POINTER(C.c_uint64)]
+    lib.b200rc_ert_plan_planes.argtypes = [vp, C.POINTER(C.c_void_p), i32, C.c_uint32, vp, vp, sz, vp, vp, C.POINTER(C.c_uint64)]
     lib.b200rc_remarch_device.argtypes = [vp, C.POINTER(Params), C.POINTER(Camera), i32, i32, vp, vp, C.POINTER(vp * 3), vp]
     lib.b200rc_image_compositor.argtypes = [vp, i32, f32, f32, f32, i32, vp, vp, vp, vp, i32, vp, vp, i32, i32, i32]
     lib.b200rc_image_background.argtypes = [vp, C.POINTER(BackgroundParams), vp, vp, i32, vp, vp, i32, i32, i32]

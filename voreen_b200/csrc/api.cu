@@ -603,6 +603,9 @@ static int render_camera_impl(b200rc_ctx* ctx, const b200rc_params* P, const b20
         if (nch != 1) { ctx->set_error("render_camera: the mip / mop merge key needs a single-channel volume"); return B200RC_ERR_INVALID; }
         p.out_key = (float*)out_color[1];
     }
+    // sort-last partial DVR image: the same plane receives the image's alpha, compact (4 B / pixel), so that the ranks behind this one can
+    // read it straight out of peer memory for the exact-ERT plan (b200rc_ert_plan_planes) -- no strided copy, no all-gather
+    if (P->partial_image && device_out && out_color && out_color[1] && p.comp[0] == B200RC_COMP_DVR && !flags && !p.simple) p.out_key = (float*)out_color[1];
     rc = run_march(ctx, P, p, nch, dtype);
     if (rc) return rc;
     if (!device_out) {
@@ -676,7 +679,26 @@ extern "C" int b200rc_ert_plan(b200rc_ctx* ctx, const float* alphas_dev, int wor
     if (!alphas_dev || !color_dev || !depth_dev || !prefix_dev || !flags_dev || world < 1 || world > 32) { ctx->set_error("ert_plan: bad arguments"); return B200RC_ERR_INVALID; }
     unsigned long long* counter = nullptr;
     if (remarch_count) { counter = ctx->d_stats + 7; RC_CHECK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), ctx->stream)); }
-    const int rc = rc_ert_plan_launch(ctx, alphas_dev, world, front_mask, color_dev, depth_dev, n, prefix_dev, flags_dev, counter);
+    const int rc = rc_ert_plan_launch(ctx, alphas_dev, nullptr, world, front_mask, color_dev, depth_dev, n, prefix_dev, flags_dev, counter);
+    if (rc) return rc;
+    if (remarch_count) {
+        unsigned long long h = 0;
+        RC_CHECK(cudaMemcpyAsync(&h, counter, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+        RC_CHECK(cudaStreamSynchronize(ctx->stream));
+        *remarch_count = h;
+    }
+    return B200RC_OK;
+}
+
+extern "C" int b200rc_ert_plan_planes(b200rc_ctx* ctx, const float* const* alpha_planes_dev, int world, uint32_t front_mask, float* color_dev, float* depth_dev,
+                                      size_t n, float* prefix_dev, uint8_t* flags_dev, uint64_t* remarch_count) {
+    CTX_GUARD();
+    if (!alpha_planes_dev || !color_dev || !depth_dev || !prefix_dev || !flags_dev || world < 1 || world > 32) { ctx->set_error("ert_plan_planes: bad arguments"); return B200RC_ERR_INVALID; }
+    for (int r = 0; r < world; ++r)
+        if (((front_mask >> r) & 1u) && !alpha_planes_dev[r]) { ctx->set_error("ert_plan_planes: no alpha plane for a rank in front_mask"); return B200RC_ERR_INVALID; }
+    unsigned long long* counter = nullptr;
+    if (remarch_count) { counter = ctx->d_stats + 7; RC_CHECK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), ctx->stream)); }
+    const int rc = rc_ert_plan_launch(ctx, nullptr, alpha_planes_dev, world, front_mask, color_dev, depth_dev, n, prefix_dev, flags_dev, counter);
     if (rc) return rc;
     if (remarch_count) {
         unsigned long long h = 0;

@@ -126,7 +126,10 @@ int rc_finalize_launch(b200rc_ctx* ctx, const float* rgba, const float* depth, s
 //   P >= 0.95                         -> the ray terminated in front of this shard: its contribution is erased
 //   0 < P, P + (1-P) A_local >= 0.95  -> the global 0.95 crossing lies inside this shard's segment: re-march (flag 2)
 //   otherwise                         -> the first-pass result stands (P == 0: local and global thresholds coincide)
-__global__ void ert_plan_kernel(const float* __restrict__ alphas, int world, unsigned front_mask, float4* __restrict__ color,
+// the alpha planes of the ranks: one gathered array (rank major) or one pointer per rank (planes in peer memory, read over NVLink)
+struct AlphaPlanes { const float* gathered; const float* plane[32]; };
+
+__global__ void ert_plan_kernel(const __grid_constant__ AlphaPlanes ap, int world, unsigned front_mask, float4* __restrict__ color,
                                 float* __restrict__ depth, size_t n, float* __restrict__ prefix, unsigned char* __restrict__ flags,
                                 unsigned long long* __restrict__ counter, unsigned int* __restrict__ list, unsigned int* __restrict__ list_n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -134,7 +137,7 @@ __global__ void ert_plan_kernel(const float* __restrict__ alphas, int world, uns
     if (i < n) {
         float T = 1.0f;
         for (int r = 0; r < world; ++r)
-            if ((front_mask >> r) & 1u) T *= 1.0f - alphas[(size_t)r * n + i];
+            if ((front_mask >> r) & 1u) T *= 1.0f - (ap.gathered ? ap.gathered[(size_t)r * n + i] : ap.plane[r][i]);
         const float P = 1.0f - T;
         const float A = color[i].w;
         if (P >= 0.95f) {
@@ -161,9 +164,12 @@ __global__ void ert_plan_kernel(const float* __restrict__ alphas, int world, uns
     }
 }
 
-int rc_ert_plan_launch(b200rc_ctx* ctx, const float* alphas, int world, unsigned front_mask, float* color, float* depth, size_t n,
+int rc_ert_plan_launch(b200rc_ctx* ctx, const float* alphas, const float* const* planes, int world, unsigned front_mask, float* color, float* depth, size_t n,
                        float* prefix, unsigned char* flags, unsigned long long* counter) {
     if (!n) return B200RC_OK;
+    AlphaPlanes ap;
+    ap.gathered = alphas;
+    for (int r = 0; r < 32; ++r) ap.plane[r] = (!alphas && planes && r < world) ? planes[r] : nullptr;
     ctx->plan_flags = nullptr; ctx->plan_n = 0;
     unsigned int* list = nullptr;
     if (n < 0xffffffffull) {
@@ -175,7 +181,7 @@ int rc_ert_plan_launch(b200rc_ctx* ctx, const float* alphas, int world, unsigned
         list = ctx->d_remarch_list;
         RC_CHECK(cudaMemsetAsync(ctx->d_tile_counter + 2, 0, sizeof(unsigned int), ctx->stream));
     }
-    ert_plan_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(alphas, world, front_mask, (float4*)color, depth, n, prefix, flags, counter,
+    ert_plan_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ap, world, front_mask, (float4*)color, depth, n, prefix, flags, counter,
                                                                          list, ctx->d_tile_counter + 2);
     if (list) { ctx->plan_flags = flags; ctx->plan_n = n; }
     ctx->launches++;

@@ -119,7 +119,7 @@ int rc_composite_keyed_launch(b200rc_ctx* ctx, const float* fc, const float* fk,
 int rc_rescale_launch(b200rc_ctx* ctx, const void* src, const float* sdepth, int sw, int sh, int format, void* dst, float* ddepth, int dw, int dh);
 int rc_composite_launch(b200rc_ctx* ctx, int mode, const float* fc, const float* fd, const float* bc, const float* bd, float* dc, float* dd, size_t n);
 int rc_finalize_launch(b200rc_ctx* ctx, const float* rgba, const float* depth, size_t n, int out_format, int snap, void* out);
-int rc_ert_plan_launch(b200rc_ctx* ctx, const float* alphas, int world, unsigned front_mask, float* color, float* depth, size_t n,
+int rc_ert_plan_launch(b200rc_ctx* ctx, const float* alphas, const float* const* planes, int world, unsigned front_mask, float* color, float* depth, size_t n,
                        float* prefix, unsigned char* flags, unsigned long long* counter);
 
 // post.cu

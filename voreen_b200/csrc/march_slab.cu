@@ -94,7 +94,8 @@ bool rc_march_slab(b200rc_ctx* ctx, const DevParams& p, int sampler, int nch, in
     SLAB_CASE(B200RC_U16, B200RC_CLASS_TF, B200RC_COMP_DVR, B200RC_SHADE_PHONG)
     SLAB_CASE(B200RC_U16, B200RC_CLASS_TF, B200RC_COMP_MIP, B200RC_SHADE_PHONG)
     SLAB_CASE(B200RC_U16, B200RC_CLASS_TF, B200RC_COMP_ISO, B200RC_SHADE_PHONG)
-    SLAB_CASE(B200RC_U16, B200RC_CLASS_PREINT, B200RC_COMP_MIP, B200RC_SHADE_PHONG)
+    // no pre-integrated MIP instantiation: SingleVolumeRaycaster switches pre-integration off when an output composites with MIP
+    // (singlevolumeraycaster.cpp:523-527); callers of the C ABI that ask for it anyway get the run-time-switched per-ray kernel
     SLAB_CASE(B200RC_U16, B200RC_CLASS_PREINT, B200RC_COMP_ISO, B200RC_SHADE_PHONG)
     SLAB_CASE(B200RC_U16, B200RC_CLASS_TF, B200RC_COMP_MOP, B200RC_SHADE_PHONG)
     SLAB_CASE(B200RC_U16, B200RC_CLASS_TF, B200RC_COMP_MIDA, B200RC_SHADE_PHONG)

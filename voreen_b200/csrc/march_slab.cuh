@@ -737,7 +737,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
             }
             store_color(p, 0, pix, result);
             if (p.out_depth) p.out_depth[pix] = p.quantize_depth24 ? depth24_roundtrip(depth) : depth;
-            if (p.out_key) p.out_key[pix] = cast ? ((comp == B200RC_COMP_MOP) ? result.w : maxI) : 0.0f;
+            if (p.out_key) p.out_key[pix] = cast ? ((comp == B200RC_COMP_MOP || comp == B200RC_COMP_DVR) ? result.w : maxI) : 0.0f;     // DVR: the partial image's alpha plane
         }
     }
 #ifdef SLAB_PROFILE

@@ -385,6 +385,13 @@ class Context:
         self._check(self.lib.b200rc_ert_plan(self.h, alphas, world, front_mask, color, depth, n, prefix, flags, C.byref(c) if count else None), "ert_plan")
         return int(c.value)
 
+    def ert_plan_planes(self, planes, front_mask, color, depth, n, prefix, flags, count=False):
+        """b200rc_ert_plan over one alpha-plane pointer per rank (e.g. peer-mapped key planes): no all-gather."""
+        c = C.c_uint64(0)
+        arr = (C.c_void_p * len(planes))(*[C.c_void_p(int(p)) if p else None for p in planes])
+        self._check(self.lib.b200rc_ert_plan_planes(self.h, arr, len(planes), front_mask, color, depth, n, prefix, flags, C.byref(c) if count else None), "ert_plan_planes")
+        return int(c.value)
+
     def remarch_device(self, params, cam, W, H, prefix, flags, out_ptrs, depth_ptr):
         ptrs = (C.c_void_p * 3)(*[C.c_void_p(p) if p else None for p in out_ptrs])
         self._check(self.lib.b200rc_remarch_device(self.h, C.byref(params), C.byref(cam), W, H, prefix, flags, C.byref(ptrs), C.c_void_p(depth_ptr) if depth_ptr else None), "remarch_device")

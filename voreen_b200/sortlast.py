@@ -282,6 +282,8 @@ class SortLast:
         self.ranges = final_ranges(self.npix, world)
         self.desc = shard_desc(self.dims, rank, world)
         self.exact_ert = True       # second pass: early ray termination on the global alpha (images match the single-GPU result)
+        import os as _os
+        self.peer_plan = _os.environ.get("B200RC_SORTLAST_PLAN", "planes") != "gather"      # A/B: alpha planes read from peer memory vs NCCL all-gather
         self.alpha = torch.empty((self.npix,), dtype=torch.float32, device=device)
         self.alphas = torch.empty((world * self.npix,), dtype=torch.float32, device=device)
         self.prefix = torch.empty((self.npix,), dtype=torch.float32, device=device)
@@ -336,7 +338,11 @@ class SortLast:
         with torch.cuda.stream(self.stream):
             if prof:
                 ev[0].record(self.stream)
-            self.ctx.render_camera_ptrs(p, eep, cam, self.W, self.H, [self.color.data_ptr(), self.key.data_ptr() if keyed else 0, 0], self.depth.data_ptr(), device=True)
+            # peer transport + DVR: the marcher also writes the partial image's alpha plane (4 B / pixel) into the key plane in peer memory;
+            # the ranks behind this one read it from there for the exact-ERT plan -- no strided copy, no all-gather
+            alpha_planes = self.peer is not None and self.exact_ert and need_ert_pass and self.world > 1 and self.peer_plan and not int(p.raycaster)
+            self.ctx.render_camera_ptrs(p, eep, cam, self.W, self.H, [self.color.data_ptr(), self.key.data_ptr() if (keyed or alpha_planes) else 0, 0],
+                                        self.depth.data_ptr(), device=True)
             march_ms = self.ctx.stats().last_march_ms
             if prof:
                 self.phases = {"first_pass_ms": march_ms}
@@ -345,10 +351,17 @@ class SortLast:
             if self.exact_ert and need_ert_pass and self.world > 1:
                 # every rank learns the alpha of every partial image, erases what a terminated ray hides and re-marches the
                 # pixels whose ray crosses the global 0.95 threshold inside its own shard
-                self.alpha.copy_(self.color[:, 3])
-                dist.all_gather_into_tensor(self.alphas, self.alpha)
-                n_flag = self.ctx.ert_plan(self.alphas.data_ptr(), self.world, front_mask(self.rank, self.world, self.dims, cam_tex),
-                                           self.color.data_ptr(), self.depth.data_ptr(), self.npix, self.prefix.data_ptr(), self.flags.data_ptr(), count=prof)
+                fm = front_mask(self.rank, self.world, self.dims, cam_tex)
+                if alpha_planes:
+                    self.peer.barrier()         # every rank's first pass (and with it its alpha plane) is complete
+                    planes = [self.peer.ptr(r, self.npix * 32) if (fm >> r) & 1 else 0 for r in range(self.world)]
+                    n_flag = self.ctx.ert_plan_planes(planes, fm, self.color.data_ptr(), self.depth.data_ptr(), self.npix, self.prefix.data_ptr(),
+                                                      self.flags.data_ptr(), count=prof)
+                else:
+                    self.alpha.copy_(self.color[:, 3])
+                    dist.all_gather_into_tensor(self.alphas, self.alpha)
+                    n_flag = self.ctx.ert_plan(self.alphas.data_ptr(), self.world, fm, self.color.data_ptr(), self.depth.data_ptr(), self.npix,
+                                               self.prefix.data_ptr(), self.flags.data_ptr(), count=prof)
                 if prof:
                     self.phases["flagged_pixels"] = n_flag
                     ev[2].record(self.stream)
