@@ -263,6 +263,7 @@ typedef struct b200rc_octree_render_params {
     float   sampling_step;
     int32_t node_level;
     int32_t filter;             /* B200RC_FILTER_* inside a brick (TEXTURE_FILTER_LINEAR define) */
+    int32_t compositing;        /* B200RC_COMP_DVR, _MIP or _MOP ("compositingMode", singleoctreeraycastercl.cpp:345-347; octree_dvr/_mip/_mop.cl) */
 } b200rc_octree_render_params;
 
 typedef struct b200rc_stats {

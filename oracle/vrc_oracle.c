@@ -1800,7 +1800,7 @@ static v4 oct_tf_linear(const uint8_t* tf, int w, float s) {      /* read_imagef
 }
 void orc_octree_raycast(const uint16_t* avg, const uint8_t* flags, const uint16_t* bricks, int levels, int B, const int32_t dims[3], int octree_dim,
                         const uint8_t* tf, int tf_width, float dom_lo, float dom_hi, float rwm_scale, float rwm_offset,
-                        float step, int lod, int filter_linear, const float* entry, const float* exitp, int W, int H, float* out, float* out_firsthit) {
+                        float step, int lod, int filter_linear, int compositing, const float* entry, const float* exitp, int W, int H, float* out, float* out_firsthit) {
     (void)levels;
     const float sc[3] = {(float)dims[0] / (float)octree_dim, (float)dims[1] / (float)octree_dim, (float)dims[2] / (float)octree_dim};
 #pragma omp parallel for schedule(dynamic, 2)
@@ -1817,6 +1817,13 @@ void orc_octree_raycast(const uint16_t* avg, const uint8_t* flags, const uint16_
             if (entry[4 * pix + 3] > 0.f || exitp[4 * pix + 3] > 0.f) {
                 float param = 0.f, tEndNode = -1.f;
                 v3 nllf = V3(0, 0, 0), nrcp = V3(1, 1, 1); size_t node = 0; int has_brick = 0;
+                /* RayInfo (singleoctreeraycaster.cl:360-368): current.intensity -1, pending.intensity 0, first hits 1 */
+                float cur_i = -1.0f, pend_i = 0.0f, cur_fh = 1.0f, pend_fh = 1.0f;
+                v4 cur_c = V4(0, 0, 0, 0), pend_c = V4(0, 0, 0, 0);
+                if (compositing == B200RC_COMP_MOP) {       /* :232-237 */
+                    cur_c = oct_tf_linear(tf, tf_width, ((cur_i * rwm_scale + rwm_offset) - dom_lo) / (dom_hi - dom_lo));
+                    pend_c = oct_tf_linear(tf, tf_width, ((pend_i * rwm_scale + rwm_offset) - dom_lo) / (dom_hi - dom_lo));
+                }
                 while (param <= tEnd) {
                     v3 s = V3(en.x + param * dir.x, en.y + param * dir.y, en.z + param * dir.z);
                     if (param > (tEndNode + 1.e-6f)) {
@@ -1873,8 +1880,26 @@ void orc_octree_raycast(const uint16_t* avg, const uint8_t* flags, const uint16_
                             intensity = (float)brick[((size_t)cz * B + cy) * B + cx] * (1.f / 65536.f);
                         }
                     } else intensity = clampf((float)avg[node] * 1.f / 65535.f, 0.f, 1.f);
+                    if (compositing == B200RC_COMP_MIP) {           /* octree_mip.cl applyTFandCombineColors */
+                        if (pend_i < intensity) {
+                            pend_i = intensity;
+                            pend_fh = gl_min(pend_fh, param / tEnd);
+                            if (cur_i < pend_i) { cur_i = pend_i; cur_fh = pend_fh; }
+                        }
+                        param += step;
+                        continue;
+                    }
                     float rw = intensity * rwm_scale + rwm_offset;
                     v4 c = oct_tf_linear(tf, tf_width, (rw - dom_lo) / (dom_hi - dom_lo));
+                    if (compositing == B200RC_COMP_MOP) {           /* octree_mop.cl applyTFandCombineColors */
+                        if (pend_c.w < c.w) {
+                            pend_c = c; pend_i = intensity;
+                            pend_fh = gl_min(pend_fh, param / tEnd);
+                            if (cur_c.w < pend_c.w) { cur_c = pend_c; cur_i = pend_i; cur_fh = pend_fh; }
+                        }
+                        param += step;
+                        continue;
+                    }
                     if (c.w > 0.f) {
                         v3 rgb = V3(gl_min(c.x, 1.f), gl_min(c.y, 1.f), gl_min(c.z, 1.f));
                         float a = 1.f - powf(1.f - c.w, step * 200.f);
@@ -1884,6 +1909,15 @@ void orc_octree_raycast(const uint16_t* avg, const uint8_t* flags, const uint16_
                     }
                     if (color.w >= 0.95f) { color.w = 1.f; param = tEnd + step; }
                     param += step;
+                }
+                if (compositing != B200RC_COMP_DVR) {       /* postRaycastingLoop, rayFinished (full-frame mode) */
+                    cur_i = pend_i; cur_fh = pend_fh;
+                    if (compositing == B200RC_COMP_MOP) cur_c = pend_c;
+                    else cur_c = oct_tf_linear(tf, tf_width, ((cur_i * rwm_scale + rwm_offset) - dom_lo) / (dom_hi - dom_lo));
+                    color = V4(0, 0, 0, 0);
+                    if (cur_c.w > 0.f) color = cur_c;
+                    color = V4(gl_min(color.x, 1.f), gl_min(color.y, 1.f), gl_min(color.z, 1.f), gl_min(color.w, 1.f));
+                    firsthit = cur_fh;
                 }
             }
             out[4 * pix] = color.x; out[4 * pix + 1] = color.y; out[4 * pix + 2] = color.z; out[4 * pix + 3] = color.w;

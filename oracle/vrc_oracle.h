@@ -168,7 +168,7 @@ void orc_tf2d_primitives_texture(const orc_tf2d_primitive* prims, int n, int wid
 /* SingleOctreeRaycasterCL DVR traversal over dense per-level node arrays (oracle/octree_ref.py builds them) */
 void orc_octree_raycast(const uint16_t* avg, const uint8_t* flags, const uint16_t* bricks, int levels, int brick_dim, const int32_t dims[3], int octree_dim,
                         const uint8_t* tf_rgba8, int tf_width, float dom_lo, float dom_hi, float rwm_scale, float rwm_offset,
-                        float step, int node_level, int filter_linear, const float* entry_rgba, const float* exit_rgba, int W, int H, float* out_rgba, float* out_firsthit);
+                        float step, int node_level, int filter_linear, int compositing /* B200RC_COMP_DVR / _MIP / _MOP */, const float* entry_rgba, const float* exit_rgba, int W, int H, float* out_rgba, float* out_firsthit);
 
 #ifdef __cplusplus
 }

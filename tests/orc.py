@@ -83,7 +83,7 @@ def lib():
         _lib.orc_image_background.argtypes = [C.POINTER(abi.BackgroundParams), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         _lib.orc_image_background.restype = None
         _lib.orc_octree_raycast.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int32 * 3), C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_float,
-                                            C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, pf, pf, C.c_int, C.c_int, pf, pf]
+                                            C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, pf, pf, C.c_int, C.c_int, pf, pf]
         _lib.orc_octree_raycast.restype = None
         _lib.orc_synth_volume.argtypes = [C.POINTER(C.c_int32 * 3), C.POINTER(C.c_int32 * 3), C.POINTER(C.c_int32 * 3), C.c_uint64, C.c_void_p]
         _lib.orc_tf2d_primitives_texture.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, pf, pf, pf, C.c_int, pf]
@@ -278,7 +278,7 @@ def image_background(W, H, color=None, depth=None, mode="monochrome", blend="alp
     return out, od
 
 
-def octree_raycast(avg, flags, pool, levels, brick_dim, dims, octree_dim, tf_tex, domain, rwm, step, node_level, linear, entry, exitp, W, H):
+def octree_raycast(avg, flags, pool, levels, brick_dim, dims, octree_dim, tf_tex, domain, rwm, step, node_level, linear, entry, exitp, W, H, compositing=0):
     """SingleOctreeRaycasterCL DVR over the dense arrays of oracle/octree_ref.pool_arrays."""
     avg = np.ascontiguousarray(avg, np.uint16); flags = np.ascontiguousarray(flags, np.uint8); pool = np.ascontiguousarray(pool, np.uint16)
     tf_tex = np.ascontiguousarray(tf_tex, np.uint8)
@@ -286,7 +286,7 @@ def octree_raycast(avg, flags, pool, levels, brick_dim, dims, octree_dim, tf_tex
     d = (C.c_int32 * 3)(*dims)
     entry = np.ascontiguousarray(entry, np.float32); exitp = np.ascontiguousarray(exitp, np.float32)
     lib().orc_octree_raycast(avg.ctypes.data, flags.ctypes.data, pool.ctypes.data, levels, brick_dim, C.byref(d), octree_dim, tf_tex.ctypes.data, tf_tex.shape[0],
-                             domain[0], domain[1], rwm[0], rwm[1], step, node_level, 1 if linear else 0, fp(entry), fp(exitp), W, H, fp(out), fp(fh))
+                             domain[0], domain[1], rwm[0], rwm[1], step, node_level, 1 if linear else 0, compositing, fp(entry), fp(exitp), W, H, fp(out), fp(fh))
     return out, fh
 
 

@@ -234,3 +234,43 @@ def test_volumeoctree_proxy_geometry(ctx, dims, brick, thr, clip):
     oe, oed, ox, oxd = orc.entry_exit(want, orc.texture_to_world(desc), eep, cam, 96, 96)
     assert np.array_equal(e, oe) and np.array_equal(x, ox) and np.array_equal(ed, oed) and np.array_equal(xd, oxd)
     assert int((e[..., 3] > 0).sum()) > 500
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("comp", ["mip", "mop"])
+@pytest.mark.parametrize("thr", [-1.0, 0.002])
+def test_octree_mip_mop_against_the_oracle(ctx, comp, thr):
+    """SingleOctreeRaycasterCL compositing modes MIP / MOP (octree_mip.cl, octree_mop.cl): the transfer function applied to the
+    maximum intensity, resp. the sample of maximum opacity; first-hit output = the ray parameter where that maximum was first raised."""
+    from voreen_b200 import host
+    from voreen_b200 import raycaster as rc
+    dims = (61, 48, 57)
+    vol = scenes.ct_like_volume(0, dims=dims)
+    desc = rc.make_volume_desc(dims)
+    ctx.upload_volume(0, vol, desc=desc)
+    brick = 8
+    info = ctx.octree_build(0, brick, thr)
+    t = oref.Octree(vol, brick, thr)
+    avg, mn, mx, flags, pool = oref.pool_arrays(t)
+    tex = host.tf1d_texture(scenes.CT_KEYS, 4096)
+    ctx.set_tf1d(0, tex, (0.0, 65535.0))
+    W, H = 96, 80
+    cam = orc.make_camera((1.3, 1.0, 2.8), W=W, H=H)
+    eep = rc.default_eep()
+    e, ed, x, xd = ctx.entry_exit(eep, cam, W, H)
+    step = 1.0 / float(sum(dims) // 3)
+    dvr, _ = ctx.octree_render(0, step, info.num_levels - 1, eep, cam, W, H)
+    for lod in (info.num_levels - 1, 1):
+        for linear in (True, False):
+            got, gfh = ctx.octree_render(0, step, lod, eep, cam, W, H, linear=linear, compositing=comp)
+            want, wfh = orc.octree_raycast(avg, flags, pool, t.num_levels, brick, dims, t.octree_dim, tex, (0.0, 65535.0), (desc.rwm_scale, desc.rwm_offset),
+                                           step, lod, linear, e, x, W, H, compositing=abi.COMP[comp])
+            frac, mxd = scenes.parity_report(want, got)
+            print(f"octree {comp} thr {thr} linear {linear} level {lod}: within 1/255 {frac:.5f} max {mxd:.2e} covered {(want[..., 3] > 0).mean():.3f}")
+            assert frac >= 0.999, (lod, frac, mxd)
+            assert float((np.abs(gfh - wfh) <= 1e-5).mean()) >= 0.999
+            assert (want[..., 3] > 0).mean() > 0.1 and float(want.max()) <= 1.0
+    full, _ = ctx.octree_render(0, step, info.num_levels - 1, eep, cam, W, H, compositing=comp)
+    assert float(np.abs(full - dvr).max()) > 0.05         # a different compositing mode, not DVR again
+    with pytest.raises(abi.B200RCError):
+        ctx.octree_render(0, step, 0, eep, cam, W, H, compositing="iso")

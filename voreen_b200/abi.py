@@ -81,7 +81,7 @@ class OctreeInfo(C.Structure):
 
 
 class OctreeRenderParams(C.Structure):
-    _fields_ = [("sampling_step", C.c_float), ("node_level", C.c_int32), ("filter", C.c_int32)]
+    _fields_ = [("sampling_step", C.c_float), ("node_level", C.c_int32), ("filter", C.c_int32), ("compositing", C.c_int32)]
 
 
 class BackgroundParams(C.Structure):

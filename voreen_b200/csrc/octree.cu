@@ -147,7 +147,7 @@ __global__ void octree_prune_kernel(OctreeDev o, int k) {
 
 // ---- the DVR traversal (singleoctreeraycaster.cl:190-300 with octree_dvr.cl:52-80; one channel) -----------------------------------
 struct OctRender {
-    float step; int lod; int filter_linear;
+    float step; int lod; int filter_linear; int comp;      // comp: B200RC_COMP_DVR / _MIP / _MOP (octree_dvr.cl / octree_mip.cl / octree_mop.cl)
     const uchar4* tf; int tf_width; float dom_lo, dom_hi, rwm_scale, rwm_offset;
     const float4* entry; const float4* exitp; float4* out; float* out_firsthit;
     int W, H; float scale[3];       // volume texture space -> octree space: dims / octreeDim (copyimage_octreecoarseness / rescale of entry/exit)
@@ -182,6 +182,11 @@ __global__ void __launch_bounds__(128) octree_march_kernel(OctreeDev o, OctRende
         float param = 0.f, tEndNode = -1.f;
         float3 nllf = f3(0.f, 0.f, 0.f), ndim_rcp = f3(1.f, 1.f, 1.f);
         size_t node = 0; bool has_brick = false;
+        // MIP / MOP ray state (singleoctreeraycaster.cl:360-368): pending intensity 0, pending first hit 1; MOP starts from the transfer
+        // function's colour at intensity 0 (:232-237).  In full-frame mode the "current" copies only mirror the pending ones.
+        float pend_i = 0.f, pend_fh = 1.0f;
+        float4 pend_c = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r.comp == B200RC_COMP_MOP) pend_c = oct_tf_linear(r, xdiv(xsub(xadd(xmul(0.f, r.rwm_scale), r.rwm_offset), r.dom_lo), xsub(r.dom_hi, r.dom_lo)));
         while (param <= tEnd) {
             const float3 s = f3(xadd(entry.x, xmul(param, dir.x)), xadd(entry.y, xmul(param, dir.y)), xadd(entry.z, xmul(param, dir.z)));
             if (param > xadd(tEndNode, 1.e-6f)) {
@@ -242,8 +247,18 @@ __global__ void __launch_bounds__(128) octree_march_kernel(OctreeDev o, OctRende
                 }
             } else intensity = fminf(fmaxf(xdiv(xmul((float)o.avg[node], 1.f), 65535.f), 0.f), 1.f);       // getNodeAvgValue0 (:150-155), 16 bits for one channel
             // applyChannelTransFunc (:402-413) + applyTFandCombineColors (octree_dvr.cl:52-80)
+            if (r.comp == B200RC_COMP_MIP) {            // octree_mip.cl:58-69: the transfer function is applied once, to the maximum
+                if (pend_i < intensity) { pend_i = intensity; pend_fh = fminf(pend_fh, xdiv(param, tEnd)); }
+                param = xadd(param, r.step);
+                continue;
+            }
             const float rw = xadd(xmul(intensity, r.rwm_scale), r.rwm_offset);
             const float4 c = oct_tf_linear(r, xdiv(xsub(rw, r.dom_lo), xsub(r.dom_hi, r.dom_lo)));
+            if (r.comp == B200RC_COMP_MOP) {            // octree_mop.cl:58-73: the sample with the largest opacity
+                if (pend_c.w < c.w) { pend_c = c; pend_i = intensity; pend_fh = fminf(pend_fh, xdiv(param, tEnd)); }
+                param = xadd(param, r.step);
+                continue;
+            }
             if (c.w > 0.f) {
                 const float3 rgb = f3(fminf(c.x, 1.f), fminf(c.y, 1.f), fminf(c.z, 1.f));
                 const float a = 1.f - powf(1.f - c.w, r.step * 200.f);
@@ -253,6 +268,11 @@ __global__ void __launch_bounds__(128) octree_march_kernel(OctreeDev o, OctRende
             }
             if (color.w >= 0.95f) { color.w = 1.f; param = xadd(tEnd, r.step); }
             param = xadd(param, r.step);
+        }
+        if (r.comp != B200RC_COMP_DVR) {                // postRaycastingLoop (octree_mip.cl:71-90, octree_mop.cl:75-96)
+            if (r.comp == B200RC_COMP_MIP) pend_c = oct_tf_linear(r, xdiv(xsub(xadd(xmul(pend_i, r.rwm_scale), r.rwm_offset), r.dom_lo), xsub(r.dom_hi, r.dom_lo)));
+            if (pend_c.w > 0.f) color = make_float4(fminf(pend_c.x, 1.f), fminf(pend_c.y, 1.f), fminf(pend_c.z, 1.f), fminf(pend_c.w, 1.f));
+            firsthit = pend_fh;
         }
     }
     r.out[pix] = color;
@@ -379,6 +399,8 @@ int rc_octree_render(b200rc_ctx* ctx, int slot, const b200rc_octree_render_param
     r.step = rp->sampling_step;
     r.lod = rp->node_level < 0 ? s->dev.levels - 1 : (rp->node_level > s->dev.levels - 1 ? s->dev.levels - 1 : rp->node_level);
     r.filter_linear = rp->filter == B200RC_FILTER_LINEAR ? 1 : 0;
+    r.comp = rp->compositing;
+    if (r.comp != B200RC_COMP_DVR && r.comp != B200RC_COMP_MIP && r.comp != B200RC_COMP_MOP) { ctx->set_error("octree render: compositing must be dvr, mip or mop"); return B200RC_ERR_INVALID; }
     r.tf = k.tf; r.tf_width = k.tf_width; r.dom_lo = k.dom[0]; r.dom_hi = k.dom[1];
     r.rwm_scale = ctx->vol[slot].desc.rwm_scale; r.rwm_offset = ctx->vol[slot].desc.rwm_offset;
     r.entry = entry; r.exitp = exitp; r.out = out; r.out_firsthit = out_firsthit; r.W = W; r.H = H;

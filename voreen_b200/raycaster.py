@@ -338,8 +338,9 @@ class Context:
                                                     br.ctypes.data if br is not None else None), "octree_download")
         return avg, mn, mx, fl, br
 
-    def octree_render(self, slot, step, node_level, eep, cam, W, H, linear=True):
+    def octree_render(self, slot, step, node_level, eep, cam, W, H, linear=True, compositing="dvr"):
         rp = abi.OctreeRenderParams(); rp.sampling_step = step; rp.node_level = node_level; rp.filter = abi.FILTER_LINEAR if linear else abi.FILTER_NEAREST
+        rp.compositing = abi.COMP[compositing] if isinstance(compositing, str) else int(compositing)
         out = np.empty((H, W, 4), np.float32); fh = np.empty((H, W), np.float32)
         self._check(self.lib.b200rc_octree_render(self.h, slot, C.byref(rp), C.byref(eep), C.byref(cam), W, H, _fp(out), _fp(fh)), "octree_render")
         return out, fh
