@@ -737,7 +737,7 @@ def _ctx_with_marcher(marcher):
 
 @pytest.mark.parametrize("cls", ["tf", "preint"])
 @pytest.mark.parametrize("nvol,dims,img,comp", [(4, (48, 40, 56), (96, 88), "dvr"), (2, (33, 47, 29), (70, 61), "dvr"), (3, (64, 64, 64), (128, 128), "mip"),
-                                                (4, (40, 40, 40), (64, 64), "fhn")])
+                                                (4, (40, 40, 40), (64, 64), "fhn"), (1, (40, 48, 36), (80, 72), "dvr")])
 def test_multivolume_staging_marcher(cls, nvol, dims, img, comp):
     """Co-registered volumes through b200rc_render_camera: the staging marcher (one shared-memory region per volume) against the
     per-ray kernel of the same library (B200RC_MARCHER=ray) -- identical sample decisions (rays, classified, shaded), images within
