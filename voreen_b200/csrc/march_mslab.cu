@@ -9,6 +9,9 @@
 #include <cstdint>
 #include <cstring>
 
+#ifndef MSLAB_SHARDED_DEFAULT
+#define MSLAB_SHARDED_DEFAULT false     // flipped to true once the sharded path has passed the GPU tests
+#endif
 template <int CLS> using MSlabCfg = MarchCfg<B200RC_SAMPLER_EXACT, 1, B200RC_U16, CLS, B200RC_GRAD_CENTRAL, B200RC_SHADE_PHONG, -1, true, true>;
 
 // t_k = fl(t_{k-1} + step) equals k * step for every k <= max_samples iff k * m fits the 24-bit significand, m = odd part of step
@@ -48,7 +51,7 @@ static int launch_mslab(b200rc_ctx* ctx, const DevParams& p0) {
         const float dmax = fmaxf(p.vol[0].dimf[0], fmaxf(p.vol[0].dimf[1], p.vol[0].dimf[2]));
         const float vpp = 1.2f * dmax / (float)(p.W > p.H ? p.W : p.H);
         sa.ext = (int)(vpp * SLAB_TILE) + 12;
-        sa.depth = env_depth; sa.dmin = 4; sa.dmax = 12;
+        sa.depth = env_depth; sa.dmin = 4; sa.dmax = 12; sa.prefetch = 0;
     }
     const size_t smem = (size_t)p.nvol * sa.cap_floats * sizeof(float);
     RC_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -80,9 +83,13 @@ bool rc_march_mslab(b200rc_ctx* ctx, const DevParams& p, int sampler, int* rc_ou
     if (!p.multi || !p.eep_shared || sampler != B200RC_SAMPLER_EXACT || p.nvol < 1 || p.nvol > B200RC_MAX_VOLUMES) return false;
     if (!p.connected[0] || p.connected[1] || p.connected[2]) return false;
     if (p.gradient != B200RC_GRAD_CENTRAL || p.comp[0] == B200RC_COMP_FHP) return false;
-    if (p.flags || p.pixel_list || p.out_key) return false;               // sort-last passes stay on the per-ray kernel
+    if (p.pixel_list) return false;                                       // compacted second pass: per-ray kernel
+    if (p.out_key && p.comp[0] != B200RC_COMP_DVR) return false;          // only the DVR alpha plane is exported here
     const VolDev& A = p.vol[0];
-    if (A.sharded) return false;
+    {   // sort-last passes (shards, second pass, alpha-plane export) on this kernel: B200RC_MSLAB_SHARDED=0 keeps them on the per-ray kernel
+        static const bool sharded_ok = !(getenv("B200RC_MSLAB_SHARDED") && atoi(getenv("B200RC_MSLAB_SHARDED")) == 0) && MSLAB_SHARDED_DEFAULT;
+        if ((A.sharded || p.flags || p.out_key) && !sharded_ok) return false;
+    }
     const int cls = p.classification[0];
     if (cls != B200RC_CLASS_TF && cls != B200RC_CLASS_PREINT) return false;
     bool ess_any = false;
@@ -95,7 +102,8 @@ bool rc_march_mslab(b200rc_ctx* ctx, const DevParams& p, int sampler, int* rc_ou
         // co-registered: one texture coordinate for all volumes at every lattice sample
         if (memcmp(B.dims, A.dims, sizeof A.dims) || memcmp(B.res_lo, A.res_lo, sizeof A.res_lo) || memcmp(B.res_dims, A.res_dims, sizeof A.res_dims) ||
             memcmp(B.clamp_lo, A.clamp_lo, sizeof A.clamp_lo) || memcmp(B.clamp_hi, A.clamp_hi, sizeof A.clamp_hi) || memcmp(B.w2t, A.w2t, sizeof A.w2t) ||
-            memcmp(B.spacing, A.spacing, sizeof A.spacing) || memcmp(B.offset, A.offset, sizeof A.offset) || B.nbx != A.nbx || B.nby != A.nby || B.sharded) return false;
+            memcmp(B.spacing, A.spacing, sizeof A.spacing) || memcmp(B.offset, A.offset, sizeof A.offset) || B.nbx != A.nbx || B.nby != A.nby || B.sharded != A.sharded ||
+            memcmp(B.own_lo, A.own_lo, sizeof A.own_lo) || memcmp(B.own_hi, A.own_hi, sizeof A.own_hi)) return false;
         ess_any = ess_any || B.ess;
     }
     if (cls == B200RC_CLASS_PREINT && ess_any) {

@@ -17,6 +17,8 @@
 // last skipped lattice sample).  Images are identical to the per-ray kernel up to the gradient's summation order (the 32-tap form of
 // march_slab.cuh); alpha > 0 decisions, sample positions and the shaded-sample counter are bit-identical.  Only the split of the
 // `skipped` counter between "tested" and "walked" samples differs (the jump bound comes from the staged level-0 cell here).
+// Sort-last: shards (every volume bricked identically) and the exact-ERT second pass are handled as march_multi handles them -- a
+// lattice sample belongs to the rank that owns its tap base index in volume 0, foreign samples only mark lastIntensity stale.
 #pragma once
 #include "march_slab.cuh"
 
@@ -63,6 +65,7 @@ __device__ __forceinline__ bool mslab_all_skip(const DevParams& p, int nv, unsig
     const float gx = sp.x * v.dimf[0] - 0.5f, gy = sp.y * v.dimf[1] - 0.5f, gz = sp.z * v.dimf[2] - 0.5f;       // as ess_empty_cell_t
     const int ix = min(max(__float2int_rd(gx), 0), v.dims[0] - 1) - v.res_lo[0], iy = min(max(__float2int_rd(gy), 0), v.dims[1] - 1) - v.res_lo[1],
               iz = min(max(__float2int_rd(gz), 0), v.dims[2] - 1) - v.res_lo[2];
+    if (v.sharded && ((unsigned)ix >= (unsigned)v.res_dims[0] || (unsigned)iy >= (unsigned)v.res_dims[1] || (unsigned)iz >= (unsigned)v.res_dims[2])) return false;
     int shift = 6;
     for (int k = 0; k < nv; ++k) {
         const VolDev& w = p.vol[k];
@@ -139,8 +142,11 @@ __global__ void __launch_bounds__(SLAB_THREADS, MSLAB_MIN_CTAS) march_mslab_kern
         const unsigned tx = (sup % super_x) * 8u + compact1by1(loc), ty = (sup / super_x) * 8u + compact1by1(loc >> 1);
         if (p.band_mod > 1 && (int)((ty * SLAB_TILE_H / (unsigned)p.band_rows) % (unsigned)p.band_mod) != p.band_rem) { __syncthreads(); continue; }
         const int px = (int)(tx * SLAB_TILE + (warp & 1u) * 8u + (lane & 7u)), py = (int)(ty * SLAB_TILE_H + (warp >> 1) * 4u + (lane >> 3));
-        const bool wanted = px < p.W && py < p.H;
-        const size_t pix = wanted ? (size_t)py * p.W + px : 0;
+        const bool inside = px < p.W && py < p.H;
+        const size_t pix = inside ? (size_t)py * p.W + px : 0;
+        const bool second_pass = p.flags != nullptr;
+        const bool wanted = inside && (!second_pass || p.flags[pix] == 2);      // sort-last second pass: flagged pixels only
+        const float prefixA = (second_pass && wanted) ? p.prefix[pix] : 0.f;
         float3 vfirst = f3(0.f, 0.f, 0.f), vdir = f3(0.f, 0.f, 1.f);
         float tEnd = 1.f;
         bool cast = false;
@@ -158,13 +164,27 @@ __global__ void __launch_bounds__(SLAB_THREADS, MSLAB_MIN_CTAS) march_mslab_kern
                 st.nominal += (unsigned long long)floorf(xdiv(tEnd, step)) + 1ull;
             }
         }
-        float4 result = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 result = make_float4(0.f, 0.f, 0.f, prefixA);
         float lastI[B200RC_MAX_VOLUMES] = {0.f, 0.f, 0.f, 0.f};
         float t = 0.0f, t_prev = 0.0f, tDepth = -1.0f, maxI = 0.f;
         int loop = 0;
         bool finished = !cast;
         unsigned prev_empty = 0u, stale = 0u;        // march_multi's per-volume bits
         const float rcpT = 1.0f / tEnd;
+        const unsigned all = (1u << nv) - 1u;
+        // sort-last shard: march only the lattice samples near the owned range (march_multi: pre-roll of the shader's own t += step)
+        const bool sharded = V.sharded != 0;
+        float tStop = tEnd;
+        if (cast && sharded) {
+            const ShardSeg seg = shard_segment(V, vfirst, f3(vdir.x * rcpT, vdir.y * rcpT, vdir.z * rcpT), tEnd, step);
+            if (!seg.any) finished = true;
+            else {
+                tStop = seg.t_stop;
+                for (int i = 0; i < seg.k0 && t <= tEnd; ++i) MSLAB_ADVANCE()
+                if (seg.k0 > 0) stale |= all;       // every volume's window is the whole ray (shared entry/exit)
+                finished = (t > tStop);
+            }
+        }
         // slab orientation: major axis + travel direction of the tile's first casting ray (voxels per unit t, up to the common 1 / tEnd)
         const float vx = vdir.x * V.dimf[0] * rcpT, vy = vdir.y * V.dimf[1] * rcpT, vz = vdir.z * V.dimf[2] * rcpT;
         int axis, DEPTH; float sgn;
@@ -203,18 +223,27 @@ __global__ void __launch_bounds__(SLAB_THREADS, MSLAB_MIN_CTAS) march_mslab_kern
         for (;;) {
             // (1) next sample of this ray, after the lattice samples at which NO volume can contribute (all in transparent cells)
             if (plan_stale) {
-                if (ess_all) {
+                if (ess_all || sharded) {
                     while (!finished) {
-                        // would every volume skip the sample at t?  (nothing is committed until all agree)
                         const float realT = xdiv(t, tEnd);
                         const float3 sp = f3(xadd(vfirst.x, xmul(realT, vdir.x)), xadd(vfirst.y, xmul(realT, vdir.y)), xadd(vfirst.z, xmul(realT, vdir.z)));
+                        if (sharded) {      // another rank's lattice sample: its owner sets lastIntensity of every volume
+                            const int x0 = (int)floorf(xsub(xmul(sp.x, V.dimf[0]), 0.5f)), y0 = (int)floorf(xsub(xmul(sp.y, V.dimf[1]), 0.5f)), z0 = (int)floorf(xsub(xmul(sp.z, V.dimf[2]), 0.5f));
+                            if (!shard_owns(V, x0, y0, z0)) {
+                                stale |= all; prev_empty = 0u;
+                                MSLAB_ADVANCE()
+                                finished = (t > tStop) || loop >= 256 * 256;
+                                continue;
+                            }
+                        }
+                        // would every volume skip the sample at t?  (nothing is committed until all agree)
                         float t_jump = 3.0e38f;
-                        if (!mslab_all_skip(p, nv, pi_mask, prev_empty, sp, vx, vy, vz, t, t_jump)) break;
-                        stale |= pi_mask & ((1u << nv) - 1u);
+                        if (!ess_all || !mslab_all_skip(p, nv, pi_mask, prev_empty, sp, vx, vy, vz, t, t_jump)) break;
+                        stale |= pi_mask & all;
                         st.skipped += (unsigned)nv;
                         MSLAB_ADVANCE()
-                        st.skipped += mslab_walk(exact, step, step_rcp, t_jump, tEnd, t, t_prev, loop);
-                        finished = (t > tEnd) || loop >= 256 * 256;
+                        st.skipped += mslab_walk(exact, step, step_rcp, t_jump, tStop, t, t_prev, loop);
+                        finished = (t > tStop) || loop >= 256 * 256;
                     }
                 }
                 zc = INT_MAX;
@@ -242,7 +271,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, MSLAB_MIN_CTAS) march_mslab_kern
                 if (part) {
                     const float um = pick3f(ux, uy, uz, axis);
                     const float dist = (float)(zmin + DEPTH) - (sgn > 0.f ? um : -um);
-                    const float dt = fminf(dist / fmaxf(vmaj, 1e-20f), tEnd - t);
+                    const float dt = fminf(dist / fmaxf(vmaj, 1e-20f), tStop - t);
                     const int jx = __float2int_rd(ux + dt * vx), jy = __float2int_rd(uy + dt * vy), jz = __float2int_rd(uz + dt * vz);
                     lo0 = min(i0x, jx); hi0 = max(i0x, jx); lo1 = min(i0y, jy); hi1 = max(i0y, jy); lo2 = min(i0z, jz); hi2 = max(i0z, jz);
                 }
@@ -318,7 +347,13 @@ __global__ void __launch_bounds__(SLAB_THREADS, MSLAB_MIN_CTAS) march_mslab_kern
                         const float fx = floorf(sux), fy = floorf(suy), fz = floorf(suz);
                         const int lx = (int)fx - rx, ly = (int)fy - ry, lz = (int)fz - rz;
                         if ((unsigned)(lx - 1) >= (unsigned)(nx - 3) || (unsigned)(ly - 1) >= (unsigned)(ny - 3) || (unsigned)(lz - 1) >= (unsigned)(nz - 3)) run = false;
-                        else {
+                        else if (sharded && !shard_owns(V, (int)fx, (int)fy, (int)fz)) {
+                            plan_stale = true;
+                            stale |= all; prev_empty = 0u;
+                            MSLAB_ADVANCE()
+                            finished = (t > tStop) || loop >= 256 * 256;
+                            run = !finished;
+                        } else {
                             plan_stale = true;
                             // per-volume emptiness of the sample's level-0 cell (staged bits), and march_multi's skip rule
                             unsigned empty = 0u;
@@ -328,7 +363,6 @@ __global__ void __launch_bounds__(SLAB_THREADS, MSLAB_MIN_CTAS) march_mslab_kern
                                     if (p.vol[v].ess && !((msh.occ[v][w] >> b) & 1u)) empty |= 1u << v;
                             }
                             const unsigned skip = empty & (~pi_mask | prev_empty);      // empty, and (pre-integration) the previous sample was too
-                            const unsigned all = (1u << nv) - 1u;
                             if (skip == all) {
                                 // no volume takes this sample: the shader's iteration does nothing but t += step; walk the lattice up to
                                 // the exit of the staged cell (rounded down: one more test at worst, never a sample too far)
@@ -350,8 +384,8 @@ __global__ void __launch_bounds__(SLAB_THREADS, MSLAB_MIN_CTAS) march_mslab_kern
                                 }
                                 const float t_jump = __fadd_rd(t, __fmul_rd(fmaxf(dt, 0.f), 0.999999f));
                                 MSLAB_ADVANCE()
-                                st.skipped += mslab_walk(exact, step, step_rcp, t_jump, tEnd, t, t_prev, loop);
-                                finished = (t > tEnd) || loop >= 256 * 256;
+                                st.skipped += mslab_walk(exact, step, step_rcp, t_jump, tStop, t, t_prev, loop);
+                                finished = (t > tStop) || loop >= 256 * 256;
                                 run = !finished;
                             } else {
                                 const float ax = xsub(sux, fx), ay = xsub(suy, fy), az = xsub(suz, fz);
@@ -447,7 +481,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, MSLAB_MIN_CTAS) march_mslab_kern
                                     finished = true;
                                 }
                                 MSLAB_ADVANCE()
-                                finished = finished || (t > tEnd) || loop >= 256 * 256;
+                                finished = finished || (t > tStop) || loop >= 256 * 256;
                                 run = !finished;
                             }
                         }
@@ -459,8 +493,13 @@ __global__ void __launch_bounds__(SLAB_THREADS, MSLAB_MIN_CTAS) march_mslab_kern
         if (wanted) {
             float depth = 1.0f;
             if (cast) depth = get_depth_value(tDepth, tEnd, p.entry_depth[pix], p.exit_depth[pix], p.near_d, p.far_d);
+            if (second_pass) {      // back to the shard-local convention the merge expects: C_local = dC / (1 - P), A_local = (A - P) / (1 - P)
+                const float k = 1.0f / (1.0f - prefixA);
+                result.x *= k; result.y *= k; result.z *= k; result.w = (result.w - prefixA) * k;
+            }
             store_color(p, 0, pix, result);
             if (p.out_depth) p.out_depth[pix] = p.quantize_depth24 ? depth24_roundtrip(depth) : depth;
+            if (p.out_key) p.out_key[pix] = result.w;       // sort-last DVR partial image: its alpha plane (first pass only)
         }
     }
     if (p.collect_stats && p.stats) {

@@ -35,6 +35,7 @@ static int launch_slab(b200rc_ctx* ctx, const DevParams& p0) {
     const int share_kb = (int)((227 * 1024 / SLAB_MIN_CTAS - 1024 - (long long)fa.sharedSizeBytes) / 1024);
     if (cap_kb + (int)((tf_bytes + 1023) / 1024) > share_kb) cap_kb = share_kb - (int)((tf_bytes + 1023) / 1024);
     SlabArgs sa; sa.depth = p0.flags ? env_depth_remarch : env_depth; sa.cap_floats = cap_kb * 256; sa.exact_lattice = 0;
+    { static const int env_pf = getenv("B200RC_SLAB_PREFETCH") ? atoi(getenv("B200RC_SLAB_PREFETCH")) : 0; sa.prefetch = env_pf; }
     {   // lateral extent of a tile's region at depth 0: 16 pixels' footprint in voxels (+ 20 % perspective spread) + apron and slack
         static const int env_ext = getenv("B200RC_SLAB_EXT") ? atoi(getenv("B200RC_SLAB_EXT")) : 16;
         const float dmax = fmaxf(p.vol[0].dimf[0], fmaxf(p.vol[0].dimf[1], p.vol[0].dimf[2]));

@@ -51,7 +51,7 @@ struct SlabShared {
     unsigned int occ[SLAB_OCC_WORDS];
 };
 
-struct SlabArgs { int depth; int cap_floats; const unsigned int* order; int exact_lattice; int ext; int dmin, dmax; };   // march_mslab: exact_lattice = (t_k = fl(t_{k-1} + step) == k * step for every k); ext = expected lateral extent of a tile's region at depth 0 (depth <= 0: per-tile depth)   // order: tile ids, most expensive first; p.tile_counter[1] of them
+struct SlabArgs { int depth; int cap_floats; const unsigned int* order; int exact_lattice; int ext; int dmin, dmax; int prefetch; };   // march_mslab: exact_lattice = (t_k = fl(t_{k-1} + step) == k * step for every k); ext = expected lateral extent of a tile's region at depth 0 (depth <= 0: per-tile depth)   // order: tile ids, most expensive first; p.tile_counter[1] of them
 
 __device__ __forceinline__ int pick3(int a, int b, int c, int axis) { return axis == 0 ? a : (axis == 1 ? b : c); }
 __device__ __forceinline__ float pick3f(float a, float b, float c, int axis) { return axis == 0 ? a : (axis == 1 ? b : c); }
@@ -72,6 +72,26 @@ __device__ __forceinline__ float u16hi_norm(unsigned w) { return xmul(xsub(__uin
 // u16: one item = one 8-voxel brick row segment (a single 16-byte load); a warp takes 32 consecutive (ly,lz) rows of the
 // same x chunk, so 8 lanes share one 128-byte line of the brick pool and -- the row pitch being odd -- the eight
 // 32-bit stores of the warp hit 32 different banks.
+// L2 prefetch of the region the NEXT round is expected to stage: this round's region moved by (ax, ay, az) voxels (one slab along the
+// major axis).  One prefetch per 128-byte brick line (8 rows of a brick share one); issued right after staging, so the DRAM reads
+// overlap the march phase.  A hint only: a wrong prediction costs bandwidth, never correctness.
+__device__ __forceinline__ void slab_prefetch_next(const VolDev& v, const SlabShared& sh, int ax, int ay, int az) {
+    const int nx = sh.rn[0], ny = sh.rn[1], nz = sh.rn[2];
+    const int xr0 = sh.rlo[0] + ax - v.res_lo[0];
+    const int c_first = xr0 >> 3, nchunks = ((xr0 + nx - 1) >> 3) - c_first + 1;
+    const int y0 = sh.rlo[1] + ay, z0 = sh.rlo[2] + az;
+    const int yb0 = (min(max(y0, v.clamp_lo[1]), v.clamp_hi[1]) - v.res_lo[1]) >> 3, yb1 = (min(max(y0 + ny - 1, v.clamp_lo[1]), v.clamp_hi[1]) - v.res_lo[1]) >> 3;
+    const int nyb = yb1 - yb0 + 1;
+    const int items = nchunks * nyb * nz;                            // (x chunk, y brick, z plane): one 128-byte line each
+    for (int it = threadIdx.x; it < items; it += SLAB_THREADS) {
+        const int c = it % nchunks, r = it / nchunks, yb = r % nyb, lz = r / nyb;
+        const int z = min(max(z0 + lz, v.clamp_lo[2]), v.clamp_hi[2]) - v.res_lo[2];
+        const int cxc = min(max(c_first + c, 0), v.nbx - 1);
+        const long long e = (long long)cxc * 512 + brick_off_y((yb0 + yb) << 3, v.nbx) + brick_off_z(z, v.nbx, v.nby);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"((const unsigned short*)v.bricks + e));
+    }
+}
+
 template <class C>
 __device__ __forceinline__ void slab_stage(const VolDev& v, const SlabShared& sh, float* __restrict__ S) {
     const int nx = sh.rn[0], ny = sh.rn[1], nz = sh.rn[2], pitch = sh.pitch;
@@ -568,6 +588,10 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
             // (4) stage voxels + occupancy bits
             slab_stage<C>(V, sh, S);
             if (V.ess) slab_stage_occ<CULL>(V, sh, sh_cmax, sh.occ);
+            if (sa.prefetch && (C::DT ? C::DT : V.dtype) == B200RC_U16) {
+                const int adv = sgn > 0.f ? DEPTH : -DEPTH;
+                slab_prefetch_next(V, sh, axis == 0 ? adv : 0, axis == 1 ? adv : 0, axis == 2 ? adv : 0);
+            }
             __syncthreads();
             PF_MARK(pf_stage)
             // (5) march while the footprint of the next sample lies inside the region.  The loop is warp-synchronous
