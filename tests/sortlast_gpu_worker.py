@@ -118,6 +118,8 @@ def main():
             ok = ok and good
             print(f"{mode} x{world} {nvol} x {size}^3 @{img}^2 {cls} view {k}: within-1/255 {frac:.6f} max|d| {d.max():.4f} depth-ok {dfrac:.6f} "
                   f"rank0 march {ms:.2f} ms frame {frame_ms:.2f} ms transport {sl.transport} {'OK' if good else 'FAIL'}", flush=True)
+        elif rank == 0:     # SL_NOREF: timing only
+            print(f"{mode} x{world} {nvol} x {size}^3 @{img}^2 {cls} view {k}: rank0 march {ms:.2f} ms frame {frame_ms:.2f} ms transport {sl.transport} phases {ph[0]}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     ctx.close()

@@ -10,7 +10,7 @@
 #include <cstring>
 
 #ifndef MSLAB_SHARDED_DEFAULT
-#define MSLAB_SHARDED_DEFAULT false     // flipped to true once the sharded path has passed the GPU tests
+#define MSLAB_SHARDED_DEFAULT true      // B200RC_MSLAB_SHARDED=0 (environment) or -DMSLAB_SHARDED_DEFAULT=false keeps the sort-last passes on the per-ray kernel
 #endif
 template <int CLS> using MSlabCfg = MarchCfg<B200RC_SAMPLER_EXACT, 1, B200RC_U16, CLS, B200RC_GRAD_CENTRAL, B200RC_SHADE_PHONG, -1, true, true>;
 
