@@ -5,7 +5,7 @@
 
 template <int DT, int CLS, int COMP, int SHADE> using SlabCfg = MarchCfg<B200RC_SAMPLER_EXACT, 1, DT, CLS, B200RC_GRAD_CENTRAL, SHADE, COMP, true, false>;
 
-template <class C>
+template <class C, bool STATS>
 static int launch_slab(b200rc_ctx* ctx, const DevParams& p0) {
     DevParams p = p0;
     p.tiles_x = (((p.W + SLAB_TILE - 1) / SLAB_TILE) + 7) / 8 * 8;
@@ -29,7 +29,7 @@ static int launch_slab(b200rc_ctx* ctx, const DevParams& p0) {
     // SLAB_MIN_CTAS CTAs share the SM's 227 KB: the staged region takes what the TF (+ LUT) leaves of one CTA's share
     int cap_kb = env_cap;
     // per CTA: 1 KB reserved by the runtime + this instantiation's static shared memory (scheduling scratch, MIP cell maxima)
-    auto kern = march_slab_kernel<C>;
+    auto kern = march_slab_kernel<C, STATS>;
     cudaFuncAttributes fa;
     RC_CHECK(cudaFuncGetAttributes(&fa, kern));
     const int share_kb = (int)((227 * 1024 / SLAB_MIN_CTAS - 1024 - (long long)fa.sharedSizeBytes) / 1024);
@@ -80,7 +80,8 @@ static int launch_slab(b200rc_ctx* ctx, const DevParams& p0) {
 
 #define SLAB_CASE(DT, CLS, COMP, SHADE)                                                                       \
     if ((DT == 0 || dtype == DT) && cls == CLS && comp == COMP && (SHADE < 0 || p.shading[0] == SHADE)) {    \
-        const int rc = launch_slab<SlabCfg<DT, CLS, COMP, SHADE>>(ctx, p);                                   \
+        const int rc = p.collect_stats ? launch_slab<SlabCfg<DT, CLS, COMP, SHADE>, true>(ctx, p)           \
+                                       : launch_slab<SlabCfg<DT, CLS, COMP, SHADE>, false>(ctx, p);         \
         if (rc >= 0) { *rc_out = rc; return true; }                                                          \
     }
 

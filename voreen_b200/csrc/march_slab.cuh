@@ -28,6 +28,9 @@
 #ifndef SLAB_MIN_CTAS
 #define SLAB_MIN_CTAS (768 / SLAB_THREADS)
 #endif
+// per-sample counters (classified / shaded / skipped): only the STATS instantiation of the kernel keeps them -- three registers and
+// two increments per sample are worth 1.1 % of the frame (profiles/r2_slab_nostats_ab.txt); b200rc_params.collect_stats selects it
+#define SLAB_STAT(x) do { if (STATS) { x; } } while (0)
 #ifndef SLAB_STAGE_BATCH
 #define SLAB_STAGE_BATCH 4      // 16-byte loads in flight per thread while staging
 #endif
@@ -195,13 +198,13 @@ __device__ __forceinline__ void slab_stage_occ(const VolDev& v, SlabShared& sh, 
 }
 
 // jump over the empty cell the sample at t lies in: returns false when the cell is not empty
-template <bool CULL>
+template <bool CULL, bool STATS>
 __device__ __forceinline__ bool slab_skip_empty(const DevParams& p, const VolDev& V, float3 first, float3 dir, float tEnd, float step,
                                                 float& t, float& t_last, int& loop, bool& finished, RayStats& st, float maxI) {
     const float3 sp = f3(xadd(first.x, xmul(t, dir.x)), xadd(first.y, xmul(t, dir.y)), xadd(first.z, xmul(t, dir.z)));
     float t_exit = 0.f;
     if (!((CULL && V.mip_cull) ? ess_empty_cell_t<true>(V, sp, dir, t, maxI, t_exit) : ess_empty_cell(V, sp, dir, t, t_exit))) return false;
-    if (t_exit > tEnd) { st.skipped += (unsigned)floorf((tEnd - t) / step) + 1u; finished = true; return true; }
+    if (t_exit > tEnd) { SLAB_STAT(st.skipped += (unsigned)floorf((tEnd - t) / step) + 1u); finished = true; return true; }
     int n = 1; float tn;
     if (p.lattice_exact) {
         int k1 = max(loop + 1, __float2int_ru(t_exit / step));
@@ -214,7 +217,7 @@ __device__ __forceinline__ bool slab_skip_empty(const DevParams& p, const VolDev
         tn = xadd(t, step);
         while (tn < t_exit && tn <= tEnd) { t_last = tn; tn = xadd(tn, step); ++n; }
     }
-    st.skipped += n; loop += n; t = tn;
+    SLAB_STAT(st.skipped += n); loop += n; t = tn;
     finished = (t > tEnd) || loop >= 256 * 256;
     return true;
 }
@@ -224,6 +227,7 @@ __device__ __forceinline__ bool slab_skip_empty(const DevParams& p, const VolDev
 // The exit parameter is rounded DOWN (1e-6 relative + directed rounding), so it never lies behind the exit the divisions would
 // give: the jump may stop one lattice sample early -- that sample is still inside the empty cell, is tested against the staged bit
 // again and skipped by the next call -- but never late.  Pixels and the classified / skipped counters are unchanged.
+template <bool STATS>
 __device__ __forceinline__ void slab_skip_cell(const DevParams& p, const VolDev& V, float3 dir, float sux, float suy, float suz, float fx, float fy, float fz,
                                                float tEnd, float step, float step_rcp, float& t, float& t_last, int& loop, bool& finished, RayStats& st) {
     float dt = 3.0e38f;
@@ -242,7 +246,7 @@ __device__ __forceinline__ void slab_skip_cell(const DevParams& p, const VolDev&
         }
     }
     const float t_exit = __fadd_rd(t, __fmul_rd(fmaxf(dt, 0.f), 0.999999f));
-    if (t_exit > tEnd) { st.skipped += (unsigned)floorf((tEnd - t) / step) + 1u; finished = true; return; }
+    if (t_exit > tEnd) { SLAB_STAT(st.skipped += (unsigned)floorf((tEnd - t) / step) + 1u); finished = true; return; }
     int n = 1; float tn;
     if (p.lattice_exact) {
         int k1 = max(loop + 1, __float2int_ru(t_exit * step_rcp));
@@ -255,7 +259,7 @@ __device__ __forceinline__ void slab_skip_cell(const DevParams& p, const VolDev&
         tn = xadd(t, step);
         while (tn < t_exit && tn <= tEnd) { t_last = tn; tn = xadd(tn, step); ++n; }
     }
-    st.skipped += n; loop += n; t = tn;
+    SLAB_STAT(st.skipped += n); loop += n; t = tn;
     finished = (t > tEnd) || loop >= 256 * 256;
 }
 
@@ -357,7 +361,7 @@ static __global__ void __launch_bounds__(1024) slab_tile_order_kernel(const floa
     if (threadIdx.x == 0) { counter[0] = 0u; counter[1] = carry; }
 }
 
-template <class C>
+template <class C, bool STATS>
 __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel(const __grid_constant__ DevParams p, const SlabArgs sa) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ SlabShared sh;
@@ -496,7 +500,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
             //     slab is staged where the ray would only skip
             if (stale) {
                 if (V.ess && (!pi_mode || prev_empty))
-                    while (!finished && slab_skip_empty<CULL>(p, V, first, dir, tStop, step, t, t_last, loop, finished, st, maxI)) { if (pi_mode) lastI_stale = true; }
+                    while (!finished && slab_skip_empty<CULL, STATS>(p, V, first, dir, tStop, step, t, t_last, loop, finished, st, maxI)) { if (pi_mode) lastI_stale = true; }
                 zc = INT_MAX;
                 if (!finished) {
                     const float3 sp = f3(xadd(first.x, xmul(t, dir.x)), xadd(first.y, xmul(t, dir.y)), xadd(first.z, xmul(t, dir.z)));
@@ -604,7 +608,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
                 const bool cull_on = CULL && V.mip_cull && V.ess && sh.cm_ok;
                 const int cm_nx = sh.cm_nx;
                 bool run = part;
-                if (p.collect_stats) { dbg_part += part ? 1u : 0u; dbg_rounds += 1u; }
+                if (STATS && p.collect_stats) { dbg_part += part ? 1u : 0u; dbg_rounds += 1u; }
                 while (__any_sync(0xffffffffu, run)) {
 #ifdef SLAB_PROFILE
                     pf_iters++; pf_lanes += __popc(__ballot_sync(0xffffffffu, run));
@@ -634,7 +638,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
                                 // pre-integration that also needs the PREVIOUS sample to lie in an empty cell: the value
                                 // ranges of the two (adjacent, overlapping) cells then form one interval on which the
                                 // transfer function is transparent, so the table entry (cur, prev) is transparent too.
-                                slab_skip_cell(p, V, dir, sux, suy, suz, fx, fy, fz, tStop, step, sh.step_rcp, t, t_last, loop, finished, st);
+                                slab_skip_cell<STATS>(p, V, dir, sux, suy, suz, fx, fy, fz, tStop, step, sh.step_rcp, t, t_last, loop, finished, st);
                                 if (pi_mode) lastI_stale = true;
                                 stale = true;
                                 run = !finished;
@@ -663,7 +667,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
                                 const float c00 = xlerp(c000, c100, ax), c10 = xlerp(c010, c110, ax), c01 = xlerp(c001, c101, ax), c11 = xlerp(c011, c111, ax);
                                 const float tex = xlerp(xlerp(c00, c10, ay), xlerp(c01, c11, ay), az);
                                 const float intensity = xadd(xmul(tex, V.rwm_scale), V.rwm_offset);
-                                st.classified++;
+                                SLAB_STAT(st.classified++);
                                 int a8 = -1;
                                 float4 color0;
                                 if (pi_mode) {
@@ -679,7 +683,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
                                     a8 = q.w;
                                     color0 = u8tof4(q);
                                 }
-                                if (color0.w > 0.f) st.shaded++;
+                                SLAB_STAT(if (color0.w > 0.f) st.shaded++);
                                 if (color0.w > 0.f && compositing_takes_sample(comp, result, intensity, color0.w, maxI, p.iso)) {
                                     float3 gradient;
                                     if (t == 0.0f) gradient = fix_clip_border_gradient(p, sp, dir, px, py);
@@ -725,7 +729,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, SLAB_MIN_CTAS) march_slab_kernel
                                     color.x = shd.x; color.y = shd.y; color.z = shd.z;
                                     result = apply_compositing(comp, 1, p.preint_comp, result, intensity, color, a8, sm.lut[0], sp, gradient, t, step, tDepth, maxI, p.gamma[0], p.iso);
                                 }
-                                if (p.collect_stats && p.touched) {
+                                if (STATS && p.collect_stats && p.touched) {
                                     const int cx = min(max((int)fx, 0), V.dims[0] - 1) / B200RC_STAT_CELL, cy = min(max((int)fy, 0), V.dims[1] - 1) / B200RC_STAT_CELL,
                                               cz = min(max((int)fz, 0), V.dims[2] - 1) / B200RC_STAT_CELL;
                                     p.touched[((size_t)cz * p.touched_dims[1] + cy) * p.touched_dims[0] + cx] = 1;
